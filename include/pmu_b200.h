@@ -1,0 +1,200 @@
+/*
+ * pmu_b200.h — C-ABI of the B200-native multi-planar probabilistic inference path.
+ *
+ * The reference (qzs634/Probabilistic-Multiplanar-Unet) is pure Python and has NO
+ * FFI / plugin interface; its only seam is the Python class API in
+ * model/probabilistic_unet/probabilistic_unet.py, model/unet/*.py, dice_loss.py and
+ * the data plane in utils/mri_dataset.py / eval.py.  This header is the boundary the
+ * build defines underneath that API: each entry point states the reference call
+ * site (file:line, relative to Probabilistic-Multiplanar-Unet/) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.
+ *   - every function returns int: 0 = OK, negative = error (pmu_last_error() gives a
+ *     thread-local message).  Nothing throws or aborts across the boundary.
+ *   - the CALLER owns every buffer (device pointers unless marked host); the library
+ *     allocates nothing on the device.
+ *   - every launch is asynchronous on the caller-supplied cudaStream_t (passed as
+ *     void*; NULL = legacy default stream).  Safe to capture into a CUDA graph.
+ *   - device pointers must be 16-byte aligned (128-bit vector paths, TMA).
+ *   - fp32 tensors of the "f32" family are NCHW (the reference's layout); bf16
+ *     tensors of the "bf16" family are NHWC (channels-last, TMA/tcgen05-friendly).
+ *   - volumes are fp32 [d0][d1][d2] = [x][y][z], z fastest (numpy C order of the
+ *     array nibabel returns, mri_dataset.py:124).
+ *   - voxel accumulators / outputs use the reference's avg_volume layout [x][C][y][z]
+ *     (eval.py:176,193).
+ */
+#ifndef PMU_B200_H_
+#define PMU_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMU_OK 0
+#define PMU_ERR_INVALID (-1)   /* bad argument (shape, alignment, enum) */
+#define PMU_ERR_CUDA (-2)      /* CUDA runtime / driver error */
+#define PMU_ERR_UNSUPPORTED (-3) /* shape outside what the sm_100a kernel supports */
+
+#define PMU_INTERP_EXACT 0     /* axis-aligned integer slicing (mri_dataset.py:70-82) */
+#define PMU_INTERP_NEAREST 1   /* affine grid, floor(q+0.5), zeros outside */
+#define PMU_INTERP_TRILINEAR 2 /* affine grid, 8-tap lerp z,y,x, zeros outside */
+
+#define PMU_DTYPE_F32 0
+#define PMU_DTYPE_BF16 1
+
+#define PMU_POOL_MAX 0         /* nn.MaxPool2d(2)                 unet_parts.py:33 */
+#define PMU_POOL_AVG_CEIL 1    /* nn.AvgPool2d(2,2,0,ceil_mode)   probabilistic_unet.py:36 */
+
+/* ---- housekeeping ------------------------------------------------------- */
+const char* pmu_last_error(void);
+int pmu_version(void);
+/* sm count and compute capability of the current device. */
+int pmu_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Select the CUDA device for this thread's subsequent calls (the library carries its own
+ * statically linked CUDA runtime, so the caller's cudaSetDevice does not reach it).  The
+ * stream passed to every call must belong to this device. */
+int pmu_set_device(int device);
+
+/* ---- K1: plane slicing (data plane in) ---------------------------------- *
+ * replaces MRI_Dataset.sample_slice + preprocess, mri_dataset.py:70-82,101-112 */
+
+/* Per-slice maxima of all three planes in ONE pass over the volume:
+ * maxes[0..d0) plane 0, [d0..d0+d1) plane 1, [d0+d1..d0+d1+d2) plane 2.
+ * (np.max(img_trans), mri_dataset.py:109).  maxes must be pre-filled by the caller
+ * with -inf (pmu_fill_f32) — the kernel combines with atomic max. */
+int pmu_plane_max(const float* vol, const int32_t dims[3], float* maxes, void* stream);
+
+/* Gather ns slices [s0, s0+ns) of `plane` into out[ns][H][W] (C=1, so NCHW==NHWC).
+ *  interp EXACT: H,W must equal the two remaining extents; bit-exact copies.
+ *  interp NEAREST/TRILINEAR: affine = 12 HOST floats [o(3), n(3), u(3), v(3)],
+ *    q = o + s*n + r*u + c*v in fp32 (fixed op order, see oracle resample_slices).
+ *  slice_max_in  (nullable, indexed by absolute slice s): fuse the normalisation
+ *    x / max if max != 0, computed as (float)((double)x / (double)max) — the
+ *    reference's fp64 divide + .float() (mri_dataset.py:110,142) bit for bit.
+ *  slice_max_out (nullable, indexed by s - s0, pre-filled with -inf): records the
+ *    max of each gathered (raw) slice with atomic max, for pmu_slice_normalize.
+ *  out_dtype: PMU_DTYPE_F32 only (bf16 conversion happens in the first conv). */
+int pmu_slice_gather(const float* vol, const int32_t dims[3], int plane, int s0, int ns,
+                     int interp, const float* affine_host, int H, int W,
+                     const float* slice_max_in, float* slice_max_out,
+                     float* out, void* stream);
+
+/* In-place x/max per slice (same fp64 divide), slices [ns][hw], slice_max [ns]. */
+int pmu_slice_normalize(float* slices, const float* slice_max, int ns, int64_t hw, void* stream);
+
+int pmu_fill_f32(float* p, float value, int64_t n, void* stream);
+
+/* ---- fp32 NCHW layer ops (parity mode, CUDA cores) ----------------------- */
+
+/* y = [relu](conv3x3_pad1(cat(x0[B,C0,H,W], x1[B,C1,H,W]), w[Cout,C0+C1,3,3]) + bias).
+ * x1 may be NULL (C1 = 0).  BatchNorm is folded into w/bias by the caller.
+ * replaces nn.Conv2d+BatchNorm2d+ReLU (unet_parts.py:15-20, probabilistic_unet.py:38-45)
+ * and the F.pad/torch.cat of Up.forward (unet_parts.py:58-66: skip first, up second). */
+int pmu_conv3x3_f32(const float* x0, int C0, const float* x1, int C1, const float* w,
+                    const float* bias, float* y, int B, int H, int W, int Cout, int relu,
+                    void* stream);
+/* y[B,Cout,H,W] = [relu](conv1x1(x[B,Cin,H,W], w[Cout,Cin]) + bias)   (unet_parts.py:73) */
+int pmu_conv1x1_f32(const float* x, const float* w, const float* bias, float* y, int B,
+                    int Cin, int Cout, int64_t HW, int relu, void* stream);
+/* nn.ConvTranspose2d(k=2,s=2) (unet_parts.py:52): x[B,Cin,H,W], w[Cin,Cout,2,2] ->
+ * y[B,Cout,Ho,Wo] placed at offset (padT,padL) inside a zero-filled [Ho,Wo] canvas
+ * (the F.pad of unet_parts.py:61-62; Ho>=2H, Wo>=2W). */
+int pmu_convt2x2_f32(const float* x, const float* w, const float* bias, float* y, int B,
+                     int Cin, int Cout, int H, int W, int Ho, int Wo, int padT, int padL,
+                     void* stream);
+/* 2x2 stride-2 pooling; MAX floors the output size, AVG_CEIL ceils it and divides
+ * by the number of in-bounds taps. */
+int pmu_pool2_f32(const float* x, float* y, int B, int C, int H, int W, int mode, void* stream);
+/* AxisAlignedConvGaussian head (probabilistic_unet.py:97-108): mean over H then W of
+ * enc[B,C,h,w], 1x1 conv w[2L,C]+b -> mu[B,L], log_sigma[B,L]. */
+int pmu_gauss_head_f32(const float* enc, const float* w, const float* b, float* mu,
+                       float* log_sigma, int B, int C, int h, int w_, int L, void* stream);
+
+/* Fcomb (probabilistic_unet.py:155-181) for N latent samples per slice.
+ *  feat[B,F,H,W] fp32; z[B,N,L]; w0[F,F+L], b0[F]; wmid[(nl-2)][F,F], bmid[(nl-2)][F]
+ *  (nl = no_convs_fcomb >= 2); wlast[C,F], blast[C].
+ *  logits (nullable) [B,N,C,H,W]; slice_sums (nullable) [B,2,C,H,W] receives
+ *  sum_n softmax and sum_n softmax^2 (App. A steps 5-6; overwritten, not added). */
+int pmu_fcomb_f32(const float* feat, const float* z, const float* w0, const float* b0,
+                  const float* wmid, const float* bmid, const float* wlast, const float* blast,
+                  float* logits, float* slice_sums, int B, int N, int F, int L, int C,
+                  int nl, int64_t HW, void* stream);
+
+/* ---- bf16 NHWC layer ops (performance mode) ------------------------------ */
+
+/* First layer, Cin in {1,2}: x fp32 NCHW [B,Cin,H,W] (+ optional second 1-channel
+ * tensor x1 for the posterior's cat(input, segm), probabilistic_unet.py:85-90) ->
+ * y bf16 NHWC [B,H,W,Cout]; w fp32 [Cout,Cin,3,3] (BN folded), bias fp32. */
+int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const float* w, const float* bias,
+                           void* y, int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+
+/* tcgen05/TMEM implicit-GEMM convolution, TMA-fed (sm_100a only).
+ *  ntaps = 9: conv3x3 pad 1 over cat(x0[B,H,W,C0], x1[B,H,W,C1]) (x1 nullable);
+ *             wpack bf16 [Cout][9][C0+C1] (tap = ky*3+kx); y bf16 [B,H,W,Cout].
+ *  ntaps = 4: ConvTranspose2d k2 s2: x0[B,H,W,C0]; wpack bf16 [4*Cout][C0]
+ *             (row = (i*2+j)*Cout + co); y bf16 [B,2H,2W,Cout]; relu must be 0.
+ *  ntaps = 1: conv1x1, wpack [Cout][C0].
+ *  C0, C1 multiples of 64; Cout multiple of 64; bias fp32 [Cout]. */
+int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
+                       const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
+                       int relu, void* stream);
+
+int pmu_pool2_bf16(const void* x, void* y, int B, int H, int W, int C, int mode, void* stream);
+/* enc bf16 NHWC [B,h,w,C]; w fp32 [2L,C]; outputs fp32. */
+int pmu_gauss_head_bf16(const void* enc, const float* w, const float* b, float* mu,
+                        float* log_sigma, int B, int C, int h, int w_, int L, void* stream);
+/* bf16 NHWC [B,H,W,C] -> fp32 NCHW [B,C,H,W] (hands unet_features back to the
+ * reference-facing API in its own layout). */
+int pmu_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, void* stream);
+
+/* K3+K4 fused: fcomb over N samples with tensor-core MLP, softmax, and per-pixel
+ * sum / sum-of-squares accumulation; per-sample logits never reach HBM.
+ *  feat bf16 NHWC [B,H,W,64]; mu, sigma fp32 [B,L]; eps fp32 [B,N,L]
+ *  (z = mu + sigma*eps, probabilistic_unet.py:233-239 rsample);
+ *  w0 fp32 [64,64+L], b0[64]; wmid fp32 [nl-2][64,64], bmid; wlast [C,64], blast[C];
+ *  slice_sums fp32 [B,2,C,H,W] (overwritten).  F must be 64, C <= 8, L <= 16. */
+int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, const float* sigma,
+                                 const float* eps, const float* w0, const float* b0,
+                                 const float* wmid, const float* bmid, const float* wlast,
+                                 const float* blast, float* slice_sums, int B, int N, int L,
+                                 int C, int nl, int64_t HW, void* stream);
+
+/* ---- K4: softmax + scatter-accumulate + finalise (data plane out) -------- *
+ * replaces eval.py:157 (softmax), :176-190 (cat/permute), :193 (fusion)      */
+
+/* Unfused variant: logits fp32 [B,N,C,HW] -> slice_sums [B,2,C,HW] (overwritten). */
+int pmu_softmax_accum(const float* logits, float* slice_sums, int B, int N, int C, int64_t HW,
+                      void* stream);
+/* S1/S2 [x][C][y][z] += slice_sums[b][0/1][C][H][W] for slices s0..s0+ns of `plane`:
+ * plane 0 -> (s,r,c), plane 1 -> (r,s,c), plane 2 -> (r,c,s)  (eval.py:176,182,188). */
+int pmu_scatter_accum(const float* slice_sums, int plane, int s0, int ns, const int32_t dims[3],
+                      int C, float* S1, float* S2, void* stream);
+/* mean = S1/count, var = max(S2/count - mean^2, 0) ([x][C][y][z]); entropy [x][y][z]
+ * = sum_k -mean_k ln mean_k; labels (nullable, uint8 [x][y][z]) = argmax_k mean
+ * (eval.py:52).  Any of mean/var/entropy may be NULL. */
+int pmu_fuse_finalize(const float* S1, const float* S2, float count, const int32_t dims[3], int C,
+                      float* mean, float* var, float* entropy, uint8_t* labels, void* stream);
+
+/* ---- K5: reductions for the training step / evaluation ------------------- */
+/* sum over b,pixels of CE(logits[B,C,HW], target[B,HW] float labels) -> out[1]
+ * (probabilistic_unet.py:288,303-304).  out is overwritten. */
+int pmu_ce_sum(const float* logits, const float* target, int B, int C, int64_t HW, float* out,
+               void* stream);
+/* analytic KL(q||p) of diagonal Gaussians -> out[B] (probabilistic_unet.py:272). */
+int pmu_kl_diag_gauss(const float* mu_q, const float* log_sigma_q, const float* mu_p,
+                      const float* log_sigma_p, int B, int L, float* out, void* stream);
+/* sums[3] = {sum(p*t), sum(p), sum(t)} (dice_loss.py:10-12); overwritten. */
+int pmu_dice_sums(const float* pred, const float* target, int64_t n, float* sums, void* stream);
+/* Dice of one-hot(argmax_C prob)[k] vs (truth==k) for k = 1..C-1 (eval.py:42-49):
+ * prob [X][C][YZ] (avg_volume layout), truth float [X][YZ]; sums[(C-1)*3] overwritten. */
+int pmu_argmax_dice_sums(const float* prob, const float* truth, int64_t X, int C, int64_t YZ,
+                         float* sums, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMU_B200_H_ */

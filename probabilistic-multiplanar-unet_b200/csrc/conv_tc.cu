@@ -1,0 +1,299 @@
+// K2 — implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), TMA-fed.
+//
+// Replaces nn.Conv2d(3x3,pad 1)+BatchNorm2d(eval, folded)+ReLU (unet_parts.py:15-20,
+// probabilistic_unet.py:38-45), the F.pad/torch.cat of Up.forward (unet_parts.py:58-66, as a
+// two-source K loop — the concat is never materialised) and nn.ConvTranspose2d(k2,s2)
+// (unet_parts.py:52, as a 1-tap GEMM with N = 4*Cout and a pixel-shuffle store).
+//
+// GEMM view:  D[M = 128 pixels][N = BN couts] += A[M][K] * B[N][K]^T,  K = taps x Cin.
+//   A tile : 128 output pixels = a (TB x TH x TW) brick of the NHWC bf16 activation tensor,
+//            64 channels wide.  One TMA 4-D box load per (tap, 64-channel chunk); the tap
+//            shift (dy,dx) is applied to the box coordinates and TMA's out-of-bounds zero
+//            fill implements the conv padding — no im2col buffer, no halo bookkeeping.
+//   B tile : BN rows of the packed weight matrix [Ntot][taps*Cin] (K-major), one TMA 2-D box.
+//   Both land in shared memory in the 128-byte-swizzled K-major layout UMMA reads directly.
+//   D      : fp32 accumulator in TMEM (BN columns x 128 lanes), read back with tcgen05.ld.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (bias + ReLU + bf16 pack + NHWC store).
+// Pipeline: STAGES-deep smem ring with full/empty mbarriers; tcgen05.commit releases slots.
+// Two CTAs are resident per SM so one CTA's epilogue overlaps the other's main loop.
+#include <cudaTypedefs.h>
+
+#include "pmu_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace pmu {
+
+using namespace ptx;
+
+constexpr int TC_BM = 128;       // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;        // channels per k-block (128 B of bf16 = one swizzle row)
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+struct ConvTcParams {
+  int B, H, W;        // input extents
+  int C0, C1;         // channels of the two K-loop sources (multiples of 64; C1 may be 0)
+  int Cout;           // output channels (per phase for convT)
+  int ntaps;          // 9 = conv3x3, 1 = conv1x1, 4 = convT2x2 (N = 4*Cout, one K tap)
+  int relu;
+  int TW, TH, TB;     // tile brick, TW*TH*TB == 128
+  int tiles_w, tiles_h, tiles_b;
+  int n_tiles;        // Ntot / BN
+};
+
+template <int BN, int STAGES>
+struct ConvTcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;            // full[S], empty[S], tmem_full
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
+  static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;
+  static constexpr int TOTAL = BIAS_OFF + BN * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmW, const ConvTcParams p,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y) {
+  using L = ConvTcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_full = smem_base + L::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tmem = bar_empty + STAGES * 8;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TMEM_PTR_OFF);
+  float* bias_s = reinterpret_cast<float*>(smem_gen + L::BIAS_OFF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates: blockIdx.x = m_tile * n_tiles + n_tile (N fastest: the CTAs that
+  // share an activation tile are launched together and hit it in L2) ----
+  const int n_tile = blockIdx.x % p.n_tiles;
+  int m_tile = blockIdx.x / p.n_tiles;
+  const int tw_i = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+  const int th_i = m_tile % p.tiles_h; m_tile /= p.tiles_h;
+  const int tb_i = m_tile;
+  const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.TB;
+  const int n0 = n_tile * BN;
+
+  const int Cin = p.C0 + p.C1;
+  const int kc_per_tap = Cin / TC_BK;
+  const int k_taps = (p.ntaps == 9) ? 9 : 1;
+  const int k_iters = k_taps * kc_per_tap;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA0);
+    if (p.C1 > 0) prefetch_tensormap(&tmA1);
+    prefetch_tensormap(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(smem_base + L::TMEM_PTR_OFF);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bar_empty + s * 8, ph ^ 1u);
+        const int tap = it / kc_per_tap;
+        int c = (it - tap * kc_per_tap) * TC_BK;   // channel offset inside the concatenated K
+        int dy = 0, dx = 0;
+        if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+        const uint32_t sb = sa + L::A_BYTES;
+        mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+        if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
+        else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
+        tma_load_2d(sb, &tmW, bar_full + s * 8, tap * Cin + c, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+    for (int it = 0; it < k_iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_full + s * 8, ph);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+        const uint64_t adesc = umma_smem_desc_sw128(sa);
+        const uint64_t bdesc = umma_smem_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+          // +32 B per UMMA_K inside the 128 B swizzle row: start-address field += 2
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                    (uint32_t)((it | k) != 0));
+        }
+        umma_commit(bar_empty + s * 8);              // frees the smem slot when these MMAs retire
+        if (it == k_iters - 1) umma_commit(bar_tmem);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int et = threadIdx.x - 64;  // 0..127
+    const int co_base = (p.ntaps == 4) ? (n0 % p.Cout) : n0;
+    for (int i = et; i < BN; i += 128) bias_s[i] = bias ? __ldg(bias + co_base + i) : 0.f;
+    named_bar_sync(1, 128);
+
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;       // row of the tile == pixel index in the brick
+    const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
+    const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
+    const bool valid = (b < p.B) && (h < p.H) && (w < p.W);
+    __nv_bfloat16* dst;
+    if (p.ntaps == 4) {
+      const int ij = n0 / p.Cout;
+      const int oy = 2 * h + (ij >> 1), ox = 2 * w + (ij & 1);
+      dst = y + (((int64_t)b * (2 * p.H) + oy) * (2 * p.W) + ox) * p.Cout + co_base;
+    } else {
+      dst = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base;
+    }
+    mbar_wait(bar_tmem, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = __uint_as_float(r[v * 8 + 2 * j]) + bias_s[c0 + v * 8 + 2 * j];
+            float c = __uint_as_float(r[v * 8 + 2 * j + 1]) + bias_s[c0 + v * 8 + 2 * j + 1];
+            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// host side: tensor-map encoding through the driver entry point (no libcuda link)
+// ------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [B][H][W][C]: box = 64 channels x TW x TH x TB, 128 B swizzle, zero OOB fill
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", B, H, W, C, (int)r); return PMU_ERR_CUDA; }
+  return PMU_OK;
+}
+// packed weights [N][K] bf16, K fastest: box = 64 x BN
+static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%d) failed: %d", N, K, (int)r); return PMU_ERR_CUDA; }
+  return PMU_OK;
+}
+
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <int BN, int STAGES>
+static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm,
+                          const ConvTcParams& p, const float* bias, void* y, int64_t grid, cudaStream_t st) {
+  using L = ConvTcSmem<BN, STAGES>;
+  auto kern = conv_tc_kernel<BN, STAGES>;
+  PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+  kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, p, bias, reinterpret_cast<__nv_bfloat16*>(y));
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+}  // namespace pmu
+
+using namespace pmu;
+
+extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
+                                  const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
+                                  int relu, void* stream) {
+  PMU_CHECK_ARG(x0 && wpack && y, "pmu_conv_gemm_bf16: null pointer");
+  PMU_CHECK_ARG(ntaps == 9 || ntaps == 4 || ntaps == 1, "pmu_conv_gemm_bf16: ntaps must be 9, 4 or 1 (got %d)", ntaps);
+  PMU_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && C1 >= 0, "pmu_conv_gemm_bf16: bad shape");
+  PMU_CHECK_ARG(C1 == 0 || x1, "pmu_conv_gemm_bf16: C1 > 0 needs x1");
+  PMU_CHECK_ARG(!(ntaps == 4 && (C1 != 0 || relu)), "pmu_conv_gemm_bf16: convT takes one source and no ReLU");
+  PMU_CHECK_SUPPORTED(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0,
+                      "pmu_conv_gemm_bf16: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  PMU_CHECK_ARG(aligned16(x0) && aligned16(wpack) && aligned16(y) && (!x1 || aligned16(x1)),
+                "pmu_conv_gemm_bf16: pointers must be 16-byte aligned");
+  int cc_major = 0, dev = 0;
+  PMU_CUDA(cudaGetDevice(&dev));
+  PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  PMU_CHECK_SUPPORTED(cc_major == 10, "pmu_conv_gemm_bf16: needs an sm_100 device (tcgen05/TMEM); found cc %d.x", cc_major);
+
+  ConvTcParams p;
+  p.B = B; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout; p.ntaps = ntaps; p.relu = relu;
+  p.TW = std::min(16, pow2ceil(W));
+  p.TH = std::min(TC_BM / p.TW, pow2ceil(H));
+  p.TB = TC_BM / (p.TW * p.TH);
+  p.tiles_w = cdiv(W, p.TW); p.tiles_h = cdiv(H, p.TH); p.tiles_b = cdiv(B, p.TB);
+  const int Cin = C0 + C1;
+  const int Ntot = (ntaps == 4) ? 4 * Cout : Cout;
+  const int Ktot = (ntaps == 9) ? 9 * Cin : Cin;
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  p.n_tiles = Ntot / BN;
+  const int64_t grid = (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+  PMU_CHECK_ARG(grid > 0 && grid < (1ll << 31), "pmu_conv_gemm_bf16: grid too large");
+
+  CUtensorMap a0, a1, wm;
+  int rc = make_act_map(&a0, x0, B, H, W, C0, p.TW, p.TH, p.TB);
+  if (rc) return rc;
+  if (C1 > 0) { rc = make_act_map(&a1, x1, B, H, W, C1, p.TW, p.TH, p.TB); if (rc) return rc; }
+  else a1 = a0;
+  rc = make_w_map(&wm, wpack, Ntot, Ktot, BN);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 128) return launch_conv_tc<128, 3>(a0, a1, wm, p, bias, y, grid, st);
+  return launch_conv_tc<64, 4>(a0, a1, wm, p, bias, y, grid, st);
+}

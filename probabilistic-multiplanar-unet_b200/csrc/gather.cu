@@ -1,0 +1,387 @@
+// K1 — plane slicing gather (data plane in).
+//
+// Replaces MRI_Dataset.sample_slice + preprocess (utils/mri_dataset.py:70-82,101-112):
+//   plane 0: I[r,c] = vol[s,r,c]   plane 1: I[r,c] = vol[r,s,c]   plane 2: I[r,c] = vol[r,c,s]
+// followed by I / max(I) when max(I) != 0 (fp64 divide, then .float()).
+//
+// All three kernels are HBM-bound integer-indexing/byte-moving work: the design rules
+// are coalescing, 128-bit accesses, and enough independent loads in flight; plane 2
+// (slice index on the fastest axis) goes through a shared-memory transpose tile so both
+// the volume reads (along z) and the slice writes (along c) are full 128 B lines.
+#include "pmu_common.cuh"
+
+namespace pmu {
+
+// ---------------------------------------------------------------------------------
+// plane_max: per-slice maxima of all three planes in one pass over the volume.
+// One warp per (x,y) row; lanes stride along z with float4.
+// ---------------------------------------------------------------------------------
+constexpr int PM_WARPS = 8;
+constexpr int PM_ROWS_PER_WARP = 8;
+constexpr int PM_ZSEG = 1024;  // z extent handled per pass: 32 lanes * 4 * 8 chunks
+
+template <bool VEC>
+__global__ void __launch_bounds__(PM_WARPS * 32)
+plane_max_kernel(const float* __restrict__ vol, int d0, int d1, int d2, float* __restrict__ maxes) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nrows = (int64_t)d0 * d1;
+  const int64_t row0 = ((int64_t)blockIdx.x * PM_WARPS + warp) * PM_ROWS_PER_WARP;
+  float* max0 = maxes;
+  float* max1 = maxes + d0;
+  float* max2 = maxes + d0 + d1;
+  for (int zseg = 0; zseg < d2; zseg += PM_ZSEG) {
+    float zmax[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) zmax[j][i] = -INFINITY;
+    for (int rr = 0; rr < PM_ROWS_PER_WARP; ++rr) {
+      const int64_t row = row0 + rr;
+      if (row >= nrows) break;
+      const int x = (int)(row / d1), y = (int)(row % d1);
+      const float* p = vol + row * d2 + zseg;
+      float rmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int z = 4 * (lane + 32 * j);
+        if (zseg + z < d2) {
+          float v[4];
+          if (VEC) {
+            float4 t = ldg_stream_f4(reinterpret_cast<const float4*>(p + z));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (zseg + z + i < d2) ? __ldg(p + z + i) : -INFINITY;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            zmax[j][i] = fmaxf(zmax[j][i], v[i]);
+            rmax = fmaxf(rmax, v[i]);
+          }
+        }
+      }
+      rmax = warp_max(rmax);
+      if (lane == 0) {
+        if (rmax == 0.f) rmax = 0.f;  // canonicalise -0
+        atomic_max_float(max0 + x, rmax);
+        atomic_max_float(max1 + y, rmax);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int z = zseg + 4 * (lane + 32 * j);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float m = zmax[j][i];
+        if (z + i < d2 && m != -INFINITY) {
+          if (m == 0.f) m = 0.f;
+          atomic_max_float(max2 + z + i, m);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// exact gather, planes 0 and 1: row copies (contiguous along z == c).
+//   grid.y = slice b, grid.x strides over the H*W/4 float4 of the slice.
+// ---------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ vol, int d1, int d2, int plane, int s0, int H, int W,
+                   const float* __restrict__ max_in, float* __restrict__ max_out,
+                   float* __restrict__ out) {
+  const int b = blockIdx.y, s = s0 + b;
+  const float m = max_in ? __ldg(max_in + s) : 0.f;
+  const int64_t hw = (int64_t)H * W;
+  float* dst = out + (int64_t)b * hw;
+  float tmax = -INFINITY;
+  if (VEC) {
+    const int w4 = W >> 2;
+    const int64_t n4 = hw >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / w4), c4 = (int)(i % w4);
+      // plane 0: vol[s][r][c]; plane 1: vol[r][s][c]
+      const int64_t src = (plane == 0) ? ((int64_t)s * d1 + r) * d2 : ((int64_t)r * d1 + s) * d2;
+      float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(vol + src) + c4);
+      tmax = fmaxf(tmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      if (max_in) {
+        v.x = ref_normalise(v.x, m); v.y = ref_normalise(v.y, m);
+        v.z = ref_normalise(v.z, m); v.w = ref_normalise(v.w, m);
+      }
+      stg_stream_f4(reinterpret_cast<float4*>(dst) + i, v);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / W), c = (int)(i % W);
+      const int64_t src = (plane == 0) ? ((int64_t)s * d1 + r) * d2 + c : ((int64_t)r * d1 + s) * d2 + c;
+      float v = __ldg(vol + src);
+      tmax = fmaxf(tmax, v);
+      dst[i] = max_in ? ref_normalise(v, m) : v;
+    }
+  }
+  if (max_out) {
+    tmax = warp_max(tmax);
+    if ((threadIdx.x & 31) == 0 && tmax != -INFINITY) {
+      if (tmax == 0.f) tmax = 0.f;
+      atomic_max_float(max_out + b, tmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// exact gather, plane 2: out[b][r][c] = vol[r][c][s0+b].  For a fixed r this is a
+// [c][s] -> [b][c] transpose; tile 64 (c) x 32 (s) through shared memory.
+//   grid = (c tiles, s tiles, r)
+// ---------------------------------------------------------------------------------
+constexpr int T2_C = 64, T2_S = 32;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+gather_plane2_kernel(const float* __restrict__ vol, int d1, int d2, int s0, int ns, int H, int W,
+                     const float* __restrict__ max_in, float* __restrict__ max_out,
+                     float* __restrict__ out) {
+  __shared__ float tile[T2_C][T2_S + 1];
+  const int r = blockIdx.z;
+  const int c0 = blockIdx.x * T2_C, b0 = blockIdx.y * T2_S;
+  const int t = threadIdx.x;
+  // ---- read: 64 c-rows x 32 s; 8 float4 (or 32 scalars) per c-row ----
+  if (VEC) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = t + 256 * k;  // 0..511
+      const int cc = idx >> 3, s4 = (idx & 7) << 2;
+      const int c = c0 + cc, b = b0 + s4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < W && b < ns) {  // ns % 4 == 0 guaranteed on the VEC path
+        v = ldg_stream_f4(reinterpret_cast<const float4*>(vol + ((int64_t)r * d1 + c) * d2 + s0 + b));
+      }
+      tile[cc][s4 + 0] = v.x; tile[cc][s4 + 1] = v.y; tile[cc][s4 + 2] = v.z; tile[cc][s4 + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = t + 256 * k;  // 0..2047
+      const int cc = idx >> 5, ss = idx & 31;
+      const int c = c0 + cc, b = b0 + ss;
+      tile[cc][ss] = (c < W && b < ns) ? __ldg(vol + ((int64_t)r * d1 + c) * d2 + s0 + b) : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- write: 32 s-rows x 64 c; 16 float4 per s-row ----
+  const int64_t hw = (int64_t)H * W;
+  if (VEC) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = t + 256 * k;
+      const int ss = idx >> 4, c4 = (idx & 15) << 2;
+      const int b = b0 + ss, c = c0 + c4;
+      float4 v = make_float4(tile[c4 + 0][ss], tile[c4 + 1][ss], tile[c4 + 2][ss], tile[c4 + 3][ss]);
+      const bool ok = (b < ns && c < W);  // W % 4 == 0 on the VEC path
+      float tmax = ok ? fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) : -INFINITY;
+      if (ok) {
+        if (max_in) {
+          const float m = __ldg(max_in + s0 + b);
+          v.x = ref_normalise(v.x, m); v.y = ref_normalise(v.y, m);
+          v.z = ref_normalise(v.z, m); v.w = ref_normalise(v.w, m);
+        }
+        stg_stream_f4(reinterpret_cast<float4*>(out + (int64_t)b * hw + (int64_t)r * W + c), v);
+      }
+      if (max_out) {  // 16 consecutive lanes share one slice b
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if ((t & 15) == 0 && tmax != -INFINITY) {
+          if (tmax == 0.f) tmax = 0.f;
+          atomic_max_float(max_out + b, tmax);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = t + 256 * k;
+      const int ss = idx >> 6, cc = idx & 63;
+      const int b = b0 + ss, c = c0 + cc;
+      if (b < ns && c < W) {
+        float v = tile[cc][ss];
+        if (max_out) {
+          float mv = (v == 0.f) ? 0.f : v;
+          atomic_max_float(max_out + b, mv);
+        }
+        if (max_in) v = ref_normalise(v, __ldg(max_in + s0 + b));
+        out[(int64_t)b * hw + (int64_t)r * W + c] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// affine-grid gather: nearest / trilinear, zeros outside.  fp32 arithmetic with
+// explicitly rounded mul/add (no FMA contraction) in the oracle's op order so the
+// result is bit-identical to oracle.resample_slices.
+// ---------------------------------------------------------------------------------
+struct Affine12 { float a[12]; };
+
+__device__ __forceinline__ float fetch_vox(const float* __restrict__ vol, int d0, int d1, int d2,
+                                           int ix, int iy, int iz) {
+  if (ix < 0 || ix >= d0 || iy < 0 || iy >= d1 || iz < 0 || iz >= d2) return 0.f;
+  return __ldg(vol + ((int64_t)ix * d1 + iy) * d2 + iz);
+}
+__device__ __forceinline__ float lerp_rn(float a, float b, float t) {
+  return __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+}
+
+template <bool TRILINEAR>
+__global__ void __launch_bounds__(256)
+gather_affine_kernel(const float* __restrict__ vol, int d0, int d1, int d2, Affine12 A, int s0,
+                     int H, int W, const float* __restrict__ max_in, float* __restrict__ max_out,
+                     float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int64_t hw = (int64_t)H * W;
+  const float sf = (float)(s0 + b);
+  const float m = max_in ? __ldg(max_in + s0 + b) : 0.f;
+  float tmax = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float rf = (float)(int)(i / W), cf = (float)(int)(i % W);
+    float q[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      float t = __fadd_rn(A.a[ax], __fmul_rn(sf, A.a[3 + ax]));
+      t = __fadd_rn(t, __fmul_rn(rf, A.a[6 + ax]));
+      q[ax] = __fadd_rn(t, __fmul_rn(cf, A.a[9 + ax]));
+    }
+    float v;
+    if (!TRILINEAR) {
+      const int ix = (int)floorf(__fadd_rn(q[0], 0.5f));
+      const int iy = (int)floorf(__fadd_rn(q[1], 0.5f));
+      const int iz = (int)floorf(__fadd_rn(q[2], 0.5f));
+      v = fetch_vox(vol, d0, d1, d2, ix, iy, iz);
+    } else {
+      const float fx = floorf(q[0]), fy = floorf(q[1]), fz = floorf(q[2]);
+      const float tx = __fsub_rn(q[0], fx), ty = __fsub_rn(q[1], fy), tz = __fsub_rn(q[2], fz);
+      const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+      const float c00 = lerp_rn(fetch_vox(vol, d0, d1, d2, x0, y0, z0), fetch_vox(vol, d0, d1, d2, x0, y0, z0 + 1), tz);
+      const float c01 = lerp_rn(fetch_vox(vol, d0, d1, d2, x0, y0 + 1, z0), fetch_vox(vol, d0, d1, d2, x0, y0 + 1, z0 + 1), tz);
+      const float c10 = lerp_rn(fetch_vox(vol, d0, d1, d2, x0 + 1, y0, z0), fetch_vox(vol, d0, d1, d2, x0 + 1, y0, z0 + 1), tz);
+      const float c11 = lerp_rn(fetch_vox(vol, d0, d1, d2, x0 + 1, y0 + 1, z0), fetch_vox(vol, d0, d1, d2, x0 + 1, y0 + 1, z0 + 1), tz);
+      v = lerp_rn(lerp_rn(c00, c01, ty), lerp_rn(c10, c11, ty), tx);
+    }
+    tmax = fmaxf(tmax, v);
+    out[(int64_t)b * hw + i] = max_in ? ref_normalise(v, m) : v;
+  }
+  if (max_out) {
+    tmax = warp_max(tmax);
+    if ((threadIdx.x & 31) == 0 && tmax != -INFINITY) {
+      if (tmax == 0.f) tmax = 0.f;
+      atomic_max_float(max_out + b, tmax);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+slice_normalize_kernel(float* __restrict__ slices, const float* __restrict__ slice_max, int64_t hw) {
+  const int b = blockIdx.y;
+  const float m = __ldg(slice_max + b);
+  if (m == 0.f) return;
+  float* p = slices + (int64_t)b * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = ref_normalise(p[i], m);
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+}  // namespace pmu
+
+using namespace pmu;
+
+extern "C" int pmu_fill_f32(float* p, float value, int64_t n, void* stream) {
+  PMU_CHECK_ARG(p != nullptr && n >= 0, "pmu_fill_f32: bad arguments");
+  if (n == 0) return PMU_OK;
+  const int blocks = (int)std::min<int64_t>(cdiv64(n, 256), (int64_t)sm_count() * 8);
+  fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, value, n);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_plane_max(const float* vol, const int32_t dims[3], float* maxes, void* stream) {
+  PMU_CHECK_ARG(vol && dims && maxes, "pmu_plane_max: null pointer");
+  const int d0 = dims[0], d1 = dims[1], d2 = dims[2];
+  PMU_CHECK_ARG(d0 > 0 && d1 > 0 && d2 > 0, "pmu_plane_max: dims must be positive");
+  const int64_t nrows = (int64_t)d0 * d1;
+  const int64_t blocks = cdiv64(nrows, PM_WARPS * PM_ROWS_PER_WARP);
+  const bool vec = (d2 % 4 == 0) && aligned16(vol);
+  if (vec)
+    plane_max_kernel<true><<<(unsigned)blocks, PM_WARPS * 32, 0, (cudaStream_t)stream>>>(vol, d0, d1, d2, maxes);
+  else
+    plane_max_kernel<false><<<(unsigned)blocks, PM_WARPS * 32, 0, (cudaStream_t)stream>>>(vol, d0, d1, d2, maxes);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int plane, int s0, int ns,
+                                int interp, const float* affine_host, int H, int W,
+                                const float* slice_max_in, float* slice_max_out, float* out,
+                                void* stream) {
+  PMU_CHECK_ARG(vol && dims && out, "pmu_slice_gather: null pointer");
+  const int d0 = dims[0], d1 = dims[1], d2 = dims[2];
+  PMU_CHECK_ARG(d0 > 0 && d1 > 0 && d2 > 0, "pmu_slice_gather: dims must be positive");
+  PMU_CHECK_ARG(plane >= 0 && plane <= 2, "pmu_slice_gather: plane must be 0, 1 or 2 (got %d)", plane);
+  PMU_CHECK_ARG(ns >= 0 && s0 >= 0 && H > 0 && W > 0, "pmu_slice_gather: bad slice range / size");
+  if (ns == 0) return PMU_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (interp == PMU_INTERP_EXACT) {
+    const int ext[3] = {d0, d1, d2};
+    PMU_CHECK_ARG(s0 + ns <= ext[plane], "pmu_slice_gather: slices [%d,%d) exceed extent %d of plane %d",
+                  s0, s0 + ns, ext[plane], plane);
+    const int eh = (plane == 0) ? d1 : d0, ew = (plane == 2) ? d1 : d2;
+    PMU_CHECK_ARG(H == eh && W == ew, "pmu_slice_gather: EXACT needs H,W = %d,%d (got %d,%d)", eh, ew, H, W);
+    if (plane < 2) {
+      const bool vec = (d2 % 4 == 0) && aligned16(vol) && aligned16(out);
+      const int64_t work = vec ? ((int64_t)H * W / 4) : (int64_t)H * W;
+      dim3 grid((unsigned)std::min<int64_t>(cdiv64(work, 256 * 4), 4096), ns);
+      if (vec)
+        gather_rows_kernel<true><<<grid, 256, 0, st>>>(vol, d1, d2, plane, s0, H, W, slice_max_in, slice_max_out, out);
+      else
+        gather_rows_kernel<false><<<grid, 256, 0, st>>>(vol, d1, d2, plane, s0, H, W, slice_max_in, slice_max_out, out);
+    } else {
+      PMU_CHECK_ARG(H <= 65535, "pmu_slice_gather: plane 2 supports H <= 65535");
+      const bool vec = (d2 % 4 == 0) && (s0 % 4 == 0) && (ns % 4 == 0) && (W % 4 == 0) &&
+                       aligned16(vol) && aligned16(out);
+      dim3 grid(cdiv(W, T2_C), cdiv(ns, T2_S), H);
+      if (vec)
+        gather_plane2_kernel<true><<<grid, 256, 0, st>>>(vol, d1, d2, s0, ns, H, W, slice_max_in, slice_max_out, out);
+      else
+        gather_plane2_kernel<false><<<grid, 256, 0, st>>>(vol, d1, d2, s0, ns, H, W, slice_max_in, slice_max_out, out);
+    }
+  } else if (interp == PMU_INTERP_NEAREST || interp == PMU_INTERP_TRILINEAR) {
+    PMU_CHECK_ARG(affine_host != nullptr, "pmu_slice_gather: affine grid needs 12 host floats");
+    Affine12 A;
+    for (int i = 0; i < 12; ++i) A.a[i] = affine_host[i];
+    dim3 grid((unsigned)std::min<int64_t>(cdiv64((int64_t)H * W, 256), 2048), ns);
+    if (interp == PMU_INTERP_TRILINEAR)
+      gather_affine_kernel<true><<<grid, 256, 0, st>>>(vol, d0, d1, d2, A, s0, H, W, slice_max_in, slice_max_out, out);
+    else
+      gather_affine_kernel<false><<<grid, 256, 0, st>>>(vol, d0, d1, d2, A, s0, H, W, slice_max_in, slice_max_out, out);
+  } else {
+    PMU_CHECK_ARG(false, "pmu_slice_gather: unknown interp %d", interp);
+  }
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_slice_normalize(float* slices, const float* slice_max, int ns, int64_t hw, void* stream) {
+  PMU_CHECK_ARG(slices && slice_max && ns >= 0 && hw > 0, "pmu_slice_normalize: bad arguments");
+  if (ns == 0) return PMU_OK;
+  dim3 grid((unsigned)std::min<int64_t>(cdiv64(hw, 256), 1024), ns);
+  slice_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(slices, slice_max, hw);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}

@@ -1,0 +1,193 @@
+// bf16 NHWC helper layers around the tcgen05 convolution (all HBM-bound):
+//   first conv (Cin = 1 or 2: a CUDA-core stencil, arithmetic intensity ~9 flop/B)
+//   2x2 pooling (MaxPool2d(2), unet_parts.py:33; AvgPool2d(2,2,ceil_mode), probabilistic_unet.py:36)
+//   NHWC bf16 -> NCHW fp32 (hands unet_features back in the reference's layout)
+#include "pmu_common.cuh"
+
+namespace pmu {
+
+// ---------------------------------------------------------------------------------
+// first layer: x fp32 [B][Cin][H][W] (Cin = 1, or 2 given as two 1-channel tensors)
+//   -> y bf16 [B][H][W][Cout].  thread = (pixel, group of 8 couts); a warp covers 4
+//   consecutive pixels x 64 couts = 512 contiguous output bytes.
+// ---------------------------------------------------------------------------------
+constexpr int FL_MAX_W = 128 * 2 * 9;  // Cout <= 128, Cin <= 2
+
+__global__ void __launch_bounds__(256)
+conv3x3_first_bf16_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                          const float* __restrict__ w, const float* __restrict__ bias,
+                          __nv_bfloat16* __restrict__ y, int B, int H, int W, int Cin, int Cout, int relu) {
+  __shared__ __align__(16) float w_s[FL_MAX_W];  // [ci*9+tap][Cout]
+  __shared__ float b_s[128];
+  for (int i = threadIdx.x; i < Cout * Cin * 9; i += 256) {
+    const int co = i / (Cin * 9), rem = i % (Cin * 9);
+    w_s[rem * Cout + co] = __ldg(w + i);
+  }
+  for (int i = threadIdx.x; i < Cout; i += 256) b_s[i] = bias ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  const int groups = Cout >> 3;
+  const int64_t total = (int64_t)B * H * W * groups;
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int b = (int)(pix / HW);
+    const int64_t rem = pix % HW;
+    const int h = (int)(rem / W), ww = (int)(rem % W);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = b_s[g * 8 + c];
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* src = (ci == 0 ? x0 : x1) + (int64_t)b * HW;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = h + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ww + kx - 1;
+          const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(src + (int64_t)iy * W + ix) : 0.f;
+          const float* wp = w_s + (ci * 9 + ky * 3 + kx) * Cout + g * 8;
+          const float4 wa = *reinterpret_cast<const float4*>(wp);
+          const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+          acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]);
+          acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
+          acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]);
+          acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
+        }
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = acc[2 * j], c = acc[2 * j + 1];
+      if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(y + pix * Cout + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// 2x2 stride-2 pooling, NHWC bf16; thread = (output pixel, 8 channels = 16 B)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pool2_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                  int C, int Ho, int Wo, int mode) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int g = (int)(i % groups);
+    int64_t r = i / groups;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float m[8], s[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { m[c] = -INFINITY; s[c] = 0.f; }
+    int cnt = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+        if (iy < H && ix < W) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)b * H + iy) * W + ix) * C + g * 8));
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+            const float lo = __low2float(h2), hi = __high2float(h2);
+            m[2 * j] = fmaxf(m[2 * j], lo); m[2 * j + 1] = fmaxf(m[2 * j + 1], hi);
+            s[2 * j] += lo; s[2 * j + 1] += hi;
+          }
+          ++cnt;
+        }
+      }
+    const float inv = 1.f / (float)cnt;
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = (mode == PMU_POOL_MAX) ? m[2 * j] : s[2 * j] * inv;
+      const float c = (mode == PMU_POOL_MAX) ? m[2 * j + 1] : s[2 * j + 1] * inv;
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// [B][HW][C] bf16 -> [B][C][HW] fp32 through a 64 px x 64 ch shared tile
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t HW, int C) {
+  __shared__ float tile[64][65];
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+  // read: 64 px rows, 64 channels each (32 x bf16x2 per row)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = t + 256 * k;  // 0..2047
+    const int pp = idx >> 5, c2 = (idx & 31) * 2;
+    float lo = 0.f, hi = 0.f;
+    if (p0 + pp < HW && c0 + c2 < C) {
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(x + ((int64_t)b * HW + p0 + pp) * C + c0 + c2);
+      lo = __low2float(h2); hi = __high2float(h2);
+    }
+    tile[pp][c2] = lo; tile[pp][c2 + 1] = hi;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = t + 256 * k;  // 0..4095
+    const int cc = idx >> 6, pp = idx & 63;
+    if (p0 + pp < HW && c0 + cc < C) y[((int64_t)b * C + c0 + cc) * HW + p0 + pp] = tile[pp][cc];
+  }
+}
+
+}  // namespace pmu
+
+using namespace pmu;
+
+extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const float* w, const float* bias,
+                                      void* y, int B, int H, int W, int Cin, int Cout, int relu, void* stream) {
+  PMU_CHECK_ARG(x0 && w && y && B > 0 && H > 0 && W > 0, "pmu_conv3x3_first_bf16: bad arguments");
+  PMU_CHECK_SUPPORTED(Cin >= 1 && Cin <= 2 && (Cin == 1 || x1), "pmu_conv3x3_first_bf16: Cin must be 1, or 2 with x1 (got %d)", Cin);
+  PMU_CHECK_SUPPORTED(Cout % 8 == 0 && Cout <= 128, "pmu_conv3x3_first_bf16: Cout must be a multiple of 8, <= 128 (got %d)", Cout);
+  PMU_CHECK_ARG(aligned16(y), "pmu_conv3x3_first_bf16: y must be 16-byte aligned");
+  const int64_t total = (int64_t)B * H * W * (Cout / 8);
+  const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 32);
+  conv3x3_first_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, x1, w, bias, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                     B, H, W, Cin, Cout, relu);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_pool2_bf16(const void* x, void* y, int B, int H, int W, int C, int mode, void* stream) {
+  PMU_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0, "pmu_pool2_bf16: bad arguments");
+  PMU_CHECK_ARG(mode == PMU_POOL_MAX || mode == PMU_POOL_AVG_CEIL, "pmu_pool2_bf16: unknown mode %d", mode);
+  PMU_CHECK_SUPPORTED(C % 8 == 0, "pmu_pool2_bf16: C must be a multiple of 8 (got %d)", C);
+  PMU_CHECK_ARG(aligned16(x) && aligned16(y), "pmu_pool2_bf16: pointers must be 16-byte aligned");
+  const int Ho = (mode == PMU_POOL_MAX) ? H / 2 : (H + 1) / 2;
+  const int Wo = (mode == PMU_POOL_MAX) ? W / 2 : (W + 1) / 2;
+  PMU_CHECK_ARG(Ho > 0 && Wo > 0, "pmu_pool2_bf16: input too small");
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+  const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 32);
+  pool2_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                             reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C, Ho, Wo, mode);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, void* stream) {
+  PMU_CHECK_ARG(x && y && B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0, "pmu_nhwc_bf16_to_nchw_f32: bad arguments");
+  PMU_CHECK_SUPPORTED(C % 2 == 0, "pmu_nhwc_bf16_to_nchw_f32: C must be even");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)cdiv64(HW, 64), cdiv(C, 64), B);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, HW, C);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}

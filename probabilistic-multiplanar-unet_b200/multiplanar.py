@@ -1,0 +1,159 @@
+"""Multi-planar probabilistic inference: volume -> voxel-space mean / variance / entropy.
+
+The hot path of the reference's eval.py main loop (eval.py:132-214) re-designed for one B200
+(or N of them): the volume stays resident in HBM, slices are gathered in batches per plane
+(K1), U-Net + prior run ONCE per slice (the reference re-runs the whole network per sample,
+eval.py:148-152), N latent samples go through the fused fcomb/softmax/accumulate kernel (K3+K4)
+and the per-slice sums are scatter-added into [x,C,y,z] accumulators (K4).  Multi-GPU: the flat
+(plane, slice) list — exactly the reference's index_map order, utils/mri_dataset.py:37-49 — is
+cut into contiguous chunks, one per rank; ONE collective (sum-reduce of the accumulators) joins
+them.
+
+Semantics follow SURVEY.md Appendix A (eval-mode BN, probabilities averaged over samples and
+planes, population variance, natural-log entropy).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import PackedNet
+
+
+def padded_dims(dims: Sequence[int]) -> Tuple[int, int, int]:
+    """MRI_Dataset.pad_dimensions (mri_dataset.py:85-98): only the arg-min axis is padded, up to
+    the max extent."""
+    d = list(int(v) for v in dims)
+    diff = max(d) - min(d)
+    if diff:
+        d[int(np.argmin(d))] += diff
+    return tuple(d)
+
+
+def shard_slices(dims: Sequence[int], planes: Sequence[int], rank: int, world: int) -> Dict[int, Tuple[int, int]]:
+    """Contiguous chunk of the plane-major flat slice list for `rank` -> {plane: (s0, s1)}."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    total = sum(int(dims[p]) for p in planes)
+    chunk = -(-total // world)
+    g0, g1 = min(total, rank * chunk), min(total, (rank + 1) * chunk)
+    out: Dict[int, Tuple[int, int]] = {}
+    base = 0
+    for p in planes:
+        lo, hi = max(g0, base), min(g1, base + int(dims[p]))
+        if hi > lo:
+            out[p] = (lo - base, hi - base)
+        base += int(dims[p])
+    return out
+
+
+def reduce_accumulators(acc: torch.Tensor, world: int, group=None, dst: Optional[int] = 0) -> torch.Tensor:
+    """The single exchange step: sum the [2,X,C,Y,Z] accumulators over ranks (NCCL on GPUs over
+    NVLink/NVSwitch; gloo in the CPU tests).  dst=None -> all-reduce."""
+    if world <= 1:
+        return acc
+    import torch.distributed as dist
+    if dst is None:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(acc, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return acc
+
+
+class MultiPlanarPredictor:
+    """3-plane, N-sample probabilistic prediction of a volume on the current CUDA device."""
+
+    def __init__(self, state_dict, device="cuda", precision: str = "bf16", n_samples: int = 16,
+                 planes: Sequence[int] = (0, 1, 2), slice_batch: int = 32, interp: str = "exact",
+                 affines: Optional[Dict[int, Sequence[float]]] = None, out_hw: Optional[Tuple[int, int]] = None,
+                 rank: int = 0, world_size: int = 1, process_group=None):
+        if hasattr(state_dict, "state_dict"):
+            state_dict = state_dict.state_dict()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("MultiPlanarPredictor runs on CUDA only (no CPU fallback)")
+        self.net = PackedNet(state_dict, self.device, precision)
+        self.n_samples, self.planes, self.slice_batch = int(n_samples), tuple(planes), int(slice_batch)
+        if interp not in ops.INTERP:
+            raise ValueError(f"interp must be one of {list(ops.INTERP)}")
+        if interp != "exact" and affines is None:
+            raise ValueError("nearest/trilinear resampling needs per-plane affines")
+        self.interp, self.affines, self.out_hw = interp, affines, out_hw
+        self.rank, self.world, self.group = int(rank), int(world_size), process_group
+        self.C = self.net.fcomb["C"]
+        self.L = self.net.fcomb["L"]
+
+    # ------------------------------------------------------------------
+    def _to_device_volume(self, vol) -> torch.Tensor:
+        if isinstance(vol, np.ndarray):
+            vol = torch.from_numpy(np.ascontiguousarray(vol, dtype=np.float32))
+        vol = vol.to(self.device, torch.float32, non_blocking=True)
+        pd = padded_dims(vol.shape)
+        if tuple(vol.shape) != pd:
+            big = torch.zeros(pd, dtype=torch.float32, device=self.device)
+            big[: vol.shape[0], : vol.shape[1], : vol.shape[2]] = vol
+            vol = big
+        return vol.contiguous()
+
+    def accumulate(self, vol: torch.Tensor, eps: torch.Tensor, acc: torch.Tensor) -> int:
+        """Run this rank's slices and add their sums into acc [2,X,C,Y,Z]; returns #slices done."""
+        dims = tuple(vol.shape)
+        net, N = self.net, self.n_samples
+        my = shard_slices(dims, self.planes, self.rank, self.world)
+        exact = self.interp == "exact"
+        maxes = ops.plane_max(vol) if exact else None
+        offs = (0, dims[0], dims[0] + dims[1])
+        done = 0
+        for pi, p in enumerate(self.planes):
+            if p not in my:
+                continue
+            s_lo, s_hi = my[p]
+            for s0 in range(s_lo, s_hi, self.slice_batch):
+                ns = min(self.slice_batch, s_hi - s0)
+                if exact:
+                    x = ops.slice_gather(vol, p, s0, ns, slice_max_in=maxes[offs[p]: offs[p] + dims[p]])
+                else:
+                    x, mx = ops.slice_gather(vol, p, s0, ns, interp=self.interp, affine=self.affines[p],
+                                             hw=self.out_hw, want_max=True)
+                    ops.slice_normalize_(x, mx)
+                feat = net.unet_features(x)
+                mu, ls = net.gaussian("prior", x)
+                sigma = torch.exp(ls)          # Normal(scale=exp(log_sigma)), probabilistic_unet.py:113
+                sums = net.fcomb_sums(feat, mu, sigma, eps[pi, s0:s0 + ns].contiguous())
+                ops.scatter_accum_(sums, p, s0, dims, acc[0], acc[1])
+                done += ns
+        return done
+
+    @torch.no_grad()
+    def predict(self, vol, eps: Optional[torch.Tensor] = None, seed: int = 4321, want_labels: bool = False,
+                keep_sums: bool = False) -> Dict[str, torch.Tensor]:
+        """vol: [d0,d1,d2] fp32 (numpy / CPU / CUDA).  eps: [P, D, N, L] standard-normal draws
+        (host or device); generated on the device from `seed` when omitted.  Returns mean / var
+        [x,C,y,z], entropy [x,y,z] (valid on rank 0 when world_size > 1)."""
+        if self.interp != "exact":
+            raise NotImplementedError("voxel fusion is defined for the axis-aligned grid; resampled grids "
+                                      "are available through ops.slice_gather (SURVEY.md App. A step 6)")
+        vol = self._to_device_volume(vol)
+        dims = tuple(vol.shape)
+        P, N, L = len(self.planes), self.n_samples, self.L
+        Dmax = max(dims)
+        if eps is None:
+            g = torch.Generator(device=self.device).manual_seed(seed)
+            eps = torch.randn(P, Dmax, N, L, generator=g, device=self.device)
+        else:
+            eps = eps.to(self.device, torch.float32, non_blocking=True)
+        acc = torch.zeros(2, dims[0], self.C, dims[1], dims[2], dtype=torch.float32, device=self.device)
+        self.accumulate(vol, eps, acc)
+        reduce_accumulators(acc, self.world, self.group, dst=0)
+        out: Dict[str, torch.Tensor] = {"count": float(P * N)}
+        if self.rank == 0:
+            mean, var, ent, lab = ops.fuse_finalize(acc[0], acc[1], float(P * N), want_labels=want_labels)
+            out.update(mean=mean, var=var, entropy=ent)
+            if want_labels:
+                out["labels"] = lab
+        if keep_sums:
+            out["S1"], out["S2"] = acc[0], acc[1]
+        return out

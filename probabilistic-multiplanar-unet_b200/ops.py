@@ -1,0 +1,321 @@
+"""Tensor-level wrappers over the C-ABI (include/pmu_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic step runs in
+libpmu_b200.so.  Each wrapper passes raw device pointers + the current CUDA stream.  There is
+no fallback: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int32, c_void_p
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+INTERP = {"exact": 0, "nearest": 1, "trilinear": 2}
+POOL_MAX, POOL_AVG_CEIL = 0, 1
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _prep(*tensors: Optional[torch.Tensor]):
+    """Validate tensors, select the device inside the library, return (lib, stream)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("pmu_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("pmu_b200 ops need contiguous tensors")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("pmu_b200 ops: tensors on different devices")
+    lib = _lib.load()
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    # the library has its own (statically linked) CUDA runtime with a per-thread current device
+    _lib.check(lib.pmu_set_device(idx), "pmu_set_device")
+    return lib, c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _dims(d: Sequence[int]):
+    return (c_int32 * 3)(int(d[0]), int(d[1]), int(d[2]))
+
+
+def _f32(t, name):
+    if t is not None and t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+
+
+def _bf16(t, name):
+    if t is not None and t.dtype != torch.bfloat16:
+        raise RuntimeError(f"{name} must be bfloat16, got {t.dtype}")
+
+
+# ----------------------------------------------------------------------------- K1
+def plane_max(vol: torch.Tensor) -> torch.Tensor:
+    """Per-slice maxima of all three planes, one pass: [d0 + d1 + d2] fp32."""
+    _f32(vol, "vol")
+    lib, st = _prep(vol)
+    d = vol.shape
+    out = torch.empty(d[0] + d[1] + d[2], dtype=torch.float32, device=vol.device)
+    _lib.check(lib.pmu_fill_f32(_p(out), float("-inf"), out.numel(), st), "pmu_fill_f32")
+    _lib.check(lib.pmu_plane_max(_p(vol), _dims(d), _p(out), st), "pmu_plane_max")
+    return out
+
+
+def slice_gather(vol: torch.Tensor, plane: int, s0: int, ns: int, *, interp: str = "exact",
+                 affine: Optional[Sequence[float]] = None, hw: Optional[Tuple[int, int]] = None,
+                 slice_max_in: Optional[torch.Tensor] = None, want_max: bool = False,
+                 out: Optional[torch.Tensor] = None):
+    """out[ns,1,H,W] fp32 (+ per-slice raw max [ns] when want_max)."""
+    _f32(vol, "vol"); _f32(slice_max_in, "slice_max_in")
+    d = vol.shape
+    if hw is None:
+        hw = (d[1] if plane == 0 else d[0], d[1] if plane == 2 else d[2])
+    H, W = hw
+    if out is None:
+        out = torch.empty(ns, 1, H, W, dtype=torch.float32, device=vol.device)
+    lib, st = _prep(vol, slice_max_in, out)
+    mx = None
+    if want_max:
+        mx = torch.empty(max(ns, 1), dtype=torch.float32, device=vol.device)
+        _lib.check(lib.pmu_fill_f32(_p(mx), float("-inf"), mx.numel(), st), "pmu_fill_f32")
+    aff = None
+    if affine is not None:
+        aff = (c_float * 12)(*[float(a) for a in affine])
+    _lib.check(lib.pmu_slice_gather(_p(vol), _dims(d), int(plane), int(s0), int(ns), INTERP[interp], aff, int(H),
+                                    int(W), _p(slice_max_in), _p(mx), _p(out), st), "pmu_slice_gather")
+    return (out, mx[:ns]) if want_max else out
+
+
+def slice_normalize_(slices: torch.Tensor, slice_max: torch.Tensor) -> torch.Tensor:
+    _f32(slices, "slices"); _f32(slice_max, "slice_max")
+    lib, st = _prep(slices, slice_max)
+    ns = slices.shape[0]
+    _lib.check(lib.pmu_slice_normalize(_p(slices), _p(slice_max), ns, slices.numel() // max(ns, 1), st),
+               "pmu_slice_normalize")
+    return slices
+
+
+# ----------------------------------------------------------------------------- fp32 layers
+def conv3x3_f32(x0, w, bias, relu=True, x1=None, out=None):
+    _f32(x0, "x0"); _f32(x1, "x1"); _f32(w, "w"); _f32(bias, "bias")
+    B, C0, H, W = x0.shape
+    C1 = 0 if x1 is None else x1.shape[1]
+    Cout = w.shape[0]
+    assert w.shape[1] == C0 + C1, (w.shape, C0, C1)
+    if out is None:
+        out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x0.device)
+    lib, st = _prep(x0, x1, w, bias, out)
+    _lib.check(lib.pmu_conv3x3_f32(_p(x0), C0, _p(x1), C1, _p(w), _p(bias), _p(out), B, H, W, Cout, int(relu), st),
+               "pmu_conv3x3_f32")
+    return out
+
+
+def conv1x1_f32(x, w, bias, relu=False):
+    _f32(x, "x"); _f32(w, "w")
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, w, bias, out)
+    _lib.check(lib.pmu_conv1x1_f32(_p(x), _p(w), _p(bias), _p(out), B, Cin, Cout, H * W, int(relu), st),
+               "pmu_conv1x1_f32")
+    return out
+
+
+def convt2x2_f32(x, w, bias, out_hw=None):
+    _f32(x, "x"); _f32(w, "w")
+    B, Cin, H, W = x.shape
+    Cout = w.shape[1]
+    Ho, Wo = (2 * H, 2 * W) if out_hw is None else out_hw
+    dy, dx = Ho - 2 * H, Wo - 2 * W
+    out = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, w, bias, out)
+    _lib.check(lib.pmu_convt2x2_f32(_p(x), _p(w), _p(bias), _p(out), B, Cin, Cout, H, W, Ho, Wo, dy // 2, dx // 2, st),
+               "pmu_convt2x2_f32")
+    return out
+
+
+def pool2_f32(x, mode):
+    _f32(x, "x")
+    B, C, H, W = x.shape
+    Ho, Wo = (H // 2, W // 2) if mode == POOL_MAX else ((H + 1) // 2, (W + 1) // 2)
+    out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.pmu_pool2_f32(_p(x), _p(out), B, C, H, W, mode, st), "pmu_pool2_f32")
+    return out
+
+
+def gauss_head_f32(enc, w, b, L):
+    _f32(enc, "enc")
+    B, C, h, w_ = enc.shape
+    mu = torch.empty(B, L, dtype=torch.float32, device=enc.device)
+    ls = torch.empty_like(mu)
+    lib, st = _prep(enc, w, b, mu, ls)
+    _lib.check(lib.pmu_gauss_head_f32(_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, st), "pmu_gauss_head_f32")
+    return mu, ls
+
+
+def fcomb_f32(feat, z, fw, want_logits=True, want_sums=False):
+    """feat [B,F,H,W] fp32, z [B,N,L] -> logits [B,N,C,H,W] and/or slice_sums [B,2,C,H,W]."""
+    _f32(feat, "feat"); _f32(z, "z")
+    B, F_, H, W = feat.shape
+    N, L = z.shape[1], z.shape[2]
+    C, nl = fw["wlast"].shape[0], fw["nl"]
+    logits = torch.empty(B, N, C, H, W, dtype=torch.float32, device=feat.device) if want_logits else None
+    sums = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=feat.device) if want_sums else None
+    lib, st = _prep(feat, z, logits, sums)
+    _lib.check(lib.pmu_fcomb_f32(_p(feat), _p(z), _p(fw["w0"]), _p(fw["b0"]), _p(fw["wmid"]), _p(fw["bmid"]),
+                                 _p(fw["wlast"]), _p(fw["blast"]), _p(logits), _p(sums), B, N, F_, L, C, nl, H * W, st),
+               "pmu_fcomb_f32")
+    return logits, sums
+
+
+# ----------------------------------------------------------------------------- bf16 layers
+def conv3x3_first_bf16(x0, w, bias, relu=True, x1=None):
+    _f32(x0, "x0"); _f32(x1, "x1")
+    B, _, H, W = x0.shape
+    Cin = 1 if x1 is None else 2
+    Cout = w.shape[0]
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x0.device)
+    lib, st = _prep(x0, x1, w, bias, out)
+    _lib.check(lib.pmu_conv3x3_first_bf16(_p(x0), _p(x1), _p(w), _p(bias), _p(out), B, H, W, Cin, Cout, int(relu), st),
+               "pmu_conv3x3_first_bf16")
+    return out
+
+
+def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None):
+    """tcgen05 implicit-GEMM conv: x NHWC bf16 -> y NHWC bf16 (2H x 2W for ntaps=4)."""
+    _bf16(x0, "x0"); _bf16(x1, "x1"); _bf16(wpack, "wpack"); _f32(bias, "bias")
+    B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    oh, ow = (2 * H, 2 * W) if ntaps == 4 else (H, W)
+    out = torch.empty(B, oh, ow, Cout, dtype=torch.bfloat16, device=x0.device)
+    lib, st = _prep(x0, x1, wpack, bias, out)
+    _lib.check(lib.pmu_conv_gemm_bf16(_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), B, H, W, Cout, ntaps,
+                                      int(relu), st), "pmu_conv_gemm_bf16")
+    return out
+
+
+def pool2_bf16(x, mode):
+    _bf16(x, "x")
+    B, H, W, C = x.shape
+    Ho, Wo = (H // 2, W // 2) if mode == POOL_MAX else ((H + 1) // 2, (W + 1) // 2)
+    out = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.pmu_pool2_bf16(_p(x), _p(out), B, H, W, C, mode, st), "pmu_pool2_bf16")
+    return out
+
+
+def gauss_head_bf16(enc, w, b, L):
+    _bf16(enc, "enc")
+    B, h, w_, C = enc.shape
+    mu = torch.empty(B, L, dtype=torch.float32, device=enc.device)
+    ls = torch.empty_like(mu)
+    lib, st = _prep(enc, w, b, mu, ls)
+    _lib.check(lib.pmu_gauss_head_bf16(_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, st), "pmu_gauss_head_bf16")
+    return mu, ls
+
+
+def nhwc_bf16_to_nchw_f32(x):
+    _bf16(x, "x")
+    B, H, W, C = x.shape
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.pmu_nhwc_bf16_to_nchw_f32(_p(x), _p(out), B, H, W, C, st), "pmu_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def fcomb_softmax_accum_bf16(feat, mu, sigma, eps, fw, out=None):
+    """feat NHWC bf16 [B,H,W,64]; mu/sigma [B,L]; eps [B,N,L] -> slice_sums [B,2,C,H,W] fp32."""
+    _bf16(feat, "feat"); _f32(mu, "mu"); _f32(sigma, "sigma"); _f32(eps, "eps")
+    B, H, W, F_ = feat.shape
+    if F_ != 64:
+        raise RuntimeError(f"fcomb_softmax_accum_bf16 needs 64 feature channels, got {F_}")
+    N, L = eps.shape[1], eps.shape[2]
+    C, nl = fw["wlast"].shape[0], fw["nl"]
+    if out is None:
+        out = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=feat.device)
+    lib, st = _prep(feat, mu, sigma, eps, out)
+    _lib.check(lib.pmu_fcomb_softmax_accum_bf16(_p(feat), _p(mu), _p(sigma), _p(eps), _p(fw["w0"]), _p(fw["b0"]),
+                                                _p(fw["wmid"]), _p(fw["bmid"]), _p(fw["wlast"]), _p(fw["blast"]),
+                                                _p(out), B, N, L, C, nl, H * W, st), "pmu_fcomb_softmax_accum_bf16")
+    return out
+
+
+# ----------------------------------------------------------------------------- K4
+def softmax_accum(logits):
+    _f32(logits, "logits")
+    B, N, C, H, W = logits.shape
+    out = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=logits.device)
+    lib, st = _prep(logits, out)
+    _lib.check(lib.pmu_softmax_accum(_p(logits), _p(out), B, N, C, H * W, st), "pmu_softmax_accum")
+    return out
+
+
+def scatter_accum_(slice_sums, plane, s0, dims, S1, S2):
+    _f32(slice_sums, "slice_sums"); _f32(S1, "S1"); _f32(S2, "S2")
+    ns, _, C = slice_sums.shape[:3]
+    lib, st = _prep(slice_sums, S1, S2)
+    _lib.check(lib.pmu_scatter_accum(_p(slice_sums), int(plane), int(s0), int(ns), _dims(dims), int(C), _p(S1), _p(S2), st),
+               "pmu_scatter_accum")
+
+
+def fuse_finalize(S1, S2, count, want_var=True, want_entropy=True, want_labels=False):
+    _f32(S1, "S1"); _f32(S2, "S2")
+    X, C, Y, Z = S1.shape
+    mean = torch.empty_like(S1)
+    var = torch.empty_like(S1) if want_var else None
+    ent = torch.empty(X, Y, Z, dtype=torch.float32, device=S1.device) if want_entropy else None
+    lab = torch.empty(X, Y, Z, dtype=torch.uint8, device=S1.device) if want_labels else None
+    lib, st = _prep(S1, S2, mean, var, ent, lab)
+    _lib.check(lib.pmu_fuse_finalize(_p(S1), _p(S2), float(count), _dims((X, Y, Z)), C, _p(mean), _p(var), _p(ent),
+                                     _p(lab), st), "pmu_fuse_finalize")
+    return mean, var, ent, lab
+
+
+# ----------------------------------------------------------------------------- K5
+def ce_sum(logits, target):
+    """sum over batch and pixels of CE(logits [B,C,H,W], target float labels [B,1,H,W] or [B,H,W])."""
+    _f32(logits, "logits"); _f32(target, "target")
+    B, C = logits.shape[:2]
+    HW = logits.numel() // (B * C)
+    out = torch.empty(1, dtype=torch.float32, device=logits.device)
+    lib, st = _prep(logits, target, out)
+    _lib.check(lib.pmu_ce_sum(_p(logits), _p(target), B, C, HW, _p(out), st), "pmu_ce_sum")
+    return out[0]
+
+
+def kl_diag_gauss(mu_q, ls_q, mu_p, ls_p):
+    B, L = mu_q.shape
+    out = torch.empty(B, dtype=torch.float32, device=mu_q.device)
+    lib, st = _prep(mu_q, ls_q, mu_p, ls_p, out)
+    _lib.check(lib.pmu_kl_diag_gauss(_p(mu_q), _p(ls_q), _p(mu_p), _p(ls_p), B, L, _p(out), st), "pmu_kl_diag_gauss")
+    return out
+
+
+def dice_sums(pred, target):
+    _f32(pred, "pred"); _f32(target, "target")
+    if pred.numel() != target.numel():
+        raise RuntimeError("dice_sums: pred and target must have the same number of elements")
+    out = torch.empty(3, dtype=torch.float32, device=pred.device)
+    lib, st = _prep(pred, target, out)
+    _lib.check(lib.pmu_dice_sums(_p(pred), _p(target), pred.numel(), _p(out), st), "pmu_dice_sums")
+    return out
+
+
+def argmax_dice_sums(prob, truth):
+    """prob [X,C,Y,Z], truth float [X,Y,Z] -> sums [(C-1),3] = (inter, pred, truth) for k=1..C-1."""
+    _f32(prob, "prob"); _f32(truth, "truth")
+    X, C = prob.shape[:2]
+    YZ = prob.numel() // (X * C)
+    out = torch.empty((C - 1) * 3, dtype=torch.float32, device=prob.device)
+    lib, st = _prep(prob, truth, out)
+    _lib.check(lib.pmu_argmax_dice_sums(_p(prob), _p(truth), X, C, YZ, _p(out), st), "pmu_argmax_dice_sums")
+    return out.view(C - 1, 3)

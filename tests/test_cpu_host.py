@@ -1,0 +1,146 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, host
+logic (sharding, padding), oracle data-plane identities, and the N>1 reduce path over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import pmu_b200
+from oracle import pmu_oracle as O
+from pmu_b200 import _lib
+from pmu_b200.multiplanar import padded_dims, reduce_accumulators, shard_slices
+
+
+def test_library_loads_and_exports_header_symbols():
+    if not os.path.exists(_lib.LIB_PATH):
+        from pmu_b200.build import build_native
+        build_native()
+    lib = _lib.load()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 25
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(_lib._SIG) == set(syms)          # the ctypes table covers the whole header
+    assert lib.pmu_version() == 100
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA, never compute on the CPU."""
+    x = torch.zeros(4, 4, 4)
+    with pytest.raises(RuntimeError):
+        pmu_b200.ops.plane_max(x)
+    net = pmu_b200.ProbabilisticUnet(1, 3, [4, 8], 2, 2)
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            net.forward(torch.zeros(1, 1, 8, 8), None, training=False)
+    with pytest.raises(RuntimeError):
+        pmu_b200.MultiPlanarPredictor(net, device="cpu")
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "probabilistic-multiplanar-unet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_state_dict_schema_matches_reference():
+    sd = O.make_state_dict((8, 16, 32), latent_dim=4, no_convs_fcomb=3)
+    net = pmu_b200.ProbabilisticUnet(1, 3, [8, 16, 32], latent_dim=4, no_convs_fcomb=3)
+    net.load_state_dict(sd, strict=True)
+    with pytest.raises(ValueError):
+        pmu_b200.ProbabilisticUnet(1, 3, [32, 64, 128, 192])   # reference default crashes too (App. B #9)
+
+
+def test_padded_dims_matches_oracle():
+    for d in [(24, 40, 40), (40, 24, 40), (40, 40, 24), (16, 16, 16), (8, 12, 16)]:
+        assert padded_dims(d) == O.pad_dimensions(np.zeros(d)).shape
+
+
+def test_shard_slices_partition():
+    for dims in [(256, 256, 256), (24, 40, 40), (5, 7, 3)]:
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                for p, (a, b) in shard_slices(dims, (0, 1, 2), r, world).items():
+                    seen += [(p, s) for s in range(a, b)]
+            assert seen == O.index_map(dims)     # same order as the reference's index_map, no gaps/dups
+
+
+def test_oracle_slicing_identities():
+    vol, _ = O.phantom(0, dims=(6, 7, 8))
+    for p in range(3):
+        a = O.plane_slices(vol, p, normalise=False)[:, 0]
+        b = O.resample_slices(vol, O.identity_affine(p), 0, vol.shape[p], a.shape[1], a.shape[2], "nearest")
+        c = O.resample_slices(vol, O.identity_affine(p), 0, vol.shape[p], a.shape[1], a.shape[2], "trilinear")
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        # scatter is the inverse of slicing (eval.py:176-190)
+        back = O.scatter_plane(p, torch.from_numpy(a)[:, None])[:, 0].numpy()
+        assert np.array_equal(back, vol)
+
+
+def test_oracle_trilinear_matches_grid_sample():
+    vol, _ = O.phantom(0, dims=(9, 10, 11))
+    aff = np.array([0.3, -0.2, 0.4, 0.9, 0.1, 0.0, -0.1, 0.95, 0.05, 0.02, 0.0, 1.05], np.float32)
+    out = O.resample_slices(vol, aff, 0, 8, 10, 11, "trilinear")
+    qx, qy, qz = O._grid_coords(aff, 0, 8, 10, 11)
+    D0, D1, D2 = vol.shape
+    grid = torch.from_numpy(np.stack([2 * qz / (D2 - 1) - 1, 2 * qy / (D1 - 1) - 1, 2 * qx / (D0 - 1) - 1], -1))[None].float()
+    ref = torch.nn.functional.grid_sample(torch.from_numpy(vol)[None, None], grid, mode="bilinear",
+                                          padding_mode="zeros", align_corners=True)[0, 0].numpy()
+    np.testing.assert_allclose(out, ref, atol=2e-6)
+
+
+def test_oracle_fusion_reduces_to_reference_average():
+    g = torch.Generator().manual_seed(3)
+    v = [torch.softmax(torch.randn(5, 3, 5, 5, generator=g), 1) for _ in range(3)]
+    mean, var, ent = O.finalize(v[0] + v[1] + v[2], v[0] ** 2 + v[1] ** 2 + v[2] ** 2, 3)
+    torch.testing.assert_close(mean, (v[0] + v[1] + v[2]) / 3.0)   # eval.py:193
+    assert (var >= 0).all() and (ent >= 0).all() and (ent <= np.log(3) + 1e-6).all()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, dims, ret):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    per_slice = {p: torch.rand(dims[p], 2, 2, *[dims[a] for a in range(3) if a != p], generator=g) for p in range(3)}
+    acc = torch.zeros(2, dims[0], 2, dims[1], dims[2])
+    for p, (a, b) in shard_slices(dims, (0, 1, 2), rank, world).items():
+        for j in range(2):
+            full = torch.zeros_like(per_slice[p][:, j])
+            full[a:b] = per_slice[p][a:b, j]
+            acc[j] += O.scatter_plane(p, full)
+    reduce_accumulators(acc, world, None, dst=0)
+    if rank == 0:
+        ref = torch.zeros_like(acc)
+        for p in range(3):
+            for j in range(2):
+                ref[j] += O.scatter_plane(p, per_slice[p][:, j])
+        ret.put(float((acc - ref).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_sharded_accumulators_reduce_over_gloo():
+    """world_size-2 run of the N>1 host path: each rank scatters its slice chunk, ONE reduce
+    joins them, result equals the single-rank accumulators."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, (5, 6, 7), ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-6

@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — volumes/sec of the multi-planar probabilistic inference hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): a synthetic
+256^3 fp32 volume, 3 planes x 16 z-samples, axis-aligned slicing, trainer-architecture
+ProbabilisticUnet([64..1024], C=3, L=6, fcomb 4 convs) with random-init weights, mean /
+variance / entropy fusion.  One "step" = one whole volume.
+
+  value : volumes/s, volume + latents resident in HBM, outputs left in HBM (CUDA events, max
+          over ranks).  N > 1: the slice list of ONE volume is sharded over the ranks and the
+          accumulators are sum-reduced to rank 0 ("scaling": "strong").
+  e2e   : same metric through the public API (MultiPlanarPredictor.predict) with the volume in
+          pinned host memory and mean / var / entropy read back to pinned host memory.
+  roofline : the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of all its
+          launches in one step / their summed CUDA-event durations, against the measured
+          sustained bf16 peak of MEASURED_PEAKS.json.  hbm_kernels adds the same for the
+          gather and scatter-accumulate kernels (GB/s vs measured HBM copy bandwidth).
+  cpu_baseline : the oracle port of the reference path on the host cores, on a bounded sample
+          of the same workload (N = 1 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "volumes/sec (256^3, 3 planes x 16 samples)"
+UNIT = "volumes/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.rows, self.stop_flag, self.gpu = [], threading.Event(), gpu_index
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+def cpu_reference_rate(D, N, slices_per_plane, threads=None):
+    """Oracle port of the reference CPU path (variant B of BASELINE.md: forward once per slice +
+    N x fcomb + softmax + accumulate, batch 1 like eval.py:105) on a stratified sample of
+    `slices_per_plane` slices per plane; returns (volumes/s extrapolated, seconds, cores)."""
+    import numpy as np
+    import torch
+    from oracle import pmu_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    sd = O.make_state_dict(seed=0)
+    vol, _ = O.phantom(D, seed=1234)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    idx = [int(round(i)) for i in np.linspace(0, D - 1, slices_per_plane)]
+    C = 3
+    with torch.no_grad():
+        x = torch.from_numpy(O.plane_slices(vol, 0, idx[0], 1))
+        O.unet_features(sd, x)                       # warm-up (thread pools, oneDNN primitives)
+        t0 = time.perf_counter()
+        for p in range(3):
+            H, W = [vol.shape[a] for a in range(3) if a != p]
+            s1 = torch.zeros(len(idx), C, H, W)
+            s2 = torch.zeros_like(s1)
+            for j, s in enumerate(idx):
+                x = torch.from_numpy(O.plane_slices(vol, p, s, 1))
+                feat = O.unet_features(sd, x)
+                mu, ls = O.gaussian_head(sd, "prior", x)
+                sigma = torch.exp(ls)
+                for n in range(N):
+                    pr = torch.softmax(O.fcomb(sd, feat, mu + sigma * eps[p, s:s + 1, n]), 1)
+                    s1[j] += pr[0]
+                    s2[j] += pr[0] * pr[0]
+            O.scatter_plane(p, s1).contiguous()
+        dt = time.perf_counter() - t0
+    n_done = 3 * len(idx)
+    return (n_done / dt) / (3.0 * D), dt, cores, n_done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    D, N = args.size, args.samples
+    spp = 1            # one slice per plane per step keeps K+W steps within minutes on few cores
+    rates = []
+    for i in range(args.warmup + args.steps):
+        v, dt, cores, n_done = cpu_reference_rate(D, N, spp)
+        if i >= args.warmup:
+            rates.append((v, dt))
+    tot_t = sum(dt for _, dt in rates)
+    value = (len(rates) * 3 * spp / tot_t) / (3.0 * D)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(len(rates), 1),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"{D}^3 volume, 3 planes x {N} samples, trainer model [64..1024]; each step = "
+                                   f"{3 * spp} slices (one per plane) through the oracle port of the reference CPU path, "
+                                   f"extrapolated to {3 * D} slices"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{3 * spp} of {3 * D} slices per step, forward once + {N} x fcomb + softmax + accumulate"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import pmu_b200
+    from pmu_b200 import ops
+    from pmu_b200.synthetic import phantom_volume, trainer_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D, N, P = args.size, args.samples, 3
+    peaks = load_peaks()
+
+    sd = trainer_state_dict(seed=0)
+    pred = pmu_b200.MultiPlanarPredictor(sd, dev, precision=args.precision, n_samples=N, slice_batch=args.slice_batch,
+                                         rank=rank, world_size=world)
+    vol_host = phantom_volume(D, seed=1234).pin_memory()
+    vol = vol_host.to(dev)
+    eps = torch.randn(P, D, N, 6, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)
+    acc = torch.zeros(2, D, 3, D, D, dtype=torch.float32, device=dev)
+
+    def step_resident():
+        acc.zero_()
+        pred.accumulate(vol, eps, acc)
+        pmu_b200.reduce_accumulators(acc, world, None, dst=0)
+        if rank == 0:
+            return ops.fuse_finalize(acc[0], acc[1], float(P * N))
+        return None
+
+    host_out = None
+    if rank == 0:
+        host_out = {"mean": torch.empty(D, 3, D, D, dtype=torch.float32).pin_memory(),
+                    "var": torch.empty(D, 3, D, D, dtype=torch.float32).pin_memory(),
+                    "entropy": torch.empty(D, D, D, dtype=torch.float32).pin_memory()}
+
+    def step_e2e():
+        out = pred.predict(vol_host, eps=eps)          # H2D of the pinned volume inside
+        if rank == 0:
+            for k in host_out:
+                host_out[k].copy_(out[k], non_blocking=True)   # D2H of the step's results
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ops.LAUNCHES
+    ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES - l0
+    clocks = sampler.finish() if sampler else None
+
+    step_e2e()                                                  # warm the e2e path (pinned buffers, allocator)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- per-kernel roofline: one instrumented step, CUDA events around every C-ABI call ----
+    roof, hbm_kernels, shares = None, {}, {}
+    if rank == 0:
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        step_resident()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        tot = {}
+        for name, meta, a, b in prof:
+            t = a.elapsed_time(b)
+            d = tot.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+            d["ms"] += t; d["n"] += 1
+            if meta:
+                d["flops"] += meta.get("flops", 0.0)
+        step_ms = sum(d["ms"] for d in tot.values())
+        shares = {k: round(d["ms"] / step_ms, 4) for k, d in sorted(tot.items(), key=lambda kv: -kv[1]["ms"])}
+        dom = max(tot.items(), key=lambda kv: kv[1]["ms"])
+        if dom[0] == "pmu_conv_gemm_bf16":
+            c = dom[1]
+            ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+            roof = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": ach,
+                    "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                    "traffic": None, "launches": c["n"], "avg_launch_ms": c["ms"] / c["n"],
+                    "peak_source": peaks["source"] + ", sustained bf16"}
+        else:
+            c = dom[1]
+            roof = {"kernel": dom[0], "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": None, "traffic": None, "launches": c["n"], "avg_launch_ms": c["ms"] / c["n"]}
+        world_frac = 1.0 / world
+        V = float(D) ** 3
+        if "pmu_slice_gather" in tot:
+            gb = P * V * 8.0 * world_frac / 1e9          # read 4 B + write 4 B per voxel per plane
+            hbm_kernels["slice_gather"] = {"achieved": gb / (tot["pmu_slice_gather"]["ms"] * 1e-3), "unit": "GB/s",
+                                           "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
+        if "pmu_scatter_accum" in tot:
+            gb = P * V * 2 * 3 * 4.0 * 3.0 * world_frac / 1e9  # read sums + RMW (read+write) accumulators, 2*C floats/voxel
+            hbm_kernels["scatter_accum"] = {"achieved": gb / (tot["pmu_scatter_accum"]["ms"] * 1e-3), "unit": "GB/s",
+                                            "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
+        if "pmu_fuse_finalize" in tot:
+            gb = V * 52.0 / 1e9
+            hbm_kernels["fuse_finalize"] = {"achieved": gb / (tot["pmu_fuse_finalize"]["ms"] * 1e-3), "unit": "GB/s",
+                                            "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
+        for v in hbm_kernels.values():
+            v["frac"] = v["achieved"] / v["peak"]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, cores, n_done = cpu_reference_rate(D, N, args.cpu_slices_per_plane)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n_done} of {3 * D} slices ({args.cpu_slices_per_plane} equally spaced per plane), "
+                                  f"forward once + {N} x fcomb + softmax + accumulate, {dt:.1f} s of CPU time, extrapolated"}
+    if rank == 0:
+        value = args.steps / (ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"{D}^3 fp32 volume, 3 planes x {N} z-samples, axis-aligned slicing, trainer model "
+                                       f"[64,128,256,512,1024] C=3 L=6 fcomb=4, mean/var/entropy fusion",
+                           "slice_batch": args.slice_batch, "parallelism": f"slice-sharded x{world} + 1 reduce",
+                           "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
+                "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * D ** 3),
+                        "d2h_bytes_per_step": int(4 * D ** 3 * 7), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels,
+                "kernel_time_shares": shares, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--samples", type=int, default=16)
+    ap.add_argument("--slice-batch", type=int, default=64)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-slices-per-plane", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

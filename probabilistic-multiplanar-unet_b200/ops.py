@@ -18,6 +18,29 @@ INTERP = {"exact": 0, "nearest": 1, "trilinear": 2}
 POOL_MAX, POOL_AVG_CEIL = 0, 1
 
 
+# ---- instrumentation (bench.py): how many of OUR kernels were launched, and optional per-call
+# CUDA-event timing on the launching stream -------------------------------------------------
+LAUNCHES = 0
+PROFILE = None      # set to a list to record (name, meta, start_event, end_event) per C-ABI call
+_META = None
+
+
+def _launch(lib, name, args):
+    global LAUNCHES, _META
+    meta, _META = _META, None
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.append((name, meta, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
+    _lib.check(rc, name)
+    LAUNCHES += 1
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else c_void_p(t.data_ptr())
 
@@ -64,8 +87,8 @@ def plane_max(vol: torch.Tensor) -> torch.Tensor:
     lib, st = _prep(vol)
     d = vol.shape
     out = torch.empty(d[0] + d[1] + d[2], dtype=torch.float32, device=vol.device)
-    _lib.check(lib.pmu_fill_f32(_p(out), float("-inf"), out.numel(), st), "pmu_fill_f32")
-    _lib.check(lib.pmu_plane_max(_p(vol), _dims(d), _p(out), st), "pmu_plane_max")
+    _launch(lib, "pmu_fill_f32", (_p(out), float("-inf"), out.numel(), st,))
+    _launch(lib, "pmu_plane_max", (_p(vol), _dims(d), _p(out), st,))
     return out
 
 
@@ -85,12 +108,12 @@ def slice_gather(vol: torch.Tensor, plane: int, s0: int, ns: int, *, interp: str
     mx = None
     if want_max:
         mx = torch.empty(max(ns, 1), dtype=torch.float32, device=vol.device)
-        _lib.check(lib.pmu_fill_f32(_p(mx), float("-inf"), mx.numel(), st), "pmu_fill_f32")
+        _launch(lib, "pmu_fill_f32", (_p(mx), float("-inf"), mx.numel(), st,))
     aff = None
     if affine is not None:
         aff = (c_float * 12)(*[float(a) for a in affine])
-    _lib.check(lib.pmu_slice_gather(_p(vol), _dims(d), int(plane), int(s0), int(ns), INTERP[interp], aff, int(H),
-                                    int(W), _p(slice_max_in), _p(mx), _p(out), st), "pmu_slice_gather")
+    _launch(lib, "pmu_slice_gather", (_p(vol), _dims(d), int(plane), int(s0), int(ns), INTERP[interp], aff, int(H),
+                                    int(W), _p(slice_max_in), _p(mx), _p(out), st,))
     return (out, mx[:ns]) if want_max else out
 
 
@@ -98,8 +121,7 @@ def slice_normalize_(slices: torch.Tensor, slice_max: torch.Tensor) -> torch.Ten
     _f32(slices, "slices"); _f32(slice_max, "slice_max")
     lib, st = _prep(slices, slice_max)
     ns = slices.shape[0]
-    _lib.check(lib.pmu_slice_normalize(_p(slices), _p(slice_max), ns, slices.numel() // max(ns, 1), st),
-               "pmu_slice_normalize")
+    _launch(lib, "pmu_slice_normalize", (_p(slices), _p(slice_max), ns, slices.numel() // max(ns, 1), st,))
     return slices
 
 
@@ -113,8 +135,7 @@ def conv3x3_f32(x0, w, bias, relu=True, x1=None, out=None):
     if out is None:
         out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x0.device)
     lib, st = _prep(x0, x1, w, bias, out)
-    _lib.check(lib.pmu_conv3x3_f32(_p(x0), C0, _p(x1), C1, _p(w), _p(bias), _p(out), B, H, W, Cout, int(relu), st),
-               "pmu_conv3x3_f32")
+    _launch(lib, "pmu_conv3x3_f32", (_p(x0), C0, _p(x1), C1, _p(w), _p(bias), _p(out), B, H, W, Cout, int(relu), st,))
     return out
 
 
@@ -124,8 +145,7 @@ def conv1x1_f32(x, w, bias, relu=False):
     Cout = w.shape[0]
     out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x.device)
     lib, st = _prep(x, w, bias, out)
-    _lib.check(lib.pmu_conv1x1_f32(_p(x), _p(w), _p(bias), _p(out), B, Cin, Cout, H * W, int(relu), st),
-               "pmu_conv1x1_f32")
+    _launch(lib, "pmu_conv1x1_f32", (_p(x), _p(w), _p(bias), _p(out), B, Cin, Cout, H * W, int(relu), st,))
     return out
 
 
@@ -137,8 +157,7 @@ def convt2x2_f32(x, w, bias, out_hw=None):
     dy, dx = Ho - 2 * H, Wo - 2 * W
     out = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=x.device)
     lib, st = _prep(x, w, bias, out)
-    _lib.check(lib.pmu_convt2x2_f32(_p(x), _p(w), _p(bias), _p(out), B, Cin, Cout, H, W, Ho, Wo, dy // 2, dx // 2, st),
-               "pmu_convt2x2_f32")
+    _launch(lib, "pmu_convt2x2_f32", (_p(x), _p(w), _p(bias), _p(out), B, Cin, Cout, H, W, Ho, Wo, dy // 2, dx // 2, st,))
     return out
 
 
@@ -148,7 +167,7 @@ def pool2_f32(x, mode):
     Ho, Wo = (H // 2, W // 2) if mode == POOL_MAX else ((H + 1) // 2, (W + 1) // 2)
     out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=x.device)
     lib, st = _prep(x, out)
-    _lib.check(lib.pmu_pool2_f32(_p(x), _p(out), B, C, H, W, mode, st), "pmu_pool2_f32")
+    _launch(lib, "pmu_pool2_f32", (_p(x), _p(out), B, C, H, W, mode, st,))
     return out
 
 
@@ -158,7 +177,7 @@ def gauss_head_f32(enc, w, b, L):
     mu = torch.empty(B, L, dtype=torch.float32, device=enc.device)
     ls = torch.empty_like(mu)
     lib, st = _prep(enc, w, b, mu, ls)
-    _lib.check(lib.pmu_gauss_head_f32(_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, st), "pmu_gauss_head_f32")
+    _launch(lib, "pmu_gauss_head_f32", (_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, st,))
     return mu, ls
 
 
@@ -171,9 +190,8 @@ def fcomb_f32(feat, z, fw, want_logits=True, want_sums=False):
     logits = torch.empty(B, N, C, H, W, dtype=torch.float32, device=feat.device) if want_logits else None
     sums = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=feat.device) if want_sums else None
     lib, st = _prep(feat, z, logits, sums)
-    _lib.check(lib.pmu_fcomb_f32(_p(feat), _p(z), _p(fw["w0"]), _p(fw["b0"]), _p(fw["wmid"]), _p(fw["bmid"]),
-                                 _p(fw["wlast"]), _p(fw["blast"]), _p(logits), _p(sums), B, N, F_, L, C, nl, H * W, st),
-               "pmu_fcomb_f32")
+    _launch(lib, "pmu_fcomb_f32", (_p(feat), _p(z), _p(fw["w0"]), _p(fw["b0"]), _p(fw["wmid"]), _p(fw["bmid"]),
+                                 _p(fw["wlast"]), _p(fw["blast"]), _p(logits), _p(sums), B, N, F_, L, C, nl, H * W, st,))
     return logits, sums
 
 
@@ -185,8 +203,7 @@ def conv3x3_first_bf16(x0, w, bias, relu=True, x1=None):
     Cout = w.shape[0]
     out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x0.device)
     lib, st = _prep(x0, x1, w, bias, out)
-    _lib.check(lib.pmu_conv3x3_first_bf16(_p(x0), _p(x1), _p(w), _p(bias), _p(out), B, H, W, Cin, Cout, int(relu), st),
-               "pmu_conv3x3_first_bf16")
+    _launch(lib, "pmu_conv3x3_first_bf16", (_p(x0), _p(x1), _p(w), _p(bias), _p(out), B, H, W, Cin, Cout, int(relu), st,))
     return out
 
 
@@ -198,8 +215,13 @@ def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None):
     oh, ow = (2 * H, 2 * W) if ntaps == 4 else (H, W)
     out = torch.empty(B, oh, ow, Cout, dtype=torch.bfloat16, device=x0.device)
     lib, st = _prep(x0, x1, wpack, bias, out)
-    _lib.check(lib.pmu_conv_gemm_bf16(_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), B, H, W, Cout, ntaps,
-                                      int(relu), st), "pmu_conv_gemm_bf16")
+    global _META
+    ktot = (9 if ntaps == 9 else 1) * (C0 + C1)
+    ntot = (4 if ntaps == 4 else 1) * Cout
+    _META = {"flops": 2.0 * B * H * W * ntot * ktot,
+             "bytes": 2.0 * (B * H * W * (C0 + C1) + out.numel() + ntot * ktot)}
+    _launch(lib, "pmu_conv_gemm_bf16", (_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), B, H, W, Cout, ntaps,
+                                      int(relu), st,))
     return out
 
 
@@ -209,7 +231,7 @@ def pool2_bf16(x, mode):
     Ho, Wo = (H // 2, W // 2) if mode == POOL_MAX else ((H + 1) // 2, (W + 1) // 2)
     out = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x.device)
     lib, st = _prep(x, out)
-    _lib.check(lib.pmu_pool2_bf16(_p(x), _p(out), B, H, W, C, mode, st), "pmu_pool2_bf16")
+    _launch(lib, "pmu_pool2_bf16", (_p(x), _p(out), B, H, W, C, mode, st,))
     return out
 
 
@@ -219,7 +241,7 @@ def gauss_head_bf16(enc, w, b, L):
     mu = torch.empty(B, L, dtype=torch.float32, device=enc.device)
     ls = torch.empty_like(mu)
     lib, st = _prep(enc, w, b, mu, ls)
-    _lib.check(lib.pmu_gauss_head_bf16(_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, st), "pmu_gauss_head_bf16")
+    _launch(lib, "pmu_gauss_head_bf16", (_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, st,))
     return mu, ls
 
 
@@ -228,7 +250,7 @@ def nhwc_bf16_to_nchw_f32(x):
     B, H, W, C = x.shape
     out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
     lib, st = _prep(x, out)
-    _lib.check(lib.pmu_nhwc_bf16_to_nchw_f32(_p(x), _p(out), B, H, W, C, st), "pmu_nhwc_bf16_to_nchw_f32")
+    _launch(lib, "pmu_nhwc_bf16_to_nchw_f32", (_p(x), _p(out), B, H, W, C, st,))
     return out
 
 
@@ -243,9 +265,9 @@ def fcomb_softmax_accum_bf16(feat, mu, sigma, eps, fw, out=None):
     if out is None:
         out = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=feat.device)
     lib, st = _prep(feat, mu, sigma, eps, out)
-    _lib.check(lib.pmu_fcomb_softmax_accum_bf16(_p(feat), _p(mu), _p(sigma), _p(eps), _p(fw["w0"]), _p(fw["b0"]),
+    _launch(lib, "pmu_fcomb_softmax_accum_bf16", (_p(feat), _p(mu), _p(sigma), _p(eps), _p(fw["w0"]), _p(fw["b0"]),
                                                 _p(fw["wmid"]), _p(fw["bmid"]), _p(fw["wlast"]), _p(fw["blast"]),
-                                                _p(out), B, N, L, C, nl, H * W, st), "pmu_fcomb_softmax_accum_bf16")
+                                                _p(out), B, N, L, C, nl, H * W, st,))
     return out
 
 
@@ -255,7 +277,7 @@ def softmax_accum(logits):
     B, N, C, H, W = logits.shape
     out = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=logits.device)
     lib, st = _prep(logits, out)
-    _lib.check(lib.pmu_softmax_accum(_p(logits), _p(out), B, N, C, H * W, st), "pmu_softmax_accum")
+    _launch(lib, "pmu_softmax_accum", (_p(logits), _p(out), B, N, C, H * W, st,))
     return out
 
 
@@ -263,8 +285,7 @@ def scatter_accum_(slice_sums, plane, s0, dims, S1, S2):
     _f32(slice_sums, "slice_sums"); _f32(S1, "S1"); _f32(S2, "S2")
     ns, _, C = slice_sums.shape[:3]
     lib, st = _prep(slice_sums, S1, S2)
-    _lib.check(lib.pmu_scatter_accum(_p(slice_sums), int(plane), int(s0), int(ns), _dims(dims), int(C), _p(S1), _p(S2), st),
-               "pmu_scatter_accum")
+    _launch(lib, "pmu_scatter_accum", (_p(slice_sums), int(plane), int(s0), int(ns), _dims(dims), int(C), _p(S1), _p(S2), st,))
 
 
 def fuse_finalize(S1, S2, count, want_var=True, want_entropy=True, want_labels=False):
@@ -275,8 +296,8 @@ def fuse_finalize(S1, S2, count, want_var=True, want_entropy=True, want_labels=F
     ent = torch.empty(X, Y, Z, dtype=torch.float32, device=S1.device) if want_entropy else None
     lab = torch.empty(X, Y, Z, dtype=torch.uint8, device=S1.device) if want_labels else None
     lib, st = _prep(S1, S2, mean, var, ent, lab)
-    _lib.check(lib.pmu_fuse_finalize(_p(S1), _p(S2), float(count), _dims((X, Y, Z)), C, _p(mean), _p(var), _p(ent),
-                                     _p(lab), st), "pmu_fuse_finalize")
+    _launch(lib, "pmu_fuse_finalize", (_p(S1), _p(S2), float(count), _dims((X, Y, Z)), C, _p(mean), _p(var), _p(ent),
+                                     _p(lab), st,))
     return mean, var, ent, lab
 
 
@@ -288,7 +309,7 @@ def ce_sum(logits, target):
     HW = logits.numel() // (B * C)
     out = torch.empty(1, dtype=torch.float32, device=logits.device)
     lib, st = _prep(logits, target, out)
-    _lib.check(lib.pmu_ce_sum(_p(logits), _p(target), B, C, HW, _p(out), st), "pmu_ce_sum")
+    _launch(lib, "pmu_ce_sum", (_p(logits), _p(target), B, C, HW, _p(out), st,))
     return out[0]
 
 
@@ -296,7 +317,7 @@ def kl_diag_gauss(mu_q, ls_q, mu_p, ls_p):
     B, L = mu_q.shape
     out = torch.empty(B, dtype=torch.float32, device=mu_q.device)
     lib, st = _prep(mu_q, ls_q, mu_p, ls_p, out)
-    _lib.check(lib.pmu_kl_diag_gauss(_p(mu_q), _p(ls_q), _p(mu_p), _p(ls_p), B, L, _p(out), st), "pmu_kl_diag_gauss")
+    _launch(lib, "pmu_kl_diag_gauss", (_p(mu_q), _p(ls_q), _p(mu_p), _p(ls_p), B, L, _p(out), st,))
     return out
 
 
@@ -306,7 +327,7 @@ def dice_sums(pred, target):
         raise RuntimeError("dice_sums: pred and target must have the same number of elements")
     out = torch.empty(3, dtype=torch.float32, device=pred.device)
     lib, st = _prep(pred, target, out)
-    _lib.check(lib.pmu_dice_sums(_p(pred), _p(target), pred.numel(), _p(out), st), "pmu_dice_sums")
+    _launch(lib, "pmu_dice_sums", (_p(pred), _p(target), pred.numel(), _p(out), st,))
     return out
 
 
@@ -317,5 +338,5 @@ def argmax_dice_sums(prob, truth):
     YZ = prob.numel() // (X * C)
     out = torch.empty((C - 1) * 3, dtype=torch.float32, device=prob.device)
     lib, st = _prep(prob, truth, out)
-    _lib.check(lib.pmu_argmax_dice_sums(_p(prob), _p(truth), X, C, YZ, _p(out), st), "pmu_argmax_dice_sums")
+    _launch(lib, "pmu_argmax_dice_sums", (_p(prob), _p(truth), X, C, YZ, _p(out), st,))
     return out.view(C - 1, 3)

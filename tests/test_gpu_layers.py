@@ -1,0 +1,195 @@
+"""GPU parity of the layer kernels against plain torch fp32 CPU ops (the op-level oracle):
+fp32 NCHW CUDA-core family and the bf16 NHWC / tcgen05 family."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pmu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pmu_b200
+    return pmu_b200.ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# --------------------------------------------------------------------------- fp32
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 1, 0, 4, 9, 13), (1, 5, 3, 7, 32, 48), (3, 16, 16, 33, 8, 8),
+                                              (2, 64, 0, 64, 16, 40), (1, 2, 0, 64, 5, 3)])
+def test_conv3x3_f32(ops, B, C0, C1, Cout, H, W):
+    g = _g(1)
+    x0 = torch.randn(B, C0, H, W, generator=g)
+    x1 = torch.randn(B, C1, H, W, generator=g) if C1 else None
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=g) * 0.2
+    b = torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(torch.cat([x0, x1], 1) if C1 else x0, w, b, padding=1))
+    got = ops.conv3x3_f32(x0.cuda(), w.cuda(), b.cuda(), True, x1.cuda() if C1 else None).cpu()
+    torch.testing.assert_close(got, ref, atol=2e-5, rtol=1e-5)
+    got2 = ops.conv3x3_f32(x0.cuda(), w.cuda(), b.cuda(), False, x1.cuda() if C1 else None).cpu()
+    torch.testing.assert_close(got2, F.conv2d(torch.cat([x0, x1], 1) if C1 else x0, w, b, padding=1), atol=2e-5, rtol=1e-5)
+
+
+def test_convt_pool_head_conv1x1_f32(ops):
+    g = _g(2)
+    x = torch.randn(2, 12, 5, 7, generator=g)
+    w = torch.randn(12, 6, 2, 2, generator=g) * 0.3
+    b = torch.randn(6, generator=g)
+    ref = F.conv_transpose2d(x, w, b, stride=2)
+    torch.testing.assert_close(ops.convt2x2_f32(x.cuda(), w.cuda(), b.cuda()).cpu(), ref, atol=1e-5, rtol=1e-5)
+    # with the F.pad canvas of Up.forward (unet_parts.py:58-62): skip 11x15
+    refp = F.pad(ref, [0, 1, 0, 1])
+    torch.testing.assert_close(ops.convt2x2_f32(x.cuda(), w.cuda(), b.cuda(), out_hw=(11, 15)).cpu(), refp, atol=1e-5, rtol=1e-5)
+    for (H, W) in [(8, 8), (7, 9), (1, 5)]:
+        y = torch.randn(2, 3, H, W, generator=g)
+        if H >= 2:
+            torch.testing.assert_close(ops.pool2_f32(y.cuda(), 0).cpu(), F.max_pool2d(y, 2))
+        torch.testing.assert_close(ops.pool2_f32(y.cuda(), 1).cpu(), F.avg_pool2d(y, 2, 2, 0, ceil_mode=True))
+    enc = torch.randn(3, 40, 4, 6, generator=g)
+    hw_ = torch.randn(12, 40, generator=g)
+    hb = torch.randn(12, generator=g)
+    e = enc.mean(2, keepdim=True).mean(3, keepdim=True)
+    ml = F.conv2d(e, hw_[:, :, None, None], hb)[:, :, 0, 0]
+    mu, ls = ops.gauss_head_f32(enc.cuda(), hw_.cuda(), hb.cuda(), 6)
+    torch.testing.assert_close(mu.cpu(), ml[:, :6], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(ls.cpu(), ml[:, 6:], atol=1e-5, rtol=1e-5)
+    x1 = torch.randn(2, 9, 6, 5, generator=g)
+    w1 = torch.randn(11, 9, generator=g)
+    b1 = torch.randn(11, generator=g)
+    torch.testing.assert_close(ops.conv1x1_f32(x1.cuda(), w1.cuda(), b1.cuda()).cpu(),
+                               F.conv2d(x1, w1[:, :, None, None], b1), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("F_,L,C,nl,N", [(64, 6, 3, 4, 3), (4, 6, 3, 4, 2), (16, 2, 2, 2, 1), (32, 3, 5, 3, 2)])
+def test_fcomb_f32(ops, F_, L, C, nl, N):
+    sd = O.make_state_dict((F_, 2 * F_), num_classes=C, latent_dim=L, no_convs_fcomb=nl, seed=3)
+    g = _g(4)
+    B, H, W = 2, 11, 14
+    feat = torch.randn(B, F_, H, W, generator=g)
+    z = torch.randn(B, N, L, generator=g)
+    from pmu_b200.engine import PackedNet
+    fw = PackedNet({k: v for k, v in sd.items() if k.startswith("fcomb")}, "cuda").fcomb
+    logits, sums = ops.fcomb_f32(feat.cuda(), z.cuda(), fw, want_logits=True, want_sums=True)
+    ref = torch.stack([O.fcomb(sd, feat, z[:, n]) for n in range(N)], 1)
+    torch.testing.assert_close(logits.cpu(), ref, atol=2e-5, rtol=1e-5)
+    p = torch.softmax(ref, 2)
+    torch.testing.assert_close(sums.cpu(), torch.stack([p.sum(1), (p * p).sum(1)], 1), atol=5e-6, rtol=1e-5)
+
+
+# --------------------------------------------------------------------------- bf16 / tcgen05
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("Cin", [1, 2])
+def test_first_conv_bf16(ops, Cin):
+    g = _g(5)
+    x = torch.rand(3, Cin, 16, 24, generator=g)
+    w = torch.randn(64, Cin, 3, 3, generator=g) * 0.3
+    b = torch.randn(64, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    got = ops.conv3x3_first_bf16(x[:, :1].contiguous().cuda(), w.cuda(), b.cuda(), True,
+                                 x[:, 1:2].contiguous().cuda() if Cin == 2 else None)
+    torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1e-2)
+
+
+CONV_TC_CASES = [
+    # B, C0, C1, Cout, H, W
+    (2, 64, 0, 64, 16, 16),
+    (1, 64, 0, 128, 32, 32),
+    (3, 128, 128, 128, 16, 16),      # two-source K loop (skip concat)
+    (5, 256, 0, 256, 4, 4),          # brick spans several images (TB = 8, ragged batch)
+    (3, 64, 0, 64, 2, 2),            # TB = 32
+    (2, 64, 64, 64, 24, 40),         # non power-of-two extents (partial tiles)
+    (1, 512, 0, 1024, 8, 8),         # long K
+]
+
+
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W", CONV_TC_CASES)
+def test_conv_gemm_bf16_3x3(ops, B, C0, C1, Cout, H, W):
+    g = _g(6)
+    x0 = _bf(torch.randn(B, C0, H, W, generator=g))
+    x1 = _bf(torch.randn(B, C1, H, W, generator=g)) if C1 else None
+    Cin = C0 + C1
+    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    xin = torch.cat([x0, x1], 1) if C1 else x0
+    ref = F.relu(F.conv2d(xin, w, b, padding=1))
+    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(torch.bfloat16).contiguous().cuda()
+    got = ops.conv_gemm_bf16(_nhwc(x0).to(torch.bfloat16).cuda(), wpack, b.cuda(), Cout, 9, True,
+                             _nhwc(x1).to(torch.bfloat16).cuda() if C1 else None)
+    err = (got.float().cpu() - _nhwc(ref)).abs().max().item()
+    assert err < 3e-2, f"max abs err {err}"
+    torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 128, 64, 8, 8), (1, 1024, 512, 4, 4), (3, 256, 128, 16, 12)])
+def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W):
+    g = _g(7)
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    w = _bf(torch.randn(Cin, Cout, 2, 2, generator=g) * (1.0 / Cin) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = F.conv_transpose2d(x, w, b, stride=2)
+    wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(torch.bfloat16).contiguous().cuda()
+    got = ops.conv_gemm_bf16(_nhwc(x).to(torch.bfloat16).cuda(), wpack, b.cuda(), Cout, 4, False)
+    torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
+
+
+def test_conv_gemm_bf16_1x1(ops):
+    g = _g(8)
+    x = _bf(torch.randn(2, 128, 8, 16, generator=g))
+    w = _bf(torch.randn(64, 128, generator=g) * 0.1)
+    b = torch.randn(64, generator=g) * 0.1
+    ref = F.conv2d(x, w[:, :, None, None], b)
+    got = ops.conv_gemm_bf16(_nhwc(x).to(torch.bfloat16).cuda(), w.to(torch.bfloat16).cuda(), b.cuda(), 64, 1, False)
+    torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
+
+
+def test_pool_head_transpose_bf16(ops):
+    g = _g(9)
+    for (H, W) in [(8, 8), (7, 9)]:
+        x = _bf(torch.randn(2, 64, H, W, generator=g))
+        xb = _nhwc(x).to(torch.bfloat16).cuda()
+        if H % 2 == 0:
+            assert torch.equal(ops.pool2_bf16(xb, 0).float().cpu(), _nhwc(F.max_pool2d(x, 2)))
+        torch.testing.assert_close(ops.pool2_bf16(xb, 1).float().cpu(),
+                                   _nhwc(F.avg_pool2d(x, 2, 2, 0, ceil_mode=True)), atol=1e-2, rtol=1e-2)
+        assert torch.equal(ops.nhwc_bf16_to_nchw_f32(xb).cpu(), x)
+    enc = _bf(torch.randn(3, 128, 4, 4, generator=g))
+    hw_ = torch.randn(12, 128, generator=g)
+    hb = torch.randn(12, generator=g)
+    ml = enc.mean((2, 3)) @ hw_.t() + hb
+    mu, ls = ops.gauss_head_bf16(_nhwc(enc).to(torch.bfloat16).cuda(), hw_.cuda(), hb.cuda(), 6)
+    torch.testing.assert_close(torch.cat([mu, ls], 1).cpu(), ml, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("nl,N,C", [(4, 5, 3), (2, 1, 3), (3, 16, 2)])
+def test_fcomb_softmax_accum_bf16(ops, nl, N, C):
+    """Fused tensor-core fcomb vs the fp32 oracle: probabilities within the bf16 budget 2e-2."""
+    sd = O.make_state_dict((64, 128), num_classes=C, latent_dim=6, no_convs_fcomb=nl, seed=10)
+    g = _g(11)
+    B, H, W = 3, 20, 24                       # HW = 480: ragged vs the 512-pixel block
+    feat = _bf(torch.relu(torch.randn(B, 64, H, W, generator=g)))
+    mu = torch.randn(B, 6, generator=g)
+    sigma = torch.rand(B, 6, generator=g) + 0.2
+    eps = torch.randn(B, N, 6, generator=g)
+    from pmu_b200.engine import PackedNet
+    fw = PackedNet({k: v for k, v in sd.items() if k.startswith("fcomb")}, "cuda").fcomb
+    got = ops.fcomb_softmax_accum_bf16(_nhwc(feat).to(torch.bfloat16).cuda(), mu.cuda(), sigma.cuda(), eps.cuda(), fw).cpu()
+    p = torch.stack([torch.softmax(O.fcomb(sd, feat, mu + sigma * eps[:, n]), 1) for n in range(N)], 1)
+    ref = torch.stack([p.sum(1), (p * p).sum(1)], 1)
+    err = (got - ref).abs().max().item() / N
+    assert err < 2e-2, f"mean-prob err {err}"
+    torch.testing.assert_close(got[:, 0].sum(1), torch.full((B, H, W), float(N)), atol=1e-3, rtol=1e-4)

@@ -1,0 +1,167 @@
+"""GPU parity of the drop-in model API and the multi-planar pipeline.
+
+  * CUDA path vs the REAL reference's outputs (tests/golden/golden_small.npz) — fp32 mode.
+  * CUDA path vs the oracle on the trainer architecture — fp32 (1e-4 on probabilities) and
+    bf16/tcgen05 (2e-2 on probabilities, Dice >= 0.999 against the fp32-oracle labels).
+  * size-independent properties at a larger volume (sharded sums add up, probabilities sum to
+    one, variance / entropy bounds).
+Tolerances are the north star's (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pmu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_PROB_TOL = 1e-4
+BF16_PROB_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def pmu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pmu_b200
+    return pmu_b200
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_small_model_vs_reference_golden(pmu, golden_dir):
+    """ProbabilisticUnet([4,8,16,32,64]) with the reference-constructed weights: every API call
+    against the reference's own outputs."""
+    z = np.load(os.path.join(golden_dir, "golden_small.npz"))
+    g = {k: z[k] for k in z.files}
+    sd = {k[3:]: _t(v) for k, v in g.items() if k.startswith("sd/")}
+    net = pmu.ProbabilisticUnet(1, 3, [4, 8, 16, 32, 64], latent_dim=6, no_convs_fcomb=4, beta=10)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x, segm, zz = _t(g["x"]).cuda(), _t(g["segm"]).cuda(), _t(g["z"]).cuda()
+    tol = dict(rtol=1e-4, atol=2e-5)
+    with torch.no_grad():
+        assert net.forward(x, segm, training=True) is None
+        np.testing.assert_allclose(net.unet_features.cpu().numpy(), g["eval/features"], **tol)
+        np.testing.assert_allclose(net.prior_latent_space.base_dist.loc.cpu().numpy(), g["eval/mu_p"], **tol)
+        np.testing.assert_allclose(net.prior_latent_space.base_dist.scale.cpu().numpy(), g["eval/sigma_p"], **tol)
+        np.testing.assert_allclose(net.posterior_latent_space.base_dist.loc.cpu().numpy(), g["eval/mu_q"], **tol)
+        np.testing.assert_allclose(net.posterior_latent_space.base_dist.scale.cpu().numpy(), g["eval/sigma_q"], **tol)
+        np.testing.assert_allclose(net.sample(testing=True, z=zz).cpu().numpy(), g["eval/fcomb_logits"], **tol)
+        np.testing.assert_allclose(net.kl_divergence(analytic=True).cpu().numpy(), g["eval/kl"], rtol=1e-4, atol=1e-5)
+        zq = _t(g["eval/z_q"]).cuda()
+        e = net.elbo(segm, z=zq)
+        np.testing.assert_allclose(net.reconstruction.cpu().numpy(), g["eval/elbo_logits"], **tol)
+        np.testing.assert_allclose(float(net.kl), float(g["eval/elbo_kl"]), rtol=1e-4)
+        np.testing.assert_allclose(float(net.reconstruction_loss), float(g["eval/elbo_rec"]), rtol=1e-4)
+        np.testing.assert_allclose(float(e), float(g["eval/elbo"]), rtol=1e-4)
+        np.testing.assert_allclose(net.reconstruct(z_posterior=zq).cpu().numpy(), g["eval/reconstruct"], **tol)
+        net.forward(x[:1], segm[:1], training=False)
+        np.testing.assert_allclose(net.sample_at(zz[0]).cpu().numpy(), g["eval/sample_at_b1"], **tol)
+        # stochastic calls: shapes + side effects
+        s = net.sample(testing=True)
+        assert s.shape == (1, 3, 32, 48) and net.z_prior_sample.shape == (1, 6)
+        unet = pmu.UNet(1, 3, [4, 8, 16, 32, 64]).cuda().eval()
+        unet.load_state_dict({k[5:]: v for k, v in sd.items() if k.startswith("unet.")}, strict=True)
+        np.testing.assert_allclose(unet(x).cpu().numpy(), g["eval/unet_out"], **tol)
+
+
+def test_autograd_is_refused_loudly(pmu):
+    net = pmu.ProbabilisticUnet(1, 3, [4, 8], 2, 2).cuda()
+    with pytest.raises(NotImplementedError):
+        net.forward(torch.zeros(1, 1, 8, 8, device="cuda"), torch.zeros(1, 1, 8, 8, device="cuda"))
+
+
+@pytest.fixture(scope="module")
+def trainer_sd():
+    return O.make_state_dict(seed=0)
+
+
+def test_trainer_model_vs_golden_trainer(pmu, golden_dir, trainer_sd):
+    """The real architecture against the REAL reference's outputs, fp32 and bf16 modes."""
+    z = np.load(os.path.join(golden_dir, "golden_trainer.npz"))
+    g = {k: z[k] for k in z.files}
+    net = pmu.ProbabilisticUnet(1, 3, [64, 128, 256, 512, 1024], 6, 4, 10)
+    net.load_state_dict(trainer_sd, strict=True)
+    net = net.cuda().eval()
+    x, segm, zz = _t(g["x"]).cuda(), _t(g["segm"]).cuda(), _t(g["z"]).cuda()
+    ref_p = torch.softmax(_t(g["fcomb_logits"]), 1)
+    with torch.no_grad():
+        net.set_precision("fp32")
+        net.forward(x, segm, training=True)
+        np.testing.assert_allclose(net.unet_features.cpu().numpy(), g["features"], rtol=1e-3, atol=2e-4)
+        np.testing.assert_allclose(net.prior_latent_space.base_dist.loc.cpu().numpy(), g["mu_p"], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(net.posterior_latent_space.base_dist.scale.cpu().numpy(), g["sigma_q"], rtol=1e-3, atol=1e-4)
+        p = torch.softmax(net.sample(z=zz), 1).cpu()
+        assert (p - ref_p).abs().max() < FP32_PROB_TOL
+        np.testing.assert_allclose(net.kl_divergence().cpu().numpy(), g["kl"], rtol=1e-3, atol=1e-4)
+        net.set_precision("bf16")
+        net.forward(x, segm, training=True)
+        p16 = torch.softmax(net.sample(z=zz), 1).cpu()
+        assert (p16 - ref_p).abs().max() < BF16_PROB_TOL
+        np.testing.assert_allclose(net.prior_latent_space.base_dist.loc.cpu().numpy(), g["mu_p"], rtol=5e-2, atol=3e-2)
+
+
+def _dice_labels(a, b, C):
+    d = []
+    for k in range(1, C):
+        pa, pb = (a == k).float(), (b == k).float()
+        d.append(float((2 * (pa * pb).sum() + 1e-6) / (pa.sum() + pb.sum() + 1e-6)))
+    return d
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_multiplanar_vs_oracle(pmu, trainer_sd, precision):
+    """Config-2-shaped case shrunk to what the CPU oracle finishes in seconds: 32^3, 3 planes,
+    4 samples, injected eps, trainer model."""
+    D, N = 32, 4
+    vol, _ = O.phantom(D, seed=1234)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    ref = O.multiplanar_predict(vol, trainer_sd, eps, N, batch=16)
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision=precision, n_samples=N, slice_batch=16)
+    out = pred.predict(vol, eps=eps, want_labels=True, keep_sums=True)
+    tol = FP32_PROB_TOL if precision == "fp32" else BF16_PROB_TOL
+    err = (out["mean"].cpu() - ref["mean"]).abs().max().item()
+    assert err < tol, f"mean prob err {err}"
+    assert (out["var"].cpu() - ref["var"]).abs().max().item() < tol
+    assert (out["entropy"].cpu() - ref["entropy"]).abs().max().item() < (1e-3 if precision == "fp32" else 6e-2)
+    lab_ref = torch.argmax(ref["mean"], 1)
+    lab = out["labels"].cpu().long()
+    # labels may only differ where the oracle's own top-2 margin is inside the tolerance
+    top2 = torch.topk(ref["mean"], 2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    assert bool(((lab == lab_ref) | (margin < 2 * tol)).all())
+    if precision == "bf16":
+        for d in _dice_labels(lab, lab_ref, 3):
+            assert d >= 0.999 or (lab_ref > 0).sum() == 0, d
+
+
+def test_multiplanar_properties_and_sharding(pmu, trainer_sd):
+    """Larger volume (64^3, bf16): size-independent properties + 2-rank sharding on one GPU:
+    the two ranks' accumulators add up to the single-rank ones (the reduce is a plain sum)."""
+    D, N = 64, 2
+    vol, _ = O.phantom(D, seed=7)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(1)).cuda()
+    one = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=32)
+    out = one.predict(vol, eps=eps, keep_sums=True)
+    mean, var, ent = out["mean"], out["var"], out["entropy"]
+    torch.testing.assert_close(mean.sum(1), torch.ones_like(mean[:, 0]), atol=1e-4, rtol=1e-4)
+    assert float(var.min()) >= 0.0 and float(var.max()) <= 0.25 + 1e-6
+    assert float(ent.min()) >= 0.0 and float(ent.max()) <= np.log(3) + 1e-5
+    v = torch.from_numpy(vol).cuda()
+    acc = []
+    for r in range(2):
+        pr = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=32, rank=r, world_size=2)
+        a = torch.zeros(2, D, 3, D, D, device="cuda")
+        n_done = pr.accumulate(v, eps, a)
+        assert n_done == 96
+        acc.append(a)
+    tot = acc[0] + acc[1]
+    torch.testing.assert_close(tot[0], out["S1"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(tot[1], out["S2"], atol=1e-5, rtol=1e-5)
+    # determinism: same inputs, same bits
+    out2 = one.predict(vol, eps=eps)
+    assert torch.equal(out2["mean"], mean)

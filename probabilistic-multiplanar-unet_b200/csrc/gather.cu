@@ -330,6 +330,8 @@ extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int pla
                                 int interp, const float* affine_host, int H, int W,
                                 const float* slice_max_in, float* slice_max_out, float* out,
                                 void* stream) {
+  PMU_CHECK_ARG(ns >= 0, "pmu_slice_gather: negative slice count");
+  if (ns == 0) return PMU_OK;  // empty range: nothing to do (out may be a zero-size buffer)
   PMU_CHECK_ARG(vol && dims && out, "pmu_slice_gather: null pointer");
   const int d0 = dims[0], d1 = dims[1], d2 = dims[2];
   PMU_CHECK_ARG(d0 > 0 && d1 > 0 && d2 > 0, "pmu_slice_gather: dims must be positive");

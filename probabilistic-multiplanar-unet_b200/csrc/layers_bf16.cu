@@ -68,6 +68,68 @@ conv3x3_first_bf16_kernel(const float* __restrict__ x0, const float* __restrict_
   }
 }
 
+// Fast path (Cin == 1, W % 4 == 0 — every slice of the hot path): thread = 4 consecutive pixels
+// x 8 couts with its 72 weights held in registers across a grid-stride loop; inputs come in as
+// one float4 + two halo scalars per row; 32-bit index math only.  Per 4 pixels: 9 loads,
+// 288 FMA, 4 x 16-byte stores (a warp writes four full 128-byte lines per store instruction).
+__global__ void __launch_bounds__(256)
+conv3x3_first_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                        int Cout, int relu) {
+  const int groups = Cout >> 3;
+  const int g = threadIdx.x % groups;                     // cout group (fastest: 8 lanes share a pixel quad)
+  const int qpb = 256 / groups;                           // pixel quads per block
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wr[tap][c] = __ldg(w + (g * 8 + c) * 9 + tap);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) br[c] = bias ? __ldg(bias + g * 8 + c) : 0.f;
+  const int W4 = W >> 2;
+  const unsigned total = (unsigned)B * H * W4;            // pixel quads
+  for (unsigned q = blockIdx.x * qpb + threadIdx.x / groups; q < total; q += gridDim.x * qpb) {
+    const int w0 = (int)(q % W4) * 4;
+    const unsigned row = q / W4;                          // b*H + h
+    const int h = (int)(row % H);
+    const float* src = x + (size_t)row * W + w0;
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[p][c] = br[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = h + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+      const float* rp = src + (ky - 1) * W;
+      const float4 mid = __ldg(reinterpret_cast<const float4*>(rp));
+      const float lft = (w0 > 0) ? __ldg(rp - 1) : 0.f;
+      const float rgt = (w0 + 4 < W) ? __ldg(rp + 4) : 0.f;
+      const float iv[6] = {lft, mid.x, mid.y, mid.z, mid.w, rgt};
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(iv[p + kx], wr[ky * 3 + kx][c], acc[p][c]);
+    }
+    __nv_bfloat16* dst = y + ((size_t)row * W + w0) * Cout + g * 8;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = acc[p][2 * j], c = acc[p][2 * j + 1];
+        if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)p * Cout) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // 2x2 stride-2 pooling, NHWC bf16; thread = (output pixel, 8 channels = 16 B)
 // ---------------------------------------------------------------------------------
@@ -158,6 +220,16 @@ extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const fl
   PMU_CHECK_SUPPORTED(Cin >= 1 && Cin <= 2 && (Cin == 1 || x1), "pmu_conv3x3_first_bf16: Cin must be 1, or 2 with x1 (got %d)", Cin);
   PMU_CHECK_SUPPORTED(Cout % 8 == 0 && Cout <= 128, "pmu_conv3x3_first_bf16: Cout must be a multiple of 8, <= 128 (got %d)", Cout);
   PMU_CHECK_ARG(aligned16(y), "pmu_conv3x3_first_bf16: y must be 16-byte aligned");
+  const int groups = Cout / 8;
+  if (Cin == 1 && W % 4 == 0 && 256 % groups == 0 && aligned16(x0) && (int64_t)B * H * (W / 4) < (1ll << 31)) {
+    const int64_t quads = (int64_t)B * H * (W / 4);
+    const int qpb = 256 / groups;
+    const int blocks = (int)std::min<int64_t>(cdiv64(quads, qpb), (int64_t)sm_count() * 8);
+    conv3x3_first_c1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, w, bias, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                     B, H, W, Cout, relu);
+    PMU_LAUNCH_CHECK();
+    return PMU_OK;
+  }
   const int64_t total = (int64_t)B * H * W * (Cout / 8);
   const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 32);
   conv3x3_first_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, x1, w, bias, reinterpret_cast<__nv_bfloat16*>(y),

@@ -111,14 +111,17 @@ class MultiPlanarPredictor:
             if p not in my:
                 continue
             s_lo, s_hi = my[p]
+            # K1 once per plane: all of this rank's slices of the plane in one launch (full-bandwidth
+            # granularity: 134 MB of traffic per 256^3 plane instead of 33 MB per batch)
+            if exact:
+                xs = ops.slice_gather(vol, p, s_lo, s_hi - s_lo, slice_max_in=maxes[offs[p]: offs[p] + dims[p]])
+            else:
+                xs, mx = ops.slice_gather(vol, p, s_lo, s_hi - s_lo, interp=self.interp, affine=self.affines[p],
+                                          hw=self.out_hw, want_max=True)
+                ops.slice_normalize_(xs, mx)
             for s0 in range(s_lo, s_hi, self.slice_batch):
                 ns = min(self.slice_batch, s_hi - s0)
-                if exact:
-                    x = ops.slice_gather(vol, p, s0, ns, slice_max_in=maxes[offs[p]: offs[p] + dims[p]])
-                else:
-                    x, mx = ops.slice_gather(vol, p, s0, ns, interp=self.interp, affine=self.affines[p],
-                                             hw=self.out_hw, want_max=True)
-                    ops.slice_normalize_(x, mx)
+                x = xs[s0 - s_lo: s0 - s_lo + ns]
                 feat = net.unet_features(x)
                 mu, ls = net.gaussian("prior", x)
                 sigma = torch.exp(ls)          # Normal(scale=exp(log_sigma)), probabilistic_unet.py:113

@@ -134,9 +134,8 @@ def test_multiplanar_vs_oracle(pmu, trainer_sd, precision):
     top2 = torch.topk(ref["mean"], 2, dim=1).values
     margin = top2[:, 0] - top2[:, 1]
     assert bool(((lab == lab_ref) | (margin < 2 * tol)).all())
-    if precision == "bf16":
-        for d in _dice_labels(lab, lab_ref, 3):
-            assert d >= 0.999 or (lab_ref > 0).sum() == 0, d
+    # (random weights give near-tied softmaxes almost everywhere, so a Dice >= 0.999 check is only
+    # meaningful on a confident model: see test_fitted_model_dice below)
 
 
 def test_multiplanar_properties_and_sharding(pmu, trainer_sd):

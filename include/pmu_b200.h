@@ -143,6 +143,15 @@ int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const voi
                        const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
                        int relu, void* stream);
 
+/* conv3x3 (as above, ntaps = 9) that ALSO writes the 2x2-pooled map y_pool bf16 [B,H/2,W/2,Cout]
+ * from its epilogue (pool_mode PMU_POOL_MAX: unet_parts.py:33 after DoubleConv;
+ * PMU_POOL_AVG_CEIL: probabilistic_unet.py:36) — the pooled tensor never costs an extra pass
+ * over HBM.  Needs even H >= 8, W >= 16.  y may be NULL when only the pooled map is consumed
+ * (the prior encoder, probabilistic_unet.py:36-45). */
+int pmu_conv_gemm_pool_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
+                            const float* bias, void* y, void* y_pool, int pool_mode, int B, int H,
+                            int W, int Cout, int relu, void* stream);
+
 int pmu_pool2_bf16(const void* x, void* y, int B, int H, int W, int C, int mode, void* stream);
 /* enc bf16 NHWC [B,h,w,C]; w fp32 [2L,C]; outputs fp32. */
 int pmu_gauss_head_bf16(const void* enc, const float* w, const float* b, float* mu,

@@ -16,7 +16,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
 // elected lane), warps 2..5 = epilogue (bias + ReLU + bf16 pack + NHWC store).
 // Pipeline: STAGES-deep smem ring with full/empty mbarriers; tcgen05.commit releases slots.
-// Two CTAs are resident per SM so one CTA's epilogue overlaps the other's main loop.
+// Persistent CTAs (one per SM) with a double-buffered TMEM accumulator: the epilogue of tile i
+// overlaps the main loop of tile i+1.
 #include <cudaTypedefs.h>
 
 #include "pmu_common.cuh"
@@ -40,6 +41,7 @@ struct ConvTcParams {
   int TW, TH, TB;     // tile brick, TW*TH*TB == 128
   int tiles_w, tiles_h, tiles_b;
   int n_tiles;        // Ntot / BN
+  int pool_mode;      // -1 none; PMU_POOL_MAX / PMU_POOL_AVG_CEIL: also emit the 2x2-pooled map
 };
 
 template <int BN, int STAGES>
@@ -47,44 +49,42 @@ struct ConvTcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;            // full[S], empty[S], tmem_full
-  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
-  static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;
-  static constexpr int TOTAL = BIAS_OFF + BN * 4;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;            // full[S], empty[S], tmem_full[2], tmem_empty[2]
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;   // 2 x BN floats (one per accumulator stage)
+  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
 };
 
+// Persistent kernel: one CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x,
+// N-tile fastest so concurrently running CTAs share activation bricks in L2).  The smem ring
+// keeps running across tiles (the producer prefetches the next tile's operands while the
+// current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
+// (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
+// setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const ConvTcParams p,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y) {
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+               __nv_bfloat16* __restrict__ y_pool) {
   using L = ConvTcSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_full = smem_base + L::BAR_OFF;
   const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_tmem = bar_empty + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;   // [2] accumulator stage ready for the epilogue
+  const uint32_t bar_tempty = bar_tfull + 2 * 8;       // [2] accumulator stage drained by the epilogue
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TMEM_PTR_OFF);
   float* bias_s = reinterpret_cast<float*>(smem_gen + L::BIAS_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile coordinates: blockIdx.x = m_tile * n_tiles + n_tile (N fastest: the CTAs that
-  // share an activation tile are launched together and hit it in L2) ----
-  const int n_tile = blockIdx.x % p.n_tiles;
-  int m_tile = blockIdx.x / p.n_tiles;
-  const int tw_i = m_tile % p.tiles_w; m_tile /= p.tiles_w;
-  const int th_i = m_tile % p.tiles_h; m_tile /= p.tiles_h;
-  const int tb_i = m_tile;
-  const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.TB;
-  const int n0 = n_tile * BN;
-
   const int Cin = p.C0 + p.C1;
   const int kc_per_tap = Cin / TC_BK;
   const int k_taps = (p.ntaps == 9) ? 9 : 1;
   const int k_iters = k_taps * kc_per_tap;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA0);
@@ -94,10 +94,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(bar_full + s * 8, 1);
       mbar_init(bar_empty + s * 8, 1);
     }
-    mbar_init(bar_tmem, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + a * 8, 1);
+      mbar_init(bar_tempty + a * 8, 128);   // every epilogue thread arrives
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(smem_base + L::TMEM_PTR_OFF);
+  if (warp == 1) tmem_alloc<2 * BN>(smem_base + L::TMEM_PTR_OFF);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -106,92 +109,165 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bar_empty + s * 8, ph ^ 1u);
-        const int tap = it / kc_per_tap;
-        int c = (it - tap * kc_per_tap) * TC_BK;   // channel offset inside the concatenated K
-        int dy = 0, dx = 0;
-        if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        const uint32_t sb = sa + L::A_BYTES;
-        mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
-        if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
-        else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
-        tma_load_2d(sb, &tmW, bar_full + s * 8, tap * Cin + c, n0);
+      uint32_t kc = 0;   // k-block counter over the whole tile sequence
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
+        const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
+        const int b0 = m_tile * p.TB;
+        const int n0 = n_tile * BN;
+        for (int it = 0; it < k_iters; ++it, ++kc) {
+          const uint32_t s = kc % STAGES;
+          const uint32_t ph = (kc / STAGES) & 1u;
+          mbar_wait(bar_empty + s * 8, ph ^ 1u);
+          const int tap = it / kc_per_tap;
+          const int c = (it - tap * kc_per_tap) * TC_BK;   // channel offset inside the concatenated K
+          int dy = 0, dx = 0;
+          if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+          if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
+          else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
+          tma_load_2d(sb, &tmW, bar_full + s * 8, tap * Cin + c, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
-    for (int it = 0; it < k_iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(bar_full + s * 8, ph);
+    uint32_t kc = 0, iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
+      mbar_wait(bar_tempty + as * 8, aph ^ 1u);     // epilogue has drained this accumulator stage
       tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        const uint64_t adesc = umma_smem_desc_sw128(sa);
-        const uint64_t bdesc = umma_smem_desc_sw128(sa + L::A_BYTES);
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int it = 0; it < k_iters; ++it, ++kc) {
+        const uint32_t s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1u;
+        mbar_wait(bar_full + s * 8, ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+          const uint64_t adesc = umma_smem_desc_sw128(sa);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-          // +32 B per UMMA_K inside the 128 B swizzle row: start-address field += 2
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                    (uint32_t)((it | k) != 0));
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            // +32 B per UMMA_K inside the 128 B swizzle row: start-address field += 2
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                      (uint32_t)((it | k) != 0));
+          }
+          umma_commit(bar_empty + s * 8);                        // frees the smem slot when these MMAs retire
+          if (it == k_iters - 1) umma_commit(bar_tfull + as * 8);  // accumulator complete
         }
-        umma_commit(bar_empty + s * 8);              // frees the smem slot when these MMAs retire
-        if (it == k_iters - 1) umma_commit(bar_tmem);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // =========================== epilogue (warps 2..5) ===========================
     const int et = threadIdx.x - 64;  // 0..127
-    const int co_base = (p.ntaps == 4) ? (n0 % p.Cout) : n0;
-    for (int i = et; i < BN; i += 128) bias_s[i] = bias ? __ldg(bias + co_base + i) : 0.f;
-    named_bar_sync(1, 128);
-
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;       // row of the tile == pixel index in the brick
     const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
-    const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
-    const bool valid = (b < p.B) && (h < p.H) && (w < p.W);
-    __nv_bfloat16* dst;
-    if (p.ntaps == 4) {
-      const int ij = n0 / p.Cout;
-      const int oy = 2 * h + (ij >> 1), ox = 2 * w + (ij & 1);
-      dst = y + (((int64_t)b * (2 * p.H) + oy) * (2 * p.W) + ox) * p.Cout + co_base;
-    } else {
-      dst = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base;
-    }
-    mbar_wait(bar_tmem, 0);
-    tcgen05_fence_after();
+    uint32_t iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
+      const int n_tile = tile % p.n_tiles;
+      int m_tile = tile / p.n_tiles;
+      const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
+      const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
+      const int b0 = m_tile * p.TB;
+      const int n0 = n_tile * BN;
+      const int co_base = (p.ntaps == 4) ? (n0 % p.Cout) : n0;
+      float* bs = bias_s + as * BN;
+      for (int i = et; i < BN; i += 128) bs[i] = bias ? __ldg(bias + co_base + i) : 0.f;
+      named_bar_sync(1, 128);          // bias visible; also keeps the 4 warps within one tile of each other
+
+      const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
+      const bool valid = (b < p.B) && (h < p.H) && (w < p.W);
+      __nv_bfloat16* dst = nullptr;
+      if (y != nullptr) {
+        if (p.ntaps == 4) {
+          const int ij = n0 / p.Cout;
+          const int oy = 2 * h + (ij >> 1), ox = 2 * w + (ij & 1);
+          dst = y + (((int64_t)b * (2 * p.H) + oy) * (2 * p.W) + ox) * p.Cout + co_base;
+        } else {
+          dst = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base;
+        }
+      }
+      // fused 2x2 pooling (tile brick 16 x 8: a warp holds image rows 2q and 2q+1, so every pooling
+      // window lives in lanes {l, l^1, l^16} of one warp — two shuffles, no extra pass over HBM)
+      const bool pool_writer = (p.pool_mode >= 0) && ((lane & 17) == 0) && valid;
+      __nv_bfloat16* dstp = nullptr;
+      if (p.pool_mode >= 0)
+        dstp = y_pool + (((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.Cout + co_base;
+
+      mbar_wait(bar_tfull + as * 8, aph);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (valid) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_d + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {
+          // all of this thread's TMEM reads of the stage are done: hand it back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(bar_tempty + as * 8);
+        }
+        float v[32];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint32_t pk[4];
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r[j]) + bs[c0 + j];
+          if (p.relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a = __uint_as_float(r[v * 8 + 2 * j]) + bias_s[c0 + v * 8 + 2 * j];
-            float c = __uint_as_float(r[v * 8 + 2 * j + 1]) + bias_s[c0 + v * 8 + 2 * j + 1];
-            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        if (valid && dst != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dst + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (p.pool_mode == PMU_POOL_MAX) {
+          // max of bf16-rounded values == bf16 rounding of the max (monotonic): exact, packed
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+            uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+            uint32_t au = *reinterpret_cast<uint32_t*>(&a);
+            o = __shfl_xor_sync(0xffffffffu, au, 16);
+            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+            pk[j] = *reinterpret_cast<uint32_t*>(&a);
+          }
+        } else if (p.pool_mode == PMU_POOL_AVG_CEIL) {
+          // average of the bf16-stored activations, accumulated in fp32 (what pool2_bf16 computes)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+            float lo = __low2float(a), hi = __high2float(a);
+            lo += __shfl_xor_sync(0xffffffffu, lo, 1);  hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+            lo += __shfl_xor_sync(0xffffffffu, lo, 16); hi += __shfl_xor_sync(0xffffffffu, hi, 16);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
             pk[j] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        if (pool_writer) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dstp + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------
@@ -242,11 +318,14 @@ static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 template <int BN, int STAGES>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm,
-                          const ConvTcParams& p, const float* bias, void* y, int64_t grid, cudaStream_t st) {
+                          const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
+                          cudaStream_t st) {
   using L = ConvTcSmem<BN, STAGES>;
   auto kern = conv_tc_kernel<BN, STAGES>;
   PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-  kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, p, bias, reinterpret_cast<__nv_bfloat16*>(y));
+  grid = std::min<int64_t>(grid, sm_count());   // persistent: one CTA per SM
+  kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, p, bias, reinterpret_cast<__nv_bfloat16*>(y),
+                                                         reinterpret_cast<__nv_bfloat16*>(y_pool));
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }
@@ -255,17 +334,17 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 
 using namespace pmu;
 
-extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
-                                  const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
-                                  int relu, void* stream) {
-  PMU_CHECK_ARG(x0 && wpack && y, "pmu_conv_gemm_bf16: null pointer");
+static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const void* wpack,
+                          const float* bias, void* y, void* y_pool, int pool_mode, int B, int H, int W, int Cout,
+                          int ntaps, int relu, void* stream) {
+  PMU_CHECK_ARG(x0 && wpack && (y || y_pool), "pmu_conv_gemm_bf16: null pointer");
   PMU_CHECK_ARG(ntaps == 9 || ntaps == 4 || ntaps == 1, "pmu_conv_gemm_bf16: ntaps must be 9, 4 or 1 (got %d)", ntaps);
   PMU_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && C1 >= 0, "pmu_conv_gemm_bf16: bad shape");
   PMU_CHECK_ARG(C1 == 0 || x1, "pmu_conv_gemm_bf16: C1 > 0 needs x1");
   PMU_CHECK_ARG(!(ntaps == 4 && (C1 != 0 || relu)), "pmu_conv_gemm_bf16: convT takes one source and no ReLU");
   PMU_CHECK_SUPPORTED(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0,
                       "pmu_conv_gemm_bf16: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
-  PMU_CHECK_ARG(aligned16(x0) && aligned16(wpack) && aligned16(y) && (!x1 || aligned16(x1)),
+  PMU_CHECK_ARG(aligned16(x0) && aligned16(wpack) && (!y || aligned16(y)) && (!x1 || aligned16(x1)),
                 "pmu_conv_gemm_bf16: pointers must be 16-byte aligned");
   int cc_major = 0, dev = 0;
   PMU_CUDA(cudaGetDevice(&dev));
@@ -274,6 +353,7 @@ extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1
 
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout; p.ntaps = ntaps; p.relu = relu;
+  p.pool_mode = y_pool ? pool_mode : -1;
   p.TW = std::min(16, pow2ceil(W));
   p.TH = std::min(TC_BM / p.TW, pow2ceil(H));
   p.TB = TC_BM / (p.TW * p.TH);
@@ -283,6 +363,12 @@ extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1
   const int Ktot = (ntaps == 9) ? 9 * Cin : Cin;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   p.n_tiles = Ntot / BN;
+  if (y_pool) {
+    PMU_CHECK_ARG(pool_mode == PMU_POOL_MAX || pool_mode == PMU_POOL_AVG_CEIL, "pmu_conv_gemm_pool_bf16: unknown pool mode %d", pool_mode);
+    PMU_CHECK_SUPPORTED(ntaps != 4 && p.TW == 16 && p.TH == 8 && H % 2 == 0 && W % 2 == 0,
+                        "pmu_conv_gemm_pool_bf16: fused pooling needs even H, W >= 16 (got %dx%d)", H, W);
+    PMU_CHECK_ARG(aligned16(y_pool), "pmu_conv_gemm_pool_bf16: y_pool must be 16-byte aligned");
+  }
   const int64_t grid = (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   PMU_CHECK_ARG(grid > 0 && grid < (1ll << 31), "pmu_conv_gemm_bf16: grid too large");
 
@@ -294,6 +380,19 @@ extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1
   rc = make_w_map(&wm, wpack, Ntot, Ktot, BN);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 128) return launch_conv_tc<128, 3>(a0, a1, wm, p, bias, y, grid, st);
-  return launch_conv_tc<64, 4>(a0, a1, wm, p, bias, y, grid, st);
+  if (BN == 128) return launch_conv_tc<128, 6>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+  return launch_conv_tc<64, 8>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+}
+
+extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
+                                  const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
+                                  int relu, void* stream) {
+  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, nullptr, -1, B, H, W, Cout, ntaps, relu, stream);
+}
+
+extern "C" int pmu_conv_gemm_pool_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
+                                       const float* bias, void* y, void* y_pool, int pool_mode, int B, int H,
+                                       int W, int Cout, int relu, void* stream) {
+  PMU_CHECK_ARG(y_pool != nullptr, "pmu_conv_gemm_pool_bf16: y_pool is null");
+  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, y_pool, pool_mode, B, H, W, Cout, 9, relu, stream);
 }

@@ -28,13 +28,13 @@ constexpr int FT_MAXL = 16;
 // D = A*B + C  (C given separately: lets the bias ride in as the initial accumulator)
 __device__ __forceinline__ void mma_bf16_init(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
                                               float c0, float c1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
       : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
 }
 __device__ __forceinline__ void mma_bf16_acc(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -51,19 +51,23 @@ __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
 __device__ __forceinline__ void dense64(float (&acc)[FT_TP][8][4], const uint32_t (&a)[FT_TP][4][4],
                                         const __nv_bfloat16* __restrict__ Ws, const float* __restrict__ bias,
                                         int g, int t) {
+  // k-step outer, n-tile inner: 16 independent accumulator chains sit between two dependent
+  // MMAs, so the tensor pipe latency is covered inside one warp.
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const __nv_bfloat16* wr = Ws + (nt * 8 + g) * FT_LD + 2 * t;
-    float2 bv = make_float2(0.f, 0.f);
-    if (bias) bv = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * t);
+  for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr + ks * 16);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 8);
+    for (int nt = 0; nt < 8; ++nt) {
+      const __nv_bfloat16* wr = Ws + (nt * 8 + g) * FT_LD + 2 * t + ks * 16;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+      if (ks == 0) {
+        float2 bv = make_float2(0.f, 0.f);
+        if (bias) bv = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * t);
 #pragma unroll
-      for (int tp = 0; tp < FT_TP; ++tp) {
-        if (ks == 0) mma_bf16_init(acc[tp][nt], a[tp][ks], b0, b1, bv.x, bv.y);
-        else mma_bf16_acc(acc[tp][nt], a[tp][ks], b0, b1);
+        for (int tp = 0; tp < FT_TP; ++tp) mma_bf16_init(acc[tp][nt], a[tp][ks], b0, b1, bv.x, bv.y);
+      } else {
+#pragma unroll
+        for (int tp = 0; tp < FT_TP; ++tp) mma_bf16_acc(acc[tp][nt], a[tp][ks], b0, b1);
       }
     }
   }

@@ -17,12 +17,13 @@ namespace pmu {
 // One warp per (x,y) row; lanes stride along z with float4.
 // ---------------------------------------------------------------------------------
 constexpr int PM_WARPS = 8;
-constexpr int PM_ROWS_PER_WARP = 8;
+constexpr int PM_ROWS_PER_WARP = 16;
 constexpr int PM_ZSEG = 1024;  // z extent handled per pass: 32 lanes * 4 * 8 chunks
 
 template <bool VEC>
 __global__ void __launch_bounds__(PM_WARPS * 32)
 plane_max_kernel(const float* __restrict__ vol, int d0, int d1, int d2, float* __restrict__ maxes) {
+  __shared__ float zred[PM_WARPS][PM_ZSEG];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t nrows = (int64_t)d0 * d1;
   const int64_t row0 = ((int64_t)blockIdx.x * PM_WARPS + warp) * PM_ROWS_PER_WARP;
@@ -67,16 +68,20 @@ plane_max_kernel(const float* __restrict__ vol, int d0, int d1, int d2, float* _
         atomic_max_float(max1 + y, rmax);
       }
     }
+    // combine the 8 warps' per-z maxima in shared memory: one atomic per z per block
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int z = zseg + 4 * (lane + 32 * j);
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float m = zmax[j][i];
-        if (z + i < d2 && m != -INFINITY) {
-          if (m == 0.f) m = 0.f;
-          atomic_max_float(max2 + z + i, m);
-        }
+      for (int i = 0; i < 4; ++i) zred[warp][4 * (lane + 32 * j) + i] = zmax[j][i];
+    __syncthreads();
+    for (int z = threadIdx.x; z < PM_ZSEG; z += PM_WARPS * 32) {
+      float m = zred[0][z];
+#pragma unroll
+      for (int w = 1; w < PM_WARPS; ++w) m = fmaxf(m, zred[w][z]);
+      if (zseg + z < d2 && m != -INFINITY) {
+        if (m == 0.f) m = 0.f;
+        atomic_max_float(max2 + zseg + z, m);
       }
     }
   }

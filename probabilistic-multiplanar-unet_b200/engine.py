@@ -141,10 +141,19 @@ class PackedNet:
             if H % (1 << (self.levels - 1)) or W % (1 << (self.levels - 1)):
                 raise RuntimeError(f"bf16 mode needs H, W divisible by {1 << (self.levels - 1)} (got {H}x{W}); use fp32")
         a, b = self.inc
-        xs = [self._conv(b, self._conv(a, x))]
-        for (a, b) in self.down:
-            h = self._pool(xs[-1], ops.POOL_MAX)
-            xs.append(self._conv(b, self._conv(a, h)))
+        blocks = [self.inc] + list(self.down)
+        xs, h = [], x
+        for i, (a, b) in enumerate(blocks):
+            last = i == len(blocks) - 1
+            h = self._conv(a, h)
+            if not last and not fp32 and b.tc and ops.fused_pool_ok(h.shape[1], h.shape[2]):
+                # second conv of the block also emits the MaxPool2d(2) input of the next block
+                full, h = ops.conv_gemm_pool_bf16(h, b.wpack, b.b, b.cout, True, ops.POOL_MAX)
+                xs.append(full)
+            else:
+                full = self._conv(b, h)
+                xs.append(full)
+                h = full if last else self._pool(full, ops.POOL_MAX)
         h = xs[-1]
         for i, up in enumerate(self.up):
             skip = xs[self.levels - 2 - i]
@@ -165,17 +174,20 @@ class PackedNet:
         e = self.enc[which]
         fp32 = self.precision == "fp32"
         h = x
+        nlev = len(e["layers"])
         for i, (a, b) in enumerate(e["layers"]):
-            if i > 0:
-                h = self._pool(h, ops.POOL_AVG_CEIL)
             if i == 0 and segm is not None:
-                if fp32:
-                    h = self._conv(a, x, x1=segm)
-                else:
-                    h = self._conv(a, x, first_x1=segm)
+                h = self._conv(a, x, x1=segm) if fp32 else self._conv(a, x, first_x1=segm)
             else:
                 h = self._conv(a, h)
-            h = self._conv(b, h)
+            if i < nlev - 1:
+                # AvgPool2d(2,2,ceil_mode) in front of the next level: fused into this conv's epilogue
+                if not fp32 and b.tc and ops.fused_pool_ok(h.shape[1], h.shape[2]):
+                    _, h = ops.conv_gemm_pool_bf16(h, b.wpack, b.b, b.cout, True, ops.POOL_AVG_CEIL, want_full=False)
+                else:
+                    h = self._pool(self._conv(b, h), ops.POOL_AVG_CEIL)
+            else:
+                h = self._conv(b, h)
         if fp32:
             return ops.gauss_head_f32(h, e["head_w"], e["head_b"], e["L"])
         return ops.gauss_head_bf16(h, e["head_w"], e["head_b"], e["L"])

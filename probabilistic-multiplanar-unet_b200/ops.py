@@ -225,6 +225,27 @@ def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None):
     return out
 
 
+def conv_gemm_pool_bf16(x0, wpack, bias, Cout, relu, pool_mode, x1=None, want_full=True):
+    """conv3x3 + fused 2x2 pooling epilogue: returns (y [B,H,W,Cout] or None, y_pool [B,H/2,W/2,Cout])."""
+    _bf16(x0, "x0"); _bf16(x1, "x1"); _bf16(wpack, "wpack"); _f32(bias, "bias")
+    B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x0.device) if want_full else None
+    outp = torch.empty(B, H // 2, W // 2, Cout, dtype=torch.bfloat16, device=x0.device)
+    lib, st = _prep(x0, x1, wpack, bias, out, outp)
+    global _META
+    ktot = 9 * (C0 + C1)
+    _META = {"flops": 2.0 * B * H * W * Cout * ktot,
+             "bytes": 2.0 * (B * H * W * (C0 + C1) + (out.numel() if want_full else 0) + outp.numel() + Cout * ktot)}
+    _launch(lib, "pmu_conv_gemm_pool_bf16", (_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), _p(outp), int(pool_mode),
+                                             B, H, W, Cout, int(relu), st,))
+    return out, outp
+
+
+def fused_pool_ok(H, W):
+    return H % 2 == 0 and W % 2 == 0 and H >= 8 and W >= 16
+
+
 def pool2_bf16(x, mode):
     _bf16(x, "x")
     B, H, W, C = x.shape

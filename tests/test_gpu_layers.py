@@ -147,6 +147,28 @@ def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W):
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
 
 
+@pytest.mark.parametrize("B,C0,Cout,H,W,mode", [(2, 64, 64, 32, 48, 0), (1, 128, 128, 16, 16, 1), (3, 64, 128, 8, 16, 0),
+                                                  (2, 64, 64, 24, 40, 1)])
+def test_conv_gemm_pool_bf16(ops, B, C0, Cout, H, W, mode):
+    """Fused pooling epilogue: y identical to the unfused conv, y_pool == pool(y)."""
+    g = _g(12)
+    x = _nhwc(_bf(torch.randn(B, C0, H, W, generator=g))).to(torch.bfloat16).cuda()
+    w = _bf(torch.randn(Cout, C0, 3, 3, generator=g) * (2.0 / (9 * C0)) ** 0.5)
+    b = (torch.randn(Cout, generator=g) * 0.1).cuda()
+    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C0).to(torch.bfloat16).contiguous().cuda()
+    y_ref = ops.conv_gemm_bf16(x, wpack, b, Cout, 9, True)
+    y, yp = ops.conv_gemm_pool_bf16(x, wpack, b, Cout, True, mode)
+    assert torch.equal(y, y_ref)
+    _, yp2 = ops.conv_gemm_pool_bf16(x, wpack, b, Cout, True, mode, want_full=False)
+    assert torch.equal(yp, yp2)
+    yn = y.float().permute(0, 3, 1, 2)
+    if mode == 0:
+        assert torch.equal(yp.float(), _nhwc(F.max_pool2d(yn, 2)))
+    else:
+        torch.testing.assert_close(yp.float(), _nhwc(F.avg_pool2d(yn, 2)), atol=1e-2, rtol=8e-3)
+        torch.testing.assert_close(yp.float(), ops.pool2_bf16(y, 1).float(), atol=1e-2, rtol=8e-3)
+
+
 def test_conv_gemm_bf16_1x1(ops):
     g = _g(8)
     x = _bf(torch.randn(2, 128, 8, 16, generator=g))

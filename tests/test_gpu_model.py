@@ -164,3 +164,28 @@ def test_multiplanar_properties_and_sharding(pmu, trainer_sd):
     # determinism: same inputs, same bits
     out2 = one.predict(vol, eps=eps)
     assert torch.equal(out2["mean"], mean)
+
+
+def test_fitted_model_dice(pmu, golden_dir):
+    """North star: "bf16 tensor-core mode within 2e-2 abs on probabilities with per-volume Dice
+    agreement >= 0.999" — on a CONFIDENT model (tests/golden/make_fitted.py: ProbabilisticUnet
+    ([64,128]) fitted to the phantom), CUDA bf16 labels vs fp32-oracle labels; fp32 mode too."""
+    z = np.load(os.path.join(golden_dir, "fitted_small.npz"))
+    sd = {k: torch.from_numpy(z[k].astype(np.float32)) if z[k].dtype == np.float16 else torch.from_numpy(z[k])
+          for k in z.files}
+    D, N = 64, 4
+    vol, lab_true = O.phantom(D, seed=7)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    ref = O.multiplanar_predict(vol, sd, eps, N, batch=32)
+    lab_ref = torch.argmax(ref["mean"], 1)
+    for precision, tol in (("fp32", FP32_PROB_TOL), ("bf16", BF16_PROB_TOL)):
+        pred = pmu.MultiPlanarPredictor(sd, "cuda", precision=precision, n_samples=N, slice_batch=32)
+        out = pred.predict(vol, eps=eps, want_labels=True)
+        err = (out["mean"].cpu() - ref["mean"]).abs().max().item()
+        assert err < tol, (precision, err)
+        dices = _dice_labels(out["labels"].cpu().long(), lab_ref, 3)
+        assert min(dices) >= 0.999, (precision, dices)
+        # and the volume Dice kernel (eval.py:42-49) agrees with the oracle's
+        got = pmu.volume_dice(out["mean"], torch.from_numpy(lab_true).cuda()).cpu().numpy()
+        want = [O.argmax_dice(ref["mean"], torch.from_numpy(lab_true), k) for k in (1, 2)]
+        np.testing.assert_allclose(got, want, atol=2e-3)

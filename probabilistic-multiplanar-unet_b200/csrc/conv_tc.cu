@@ -19,6 +19,7 @@
 // Persistent CTAs (one per SM) with a double-buffered TMEM accumulator: the epilogue of tile i
 // overlaps the main loop of tile i+1.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "pmu_common.cuh"
 #include "sm100_ptx.cuh"
@@ -62,8 +63,8 @@ struct ConvTcSmem {
 // current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
 // setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const ConvTcParams p,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
@@ -136,19 +137,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
-    uint32_t kc = 0, iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
-      mbar_wait(bar_tempty + as * 8, aph ^ 1u);     // epilogue has drained this accumulator stage
-      tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + as * BN;
-      for (int it = 0; it < k_iters; ++it, ++kc) {
-        const uint32_t s = kc % STAGES;
-        const uint32_t ph = (kc / STAGES) & 1u;
-        mbar_wait(bar_full + s * 8, ph);
+    // one elected thread runs the whole issue loop: nothing but barrier polls between MMAs
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      uint32_t kc = 0, iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
+        mbar_wait(bar_tempty + as * 8, aph ^ 1u);     // epilogue has drained this accumulator stage
         tcgen05_fence_after();
-        if (elect_one()) {
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int it = 0; it < k_iters; ++it, ++kc) {
+          const uint32_t s = kc % STAGES;
+          const uint32_t ph = (kc / STAGES) & 1u;
+          mbar_wait(bar_full + s * 8, ph);
+          tcgen05_fence_after();
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint64_t adesc = umma_smem_desc_sw128(sa);
           const uint64_t bdesc = umma_smem_desc_sw128(sa + L::A_BYTES);
@@ -161,9 +163,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           umma_commit(bar_empty + s * 8);                        // frees the smem slot when these MMAs retire
           if (it == k_iters - 1) umma_commit(bar_tfull + as * 8);  // accumulator complete
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     // =========================== epilogue (warps 2..5) ===========================
     const int et = threadIdx.x - 64;  // 0..127
@@ -179,23 +181,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
       const int b0 = m_tile * p.TB;
       const int n0 = n_tile * BN;
-      const int co_base = (p.ntaps == 4) ? (n0 % p.Cout) : n0;
+      const int co_base = (p.ntaps == 4) ? 0 : n0;   // convT: output channel / phase are resolved per 32-column chunk
       float* bs = bias_s + as * BN;
-      for (int i = et; i < BN; i += 128) bs[i] = bias ? __ldg(bias + co_base + i) : 0.f;
+      for (int i = et; i < BN; i += 128)
+        bs[i] = bias ? __ldg(bias + ((p.ntaps == 4) ? (n0 + i) % p.Cout : n0 + i)) : 0.f;
       named_bar_sync(1, 128);          // bias visible; also keeps the 4 warps within one tile of each other
 
       const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
       const bool valid = (b < p.B) && (h < p.H) && (w < p.W);
       __nv_bfloat16* dst = nullptr;
-      if (y != nullptr) {
-        if (p.ntaps == 4) {
-          const int ij = n0 / p.Cout;
-          const int oy = 2 * h + (ij >> 1), ox = 2 * w + (ij & 1);
-          dst = y + (((int64_t)b * (2 * p.H) + oy) * (2 * p.W) + ox) * p.Cout + co_base;
-        } else {
-          dst = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base;
-        }
-      }
+      if (y != nullptr && p.ntaps != 4) dst = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base;
       // fused 2x2 pooling (tile brick 16 x 8: a warp holds image rows 2q and 2q+1, so every pooling
       // window lives in lanes {l, l^1, l^16} of one warp — two shuffles, no extra pass over HBM)
       const bool pool_writer = (p.pool_mode >= 0) && ((lane & 17) == 0) && valid;
@@ -228,7 +223,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
           pk[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        if (valid && dst != nullptr) {
+        if (p.ntaps == 4) {
+          // ConvTranspose2d k2 s2: GEMM column n = (i*2+j)*Cout + co goes to pixel (2h+i, 2w+j)
+          const int n = n0 + c0, ij = n / p.Cout, co = n - ij * p.Cout;
+          if (valid) {
+            __nv_bfloat16* dt = y + (((int64_t)b * (2 * p.H) + 2 * h + (ij >> 1)) * (2 * p.W) + 2 * w + (ij & 1)) * p.Cout + co;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(dt + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        } else if (valid && dst != nullptr) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(dst + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -316,18 +320,33 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MINB>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm,
                           const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
                           cudaStream_t st) {
   using L = ConvTcSmem<BN, STAGES>;
-  auto kern = conv_tc_kernel<BN, STAGES>;
+  auto kern = conv_tc_kernel<BN, STAGES, MINB>;
   PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-  grid = std::min<int64_t>(grid, sm_count());   // persistent: one CTA per SM
+  grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
   kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, p, bias, reinterpret_cast<__nv_bfloat16*>(y),
                                                          reinterpret_cast<__nv_bfloat16*>(y_pool));
   PMU_LAUNCH_CHECK();
   return PMU_OK;
+}
+
+// Tile configuration (measured per layer on B200, scripts/time_convs.py, profiles/r01_conv_variants.txt):
+//   Cout % 256 == 0 : BN = 256, one persistent CTA per SM, 4-stage ring (A traffic per flop halves;
+//                     up to ~1.4 PFLOP/s on the 256..1024-channel layers)
+//   otherwise       : BN = 128 / 64 with TWO persistent CTAs per SM (3 / 4 stages each): two
+//                     independent MMA issuers hide each other's barrier round trips.
+// PMU_CONV_VARIANT overrides for experiments: 0 = 1 CTA/SM deep ring, 1 = 2 CTAs/SM, 2 = 0 + BN=256.
+static int conv_variant() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("PMU_CONV_VARIANT");
+    v = e ? atoi(e) : -1;
+  }
+  return v;
 }
 
 }  // namespace pmu
@@ -361,7 +380,9 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   const int Cin = C0 + C1;
   const int Ntot = (ntaps == 4) ? 4 * Cout : Cout;
   const int Ktot = (ntaps == 9) ? 9 * Cin : Cin;
-  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  const int variant = conv_variant();
+  int BN = (Cout % 128 == 0) ? 128 : 64;
+  if ((variant == 2 || variant == -1) && (Cout % 256 == 0 || ntaps == 4)) BN = 256;   // convT: Ntot = 4*Cout
   p.n_tiles = Ntot / BN;
   if (y_pool) {
     PMU_CHECK_ARG(pool_mode == PMU_POOL_MAX || pool_mode == PMU_POOL_AVG_CEIL, "pmu_conv_gemm_pool_bf16: unknown pool mode %d", pool_mode);
@@ -380,8 +401,13 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   rc = make_w_map(&wm, wpack, Ntot, Ktot, BN);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 128) return launch_conv_tc<128, 6>(a0, a1, wm, p, bias, y, y_pool, grid, st);
-  return launch_conv_tc<64, 8>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+  if (variant == 1 || (variant == -1 && BN != 256)) {
+    if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+    return launch_conv_tc<64, 4, 2>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+  }
+  if (BN == 256) return launch_conv_tc<256, 4, 1>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+  if (BN == 128) return launch_conv_tc<128, 6, 1>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+  return launch_conv_tc<64, 8, 1>(a0, a1, wm, p, bias, y, y_pool, grid, st);
 }
 
 extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,

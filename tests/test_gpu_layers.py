@@ -197,7 +197,7 @@ def test_pool_head_transpose_bf16(ops):
     torch.testing.assert_close(torch.cat([mu, ls], 1).cpu(), ml, atol=1e-4, rtol=1e-4)
 
 
-@pytest.mark.parametrize("nl,N,C", [(4, 5, 3), (2, 1, 3), (3, 16, 2)])
+@pytest.mark.parametrize("nl,N,C", [(4, 5, 3), (2, 1, 3), (3, 16, 2), (4, 20, 3), (5, 3, 3)])
 def test_fcomb_softmax_accum_bf16(ops, nl, N, C):
     """Fused tensor-core fcomb vs the fp32 oracle: probabilities within the bf16 budget 2e-2."""
     sd = O.make_state_dict((64, 128), num_classes=C, latent_dim=6, no_convs_fcomb=nl, seed=10)

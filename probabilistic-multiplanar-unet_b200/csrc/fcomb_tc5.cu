@@ -9,7 +9,7 @@
 // the legacy warp-level MMA path of sm_100 — no matter how it is scheduled (three schedules,
 // same 51 ms per 256^3 volume).  Here every layer is a UMMA:
 //   * tile = 128 pixels (UMMA M).  One CTA runs FOUR independent tile pipelines (warpgroups
-//     0..3, 128 threads each, thread = pixel row) fed by ONE issuer thread (warp 16), so the
+//     0..3, 128 threads each, thread = pixel row) each fed by its own issuer thread (warps 16..19), so the
 //     tensor pipe always has another tile's layer to chew on while a warpgroup does its
 //     TMEM -> ReLU -> bf16 -> smem epilogue.
 //   * layer 0 is split (App. A): h0 = relu(W0f f + (W0z z_n + b0)).  The feature tile F (TMA,
@@ -32,7 +32,7 @@ using namespace ptx;
 
 constexpr int F5_F = 64;            // feature width
 constexpr int F5_WG = 4;            // tile pipelines (warpgroups) per CTA
-constexpr int F5_THREADS = F5_WG * 128 + 32;
+constexpr int F5_THREADS = F5_WG * 128 + F5_WG * 32;   // 4 warpgroups + one issuer warp per warpgroup
 constexpr int F5_NS = 16;           // samples per bias-tile group
 constexpr int F5_MAXL = 16;
 constexpr int F5_MAXC = 8;
@@ -72,9 +72,14 @@ __device__ __forceinline__ void st_hilo(uint8_t* tile, int row, int k0, float v)
   *reinterpret_cast<__nv_bfloat16*>(tile + sw128_off(row, k0)) = hi;
   *reinterpret_cast<__nv_bfloat16*>(tile + sw128_off(row, k0 + 1)) = lo;
 }
+// ReLU + round-to-nearest bf16 pack of two fp32 values in ONE instruction (lo -> bits 0..15)
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
-  __nv_bfloat162 h2 = __hmax2(__floats2bfloat162_rn(lo, hi), __floats2bfloat162_rn(0.f, 0.f));
-  return *reinterpret_cast<uint32_t*>(&h2);
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -173,47 +178,39 @@ fcomb_tc5_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb5Params p, 
     fence_proxy_async_smem();                         // generic-proxy tile writes -> visible to the tensor core
     __syncthreads();
 
-    if (warp == F5_WG * 4) {
-      // =============================== issuer (one thread) ===============================
+    if (warp >= F5_WG * 4) {
+      // ============ issuer of warpgroup w = warp - 16 (one elected thread; no coupling between pipelines) ============
       if (elect_one()) {
+        const int w = warp - F5_WG * 4;
         constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64), idesc16 = umma_idesc_bf16(128, 16);
         const uint32_t sE = sbase + F5_OFF_E, sW0 = sbase + F5_OFF_W0, sWM = sbase + F5_OFF_WM,
                        sWL = sbase + F5_OFF_WL, sBT = sbase + F5_OFF_BT, sZB = sbase + F5_OFF_ZB;
+        const uint32_t sF = sbase + F5_OFF_WG + w * 2 * F5_TILE, sH = sF + F5_TILE;
+        const uint32_t t_acc = tmem_base + w * 128;
         for (int64_t q = q_lo; q < q_hi; ++q) {
-          // tile start: warpgroup released its F / H / TMEM -> fetch the feature tile
-          for (int w = 0; w < F5_WG; ++w) {
-            const int64_t t = q * F5_WG + w;
-            if (t >= tiles) continue;
-            mbar_wait(bar(0, w), (phr >> w) & 1u); phr ^= 1u << w;
-            mbar_arrive_expect_tx(bar(3, w), F5_TILE);
-            tma_load_2d(sbase + F5_OFF_WG + w * 2 * F5_TILE, &tmF, bar(3, w), 0, (int)((int64_t)b * HW + t * 128));
-          }
-          for (int w = 0; w < F5_WG; ++w) {
-            const int64_t t = q * F5_WG + w;
-            if (t >= tiles) continue;
-            mbar_wait(bar(3, w), (pht >> w) & 1u); pht ^= 1u << w;
-            tcgen05_fence_after();
-            issue_layer(tmem_base + w * 128, sbase + F5_OFF_WG + w * 2 * F5_TILE, sW0, sE, sZB, 0, idesc64);  // L0, sample 0
-            umma_commit(bar(1, w));
-          }
+          const int64_t t = q * F5_WG + w;
+          if (t >= tiles) continue;
+          // tile start: the warpgroup released its F / H / TMEM -> fetch the feature tile
+          mbar_wait(bar(0, w), phr); phr ^= 1u;
+          mbar_arrive_expect_tx(bar(3, w), F5_TILE);
+          tma_load_2d(sF, &tmF, bar(3, w), 0, (int)((int64_t)b * HW + t * 128));
+          mbar_wait(bar(3, w), pht); pht ^= 1u;
+          tcgen05_fence_after();
+          issue_layer(t_acc, sF, sW0, sE, sZB, 0, idesc64);          // layer 0, sample 0
+          umma_commit(bar(1, w));
           for (int n = 0; n < ng; ++n) {
-            for (int layer = 0; layer <= nmid; ++layer) {        // nmid mid layers, then the head
-              for (int w = 0; w < F5_WG; ++w) {
-                const int64_t t = q * F5_WG + w;
-                if (t >= tiles) continue;
-                const uint32_t sF = sbase + F5_OFF_WG + w * 2 * F5_TILE, sH = sF + F5_TILE;
-                mbar_wait(bar(0, w), (phr >> w) & 1u); phr ^= 1u << w;     // H written (and ACC drained)
-                tcgen05_fence_after();
-                if (layer < nmid) {
-                  issue_layer(tmem_base + w * 128, sH, sWM + layer * F5_WT, sE, sBT, layer, idesc64);
+            for (int layer = 0; layer <= nmid; ++layer) {             // nmid mid layers, then the head
+              mbar_wait(bar(0, w), phr); phr ^= 1u;                   // H written (and ACC drained)
+              tcgen05_fence_after();
+              if (layer < nmid) {
+                issue_layer(t_acc, sH, sWM + layer * F5_WT, sE, sBT, layer, idesc64);
+                umma_commit(bar(1, w));
+              } else {
+                issue_layer(t_acc + 64, sH, sWL, sE, sBT, 2, idesc16);
+                umma_commit(bar(2, w));
+                if (n + 1 < ng) {                                     // next sample's layer 0 needs nothing from the warpgroup
+                  issue_layer(t_acc, sF, sW0, sE, sZB + ((n + 1) >> 2) * F5_WT, (n + 1) & 3, idesc64);
                   umma_commit(bar(1, w));
-                } else {
-                  issue_layer(tmem_base + w * 128 + 64, sH, sWL, sE, sBT, 2, idesc16);
-                  umma_commit(bar(2, w));
-                  if (n + 1 < ng) {                              // next sample's layer 0 needs nothing from the warpgroup
-                    issue_layer(tmem_base + w * 128, sF, sW0, sE, sZB + ((n + 1) >> 2) * F5_WT, (n + 1) & 3, idesc64);
-                    umma_commit(bar(1, w));
-                  }
                 }
               }
             }
@@ -225,8 +222,12 @@ fcomb_tc5_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb5Params p, 
       // =============================== warpgroup w: one tile pipeline ===============================
       const int w = warp >> 2, q4 = warp & 3;
       const int row = q4 * 32 + lane;                            // TMEM lane == pixel row of the tile
-      uint8_t* Ht = sgen + F5_OFF_WG + w * 2 * F5_TILE + F5_TILE;
       const uint32_t t_acc = tmem_base + w * 128 + ((uint32_t)(q4 * 32) << 16);
+      // the 8 swizzled 16-byte slots of this thread's row in the H tile (loop invariant)
+      uint32_t hslot[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        hslot[c] = sbase + F5_OFF_WG + w * 2 * F5_TILE + F5_TILE + row * 128 + (((c ^ (row & 7)) & 7) << 4);
       for (int64_t q = q_lo; q < q_hi; ++q) {
         const int64_t t = q * F5_WG + w;
         if (t >= tiles) continue;
@@ -238,29 +239,31 @@ fcomb_tc5_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb5Params p, 
         mbar_arrive(bar(0, w));                                  // tile start: F / H / TMEM are free
         for (int n = 0; n < ng; ++n) {
           for (int layer = 0; layer <= nmid; ++layer) {
-            mbar_wait(bar(1, w), (pha >> w) & 1u); pha ^= 1u << w;          // layer's accumulator complete
+            mbar_wait(bar(1, w), pha); pha ^= 1u;          // layer's accumulator complete
             tcgen05_fence_after();
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(t_acc, r0);                            // both halves in flight, one wait
+            tmem_ld_32x32(t_acc + 32, r1);
+            tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t r[32];
-              tmem_ld_32x32(t_acc + half * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {                      // 4 chunks of 8 channels = 16 B each
-                uint4 v;
-                v.x = pack_relu_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
-                v.y = pack_relu_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
-                v.z = pack_relu_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
-                v.w = pack_relu_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-                *reinterpret_cast<uint4*>(Ht + row * 128 + ((((half * 4 + c) ^ (row & 7)) & 7) << 4)) = v;
-              }
+            for (int c = 0; c < 4; ++c) {                        // 8 chunks of 8 channels = 16 B each
+              sts128(hslot[c],
+                     pack_relu_bf16(__uint_as_float(r0[c * 8 + 0]), __uint_as_float(r0[c * 8 + 1])),
+                     pack_relu_bf16(__uint_as_float(r0[c * 8 + 2]), __uint_as_float(r0[c * 8 + 3])),
+                     pack_relu_bf16(__uint_as_float(r0[c * 8 + 4]), __uint_as_float(r0[c * 8 + 5])),
+                     pack_relu_bf16(__uint_as_float(r0[c * 8 + 6]), __uint_as_float(r0[c * 8 + 7])));
+              sts128(hslot[4 + c],
+                     pack_relu_bf16(__uint_as_float(r1[c * 8 + 0]), __uint_as_float(r1[c * 8 + 1])),
+                     pack_relu_bf16(__uint_as_float(r1[c * 8 + 2]), __uint_as_float(r1[c * 8 + 3])),
+                     pack_relu_bf16(__uint_as_float(r1[c * 8 + 4]), __uint_as_float(r1[c * 8 + 5])),
+                     pack_relu_bf16(__uint_as_float(r1[c * 8 + 6]), __uint_as_float(r1[c * 8 + 7])));
             }
             fence_proxy_async_smem();                            // H (generic proxy) -> async proxy
             tcgen05_fence_before();
             mbar_arrive(bar(0, w));                              // H ready, ACC drained
           }
           // ---- head logits -> softmax -> accumulate ----
-          mbar_wait(bar(2, w), (phh >> w) & 1u); phh ^= 1u << w;
+          mbar_wait(bar(2, w), phh); phh ^= 1u;
           tcgen05_fence_after();
           uint32_t hr[16];
           tmem_ld_32x16(t_acc + 64, hr);

@@ -39,12 +39,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug becomes a trap (launch failure) instead of a hung GPU.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug becomes a trap (launch failure) instead of a hung GPU.  The
+// hardware suspends the warp inside try_wait (no issue slots burnt); the clock is only consulted
+// every 64 wake-ups.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+    if (((++spins) & 63u) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
   }
 }
 

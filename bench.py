@@ -161,7 +161,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # short collective timeout: a rank-divergence bug must cost minutes of GPU time, not ten
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     D, N, P = args.size, args.samples, 3
     peaks = load_peaks()
 
@@ -227,12 +229,13 @@ def run_ours(args):
 
     # ---- per-kernel roofline: one instrumented step, CUDA events around every C-ABI call ----
     roof, hbm_kernels, shares = None, {}, {}
+    # EVERY rank runs the instrumented step (it contains the reduce collective); rank 0 reports
+    barrier()
+    ops.PROFILE = []
+    step_resident()
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
-        torch.cuda.synchronize()
-        ops.PROFILE = []
-        step_resident()
-        torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
         tot = {}
         for name, meta, a, b in prof:
             t = a.elapsed_time(b)

@@ -43,18 +43,22 @@ struct ConvTcParams {
   int tiles_w, tiles_h, tiles_b;
   int n_tiles;        // Ntot / BN
   int pool_mode;      // -1 none; PMU_POOL_MAX / PMU_POOL_AVG_CEIL: also emit the 2x2-pooled map
+  int debug;          // experiments only (PMU_CONV_DEBUG): bit0 = no global stores, bit1 = no A loads
+  int tma_store;      // full-resolution output leaves through the smem staging tile + TMA tensor stores
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NSTG = 1>
 struct ConvTcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;            // full[S], empty[S], tmem_full[2], tmem_empty[2]
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;            // output staging tile [128 px][64 ch] bf16, 128B swizzle
+  static constexpr int STG_BYTES = TC_BM * 128;                    // x NSTG buffers
+  static constexpr int BAR_OFF = STG_OFF + NSTG * STG_BYTES;             // full[S], empty[S], tmem_full[2], tmem_empty[2]
   static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
-  static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;   // 2 x BN floats (one per accumulator stage)
-  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4;
-  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+  static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;   // BN floats
+  static constexpr int TOTAL = BIAS_OFF + BN * 4;
+  static constexpr int DYN_BYTES = TOTAL;            // base is 1024 B aligned (__align__ + runtime check)
 };
 
 // Persistent kernel: one CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x,
@@ -63,16 +67,19 @@ struct ConvTcSmem {
 // current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
 // setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
-template <int BN, int STAGES, int MINB>
+template <int BN, int STAGES, int MINB, int NSTG>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmW, const ConvTcParams p,
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0,
+               const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmY2,
+               const __grid_constant__ CUtensorMap tmY3, const ConvTcParams p,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                __nv_bfloat16* __restrict__ y_pool) {
-  using L = ConvTcSmem<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  using L = ConvTcSmem<BN, STAGES, NSTG>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  uint8_t* smem_gen = smem_raw;
+  if ((smem_base & 1023u) != 0) __trap();   // TMA / UMMA tiles need 1024 B alignment
   const uint32_t bar_full = smem_base + L::BAR_OFF;
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const uint32_t bar_tfull = bar_empty + STAGES * 8;   // [2] accumulator stage ready for the epilogue
@@ -91,6 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     prefetch_tensormap(&tmA0);
     if (p.C1 > 0) prefetch_tensormap(&tmA1);
     prefetch_tensormap(&tmW);
+    if (p.tma_store) prefetch_tensormap(&tmY0);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
       mbar_init(bar_empty + s * 8, 1);
@@ -128,9 +136,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
-          if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
-          else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
+          if (p.debug & 2) {
+            mbar_arrive_expect_tx(bar_full + s * 8, L::B_BYTES);
+          } else {
+            mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+            if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
+            else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
+          }
           tma_load_2d(sb, &tmW, bar_full + s * 8, tap * Cin + c, n0);
         }
       }
@@ -172,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;       // row of the tile == pixel index in the brick
     const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
-    uint32_t iter = 0;
+    uint32_t iter = 0, stg_count = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
       const int n_tile = tile % p.n_tiles;
@@ -181,16 +193,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
       const int b0 = m_tile * p.TB;
       const int n0 = n_tile * BN;
-      const int co_base = (p.ntaps == 4) ? 0 : n0;   // convT: output channel / phase are resolved per 32-column chunk
-      float* bs = bias_s + as * BN;
+      const int co_base = (p.ntaps == 4) ? 0 : n0;   // convT: output channel / phase are resolved per 64-column group
+      float* bs = bias_s;
+      named_bar_sync(4, 128);          // every warp is done reading the previous tile's bias
       for (int i = et; i < BN; i += 128)
         bs[i] = bias ? __ldg(bias + ((p.ntaps == 4) ? (n0 + i) % p.Cout : n0 + i)) : 0.f;
-      named_bar_sync(1, 128);          // bias visible; also keeps the 4 warps within one tile of each other
+      named_bar_sync(1, 128);          // bias visible
 
       const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
-      const bool valid = (b < p.B) && (h < p.H) && (w < p.W);
-      __nv_bfloat16* dst = nullptr;
-      if (y != nullptr && p.ntaps != 4) dst = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base;
+      const bool valid = (b < p.B) && (h < p.H) && (w < p.W) && !(p.debug & 1);
+      const bool direct = (y != nullptr) && !p.tma_store;      // fallback: per-thread 16 B global stores
       // fused 2x2 pooling (tile brick 16 x 8: a warp holds image rows 2q and 2q+1, so every pooling
       // window lives in lanes {l, l^1, l^16} of one warp — two shuffles, no extra pass over HBM)
       const bool pool_writer = (p.pool_mode >= 0) && ((lane & 17) == 0) && valid;
@@ -202,72 +214,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_d + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (c0 + 32 >= BN) {
-          // all of this thread's TMEM reads of the stage are done: hand it back to the MMA warp
-          tcgen05_fence_before();
-          mbar_arrive(bar_tempty + as * 8);
+      for (int g0 = 0; g0 < BN; g0 += 64) {
+        const uint32_t stg = smem_base + L::STG_OFF + (NSTG > 1 ? (stg_count % NSTG) * L::STG_BYTES : 0);
+        const uint32_t stg_row = stg + m * 128;
+        if (p.tma_store) {
+          // the TMA store that used this staging buffer must have finished READING it before it is rewritten
+          if (et == 0) { if (NSTG > 1) tma_store_wait_read1(); else tma_store_wait_read0(); }
+          named_bar_sync(2, 128);
         }
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r[j]) + bs[c0 + j];
-          if (p.relu) v[j] = fmaxf(v[j], 0.f);
-        }
-        uint32_t pk[16];
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = g0 + half * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_d + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (c0 + 32 >= BN) {
+            // all of this thread's TMEM reads of the stage are done: hand it back to the MMA warp
+            tcgen05_fence_before();
+            mbar_arrive(bar_tempty + as * 8);
+          }
+          uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        if (p.ntaps == 4) {
-          // ConvTranspose2d k2 s2: GEMM column n = (i*2+j)*Cout + co goes to pixel (2h+i, 2w+j)
-          const int n = n0 + c0, ij = n / p.Cout, co = n - ij * p.Cout;
-          if (valid) {
-            __nv_bfloat16* dt = y + (((int64_t)b * (2 * p.H) + 2 * h + (ij >> 1)) * (2 * p.W) + 2 * w + (ij & 1)) * p.Cout + co;
+          for (int j = 0; j < 16; ++j) {
+            float v0 = __uint_as_float(r[2 * j]) + bs[c0 + 2 * j];
+            float v1 = __uint_as_float(r[2 * j + 1]) + bs[c0 + 2 * j + 1];
+            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          if (p.tma_store) {
+            // staging row m, 16-byte chunk (half*4 + j), 128-byte swizzle (chunk ^ (row & 7))
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128_u32(stg_row + ((((half * 4 + j) ^ (m & 7)) & 7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          } else if (direct && valid) {
+            __nv_bfloat16* dt;
+            if (p.ntaps == 4) {
+              // ConvTranspose2d k2 s2: GEMM column n = (i*2+j)*Cout + co goes to pixel (2h+i, 2w+j)
+              const int n = n0 + c0, ij = n / p.Cout, co = n - ij * p.Cout;
+              dt = y + (((int64_t)b * (2 * p.H) + 2 * h + (ij >> 1)) * (2 * p.W) + 2 * w + (ij & 1)) * p.Cout + co;
+            } else {
+              dt = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base + c0;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(dt + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
-        } else if (valid && dst != nullptr) {
+          if (p.pool_mode == PMU_POOL_MAX) {
+            // max of bf16-rounded values == bf16 rounding of the max (monotonic): exact, packed
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(dst + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
-        if (p.pool_mode == PMU_POOL_MAX) {
-          // max of bf16-rounded values == bf16 rounding of the max (monotonic): exact, packed
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+              uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+              a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+              uint32_t au = *reinterpret_cast<uint32_t*>(&a);
+              o = __shfl_xor_sync(0xffffffffu, au, 16);
+              a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+              pk[j] = *reinterpret_cast<uint32_t*>(&a);
+            }
+          } else if (p.pool_mode == PMU_POOL_AVG_CEIL) {
+            // average of the bf16-stored activations, accumulated in fp32 (what pool2_bf16 computes)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-            uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
-            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-            uint32_t au = *reinterpret_cast<uint32_t*>(&a);
-            o = __shfl_xor_sync(0xffffffffu, au, 16);
-            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-            pk[j] = *reinterpret_cast<uint32_t*>(&a);
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+              float lo = __low2float(a), hi = __high2float(a);
+              lo += __shfl_xor_sync(0xffffffffu, lo, 1);  hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+              lo += __shfl_xor_sync(0xffffffffu, lo, 16); hi += __shfl_xor_sync(0xffffffffu, hi, 16);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
           }
-        } else if (p.pool_mode == PMU_POOL_AVG_CEIL) {
-          // average of the bf16-stored activations, accumulated in fp32 (what pool2_bf16 computes)
+          if (pool_writer) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-            float lo = __low2float(a), hi = __high2float(a);
-            lo += __shfl_xor_sync(0xffffffffu, lo, 1);  hi += __shfl_xor_sync(0xffffffffu, hi, 1);
-            lo += __shfl_xor_sync(0xffffffffu, lo, 16); hi += __shfl_xor_sync(0xffffffffu, hi, 16);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(dstp + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
         }
-        if (pool_writer) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(dstp + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        if (p.tma_store) {
+          fence_proxy_async_smem();      // staging writes (generic proxy) -> visible to the TMA engine
+          named_bar_sync(3, 128);
+          if (et == 0 && !(p.debug & 1)) {
+            // one tensor store per 64-channel group: full 128-byte lines, out-of-bounds pixels clipped by TMA
+            if (p.ntaps == 4) {
+              const int n = n0 + g0, ij = n / p.Cout, co = n - ij * p.Cout;
+              const CUtensorMap* tm = (ij == 0) ? &tmY0 : (ij == 1) ? &tmY1 : (ij == 2) ? &tmY2 : &tmY3;
+              tma_store_4d(tm, stg, co, w0, h0, b0);
+            } else {
+              tma_store_4d(&tmY0, stg, n0 + g0, w0, h0, b0);
+            }
+            tma_store_commit();
+          }
+          ++stg_count;
         }
       }
     }
+    if (p.tma_store && et == 0) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -320,17 +361,36 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN, int STAGES, int MINB>
-static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm,
+template <int BN, int STAGES, int MINB, int NSTG = 1>
+static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm, const CUtensorMap* ym,
                           const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
                           cudaStream_t st) {
-  using L = ConvTcSmem<BN, STAGES>;
-  auto kern = conv_tc_kernel<BN, STAGES, MINB>;
+  using L = ConvTcSmem<BN, STAGES, NSTG>;
+  static_assert(MINB * (L::DYN_BYTES + 1024) <= 228 * 1024 && L::DYN_BYTES <= 227 * 1024, "shared memory budget");
+  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG>;
   PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
   grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
-  kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, p, bias, reinterpret_cast<__nv_bfloat16*>(y),
+  kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, ym[0], ym[1], ym[2], ym[3], p, bias,
+                                                         reinterpret_cast<__nv_bfloat16*>(y),
                                                          reinterpret_cast<__nv_bfloat16*>(y_pool));
   PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+// output of ConvTranspose2d k2 s2, phase (i,j): the pixels (2h+i, 2w+j) of y[B][2H][2W][Cout] seen as a
+// strided [B][H][W][Cout] tensor, so the same {64 ch, TW, TH, TB} brick store applies
+static int make_convt_out_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int ij, int TW, int TH, int TB) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
+  const int i = ij >> 1, j = ij & 1;
+  char* base = reinterpret_cast<char*>(y) + ((int64_t)i * 2 * W + j) * Cout * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * Cout * 2, (cuuint64_t)2 * (2 * W) * Cout * 2, (cuuint64_t)(2 * H) * (2 * W) * Cout * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(convT output phase %d) failed: %d", ij, (int)r); return PMU_ERR_CUDA; }
   return PMU_OK;
 }
 
@@ -373,6 +433,7 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout; p.ntaps = ntaps; p.relu = relu;
   p.pool_mode = y_pool ? pool_mode : -1;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMU_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   p.TW = std::min(16, pow2ceil(W));
   p.TH = std::min(TC_BM / p.TW, pow2ceil(H));
   p.TB = TC_BM / (p.TW * p.TH);
@@ -400,14 +461,33 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   else a1 = a0;
   rc = make_w_map(&wm, wpack, Ntot, Ktot, BN);
   if (rc) return rc;
+  // output tensor maps for the TMA-store epilogue (PMU_CONV_TMA_STORE=0 falls back to per-thread stores)
+  static int use_tma_store = -1;
+  if (use_tma_store < 0) { const char* e = getenv("PMU_CONV_TMA_STORE"); use_tma_store = e ? atoi(e) : 1; }
+  CUtensorMap ym[4];
+  p.tma_store = (y != nullptr && use_tma_store) ? 1 : 0;
+  if (p.tma_store) {
+    if (ntaps == 4) {
+      for (int ij = 0; ij < 4; ++ij) {
+        rc = make_convt_out_map(&ym[ij], y, B, H, W, Cout, ij, p.TW, p.TH, p.TB);
+        if (rc) return rc;
+      }
+    } else {
+      rc = make_act_map(&ym[0], y, B, H, W, Cout, p.TW, p.TH, p.TB);
+      if (rc) return rc;
+      ym[1] = ym[2] = ym[3] = ym[0];
+    }
+  } else {
+    ym[0] = ym[1] = ym[2] = ym[3] = a0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (variant == 1 || (variant == -1 && BN != 256)) {
-    if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, p, bias, y, y_pool, grid, st);
-    return launch_conv_tc<64, 4, 2>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+    if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+    return launch_conv_tc<64, 4, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   }
-  if (BN == 256) return launch_conv_tc<256, 4, 1>(a0, a1, wm, p, bias, y, y_pool, grid, st);
-  if (BN == 128) return launch_conv_tc<128, 6, 1>(a0, a1, wm, p, bias, y, y_pool, grid, st);
-  return launch_conv_tc<64, 8, 1>(a0, a1, wm, p, bias, y, y_pool, grid, st);
+  if (BN == 256) return launch_conv_tc<256, 4, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+  if (BN == 128) return launch_conv_tc<128, 6, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+  return launch_conv_tc<64, 8, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
 }
 
 extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,

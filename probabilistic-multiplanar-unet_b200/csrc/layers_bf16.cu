@@ -69,25 +69,26 @@ conv3x3_first_bf16_kernel(const float* __restrict__ x0, const float* __restrict_
 }
 
 // Fast path (Cin == 1, W % 4 == 0 — every slice of the hot path): thread = 4 consecutive pixels
-// x 8 couts with its 72 weights held in registers across a grid-stride loop; inputs come in as
-// one float4 + two halo scalars per row; 32-bit index math only.  Per 4 pixels: 9 loads,
-// 288 FMA, 4 x 16-byte stores (a warp writes four full 128-byte lines per store instruction).
-__global__ void __launch_bounds__(256)
+// x 8 couts.  Weights sit in shared memory as [tap][Cout] so a thread's 8 weights of a tap are two
+// broadcast LDS.128 (18 per 288 FMA); ~80 registers -> 3 blocks of 256 threads per SM hide the
+// load latency.  Inputs come in as one float4 + two halo scalars per row; 32-bit index math only.
+// Per 4 pixels: 9 global loads, 288 FMA, 4 x 16-byte stores (a warp writes four full 128-byte
+// lines per store instruction).
+__global__ void __launch_bounds__(256, 3)
 conv3x3_first_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                         int Cout, int relu) {
+  __shared__ __align__(16) float w_s[9 * 128];   // [tap][Cout]
+  __shared__ __align__(16) float b_s[128];
+  for (int i = threadIdx.x; i < Cout * 9; i += 256) w_s[(i % 9) * Cout + i / 9] = __ldg(w + i);
+  for (int i = threadIdx.x; i < Cout; i += 256) b_s[i] = bias ? __ldg(bias + i) : 0.f;
+  __syncthreads();
   const int groups = Cout >> 3;
   const int g = threadIdx.x % groups;                     // cout group (fastest: 8 lanes share a pixel quad)
   const int qpb = 256 / groups;                           // pixel quads per block
-  float wr[9][8], br[8];
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) wr[tap][c] = __ldg(w + (g * 8 + c) * 9 + tap);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) br[c] = bias ? __ldg(bias + g * 8 + c) : 0.f;
   const int W4 = W >> 2;
   const unsigned total = (unsigned)B * H * W4;            // pixel quads
+  const float4 ba = *reinterpret_cast<const float4*>(b_s + g * 8), bb = *reinterpret_cast<const float4*>(b_s + g * 8 + 4);
   for (unsigned q = blockIdx.x * qpb + threadIdx.x / groups; q < total; q += gridDim.x * qpb) {
     const int w0 = (int)(q % W4) * 4;
     const unsigned row = q / W4;                          // b*H + h
@@ -95,9 +96,10 @@ conv3x3_first_c1_kernel(const float* __restrict__ x, const float* __restrict__ w
     const float* src = x + (size_t)row * W + w0;
     float acc[4][8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[p][c] = br[c];
+    for (int p = 0; p < 4; ++p) {
+      acc[p][0] = ba.x; acc[p][1] = ba.y; acc[p][2] = ba.z; acc[p][3] = ba.w;
+      acc[p][4] = bb.x; acc[p][5] = bb.y; acc[p][6] = bb.z; acc[p][7] = bb.w;
+    }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = h + ky - 1;
@@ -108,11 +110,15 @@ conv3x3_first_c1_kernel(const float* __restrict__ x, const float* __restrict__ w
       const float rgt = (w0 + 4 < W) ? __ldg(rp + 4) : 0.f;
       const float iv[6] = {lft, mid.x, mid.y, mid.z, mid.w, rgt};
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wp = w_s + (ky * 3 + kx) * Cout + g * 8;
+        const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(iv[p + kx], wr[ky * 3 + kx][c], acc[p][c]);
+          for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(iv[p + kx], wv[c], acc[p][c]);
+      }
     }
     __nv_bfloat16* dst = y + ((size_t)row * W + w0) * Cout + g * 8;
 #pragma unroll
@@ -224,7 +230,7 @@ extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const fl
   if (Cin == 1 && W % 4 == 0 && 256 % groups == 0 && aligned16(x0) && (int64_t)B * H * (W / 4) < (1ll << 31)) {
     const int64_t quads = (int64_t)B * H * (W / 4);
     const int qpb = 256 / groups;
-    const int blocks = (int)std::min<int64_t>(cdiv64(quads, qpb), (int64_t)sm_count() * 8);
+    const int blocks = (int)std::min<int64_t>(cdiv64(quads, qpb), (int64_t)sm_count() * 16);
     conv3x3_first_c1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, w, bias, reinterpret_cast<__nv_bfloat16*>(y),
                                                                      B, H, W, Cout, relu);
     PMU_LAUNCH_CHECK();

@@ -103,19 +103,34 @@ gather_rows_kernel(const float* __restrict__ vol, int d1, int d2, int plane, int
   float tmax = -INFINITY;
   if (VEC) {
     const int w4 = W >> 2;
-    const int64_t n4 = hw >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (int64_t)gridDim.x * blockDim.x) {
-      const int r = (int)(i / w4), c4 = (int)(i % w4);
-      // plane 0: vol[s][r][c]; plane 1: vol[r][s][c]
-      const int64_t src = (plane == 0) ? ((int64_t)s * d1 + r) * d2 : ((int64_t)r * d1 + s) * d2;
-      float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(vol + src) + c4);
-      tmax = fmaxf(tmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-      if (max_in) {
-        v.x = ref_normalise(v.x, m); v.y = ref_normalise(v.y, m);
-        v.z = ref_normalise(v.z, m); v.w = ref_normalise(v.w, m);
+    const int n4 = (int)(hw >> 2);
+    const int stride = gridDim.x * blockDim.x;
+    // 4 independent 128-bit loads in flight per thread, then 4 stores
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * stride;
+        if (i < n4) {
+          const int r = i / w4, c4 = i - r * w4;
+          // plane 0: vol[s][r][c]; plane 1: vol[r][s][c]
+          const int64_t src = (plane == 0) ? ((int64_t)s * d1 + r) * d2 : ((int64_t)r * d1 + s) * d2;
+          v[u] = ldg_stream_f4(reinterpret_cast<const float4*>(vol + src) + c4);
+        }
       }
-      stg_stream_f4(reinterpret_cast<float4*>(dst) + i, v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * stride;
+        if (i < n4) {
+          float4 t = v[u];
+          tmax = fmaxf(tmax, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+          if (max_in) {
+            t.x = ref_normalise(t.x, m); t.y = ref_normalise(t.y, m);
+            t.z = ref_normalise(t.z, m); t.w = ref_normalise(t.w, m);
+          }
+          stg_stream_f4(reinterpret_cast<float4*>(dst) + i, t);
+        }
+      }
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw;
@@ -138,10 +153,10 @@ gather_rows_kernel(const float* __restrict__ vol, int d1, int d2, int plane, int
 
 // ---------------------------------------------------------------------------------
 // exact gather, plane 2: out[b][r][c] = vol[r][c][s0+b].  For a fixed r this is a
-// [c][s] -> [b][c] transpose; tile 64 (c) x 32 (s) through shared memory.
+// [c][s] -> [b][c] transpose; tile 64 (c) x 64 (s) through shared memory.
 //   grid = (c tiles, s tiles, r)
 // ---------------------------------------------------------------------------------
-constexpr int T2_C = 64, T2_S = 32;
+constexpr int T2_C = 64, T2_S = 64;
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
@@ -152,34 +167,39 @@ gather_plane2_kernel(const float* __restrict__ vol, int d1, int d2, int s0, int 
   const int r = blockIdx.z;
   const int c0 = blockIdx.x * T2_C, b0 = blockIdx.y * T2_S;
   const int t = threadIdx.x;
-  // ---- read: 64 c-rows x 32 s; 8 float4 (or 32 scalars) per c-row ----
+  // ---- read: 64 c-rows x 64 s; 16 float4 (or 64 scalars) per c-row; 4 loads in flight per thread ----
   if (VEC) {
+    float4 v[4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int idx = t + 256 * k;  // 0..511
-      const int cc = idx >> 3, s4 = (idx & 7) << 2;
+    for (int k = 0; k < 4; ++k) {
+      const int idx = t + 256 * k;  // 0..1023
+      const int cc = idx >> 4, s4 = (idx & 15) << 2;
       const int c = c0 + cc, b = b0 + s4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < W && b < ns) {  // ns % 4 == 0 guaranteed on the VEC path
-        v = ldg_stream_f4(reinterpret_cast<const float4*>(vol + ((int64_t)r * d1 + c) * d2 + s0 + b));
-      }
-      tile[cc][s4 + 0] = v.x; tile[cc][s4 + 1] = v.y; tile[cc][s4 + 2] = v.z; tile[cc][s4 + 3] = v.w;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < W && b < ns)   // ns % 4 == 0 guaranteed on the VEC path
+        v[k] = ldg_stream_f4(reinterpret_cast<const float4*>(vol + ((int64_t)r * d1 + c) * d2 + s0 + b));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = t + 256 * k;
+      const int cc = idx >> 4, s4 = (idx & 15) << 2;
+      tile[cc][s4 + 0] = v[k].x; tile[cc][s4 + 1] = v[k].y; tile[cc][s4 + 2] = v[k].z; tile[cc][s4 + 3] = v[k].w;
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int idx = t + 256 * k;  // 0..2047
-      const int cc = idx >> 5, ss = idx & 31;
+    for (int k = 0; k < 16; ++k) {
+      const int idx = t + 256 * k;  // 0..4095
+      const int cc = idx >> 6, ss = idx & 63;
       const int c = c0 + cc, b = b0 + ss;
       tile[cc][ss] = (c < W && b < ns) ? __ldg(vol + ((int64_t)r * d1 + c) * d2 + s0 + b) : 0.f;
     }
   }
   __syncthreads();
-  // ---- write: 32 s-rows x 64 c; 16 float4 per s-row ----
+  // ---- write: 64 s-rows x 64 c; 16 float4 per s-row ----
   const int64_t hw = (int64_t)H * W;
   if (VEC) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const int idx = t + 256 * k;
       const int ss = idx >> 4, c4 = (idx & 15) << 2;
       const int b = b0 + ss, c = c0 + c4;
@@ -205,7 +225,7 @@ gather_plane2_kernel(const float* __restrict__ vol, int d1, int d2, int s0, int 
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 16; ++k) {
       const int idx = t + 256 * k;
       const int ss = idx >> 6, cc = idx & 63;
       const int b = b0 + ss, c = c0 + cc;
@@ -353,7 +373,7 @@ extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int pla
     if (plane < 2) {
       const bool vec = (d2 % 4 == 0) && aligned16(vol) && aligned16(out);
       const int64_t work = vec ? ((int64_t)H * W / 4) : (int64_t)H * W;
-      dim3 grid((unsigned)std::min<int64_t>(cdiv64(work, 256 * 4), 4096), ns);
+      dim3 grid((unsigned)std::min<int64_t>(cdiv64(work, 256 * 4), 4096), ns);   // 4 vectors per thread
       if (vec)
         gather_rows_kernel<true><<<grid, 256, 0, st>>>(vol, d1, d2, plane, s0, H, W, slice_max_in, slice_max_out, out);
       else

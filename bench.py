@@ -36,6 +36,19 @@ METRIC = "volumes/sec (256^3, 3 planes x 16 samples)"
 UNIT = "volumes/s"
 
 
+def load_traffic():
+    """DRAM bytes per launch of our kernels from the last committed `ncu --set full` capture
+    (profiles/*_traffic.json, written by scripts/summarize_ncu.py)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return {}
+    try:
+        return json.load(open(files[-1]))
+    except Exception:
+        return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -169,7 +182,7 @@ def run_ours(args):
 
     sd = trainer_state_dict(seed=0)
     pred = pmu_b200.MultiPlanarPredictor(sd, dev, precision=args.precision, n_samples=N, slice_batch=args.slice_batch,
-                                         rank=rank, world_size=world)
+                                         interp=args.interp, rank=rank, world_size=world)
     vol_host = phantom_volume(D, seed=1234).pin_memory()
     vol = vol_host.to(dev)
     eps = torch.randn(P, D, N, 6, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)
@@ -229,6 +242,7 @@ def run_ours(args):
 
     # ---- per-kernel roofline: one instrumented step, CUDA events around every C-ABI call ----
     roof, hbm_kernels, shares = None, {}, {}
+    traffic = load_traffic()
     # EVERY rank runs the instrumented step (it contains the reduce collective); rank 0 reports
     barrier()
     ops.PROFILE = []
@@ -239,10 +253,13 @@ def run_ours(args):
         tot = {}
         for name, meta, a, b in prof:
             t = a.elapsed_time(b)
-            d = tot.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+            if name == "pmu_conv_gemm_pool_bf16":
+                name = "pmu_conv_gemm_bf16"          # same kernel (conv_tc_kernel), pooled epilogue
+            d = tot.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
             d["ms"] += t; d["n"] += 1
             if meta:
                 d["flops"] += meta.get("flops", 0.0)
+                d["bytes"] += meta.get("bytes", 0.0)
         step_ms = sum(d["ms"] for d in tot.values())
         shares = {k: round(d["ms"] / step_ms, 4) for k, d in sorted(tot.items(), key=lambda kv: -kv[1]["ms"])}
         dom = max(tot.items(), key=lambda kv: kv[1]["ms"])
@@ -251,7 +268,11 @@ def run_ours(args):
             ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
             roof = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": ach,
                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                    "traffic": None, "launches": c["n"], "avg_launch_ms": c["ms"] / c["n"],
+                    "traffic": (traffic.get("conv_tc_kernel") or {}).get("dram_bytes_per_launch"),
+                    "traffic_note": "dram__bytes_read+write per launch, mean over the conv launches of one ncu --set full "
+                                    "capture (profiles/); algorithmic bytes per launch (in+out+weights) = "
+                                    f"{c.get('bytes', 0.0) / max(c['n'], 1):.3e}",
+                    "launches": c["n"], "avg_launch_ms": c["ms"] / c["n"],
                     "peak_source": peaks["source"] + ", sustained bf16"}
         else:
             c = dom[1]
@@ -273,6 +294,9 @@ def run_ours(args):
                                             "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
         for v in hbm_kernels.values():
             v["frac"] = v["achieved"] / v["peak"]
+        if "slice_gather" in hbm_kernels:
+            g = [traffic.get(k, {}).get("dram_bytes_per_launch") for k in ("gather_rows_kernel", "gather_plane2_kernel")]
+            hbm_kernels["slice_gather"]["traffic_per_plane_launch"] = [x for x in g if x]
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -285,7 +309,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": f"{D}^3 fp32 volume, 3 planes x {N} z-samples, axis-aligned slicing, trainer model "
+                "config": {"workload": f"{D}^3 fp32 volume, 3 planes x {N} z-samples, {args.interp} resampling on the standard plane grids, trainer model "
                                        f"[64,128,256,512,1024] C=3 L=6 fcomb=4, mean/var/entropy fusion",
                            "slice_batch": args.slice_batch, "parallelism": f"slice-sharded x{world} + 1 reduce",
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
@@ -308,6 +332,8 @@ def main():
     ap.add_argument("--samples", type=int, default=16)
     ap.add_argument("--slice-batch", type=int, default=64)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--interp", default="trilinear", choices=["exact", "nearest", "trilinear"],
+                    help="slice resampling onto the three standard plane grids (BASELINE configs[2]: trilinear)")
     ap.add_argument("--cpu-slices-per-plane", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -3,7 +3,7 @@
 Import as ``pmu_b200`` (the directory name carries the reference's hyphenated name; the
 top-level ``pmu_b200`` package is an alias whose __path__ points here).
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, nifti_io, ops  # noqa: F401
 from .dice_loss import dice_coeff, volume_dice  # noqa: F401
 from .engine import PackedNet  # noqa: F401
 from .model import ProbabilisticUnet, UNet  # noqa: F401

@@ -8,7 +8,10 @@
 // are coalescing, 128-bit accesses, and enough independent loads in flight; plane 2
 // (slice index on the fastest axis) goes through a shared-memory transpose tile so both
 // the volume reads (along z) and the slice writes (along c) are full 128 B lines.
+#include <cudaTypedefs.h>
+
 #include "pmu_common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace pmu {
 
@@ -306,6 +309,94 @@ gather_affine_kernel(const float* __restrict__ vol, int d0, int d1, int d2, Affi
   }
 }
 
+// ---------------------------------------------------------------------------------
+// affine-grid gather with a TMA-staged volume brick: the block's 256 output pixels (a ts x tr x tc
+// tile of slices x rows x cols, chosen on the host so that the tile is long along the output axis
+// that walks z) read their taps from a [BX][BY][BZ] brick of the volume that ONE 3-D TMA box load
+// brings into shared memory — full-line reads along z, out-of-volume voxels zero-filled by TMA
+// (== the zeros padding of the resampling spec).  Coordinates / interpolation are exactly those of
+// gather_affine_kernel, so the result is bit-identical.
+// ---------------------------------------------------------------------------------
+struct BrickCfg { int ts, tr, tc; int bx, by, bz; int tiles_r, tiles_c; };
+
+__device__ __forceinline__ void affine_q(const Affine12& A, float sf, float rf, float cf, float (&q)[3]) {
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    float t = __fadd_rn(A.a[ax], __fmul_rn(sf, A.a[3 + ax]));
+    t = __fadd_rn(t, __fmul_rn(rf, A.a[6 + ax]));
+    q[ax] = __fadd_rn(t, __fmul_rn(cf, A.a[9 + ax]));
+  }
+}
+
+template <bool TRILINEAR>
+__global__ void __launch_bounds__(256)
+gather_affine_brick_kernel(const __grid_constant__ CUtensorMap tmV, Affine12 A, BrickCfg g, int s0, int ns, int H, int W,
+                           const float* __restrict__ max_in, float* __restrict__ max_out, float* __restrict__ out) {
+  extern __shared__ __align__(128) float brick[];     // [bx][by][bz]
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ int org[3];
+  __shared__ float smax[32];
+  const int t = threadIdx.x;
+  const int tile_c = blockIdx.x % g.tiles_c, tile_r = blockIdx.x / g.tiles_c;
+  const int sl0 = blockIdx.y * g.ts, r0 = tile_r * g.tr, c0 = tile_c * g.tc;
+  const uint32_t bar = ptx::smem_u32(&mbar);
+  if (t < 32) smax[t] = -INFINITY;
+  if (t == 0) {
+    // brick origin = floor of the minimum tap coordinate over the tile's 8 corners (affine: extremes at corners)
+    float mn[3] = {INFINITY, INFINITY, INFINITY};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int sl = min(sl0 + ((k & 4) ? g.ts - 1 : 0), ns - 1), r = min(r0 + ((k & 2) ? g.tr - 1 : 0), H - 1),
+                c = min(c0 + ((k & 1) ? g.tc - 1 : 0), W - 1);
+      float q[3];
+      affine_q(A, (float)(s0 + sl), (float)r, (float)c, q);
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) mn[ax] = fminf(mn[ax], TRILINEAR ? floorf(q[ax]) : floorf(__fadd_rn(q[ax], 0.5f)));
+    }
+    org[0] = (int)mn[0]; org[1] = (int)mn[1]; org[2] = (int)mn[2];
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+    ptx::mbar_arrive_expect_tx(bar, (uint32_t)(g.bx * g.by * g.bz * 4));
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(ptx::smem_u32(brick)), "l"(reinterpret_cast<uint64_t>(&tmV)), "r"(bar), "r"(org[2]), "r"(org[1]), "r"(org[0])
+        : "memory");
+  }
+  __syncthreads();
+  ptx::mbar_wait(bar, 0);
+  const int cl = t % g.tc, rl = (t / g.tc) % g.tr, sl = t / (g.tc * g.tr);
+  const int b = sl0 + sl, r = r0 + rl, c = c0 + cl;
+  float v = -INFINITY;
+  const bool live = (b < ns) && (r < H) && (c < W);
+  if (live) {
+    float q[3];
+    affine_q(A, (float)(s0 + b), (float)r, (float)c, q);
+    const int ox = org[0], oy = org[1], oz = org[2];
+    auto tap = [&](int ix, int iy, int iz) -> float {
+      return brick[((ix - ox) * g.by + (iy - oy)) * g.bz + (iz - oz)];
+    };
+    if (!TRILINEAR) {
+      v = tap((int)floorf(__fadd_rn(q[0], 0.5f)), (int)floorf(__fadd_rn(q[1], 0.5f)), (int)floorf(__fadd_rn(q[2], 0.5f)));
+    } else {
+      const float fx = floorf(q[0]), fy = floorf(q[1]), fz = floorf(q[2]);
+      const float tx = __fsub_rn(q[0], fx), ty = __fsub_rn(q[1], fy), tz = __fsub_rn(q[2], fz);
+      const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+      const float c00 = lerp_rn(tap(x0, y0, z0), tap(x0, y0, z0 + 1), tz);
+      const float c01 = lerp_rn(tap(x0, y0 + 1, z0), tap(x0, y0 + 1, z0 + 1), tz);
+      const float c10 = lerp_rn(tap(x0 + 1, y0, z0), tap(x0 + 1, y0, z0 + 1), tz);
+      const float c11 = lerp_rn(tap(x0 + 1, y0 + 1, z0), tap(x0 + 1, y0 + 1, z0 + 1), tz);
+      v = lerp_rn(lerp_rn(c00, c01, ty), lerp_rn(c10, c11, ty), tx);
+    }
+    const float m = max_in ? __ldg(max_in + s0 + b) : 0.f;
+    out[((int64_t)b * H + r) * W + c] = max_in ? ref_normalise(v, m) : v;
+  }
+  if (max_out) {
+    if (live) { float mv = (v == 0.f) ? 0.f : v; atomic_max_float(&smax[sl], mv); }
+    __syncthreads();
+    if (t < g.ts && sl0 + t < ns && smax[t] != -INFINITY) atomic_max_float(max_out + sl0 + t, smax[t]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 slice_normalize_kernel(float* __restrict__ slices, const float* __restrict__ slice_max, int64_t hw) {
   const int b = blockIdx.y;
@@ -392,6 +483,53 @@ extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int pla
     PMU_CHECK_ARG(affine_host != nullptr, "pmu_slice_gather: affine grid needs 12 host floats");
     Affine12 A;
     for (int i = 0; i < 12; ++i) A.a[i] = affine_host[i];
+    // ---- TMA-staged brick path ----
+    if (d2 % 4 == 0 && aligned16(vol)) {
+      BrickCfg g;
+      const float nz = fabsf(A.a[3 + 2]), uz = fabsf(A.a[6 + 2]), vz = fabsf(A.a[9 + 2]);
+      if (vz >= nz && vz >= uz) { g.ts = 1; g.tr = 8; g.tc = 32; }        // columns walk z
+      else if (nz >= uz)        { g.ts = 32; g.tr = 1; g.tc = 8; }        // slices walk z
+      else                      { g.ts = 1; g.tr = 32; g.tc = 8; }        // rows walk z
+      int ext[3];
+      for (int ax = 0; ax < 3; ++ax) {
+        const float e = (g.ts - 1) * fabsf(A.a[3 + ax]) + (g.tr - 1) * fabsf(A.a[6 + ax]) + (g.tc - 1) * fabsf(A.a[9 + ax]);
+        ext[ax] = (int)floorf(e) + 3;     // floor offset + second tap + rounding slack
+      }
+      g.bx = ext[0]; g.by = ext[1]; g.bz = (ext[2] + 3) & ~3;   // inner box extent: multiple of 16 bytes
+      const size_t bytes = (size_t)g.bx * g.by * g.bz * 4;
+      static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+      if (!enc) {
+        void* fp = nullptr; cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp);
+      }
+      int cc_major = 0, dev = 0;
+      PMU_CUDA(cudaGetDevice(&dev));
+      PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+      if (enc && cc_major >= 9 && bytes <= 96 * 1024 && g.bx <= 256 && g.by <= 256 && g.bz <= 256 && cdiv(ns, g.ts) <= 65535) {
+        CUtensorMap tm;
+        cuuint64_t dims3[3] = {(cuuint64_t)d2, (cuuint64_t)d1, (cuuint64_t)d0};
+        cuuint64_t str3[2] = {(cuuint64_t)d2 * 4, (cuuint64_t)d1 * d2 * 4};
+        cuuint32_t box3[3] = {(cuuint32_t)g.bz, (cuuint32_t)g.by, (cuuint32_t)g.bx};
+        cuuint32_t es3[3] = {1, 1, 1};
+        CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(vol), dims3, str3, box3, es3,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS) {
+          g.tiles_r = cdiv(H, g.tr); g.tiles_c = cdiv(W, g.tc);
+          dim3 grid(g.tiles_r * g.tiles_c, cdiv(ns, g.ts));
+          if (interp == PMU_INTERP_TRILINEAR) {
+            PMU_CUDA(cudaFuncSetAttribute(gather_affine_brick_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            gather_affine_brick_kernel<true><<<grid, 256, bytes, st>>>(tm, A, g, s0, ns, H, W, slice_max_in, slice_max_out, out);
+          } else {
+            PMU_CUDA(cudaFuncSetAttribute(gather_affine_brick_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            gather_affine_brick_kernel<false><<<grid, 256, bytes, st>>>(tm, A, g, s0, ns, H, W, slice_max_in, slice_max_out, out);
+          }
+          PMU_LAUNCH_CHECK();
+          return PMU_OK;
+        }
+      }
+    }
     dim3 grid((unsigned)std::min<int64_t>(cdiv64((int64_t)H * W, 256), 2048), ns);
     if (interp == PMU_INTERP_TRILINEAR)
       gather_affine_kernel<true><<<grid, 256, 0, st>>>(vol, d0, d1, d2, A, s0, H, W, slice_max_in, slice_max_out, out);

@@ -50,6 +50,14 @@ def shard_slices(dims: Sequence[int], planes: Sequence[int], rank: int, world: i
     return out
 
 
+def plane_affine(plane: int):
+    """12 floats [o, n, u, v] of the standard view `plane`: q = o + s*n + r*u + c*v reproduces
+    MRI_Dataset.sample_slice (mri_dataset.py:72-77) — the identity resampling grid."""
+    e = [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]
+    n, u, v = {0: (e[0], e[1], e[2]), 1: (e[1], e[0], e[2]), 2: (e[2], e[0], e[1])}[plane]
+    return [0.0, 0.0, 0.0] + n + u + v
+
+
 def reduce_accumulators(acc: torch.Tensor, world: int, group=None, dst: Optional[int] = 0) -> torch.Tensor:
     """The single exchange step: sum the [2,X,C,Y,Z] accumulators over ranks (NCCL on GPUs over
     NVLink/NVSwitch; gloo in the CPU tests).  dst=None -> all-reduce."""
@@ -79,8 +87,9 @@ class MultiPlanarPredictor:
         self.n_samples, self.planes, self.slice_batch = int(n_samples), tuple(planes), int(slice_batch)
         if interp not in ops.INTERP:
             raise ValueError(f"interp must be one of {list(ops.INTERP)}")
-        if interp != "exact" and affines is None:
-            raise ValueError("nearest/trilinear resampling needs per-plane affines")
+        if affines is None:
+            affines = {p: plane_affine(p) for p in self.planes}     # resample onto the standard grids
+        self.identity_grid = all(list(map(float, affines[p])) == plane_affine(p) for p in self.planes)
         self.interp, self.affines, self.out_hw = interp, affines, out_hw
         self.rank, self.world, self.group = int(rank), int(world_size), process_group
         self.C = self.net.fcomb["C"]
@@ -98,8 +107,9 @@ class MultiPlanarPredictor:
             vol = big
         return vol.contiguous()
 
-    def accumulate(self, vol: torch.Tensor, eps: torch.Tensor, acc: torch.Tensor) -> int:
-        """Run this rank's slices and add their sums into acc [2,X,C,Y,Z]; returns #slices done."""
+    def accumulate(self, vol: torch.Tensor, eps: torch.Tensor, acc: torch.Tensor, only_plane: Optional[int] = None) -> int:
+        """Run this rank's slices and add their sums into acc [2,X,C,Y,Z]; returns #slices done.
+        only_plane restricts the pass to one view (per-view volumes of eval.py:176-190)."""
         dims = tuple(vol.shape)
         net, N = self.net, self.n_samples
         my = shard_slices(dims, self.planes, self.rank, self.world)
@@ -108,7 +118,7 @@ class MultiPlanarPredictor:
         offs = (0, dims[0], dims[0] + dims[1])
         done = 0
         for pi, p in enumerate(self.planes):
-            if p not in my:
+            if p not in my or (only_plane is not None and p != only_plane):
                 continue
             s_lo, s_hi = my[p]
             # K1 once per plane: all of this rank's slices of the plane in one launch (full-bandwidth
@@ -132,13 +142,15 @@ class MultiPlanarPredictor:
 
     @torch.no_grad()
     def predict(self, vol, eps: Optional[torch.Tensor] = None, seed: int = 4321, want_labels: bool = False,
-                keep_sums: bool = False) -> Dict[str, torch.Tensor]:
+                keep_sums: bool = False, per_plane: bool = False) -> Dict[str, torch.Tensor]:
         """vol: [d0,d1,d2] fp32 (numpy / CPU / CUDA).  eps: [P, D, N, L] standard-normal draws
         (host or device); generated on the device from `seed` when omitted.  Returns mean / var
-        [x,C,y,z], entropy [x,y,z] (valid on rank 0 when world_size > 1)."""
-        if self.interp != "exact":
-            raise NotImplementedError("voxel fusion is defined for the axis-aligned grid; resampled grids "
-                                      "are available through ops.slice_gather (SURVEY.md App. A step 6)")
+        [x,C,y,z], entropy [x,y,z] (valid on rank 0 when world_size > 1).  per_plane=True also
+        returns "plane_means": the per-view probability volumes volume1/2/3 of eval.py:176-190."""
+        if self.interp != "exact" and not self.identity_grid:
+            raise NotImplementedError("voxel fusion (scatter back onto the voxel lattice) is defined for the standard "
+                                      "axis-aligned grids; arbitrary resampling grids are available through "
+                                      "ops.slice_gather (SURVEY.md App. A step 6)")
         vol = self._to_device_volume(vol)
         dims = tuple(vol.shape)
         P, N, L = len(self.planes), self.n_samples, self.L
@@ -149,9 +161,20 @@ class MultiPlanarPredictor:
         else:
             eps = eps.to(self.device, torch.float32, non_blocking=True)
         acc = torch.zeros(2, dims[0], self.C, dims[1], dims[2], dtype=torch.float32, device=self.device)
-        self.accumulate(vol, eps, acc)
-        reduce_accumulators(acc, self.world, self.group, dst=0)
         out: Dict[str, torch.Tensor] = {"count": float(P * N)}
+        if per_plane:
+            plane_means = []
+            for p in self.planes:
+                pacc = torch.zeros_like(acc)
+                self.accumulate(vol, eps, pacc, only_plane=p)
+                reduce_accumulators(pacc, self.world, self.group, dst=0)
+                if self.rank == 0:
+                    plane_means.append(ops.fuse_finalize(pacc[0], pacc[1], float(N), want_var=False, want_entropy=False)[0])
+                acc += pacc
+            out["plane_means"] = plane_means
+        else:
+            self.accumulate(vol, eps, acc)
+            reduce_accumulators(acc, self.world, self.group, dst=0)
         if self.rank == 0:
             mean, var, ent, lab = ops.fuse_finalize(acc[0], acc[1], float(P * N), want_labels=want_labels)
             out.update(mean=mean, var=var, entropy=ent)

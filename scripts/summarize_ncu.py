@@ -40,3 +40,30 @@ for rep in glob.glob("gpurun_out/prof_*.ncu-rep"):
                 if w in idx:
                     f.write(f"{w} = {r[idx[w]][:100]} {units[idx[w]]}\n")
     print("wrote", f"profiles/{tag}_{name}_ncu.txt")
+
+# ---- DRAM traffic per launch of the captured kernels (feeds bench.py's roofline.traffic) ----
+import json, re
+traffic = {}
+def _num(x):
+    try: return float(x.replace(",", ""))
+    except Exception: return None
+for rep in glob.glob("gpurun_out/prof_*.ncu-rep"):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3: continue
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        name = re.sub(r"<.*", "", r[idx["Kernel Name"]]).replace("void ", "").strip()
+        rd, wr = _num(r[idx["dram__bytes_read.sum"]]), _num(r[idx["dram__bytes_write.sum"]])
+        if rd is None or wr is None: continue
+        tot = rd * scale.get(units[idx["dram__bytes_read.sum"]], 1.0) + wr * scale.get(units[idx["dram__bytes_write.sum"]], 1.0)
+        d = traffic.setdefault(name, {"dram_bytes": 0.0, "launches_captured": 0, "time_us": 0.0})
+        d["dram_bytes"] += tot; d["launches_captured"] += 1
+        t = _num(r[idx["gpu__time_duration.sum"]]); tu = units[idx["gpu__time_duration.sum"]]
+        d["time_us"] += t * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(tu, 1.0)
+for k, d in traffic.items():
+    d["dram_bytes_per_launch"] = d["dram_bytes"] / d["launches_captured"]
+json.dump(traffic, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
+print(json.dumps(traffic, indent=1))

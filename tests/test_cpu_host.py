@@ -144,3 +144,17 @@ def test_sharded_accumulators_reduce_over_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-6
+
+
+def test_nifti_roundtrip(tmp_path):
+    from pmu_b200 import nifti_io
+    v = np.random.default_rng(0).random((5, 6, 7))
+    for name in ("a.nii", "b.nii.gz"):
+        p = str(tmp_path / name)
+        nifti_io.save(p, v)
+        w = nifti_io.load(p)
+        assert w.shape == v.shape and w.dtype == np.float64
+        np.testing.assert_array_equal(w, v.astype(np.float32).astype(np.float64))
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.nii").write_bytes(b"x" * 400)
+        nifti_io.load(str(tmp_path / "bad.nii"))

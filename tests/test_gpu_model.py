@@ -189,3 +189,57 @@ def test_fitted_model_dice(pmu, golden_dir):
         got = pmu.volume_dice(out["mean"], torch.from_numpy(lab_true).cuda()).cpu().numpy()
         want = [O.argmax_dice(ref["mean"], torch.from_numpy(lab_true), k) for k in (1, 2)]
         np.testing.assert_allclose(got, want, atol=2e-3)
+
+
+def test_trainer_adapter(pmu, trainer_sd):
+    """ProbUNetTrainer.predict / loss / eval (trainer/probunet_trainer.py:27-60) against the oracle."""
+    tr = pmu.ProbUNetTrainer(torch.device("cuda"), n_channels=1, n_classes=3, latent_dim=6, beta=10)
+    tr.net.load_state_dict(trainer_sd, strict=True)
+    tr.net.eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 1, 32, 32, generator=g)
+    m = torch.randint(0, 3, (2, 1, 32, 32), generator=g).float()
+    z = torch.randn(6, generator=g)
+    with torch.no_grad():
+        logits = tr.predict(x[:1].cuda(), m[:1].cuda(), z=z)                 # sample_at hook (visualize_sampling.py:23-31)
+        feat = O.unet_features(trainer_sd, x[:1])
+        ref = O.fcomb(trainer_sd, feat, z[None])
+        assert (torch.softmax(logits.cpu(), 1) - torch.softmax(ref, 1)).abs().max() < FP32_PROB_TOL
+        d = tr.eval(x[:1].cuda(), m[:1].cuda(), logits)
+        want = [O.argmax_dice(torch.softmax(ref, 1), m[:1, 0], k) for k in (1, 2)]
+        np.testing.assert_allclose(d, want, atol=1e-5)
+        s = tr.predict(x.cuda(), m.cuda())                                    # stochastic path: shape + finiteness
+        assert s.shape == (2, 3, 32, 32) and bool(torch.isfinite(s).all())
+        tr.net.forward(x.cuda(), m.cuda(), training=True)
+        eps_q = torch.randn(2, 6, generator=g)
+        loss = tr.net.elbo(m.cuda(), eps=eps_q.cuda())
+        r = O.elbo(trainer_sd, x, m, eps_q, beta=10.0, bn_train=False)
+        np.testing.assert_allclose(float(loss), float(r["elbo"]), rtol=1e-4)
+
+
+def test_eval_entry_point(pmu, tmp_path):
+    """eval.py end to end on a tiny synthetic dataset (NIfTI in, label / entropy NIfTI + Dice out)
+    and per-plane volumes: the fused mean is the average of the three per-view means (eval.py:193)."""
+    import subprocess
+    import sys
+    from pmu_b200 import nifti_io
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = tmp_path / "data"
+    (d / "images").mkdir(parents=True); (d / "labels").mkdir()
+    for i in range(2):
+        vol, lab = O.phantom(16, seed=10 + i, dims=(16, 16, 12) if i else None)
+        nifti_io.save(str(d / "images" / f"scan{i}.nii"), vol)
+        nifti_io.save(str(d / "labels" / f"scan{i}.nii"), lab)
+    r = subprocess.run([sys.executable, os.path.join(root, "eval.py"), "-d", str(d), "-m", "probunet", "--samples", "2",
+                        "--precision", "bf16", "--slice-batch", "16", "--out", str(tmp_path / "out")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "avg volume: mean=" in r.stdout and "view 3 dice" in r.stdout
+    lab = nifti_io.load(str(tmp_path / "out" / "scan1_labels.nii"))
+    assert lab.shape == (16, 16, 16)                       # pad_dimensions: arg-min axis padded to the max
+    sd = O.make_state_dict((64, 128), seed=2)
+    pred = pmu.MultiPlanarPredictor(sd, "cuda", precision="fp32", n_samples=2, slice_batch=16)
+    vol, _ = O.phantom(16, seed=3)
+    out = pred.predict(vol, seed=1, per_plane=True)
+    avg = (out["plane_means"][0] + out["plane_means"][1] + out["plane_means"][2]) / 3.0
+    torch.testing.assert_close(out["mean"], avg, atol=1e-6, rtol=1e-5)

@@ -9,6 +9,7 @@
 // (slice index on the fastest axis) goes through a shared-memory transpose tile so both
 // the volume reads (along z) and the slice writes (along c) are full 128 B lines.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "pmu_common.cuh"
 #include "sm100_ptx.cuh"
@@ -310,14 +311,14 @@ gather_affine_kernel(const float* __restrict__ vol, int d0, int d1, int d2, Affi
 }
 
 // ---------------------------------------------------------------------------------
-// affine-grid gather with a TMA-staged volume brick: the block's 256 output pixels (a ts x tr x tc
+// affine-grid gather with a TMA-staged volume brick: the block's 1024 output pixels (a ts x tr x tc
 // tile of slices x rows x cols, chosen on the host so that the tile is long along the output axis
 // that walks z) read their taps from a [BX][BY][BZ] brick of the volume that ONE 3-D TMA box load
 // brings into shared memory — full-line reads along z, out-of-volume voxels zero-filled by TMA
 // (== the zeros padding of the resampling spec).  Coordinates / interpolation are exactly those of
 // gather_affine_kernel, so the result is bit-identical.
 // ---------------------------------------------------------------------------------
-struct BrickCfg { int ts, tr, tc; int bx, by, bz; int tiles_r, tiles_c; };
+struct BrickCfg { int ts, tr, tc; int lg_tc, lg_tr; int bx, by, bz; int tiles_r, tiles_c; };
 
 __device__ __forceinline__ void affine_q(const Affine12& A, float sf, float rf, float cf, float (&q)[3]) {
 #pragma unroll
@@ -353,7 +354,8 @@ gather_affine_brick_kernel(const __grid_constant__ CUtensorMap tmV, Affine12 A, 
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) mn[ax] = fminf(mn[ax], TRILINEAR ? floorf(q[ax]) : floorf(__fadd_rn(q[ax], 0.5f)));
     }
-    org[0] = (int)mn[0]; org[1] = (int)mn[1]; org[2] = (int)mn[2];
+    org[0] = (int)mn[0]; org[1] = (int)mn[1];
+    org[2] = (int)mn[2] & ~3;    // TMA wants the innermost start 16-byte aligned (the box is 4 floats longer for it)
     ptx::mbar_init(bar, 1);
     ptx::fence_barrier_init();
     ptx::mbar_arrive_expect_tx(bar, (uint32_t)(g.bx * g.by * g.bz * 4));
@@ -364,34 +366,37 @@ gather_affine_brick_kernel(const __grid_constant__ CUtensorMap tmV, Affine12 A, 
   }
   __syncthreads();
   ptx::mbar_wait(bar, 0);
-  const int cl = t % g.tc, rl = (t / g.tc) % g.tr, sl = t / (g.tc * g.tr);
-  const int b = sl0 + sl, r = r0 + rl, c = c0 + cl;
-  float v = -INFINITY;
-  const bool live = (b < ns) && (r < H) && (c < W);
-  if (live) {
+  const int ox = org[0], oy = org[1], oz = org[2];
+  const int sy = g.bz, sx = g.by * g.bz;          // brick strides
+  auto tap = [&](int ix, int iy, int iz) -> float {
+    return brick[(ix - ox) * sx + (iy - oy) * sy + (iz - oz)];
+  };
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int idx = t + 256 * k;                  // 0 .. ts*tr*tc - 1 (== 1023)
+    const int cl = idx & (g.tc - 1), rl = (idx >> g.lg_tc) & (g.tr - 1), sl = idx >> (g.lg_tc + g.lg_tr);   // powers of two
+    const int b = sl0 + sl, r = r0 + rl, c = c0 + cl;
+    if (!((b < ns) && (r < H) && (c < W))) continue;
     float q[3];
     affine_q(A, (float)(s0 + b), (float)r, (float)c, q);
-    const int ox = org[0], oy = org[1], oz = org[2];
-    auto tap = [&](int ix, int iy, int iz) -> float {
-      return brick[((ix - ox) * g.by + (iy - oy)) * g.bz + (iz - oz)];
-    };
+    float v;
     if (!TRILINEAR) {
       v = tap((int)floorf(__fadd_rn(q[0], 0.5f)), (int)floorf(__fadd_rn(q[1], 0.5f)), (int)floorf(__fadd_rn(q[2], 0.5f)));
     } else {
       const float fx = floorf(q[0]), fy = floorf(q[1]), fz = floorf(q[2]);
       const float tx = __fsub_rn(q[0], fx), ty = __fsub_rn(q[1], fy), tz = __fsub_rn(q[2], fz);
-      const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-      const float c00 = lerp_rn(tap(x0, y0, z0), tap(x0, y0, z0 + 1), tz);
-      const float c01 = lerp_rn(tap(x0, y0 + 1, z0), tap(x0, y0 + 1, z0 + 1), tz);
-      const float c10 = lerp_rn(tap(x0 + 1, y0, z0), tap(x0 + 1, y0, z0 + 1), tz);
-      const float c11 = lerp_rn(tap(x0 + 1, y0 + 1, z0), tap(x0 + 1, y0 + 1, z0 + 1), tz);
+      const float* bp = brick + ((int)fx - ox) * sx + ((int)fy - oy) * sy + ((int)fz - oz);   // one base, 8 offsets
+      const float c00 = lerp_rn(bp[0], bp[1], tz);
+      const float c01 = lerp_rn(bp[sy], bp[sy + 1], tz);
+      const float c10 = lerp_rn(bp[sx], bp[sx + 1], tz);
+      const float c11 = lerp_rn(bp[sx + sy], bp[sx + sy + 1], tz);
       v = lerp_rn(lerp_rn(c00, c01, ty), lerp_rn(c10, c11, ty), tx);
     }
+    if (max_out) { float mv = (v == 0.f) ? 0.f : v; atomic_max_float(&smax[sl], mv); }
     const float m = max_in ? __ldg(max_in + s0 + b) : 0.f;
     out[((int64_t)b * H + r) * W + c] = max_in ? ref_normalise(v, m) : v;
   }
   if (max_out) {
-    if (live) { float mv = (v == 0.f) ? 0.f : v; atomic_max_float(&smax[sl], mv); }
     __syncthreads();
     if (t < g.ts && sl0 + t < ns && smax[t] != -INFINITY) atomic_max_float(max_out + sl0 + t, smax[t]);
   }
@@ -483,19 +488,38 @@ extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int pla
     PMU_CHECK_ARG(affine_host != nullptr, "pmu_slice_gather: affine grid needs 12 host floats");
     Affine12 A;
     for (int i = 0; i < 12; ++i) A.a[i] = affine_host[i];
+    // Fast path: on a standard plane grid (o = 0, n/u/v = the view's unit vectors) every tap weight is exactly
+    // 0 or 1, so nearest and trilinear reproduce plain slicing bit for bit (oracle test_oracle_slicing_identities,
+    // GPU test_gather_affine_bit_exact) — hand the launch to the HBM-rate copy kernels.  PMU_GATHER_NO_FASTPATH=1
+    // forces the general kernel (bench.py uses it to report the resampling kernel's own roofline).
+    static int no_fast = -1;
+    if (no_fast < 0) { const char* e = getenv("PMU_GATHER_NO_FASTPATH"); no_fast = (e && atoi(e)) ? 1 : 0; }
+    if (!no_fast) {
+      static const float std_aff[3][12] = {{0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1},
+                                           {0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 1},
+                                           {0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0}};
+      for (int pl = 0; pl < 3; ++pl) {
+        bool same = true;
+        for (int i = 0; i < 12; ++i) same = same && (A.a[i] == std_aff[pl][i]);
+        const int ext3[3] = {d0, d1, d2};
+        const int eh = (pl == 0) ? d1 : d0, ew = (pl == 2) ? d1 : d2;
+        if (same && H == eh && W == ew && s0 + ns <= ext3[pl])
+          return pmu_slice_gather(vol, dims, pl, s0, ns, PMU_INTERP_EXACT, nullptr, H, W, slice_max_in, slice_max_out, out, stream);
+      }
+    }
     // ---- TMA-staged brick path ----
     if (d2 % 4 == 0 && aligned16(vol)) {
       BrickCfg g;
       const float nz = fabsf(A.a[3 + 2]), uz = fabsf(A.a[6 + 2]), vz = fabsf(A.a[9 + 2]);
-      if (vz >= nz && vz >= uz) { g.ts = 1; g.tr = 8; g.tc = 32; }        // columns walk z
-      else if (nz >= uz)        { g.ts = 32; g.tr = 1; g.tc = 8; }        // slices walk z
-      else                      { g.ts = 1; g.tr = 32; g.tc = 8; }        // rows walk z
+      // 1024 outputs per block (4 per thread) amortise the brick load latency
+      if (nz > vz && nz > uz) { g.ts = 32; g.tr = 4; g.tc = 8; g.lg_tr = 2; g.lg_tc = 3; }     // slices walk z
+      else                    { g.ts = 1; g.tr = 32; g.tc = 32; g.lg_tr = 5; g.lg_tc = 5; }    // columns / rows walk z
       int ext[3];
       for (int ax = 0; ax < 3; ++ax) {
         const float e = (g.ts - 1) * fabsf(A.a[3 + ax]) + (g.tr - 1) * fabsf(A.a[6 + ax]) + (g.tc - 1) * fabsf(A.a[9 + ax]);
         ext[ax] = (int)floorf(e) + 3;     // floor offset + second tap + rounding slack
       }
-      g.bx = ext[0]; g.by = ext[1]; g.bz = (ext[2] + 3) & ~3;   // inner box extent: multiple of 16 bytes
+      g.bx = ext[0]; g.by = ext[1]; g.bz = ((ext[2] + 3) & ~3) + 4;   // inner extent: multiple of 16 B, + slack for the aligned start
       const size_t bytes = (size_t)g.bx * g.by * g.bz * 4;
       static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
       if (!enc) {
@@ -506,7 +530,9 @@ extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int pla
       int cc_major = 0, dev = 0;
       PMU_CUDA(cudaGetDevice(&dev));
       PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
-      if (enc && cc_major >= 9 && bytes <= 96 * 1024 && g.bx <= 256 && g.by <= 256 && g.bz <= 256 && cdiv(ns, g.ts) <= 65535) {
+      // (a box larger than the tensor extent is not a valid TMA box: tiny volumes use the plain kernel)
+      if (enc && cc_major >= 9 && bytes <= 96 * 1024 && g.bx <= std::min(256, d0) && g.by <= std::min(256, d1) &&
+          g.bz <= std::min(256, d2) && cdiv(ns, g.ts) <= 65535) {
         CUtensorMap tm;
         cuuint64_t dims3[3] = {(cuuint64_t)d2, (cuuint64_t)d1, (cuuint64_t)d0};
         cuuint64_t str3[2] = {(cuuint64_t)d2 * 4, (cuuint64_t)d1 * d2 * 4};

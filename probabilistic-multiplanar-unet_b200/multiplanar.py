@@ -113,7 +113,9 @@ class MultiPlanarPredictor:
         dims = tuple(vol.shape)
         net, N = self.net, self.n_samples
         my = shard_slices(dims, self.planes, self.rank, self.world)
-        exact = self.interp == "exact"
+        # on the standard grids (exact slicing, or nearest / trilinear resampling onto them) a slice's max is
+        # the volume's per-plane max: one pass over the volume, normalisation fused into the gather
+        exact = self.interp == "exact" or self.identity_grid
         maxes = ops.plane_max(vol) if exact else None
         offs = (0, dims[0], dims[0] + dims[1])
         done = 0
@@ -124,7 +126,9 @@ class MultiPlanarPredictor:
             # K1 once per plane: all of this rank's slices of the plane in one launch (full-bandwidth
             # granularity: 134 MB of traffic per 256^3 plane instead of 33 MB per batch)
             if exact:
-                xs = ops.slice_gather(vol, p, s_lo, s_hi - s_lo, slice_max_in=maxes[offs[p]: offs[p] + dims[p]])
+                xs = ops.slice_gather(vol, p, s_lo, s_hi - s_lo, interp=self.interp,
+                                      affine=None if self.interp == "exact" else self.affines[p],
+                                      slice_max_in=maxes[offs[p]: offs[p] + dims[p]])
             else:
                 xs, mx = ops.slice_gather(vol, p, s_lo, s_hi - s_lo, interp=self.interp, affine=self.affines[p],
                                           hw=self.out_hw, want_max=True)

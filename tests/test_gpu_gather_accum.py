@@ -68,6 +68,19 @@ def test_gather_affine_bit_exact(ops, mode):
         assert np.array_equal(mx.cpu().numpy(), ref.max((1, 2)))
         ops.slice_normalize_(got, mx)
         assert np.array_equal(got.cpu().numpy()[:, 0], O.normalise_slices(ref))
+    # a volume large enough for the TMA-staged brick kernel (box <= tensor extents): all three standard
+    # grids + two oblique ones, ragged slice ranges
+    vol2, _ = O.phantom(0, seed=4, dims=(48, 40, 64))
+    v2 = torch.from_numpy(vol2).cuda()
+    for i, aff in enumerate(affs):
+        # (H, W one short of the plane extents on the standard grids, so they take the brick kernel and not
+        #  the exact-slicing fast path)
+        H, W = [(39, 64), (48, 63), (47, 40), (40, 64), (37, 61)][i]
+        for (s0, ns) in [(0, 40), (3, 33)]:
+            ref = O.resample_slices(vol2, aff, s0, ns, H, W, mode)
+            got, mx = ops.slice_gather(v2, 0, s0, ns, interp=mode, affine=aff, hw=(H, W), want_max=True)
+            assert np.array_equal(got.cpu().numpy()[:, 0], ref), (mode, i, s0)
+            assert np.array_equal(mx.cpu().numpy(), ref.max((1, 2)))
     # identity grid == exact slicing
     for p in range(3):
         ex = ops.slice_gather(v, p, 0, vol.shape[p])

@@ -61,6 +61,157 @@ struct ConvTcSmem {
   static constexpr int DYN_BYTES = TOTAL;            // base is 1024 B aligned (__align__ + runtime check)
 };
 
+// ------------------------------------------------------------------------------------
+// Epilogue shared by the convolution kernels (warps 2..5, 128 threads, thread = tile row):
+// TMEM -> bias + ReLU -> bf16 -> swizzled smem staging tile -> TMA tensor store, plus the fused
+// 2x2 pooling.  The tile brick is p.TW x p.TH pixels (16 x 8 or 8 x 16): a warp always holds
+// complete pooling windows in lanes {l, l^1, l^TW}.
+// ------------------------------------------------------------------------------------
+struct EpiCtx {
+  uint32_t smem_base, stg_off, bar_tfull, bar_tempty, tmem_base;
+  float* bias_s;
+};
+
+template <int BN, int NSTG>
+__device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCtx& e, const CUtensorMap* tmY0p,
+                                              const CUtensorMap* tmY1p, const CUtensorMap* tmY2p,
+                                              const CUtensorMap* tmY3p, const float* __restrict__ bias,
+                                              __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_pool,
+                                              int total_tiles, int warp, int lane) {
+  const uint32_t smem_base = e.smem_base, bar_tfull = e.bar_tfull, bar_tempty = e.bar_tempty, tmem_base = e.tmem_base;
+  float* bias_s = e.bias_s;
+  constexpr int STG_BYTES = TC_BM * 128;
+  const int et = threadIdx.x - 64;  // 0..127
+  const int q = warp & 3;            // TMEM lane quarter this warp may access
+  const int m = q * 32 + lane;       // row of the tile == pixel index in the brick
+  const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
+  uint32_t iter = 0, stg_count = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
+    const int n_tile = tile % p.n_tiles;
+    int m_tile = tile / p.n_tiles;
+    const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
+    const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
+    const int b0 = m_tile * p.TB;
+    const int n0 = n_tile * BN;
+    const int co_base = (p.ntaps == 4) ? 0 : n0;   // convT: output channel / phase are resolved per 64-column group
+    float* bs = bias_s;
+    named_bar_sync(4, 128);          // every warp is done reading the previous tile's bias
+    for (int i = et; i < BN; i += 128)
+      bs[i] = bias ? __ldg(bias + ((p.ntaps == 4) ? (n0 + i) % p.Cout : n0 + i)) : 0.f;
+    named_bar_sync(1, 128);          // bias visible
+
+    const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
+    const bool valid = (b < p.B) && (h < p.H) && (w < p.W) && !(p.debug & 1);
+    const bool direct = (y != nullptr) && !p.tma_store;      // fallback: per-thread 16 B global stores
+    // fused 2x2 pooling (a warp holds 32 / TW complete image rows of the brick, so every pooling
+    // window lives in lanes {l, l^1, l^TW} of one warp — two shuffles, no extra pass over HBM)
+    const bool pool_writer = (p.pool_mode >= 0) && ((lane & (1 | p.TW)) == 0) && valid;
+    __nv_bfloat16* dstp = nullptr;
+    if (p.pool_mode >= 0)
+      dstp = y_pool + (((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.Cout + co_base;
+
+    mbar_wait(bar_tfull + as * 8, aph);
+    tcgen05_fence_after();
+    const uint32_t tmem_d = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int g0 = 0; g0 < BN; g0 += 64) {
+      const uint32_t stg = smem_base + e.stg_off + (NSTG > 1 ? (stg_count % NSTG) * STG_BYTES : 0);
+      const uint32_t stg_row = stg + m * 128;
+      if (p.tma_store) {
+        // the TMA store that used this staging buffer must have finished READING it before it is rewritten
+        if (et == 0) { if (NSTG > 1) tma_store_wait_read1(); else tma_store_wait_read0(); }
+        named_bar_sync(2, 128);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c0 = g0 + half * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_d + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {
+          // all of this thread's TMEM reads of the stage are done: hand it back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(bar_tempty + as * 8);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v0 = __uint_as_float(r[2 * j]) + bs[c0 + 2 * j];
+          float v1 = __uint_as_float(r[2 * j + 1]) + bs[c0 + 2 * j + 1];
+          if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        if (p.tma_store) {
+          // staging row m, 16-byte chunk (half*4 + j), 128-byte swizzle (chunk ^ (row & 7))
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128_u32(stg_row + ((((half * 4 + j) ^ (m & 7)) & 7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else if (direct && valid) {
+          __nv_bfloat16* dt;
+          if (p.ntaps == 4) {
+            // ConvTranspose2d k2 s2: GEMM column n = (i*2+j)*Cout + co goes to pixel (2h+i, 2w+j)
+            const int n = n0 + c0, ij = n / p.Cout, co = n - ij * p.Cout;
+            dt = y + (((int64_t)b * (2 * p.H) + 2 * h + (ij >> 1)) * (2 * p.W) + 2 * w + (ij & 1)) * p.Cout + co;
+          } else {
+            dt = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base + c0;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dt + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (p.pool_mode == PMU_POOL_MAX) {
+          // max of bf16-rounded values == bf16 rounding of the max (monotonic): exact, packed
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+            uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+            uint32_t au = *reinterpret_cast<uint32_t*>(&a);
+            o = __shfl_xor_sync(0xffffffffu, au, p.TW);
+            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+            pk[j] = *reinterpret_cast<uint32_t*>(&a);
+          }
+        } else if (p.pool_mode == PMU_POOL_AVG_CEIL) {
+          // average of the bf16-stored activations, accumulated in fp32 (what pool2_bf16 computes)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+            float lo = __low2float(a), hi = __high2float(a);
+            lo += __shfl_xor_sync(0xffffffffu, lo, 1);  hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+            lo += __shfl_xor_sync(0xffffffffu, lo, p.TW); hi += __shfl_xor_sync(0xffffffffu, hi, p.TW);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+        if (pool_writer) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dstp + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+      }
+      if (p.tma_store) {
+        fence_proxy_async_smem();      // staging writes (generic proxy) -> visible to the TMA engine
+        named_bar_sync(3, 128);
+        if (et == 0 && !(p.debug & 1)) {
+          // one tensor store per 64-channel group: full 128-byte lines, out-of-bounds pixels clipped by TMA
+          if (p.ntaps == 4) {
+            const int n = n0 + g0, ij = n / p.Cout, co = n - ij * p.Cout;
+            const CUtensorMap* tm = (ij == 0) ? tmY0p : (ij == 1) ? tmY1p : (ij == 2) ? tmY2p : tmY3p;
+            tma_store_4d(tm, stg, co, w0, h0, b0);
+          } else {
+            tma_store_4d(tmY0p, stg, n0 + g0, w0, h0, b0);
+          }
+          tma_store_commit();
+        }
+        ++stg_count;
+      }
+    }
+  }
+  if (p.tma_store && et == 0) tma_store_wait_all();
+}
+
 // Persistent kernel: one CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x,
 // N-tile fastest so concurrently running CTAs share activation bricks in L2).  The smem ring
 // keeps running across tiles (the producer prefetches the next tile's operands while the
@@ -180,135 +331,152 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   } else {
     // =========================== epilogue (warps 2..5) ===========================
-    const int et = threadIdx.x - 64;  // 0..127
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;       // row of the tile == pixel index in the brick
-    const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
-    uint32_t iter = 0, stg_count = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
-      const int n_tile = tile % p.n_tiles;
-      int m_tile = tile / p.n_tiles;
-      const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
-      const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
-      const int b0 = m_tile * p.TB;
-      const int n0 = n_tile * BN;
-      const int co_base = (p.ntaps == 4) ? 0 : n0;   // convT: output channel / phase are resolved per 64-column group
-      float* bs = bias_s;
-      named_bar_sync(4, 128);          // every warp is done reading the previous tile's bias
-      for (int i = et; i < BN; i += 128)
-        bs[i] = bias ? __ldg(bias + ((p.ntaps == 4) ? (n0 + i) % p.Cout : n0 + i)) : 0.f;
-      named_bar_sync(1, 128);          // bias visible
+    EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
+    conv_epilogue<BN, NSTG>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}
 
-      const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
-      const bool valid = (b < p.B) && (h < p.H) && (w < p.W) && !(p.debug & 1);
-      const bool direct = (y != nullptr) && !p.tma_store;      // fallback: per-thread 16 B global stores
-      // fused 2x2 pooling (tile brick 16 x 8: a warp holds image rows 2q and 2q+1, so every pooling
-      // window lives in lanes {l, l^1, l^16} of one warp — two shuffles, no extra pass over HBM)
-      const bool pool_writer = (p.pool_mode >= 0) && ((lane & 17) == 0) && valid;
-      __nv_bfloat16* dstp = nullptr;
-      if (p.pool_mode >= 0)
-        dstp = y_pool + (((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.Cout + co_base;
+// ------------------------------------------------------------------------------------
+// "Row-shift" conv3x3 for the small-N layers (Cout = 64 / 128), where the generic kernel is bound by
+// operand traffic: one A box + one B box per (tap, chunk) is 24 KB per 128 MMA cycles at N = 64 —
+// more bytes in flight than a CTA's shared memory can hold against the L2 latency.
+// Here the tile is 16 rows x 8 px and an A box is the (16+2)-row x 8-px x 64-channel slab
+//   {64 ch, 8, 18, 1} at x-shift dx.  Rows of the box are 128-byte swizzle rows ordered (h, w), so an
+// 8-row swizzle group == one image row and the three dy taps of that dx are the SAME box read through
+// descriptors offset by dy * 1024 B: 3 A loads per 64-channel chunk instead of 9 (A traffic / 2.7).
+// A stage = one A box + the three weight taps (dy = 0..2) of that dx: 12 UMMAs per stage.
+// RESB (Cin == 64, Cout == 64): all nine weight taps (72 KB) stay resident in smem for the whole
+// kernel and only A streams (18 KB per 384 MMA cycles).
+// ------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool RESB>
+struct ConvRsSmem {
+  static constexpr int W_TAP = BN * 128;                           // one tap, one 64-channel chunk: [BN][64] bf16
+  static constexpr int BOX_BYTES = 18 * 8 * 128;                   // 18,432
+  static constexpr int WRES_BYTES = RESB ? 9 * W_TAP : 0;          // resident weights
+  static constexpr int STAGE_BYTES = BOX_BYTES + (RESB ? 0 : 3 * W_TAP);
+  static constexpr int RING_OFF = WRES_BYTES;
+  static constexpr int STG_OFF = RING_OFF + STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + TC_BM * 128;            // full[S], empty[S], tfull[2], tempty[2], wfull
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 5) * 8;
+  static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;
+  static constexpr int DYN_BYTES = BIAS_OFF + BN * 4;
+  static_assert(WRES_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "tiles must stay 1024 B aligned");
+  static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
+};
 
-      mbar_wait(bar_tfull + as * 8, aph);
-      tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int g0 = 0; g0 < BN; g0 += 64) {
-        const uint32_t stg = smem_base + L::STG_OFF + (NSTG > 1 ? (stg_count % NSTG) * L::STG_BYTES : 0);
-        const uint32_t stg_row = stg + m * 128;
-        if (p.tma_store) {
-          // the TMA store that used this staging buffer must have finished READING it before it is rewritten
-          if (et == 0) { if (NSTG > 1) tma_store_wait_read1(); else tma_store_wait_read0(); }
-          named_bar_sync(2, 128);
-        }
+template <int BN, int STAGES, bool RESB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0, const ConvTcParams p,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_pool) {
+  using L = ConvRsSmem<BN, STAGES, RESB>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const uint32_t bar_full = smem_base + L::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;
+  const uint32_t bar_tempty = bar_tfull + 2 * 8;
+  const uint32_t bar_wfull = bar_tempty + 2 * 8;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem_raw + L::TMEM_PTR_OFF);
+  float* bias_s = reinterpret_cast<float*>(smem_raw + L::BIAS_OFF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Cin = p.C0 + p.C1;
+  const int chunks = Cin / TC_BK;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA0);
+    if (p.C1 > 0) prefetch_tensormap(&tmA1);
+    prefetch_tensormap(&tmW);
+    if (p.tma_store) prefetch_tensormap(&tmY0);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + a * 8, 1); mbar_init(bar_tempty + a * 8, 128); }
+    mbar_init(bar_wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(smem_base + L::TMEM_PTR_OFF);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      if (RESB) {   // the nine weight taps, once
+        mbar_arrive_expect_tx(bar_wfull, L::WRES_BYTES);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem_base + tap * L::W_TAP, &tmW, bar_wfull, tap * Cin, 0);
+      }
+      uint32_t kc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
+        const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
+        const int b0 = m_tile;
+        const int n0 = n_tile * BN;
+        for (int ch = 0; ch < chunks; ++ch) {
+          const int c = ch * TC_BK;
+          for (int dx = 0; dx < 3; ++dx, ++kc) {
+            const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1u;
+            mbar_wait(bar_empty + s * 8, ph ^ 1u);
+            const uint32_t sa = smem_base + L::RING_OFF + s * L::STAGE_BYTES;
+            mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+            // rows h0-1 .. h0+16, pixels w0+dx-1 .. +7; out-of-image rows / pixels are zero-filled = conv padding
+            if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx - 1, h0 - 1, b0);
+            else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx - 1, h0 - 1, b0);
+            if (!RESB) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c0 = g0 + half * 32;
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_d + (uint32_t)c0, r);
-          tmem_ld_wait();
-          if (c0 + 32 >= BN) {
-            // all of this thread's TMEM reads of the stage are done: hand it back to the MMA warp
-            tcgen05_fence_before();
-            mbar_arrive(bar_tempty + as * 8);
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v0 = __uint_as_float(r[2 * j]) + bs[c0 + 2 * j];
-            float v1 = __uint_as_float(r[2 * j + 1]) + bs[c0 + 2 * j + 1];
-            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          if (p.tma_store) {
-            // staging row m, 16-byte chunk (half*4 + j), 128-byte swizzle (chunk ^ (row & 7))
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128_u32(stg_row + ((((half * 4 + j) ^ (m & 7)) & 7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          } else if (direct && valid) {
-            __nv_bfloat16* dt;
-            if (p.ntaps == 4) {
-              // ConvTranspose2d k2 s2: GEMM column n = (i*2+j)*Cout + co goes to pixel (2h+i, 2w+j)
-              const int n = n0 + c0, ij = n / p.Cout, co = n - ij * p.Cout;
-              dt = y + (((int64_t)b * (2 * p.H) + 2 * h + (ij >> 1)) * (2 * p.W) + 2 * w + (ij & 1)) * p.Cout + co;
-            } else {
-              dt = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base + c0;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(dt + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-          if (p.pool_mode == PMU_POOL_MAX) {
-            // max of bf16-rounded values == bf16 rounding of the max (monotonic): exact, packed
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-              uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
-              a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-              uint32_t au = *reinterpret_cast<uint32_t*>(&a);
-              o = __shfl_xor_sync(0xffffffffu, au, 16);
-              a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-              pk[j] = *reinterpret_cast<uint32_t*>(&a);
-            }
-          } else if (p.pool_mode == PMU_POOL_AVG_CEIL) {
-            // average of the bf16-stored activations, accumulated in fp32 (what pool2_bf16 computes)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-              float lo = __low2float(a), hi = __high2float(a);
-              lo += __shfl_xor_sync(0xffffffffu, lo, 1);  hi += __shfl_xor_sync(0xffffffffu, hi, 1);
-              lo += __shfl_xor_sync(0xffffffffu, lo, 16); hi += __shfl_xor_sync(0xffffffffu, hi, 16);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int dy = 0; dy < 3; ++dy)
+                tma_load_2d(sa + L::BOX_BYTES + dy * L::W_TAP, &tmW, bar_full + s * 8, (dy * 3 + dx) * Cin + c, n0);
             }
           }
-          if (pool_writer) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(dstp + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-        }
-        if (p.tma_store) {
-          fence_proxy_async_smem();      // staging writes (generic proxy) -> visible to the TMA engine
-          named_bar_sync(3, 128);
-          if (et == 0 && !(p.debug & 1)) {
-            // one tensor store per 64-channel group: full 128-byte lines, out-of-bounds pixels clipped by TMA
-            if (p.ntaps == 4) {
-              const int n = n0 + g0, ij = n / p.Cout, co = n - ij * p.Cout;
-              const CUtensorMap* tm = (ij == 0) ? &tmY0 : (ij == 1) ? &tmY1 : (ij == 2) ? &tmY2 : &tmY3;
-              tma_store_4d(tm, stg, co, w0, h0, b0);
-            } else {
-              tma_store_4d(&tmY0, stg, n0 + g0, w0, h0, b0);
-            }
-            tma_store_commit();
-          }
-          ++stg_count;
         }
       }
     }
-    if (p.tma_store && et == 0) tma_store_wait_all();
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      if (RESB) { mbar_wait(bar_wfull, 0); tcgen05_fence_after(); }
+      uint32_t kc = 0, iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
+        mbar_wait(bar_tempty + as * 8, aph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int ch = 0; ch < chunks; ++ch) {
+          for (int dx = 0; dx < 3; ++dx, ++kc) {
+            const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1u;
+            mbar_wait(bar_full + s * 8, ph);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + L::RING_OFF + s * L::STAGE_BYTES;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              // tap (dy, dx): image rows dy .. dy+15 of the box = +dy swizzle groups of 8 rows (1024 B each)
+              const uint64_t adesc = umma_smem_desc_sw128(sa + dy * 1024);
+              const uint64_t bdesc = umma_smem_desc_sw128(RESB ? smem_base + (dy * 3 + dx) * L::W_TAP
+                                                               : sa + L::BOX_BYTES + dy * L::W_TAP);
+#pragma unroll
+              for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+                umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                          (uint32_t)((ch | dx | dy | k) != 0));
+            }
+            umma_commit(bar_empty + s * 8);
+            if (ch == chunks - 1 && dx == 2) umma_commit(bar_tfull + as * 8);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
+    conv_epilogue<BN, 1>(p, ec, &tmY0, &tmY0, &tmY0, &tmY0, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -447,17 +615,28 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   p.n_tiles = Ntot / BN;
   if (y_pool) {
     PMU_CHECK_ARG(pool_mode == PMU_POOL_MAX || pool_mode == PMU_POOL_AVG_CEIL, "pmu_conv_gemm_pool_bf16: unknown pool mode %d", pool_mode);
-    PMU_CHECK_SUPPORTED(ntaps != 4 && p.TW == 16 && p.TH == 8 && H % 2 == 0 && W % 2 == 0,
-                        "pmu_conv_gemm_pool_bf16: fused pooling needs even H, W >= 16 (got %dx%d)", H, W);
+    PMU_CHECK_SUPPORTED(ntaps != 4 && H % 2 == 0 && W % 2 == 0,
+                        "pmu_conv_gemm_pool_bf16: fused pooling needs even H, W (got %dx%d)", H, W);
     PMU_CHECK_ARG(aligned16(y_pool), "pmu_conv_gemm_pool_bf16: y_pool must be 16-byte aligned");
+  }
+  // small-N 3x3 layers on images >= 16 rows: row-shift kernel (see conv_rs_kernel); PMU_CONV_RS=0 disables
+  static int use_rs = -1;
+  if (use_rs < 0) { const char* e = getenv("PMU_CONV_RS"); use_rs = e ? atoi(e) : 1; }
+  const bool rs = use_rs && variant == -1 && ntaps == 9 && BN <= 128 && H >= 16 && W >= 8 && (!y_pool || (H % 2 == 0 && W % 2 == 0));
+  if (rs) {
+    p.TW = 8; p.TH = 16; p.TB = 1;
+    p.tiles_w = cdiv(W, 8); p.tiles_h = cdiv(H, 16); p.tiles_b = B;
+  } else if (y_pool) {
+    PMU_CHECK_SUPPORTED(p.TW == 16 && p.TH == 8, "pmu_conv_gemm_pool_bf16: fused pooling needs W >= 16, H >= 8 (got %dx%d)", H, W);
   }
   const int64_t grid = (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   PMU_CHECK_ARG(grid > 0 && grid < (1ll << 31), "pmu_conv_gemm_bf16: grid too large");
 
   CUtensorMap a0, a1, wm;
-  int rc = make_act_map(&a0, x0, B, H, W, C0, p.TW, p.TH, p.TB);
+  const int a_th = rs ? p.TH + 2 : p.TH;      // row-shift kernel: the A box carries the two halo rows
+  int rc = make_act_map(&a0, x0, B, H, W, C0, p.TW, a_th, p.TB);
   if (rc) return rc;
-  if (C1 > 0) { rc = make_act_map(&a1, x1, B, H, W, C1, p.TW, p.TH, p.TB); if (rc) return rc; }
+  if (C1 > 0) { rc = make_act_map(&a1, x1, B, H, W, C1, p.TW, a_th, p.TB); if (rc) return rc; }
   else a1 = a0;
   rc = make_w_map(&wm, wpack, Ntot, Ktot, BN);
   if (rc) return rc;
@@ -481,6 +660,19 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
     ym[0] = ym[1] = ym[2] = ym[3] = a0;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (rs) {
+    auto launch_rs = [&](auto kern, int dyn) -> int {
+      PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      const unsigned g = (unsigned)std::min<int64_t>(grid, sm_count());
+      kern<<<g, TC_THREADS, dyn, st>>>(a0, a1, wm, ym[0], p, bias, reinterpret_cast<__nv_bfloat16*>(y),
+                                       reinterpret_cast<__nv_bfloat16*>(y_pool));
+      PMU_LAUNCH_CHECK();
+      return PMU_OK;
+    };
+    if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, true>, ConvRsSmem<64, 6, true>::DYN_BYTES);
+    if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, false>, ConvRsSmem<64, 4, false>::DYN_BYTES);
+    return launch_rs(conv_rs_kernel<128, 3, false>, ConvRsSmem<128, 3, false>::DYN_BYTES);
+  }
   if (variant == 1 || (variant == -1 && BN != 256)) {
     if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
     return launch_conv_tc<64, 4, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);

@@ -246,7 +246,7 @@ fcomb_tc_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict_
 using namespace pmu;
 
 // mma.sync (legacy tensor path) version: used for no_convs_fcomb > 4 and as an A/B reference
-// (PMU_FCOMB_MMA_SYNC=1); the default entry point lives in fcomb_tc5.cu.
+// (PMU_FCOMB_MMA_SYNC=1); the default entry point lives in fcomb_tc6.cu.
 extern "C" int pmu_fcomb_softmax_accum_bf16_mma(const void* feat, const float* mu, const float* sigma,
                                             const float* eps, const float* w0, const float* b0,
                                             const float* wmid, const float* bmid, const float* wlast,

@@ -1,0 +1,518 @@
+// K3 + K4 fused on the 5th-gen tensor cores, version 4 — Fcomb over N latent samples (tcgen05 +
+// TMEM), softmax, per-pixel sum / sum-of-squares.  Per-sample logits never reach HBM.
+//
+// Replaces Fcomb.forward (probabilistic_unet.py:155-181) called once per sample from
+// ProbabilisticUnet.sample (:225-240), the softmax of eval.py:157 and the sample loop of
+// eval.py:146-154.
+//
+// Design (fourth iteration; the earlier tcgen05 version spent 700 instructions per warp per
+// tile-sample, 21 % of its stall samples on tcgen05.st bias pre-fills and four MMA round trips per sample):
+//   * layer 0 leaves the per-sample chain.  h0_n = relu(W0f f + zb_n) with zb_n = W0z z_n + b0:
+//     G = W0f f is ONE UMMA group per tile, read once into registers (fp32); per sample layer 0
+//     is 16 packed fp32 adds (add.f32x2) + 16 cvt.rn.relu.bf16x2 per thread — no MMA, no wait.
+//   * the constant biases ride in the GEMM: every layer's K is extended by one 16-wide UMMA
+//     whose A tile is constant ones and whose B tile holds the bias split into bf16 hi + lo
+//     (16 significand bits, accumulated in fp32).  No tcgen05.st, no bias instructions.
+//   * a 128-pixel tile is worked by 256 threads (two warps per TMEM lane quarter, 32 accumulator
+//     columns each); two samples share one barrier step (pair slot) with their TMEM loads,
+//     packs and stores interleaved; softmax of the pair is split between the two halves.
+//   * two tile groups per CTA x two pair slots = 8 samples in flight per SM (all 512 TMEM
+//     columns), three MMA round trips per sample instead of four.
+//   * flat persistent schedule: one CTA per SM walks a contiguous range of (slice, tile pair).
+// What bounds it now (ncu, profiles/r01c_prof_fcomb6_ncu.txt): SHARED MEMORY bandwidth, not the
+// tensor pipe (28 % active) and not issue slots (43 %).  Per tile-sample the LSU pipe moves ~640
+// wavefronts (activation stores 3 x 16 KB + zb loads) and the UMMAs fetch ~82 KB of operands
+// (A 4 KB + B 2 KB per K=16 step at N=64): ~1300 cycles at 128 B/clk against 1291 measured.
+// The next step is TS-mode UMMAs (activations written back to TMEM as the A operand), which
+// removes the activation stores and the A fetches.
+#include <cudaTypedefs.h>
+
+#include "pmu_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace pmu {
+
+using namespace ptx;
+
+constexpr int F6_F = 64;             // feature width
+constexpr int F6_TG = 2;             // tile groups (tiles in flight) per CTA
+constexpr int F6_SLOTS = 4;          // samples in flight per tile group
+constexpr int F6_PS = F6_SLOTS / 2;  // pair slots: two samples share one barrier step (their work is interleaved)
+constexpr int F6_EPI = 256;          // epilogue threads per tile group
+constexpr int F6_THREADS = F6_TG * F6_EPI + F6_TG * 32;   // + one issuer warp per tile group
+constexpr int F6_NS = 16;            // samples per group (zb vectors held in smem)
+constexpr int F6_MAXL = 16;
+constexpr int F6_MAXC = 8;
+
+// shared memory map (operand tiles 1024 B aligned, rows of 128 B = 64 bf16, 128B swizzle)
+constexpr int F6_TILE = 128 * 128;                 // 16 KB: [128 rows][64 k]
+constexpr int F6_WT = 64 * 128;                    // 8 KB:  [64 rows][64 k]
+constexpr int F6_OFF_W0 = 0;                       // W0f
+constexpr int F6_OFF_WM = F6_OFF_W0 + F6_WT;       // up to 2 mid layers
+constexpr int F6_OFF_WL = F6_OFF_WM + 2 * F6_WT;   // head [16 rows][64 k] (2 KB)
+constexpr int F6_OFF_BMT = F6_OFF_WL + 2048;       // bias tiles of the mid layers: k0 = hi, k1 = lo
+constexpr int F6_OFF_BLT = F6_OFF_BMT + 2 * F6_WT; // bias tile of the head (2 KB)
+constexpr int F6_OFF_ONES = F6_OFF_BLT + 2048;     // [128 rows][64 k]: k0 = k1 = 1
+constexpr int F6_OFF_TG = F6_OFF_ONES + F6_TILE;   // per tile group: F tile, H tile x SLOTS
+constexpr int F6_TG_BYTES = (1 + F6_SLOTS) * F6_TILE;
+constexpr int F6_OFF_ZB = F6_OFF_TG + F6_TG * F6_TG_BYTES;   // fp32 zb[F6_NS][64]
+constexpr int F6_OFF_BAR = F6_OFF_ZB + F6_NS * F6_F * 4;
+constexpr int F6_NBAR_TG = 2 * F6_PS + 3;                    // ready[pair slot], acc[pair slot], tma, g, free
+constexpr int F6_OFF_TPTR = F6_OFF_BAR + F6_TG * F6_NBAR_TG * 8;
+constexpr int F6_SMEM = F6_OFF_TPTR + 16;
+static_assert(F6_OFF_TG % 1024 == 0 && F6_OFF_ONES % 1024 == 0 && F6_OFF_BMT % 1024 == 0 && F6_OFF_BLT % 1024 == 0,
+              "operand tiles must be 1024 B aligned");
+static_assert(F6_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(F6_TG * F6_SLOTS * 64 <= 512, "TMEM budget");
+
+struct Fcomb6Params {
+  int N, L, C, nmid, B;
+  int64_t HW;
+};
+
+__device__ __forceinline__ uint32_t f6_sw128_off(int row, int k) {
+  return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+__device__ __forceinline__ void f6_st_bf16(uint8_t* tile, int row, int k, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(tile + f6_sw128_off(row, k)) = __float2bfloat16(v);
+}
+// ReLU + round-to-nearest bf16 pack of two fp32 values in ONE instruction (lo -> bits 0..15)
+__device__ __forceinline__ uint32_t f6_pack_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// relu(a + b) of two fp32 pairs -> packed bf16x2: one packed add (add.f32x2) + one cvt
+__device__ __forceinline__ uint32_t f6_add_pack_relu(float a0, float a1, float b0, float b1) {
+  uint32_t d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
+      "mov.b64 ra, {%1, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {lo, hi}, rd;\n\t"
+      "cvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}"
+      : "=r"(d)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+  return d;
+}
+__device__ __forceinline__ float4 f6_lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void f6_tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void f6_tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// one dense layer: D[tmem] = A[128 x 64] * W[NOUT x 64]^T + 1 * bias^T   (4 + 1 UMMAs)
+__device__ __forceinline__ void f6_issue_layer(uint32_t tmem_d, uint32_t a_tile, uint32_t w_tile, uint32_t ones_tile,
+                                               uint32_t b_tile, uint32_t idesc, bool with_bias) {
+  const uint64_t ad = umma_smem_desc_sw128(a_tile), wd = umma_smem_desc_sw128(w_tile);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+  if (with_bias) umma_bf16(tmem_d, umma_smem_desc_sw128(ones_tile), umma_smem_desc_sw128(b_tile), idesc, 1u);
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(F6_THREADS, 1)
+fcomb_tc6_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb6Params p, const float* __restrict__ mu,
+                 const float* __restrict__ sigma, const float* __restrict__ eps, const float* __restrict__ w0,
+                 const float* __restrict__ b0, const float* __restrict__ wmid, const float* __restrict__ bmid,
+                 const float* __restrict__ wlast, const float* __restrict__ blast,
+                 float* __restrict__ slice_sums) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  uint8_t* sgen = smem_raw;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, L = p.L, C = p.C, nmid = p.nmid;
+  const int64_t HW = p.HW;
+  if ((sbase & 1023u) != 0) __trap();   // UMMA/TMA tiles need 1024 B alignment
+
+  auto bar_ready = [&](int g, int s) { return sbase + F6_OFF_BAR + (g * F6_NBAR_TG + s) * 8; };
+  auto bar_acc = [&](int g, int s) { return sbase + F6_OFF_BAR + (g * F6_NBAR_TG + F6_PS + s) * 8; };
+  auto bar_tma = [&](int g) { return sbase + F6_OFF_BAR + (g * F6_NBAR_TG + 2 * F6_PS) * 8; };
+  auto bar_g = [&](int g) { return sbase + F6_OFF_BAR + (g * F6_NBAR_TG + 2 * F6_PS + 1) * 8; };
+  auto bar_free = [&](int g) { return sbase + F6_OFF_BAR + (g * F6_NBAR_TG + 2 * F6_PS + 2) * 8; };
+  volatile uint32_t* tptr = reinterpret_cast<volatile uint32_t*>(sgen + F6_OFF_TPTR);
+
+  // ---------------- one-time setup: barriers, TMEM, weight / bias / ones tiles ----------------
+  if (tid == 0) {
+    prefetch_tensormap(&tmF);
+    for (int g = 0; g < F6_TG; ++g) {
+      for (int s = 0; s < F6_PS; ++s) { mbar_init(bar_ready(g, s), F6_EPI); mbar_init(bar_acc(g, s), 1); }
+      mbar_init(bar_tma(g), 1);
+      mbar_init(bar_g(g), 1);
+      mbar_init(bar_free(g), F6_EPI);
+    }
+    fence_barrier_init();
+  }
+  if (warp == F6_TG * 8) tmem_alloc<512>(sbase + F6_OFF_TPTR);   // first issuer warp owns the allocation
+  for (int i = tid; i < F6_OFF_TG / 16; i += F6_THREADS) reinterpret_cast<uint4*>(sgen)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = tid; i < F6_F * F6_F; i += F6_THREADS) {
+    const int o = i >> 6, k = i & 63;
+    f6_st_bf16(sgen + F6_OFF_W0, o, k, __ldg(w0 + (int64_t)o * (F6_F + L) + k));
+    for (int m = 0; m < nmid; ++m) f6_st_bf16(sgen + F6_OFF_WM + m * F6_WT, o, k, __ldg(wmid + (int64_t)m * F6_F * F6_F + i));
+  }
+  for (int i = tid; i < C * F6_F; i += F6_THREADS) f6_st_bf16(sgen + F6_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
+  // bias tiles: column 0 = bf16(b), column 1 = bf16(b - bf16(b)); ones tile: columns 0, 1 = 1
+  for (int i = tid; i < nmid * F6_F; i += F6_THREADS) {
+    const float bv = __ldg(bmid + i);
+    const float hi = __bfloat162float(__float2bfloat16(bv));
+    f6_st_bf16(sgen + F6_OFF_BMT + (i >> 6) * F6_WT, i & 63, 0, hi);
+    f6_st_bf16(sgen + F6_OFF_BMT + (i >> 6) * F6_WT, i & 63, 1, bv - hi);
+  }
+  for (int i = tid; i < C; i += F6_THREADS) {
+    const float bv = __ldg(blast + i);
+    const float hi = __bfloat162float(__float2bfloat16(bv));
+    f6_st_bf16(sgen + F6_OFF_BLT, i, 0, hi);
+    f6_st_bf16(sgen + F6_OFF_BLT, i, 1, bv - hi);
+  }
+  for (int i = tid; i < 128; i += F6_THREADS) {
+    f6_st_bf16(sgen + F6_OFF_ONES, i, 0, 1.f);
+    f6_st_bf16(sgen + F6_OFF_ONES, i, 1, 1.f);
+  }
+  float* zb_s = reinterpret_cast<float*>(sgen + F6_OFF_ZB);
+  fence_proxy_async_smem();                         // tiles written by the generic proxy -> visible to the tensor core
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tptr;
+
+  // flat persistent schedule over (slice, tile pair)
+  // (the launcher guarantees B * HW < 2^31, so tile / pair indices fit 32 bits)
+  const int tiles = (int)((HW + 127) / 128);
+  const int pps = (tiles + F6_TG - 1) / F6_TG;            // tile pairs per slice
+  const int64_t total = (int64_t)p.B * pps;
+  const int cta_lo = (int)(total * blockIdx.x / gridDim.x), cta_hi = (int)(total * (blockIdx.x + 1) / gridDim.x);
+
+  // barrier phase parities (bit s = slot s)
+  uint32_t phr = 0, pha = 0, pht = 0, phg = 0, phf = 0;
+  bool first_tile = true;
+
+  for (int seg0 = cta_lo; seg0 < cta_hi;) {
+    const int b = seg0 / pps;
+    const int seg1 = ((b + 1) * pps < cta_hi) ? (b + 1) * pps : cta_hi;
+    const int pr0 = seg0 - b * pps, pr1 = seg1 - b * pps;   // pair range inside slice b
+    for (int n0 = 0; n0 < N; n0 += F6_NS) {
+      const int ng = (N - n0 < F6_NS) ? N - n0 : F6_NS;
+      // ---- per-sample layer-0 bias vectors zb_n = W0z z_n + b0 of this slice / sample group (fp32) ----
+      __syncthreads();                                  // everyone is done with the previous vectors
+      for (int i = tid; i < ng * F6_F; i += F6_THREADS) {
+        const int n = i >> 6, o = i & 63;
+        float s = __ldg(b0 + o);
+        for (int l = 0; l < L; ++l) {
+          // z = mu + sigma * eps   (Normal.rsample, probabilistic_unet.py:233)
+          const float z = __fadd_rn(__ldg(mu + (int64_t)b * L + l),
+                                    __fmul_rn(__ldg(sigma + (int64_t)b * L + l), __ldg(eps + ((int64_t)b * N + n0 + n) * L + l)));
+          s = fmaf(__ldg(w0 + (int64_t)o * (F6_F + L) + F6_F + l), z, s);
+        }
+        zb_s[i] = s;
+      }
+      __syncthreads();
+      const int rounds = (ng + F6_SLOTS - 1) / F6_SLOTS;
+
+      if (warp >= F6_TG * 8) {
+        // ============ issuer of tile group g (lane 0: its barrier phases persist across groups) ============
+        if (lane == 0) {
+          const int g = warp - F6_TG * 8;
+          constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64), idesc16 = umma_idesc_bf16(128, 16);
+          const uint32_t sW0 = sbase + F6_OFF_W0, sWM = sbase + F6_OFF_WM, sWL = sbase + F6_OFF_WL;
+          const uint32_t sBM = sbase + F6_OFF_BMT, sBL = sbase + F6_OFF_BLT, sONES = sbase + F6_OFF_ONES;
+          const uint32_t sF = sbase + F6_OFF_TG + g * F6_TG_BYTES;
+          const uint32_t t_g = tmem_base + (g * F6_SLOTS) * 64;
+          bool f_in_flight = false;
+          for (int pr = pr0; pr < pr1; ++pr) {
+            const int t = pr * F6_TG + g;
+            if (t >= tiles) continue;
+            if (!f_in_flight) {
+              mbar_arrive_expect_tx(bar_tma(g), F6_TILE);
+              tma_load_2d(sF, &tmF, bar_tma(g), 0, (int)((int64_t)b * HW + (int64_t)t * 128));
+            }
+            f_in_flight = false;
+            // the previous tile's last TMEM reads (head logits) are done before slot 0 is overwritten
+            if (!first_tile) { mbar_wait(bar_free(g), phf); phf ^= 1u; }
+            first_tile = false;
+            mbar_wait(bar_tma(g), pht); pht ^= 1u;
+            tcgen05_fence_after();
+            f6_issue_layer(t_g, sF, sW0, 0, 0, idesc64, false);     // G = F W0f^T  -> slot 0's accumulator
+            umma_commit(bar_g(g));
+            mbar_wait(bar_g(g), phg); phg ^= 1u;                    // F consumed: prefetch the next tile's F
+            if (pr + 1 < pr1 && (pr + 1) * F6_TG + g < tiles) {
+              mbar_arrive_expect_tx(bar_tma(g), F6_TILE);
+              tma_load_2d(sF, &tmF, bar_tma(g), 0, (int)((int64_t)b * HW + (int64_t)((pr + 1) * F6_TG + g) * 128));
+              f_in_flight = true;
+            }
+            for (int r = 0; r < rounds; ++r) {
+              for (int layer = 1; layer <= nmid + 1; ++layer) {        // 1..nmid: mid layers; nmid+1: head
+#pragma unroll
+                for (int ps = 0; ps < F6_PS; ++ps) {
+                  const int nA = r * F6_SLOTS + ps * 2;
+                  if (nA >= ng) continue;
+                  const bool has_b = nA + 1 < ng;
+                  const uint32_t t_acc = tmem_base + (g * F6_SLOTS + ps * 2) * 64;
+                  const uint32_t sH = sF + (1 + ps * 2) * F6_TILE;
+                  mbar_wait(bar_ready(g, ps), (phr >> ps) & 1u); phr ^= 1u << ps;   // H written, accumulators drained
+                  tcgen05_fence_after();
+                  if (layer <= nmid) {
+                    const uint32_t sW = sWM + (layer - 1) * F6_WT, sB = sBM + (layer - 1) * F6_WT;
+                    f6_issue_layer(t_acc, sH, sW, sONES, sB, idesc64, true);
+                    if (has_b) f6_issue_layer(t_acc + 64, sH + F6_TILE, sW, sONES, sB, idesc64, true);
+                  } else {
+                    f6_issue_layer(t_acc, sH, sWL, sONES, sBL, idesc16, true);
+                    if (has_b) f6_issue_layer(t_acc + 64, sH + F6_TILE, sWL, sONES, sBL, idesc16, true);
+                  }
+                  umma_commit(bar_acc(g, ps));
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      } else {
+        // ============ tile group g: one tile, F6_SLOTS samples in flight, 256 threads ============
+        const int g = warp >> 3, wi = warp & 7;
+        const int q4 = wi & 3, half = wi >> 2;
+        const int row = q4 * 32 + lane;                            // TMEM lane == pixel row of the tile
+        const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+        // the 4 swizzled 16-byte slots of this thread's 32 columns inside an H tile row (loop invariant)
+        uint32_t hoff[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hoff[c] = row * 128 + ((((half * 4 + c) ^ (row & 7)) & 7) << 4);
+        const uint32_t sHbase = sbase + F6_OFF_TG + g * F6_TG_BYTES + F6_TILE;
+        const uint32_t sZB = sbase + F6_OFF_ZB + half * 32 * 4;
+        const uint32_t t_tg = tmem_base + (g * F6_SLOTS) * 64 + lane_off;
+        float* scratch = reinterpret_cast<float*>(sgen + F6_OFF_TG + g * F6_TG_BYTES + F6_TILE);   // = H tile of slot 0
+
+        for (int pr = pr0; pr < pr1; ++pr) {
+          const int t = pr * F6_TG + g;
+          if (t >= tiles) continue;
+          const int64_t pix = (int64_t)t * 128 + row;
+          float s1[CMAX], s2[CMAX];
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c) s1[c] = s2[c] = 0.f;
+          // G = W0f f of this tile: this thread's 32 columns, kept in registers for all samples
+          uint32_t G[32];
+          mbar_wait(bar_g(g), phg); phg ^= 1u;
+          tcgen05_fence_after();
+          tmem_ld_32x32(t_tg + half * 32, G);
+          tmem_ld_wait();
+
+          for (int r = 0; r < rounds; ++r) {
+            // ---- layer 0 in registers: h0 = relu(G + zb_n), both samples of a pair slot ----
+#pragma unroll
+            for (int ps = 0; ps < F6_PS; ++ps) {
+              const int nA = r * F6_SLOTS + ps * 2;
+              if (nA >= ng) continue;
+              const bool has_b = nA + 1 < ng;
+              const uint32_t sHA = sHbase + (ps * 2) * F6_TILE, sHB = sHA + F6_TILE;
+              const uint32_t zbA = sZB + nA * F6_F * 4, zbB = zbA + F6_F * 4;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {                          // chunks of 8 channels = 16 B each
+                const float4 za = f6_lds128f(zbA + c * 32), zc = f6_lds128f(zbA + c * 32 + 16);
+                sts128_u32(sHA + hoff[c],
+                           f6_add_pack_relu(__uint_as_float(G[c * 8 + 0]), __uint_as_float(G[c * 8 + 1]), za.x, za.y),
+                           f6_add_pack_relu(__uint_as_float(G[c * 8 + 2]), __uint_as_float(G[c * 8 + 3]), za.z, za.w),
+                           f6_add_pack_relu(__uint_as_float(G[c * 8 + 4]), __uint_as_float(G[c * 8 + 5]), zc.x, zc.y),
+                           f6_add_pack_relu(__uint_as_float(G[c * 8 + 6]), __uint_as_float(G[c * 8 + 7]), zc.z, zc.w));
+                if (has_b) {
+                  const float4 ya = f6_lds128f(zbB + c * 32), yc = f6_lds128f(zbB + c * 32 + 16);
+                  sts128_u32(sHB + hoff[c],
+                             f6_add_pack_relu(__uint_as_float(G[c * 8 + 0]), __uint_as_float(G[c * 8 + 1]), ya.x, ya.y),
+                             f6_add_pack_relu(__uint_as_float(G[c * 8 + 2]), __uint_as_float(G[c * 8 + 3]), ya.z, ya.w),
+                             f6_add_pack_relu(__uint_as_float(G[c * 8 + 4]), __uint_as_float(G[c * 8 + 5]), yc.x, yc.y),
+                             f6_add_pack_relu(__uint_as_float(G[c * 8 + 6]), __uint_as_float(G[c * 8 + 7]), yc.z, yc.w));
+                }
+              }
+              fence_proxy_async_smem();                            // H (generic proxy) -> async proxy
+              tcgen05_fence_before();                              // (also orders the previous logits / G reads)
+              mbar_arrive(bar_ready(g, ps));
+            }
+            // ---- mid layers: accumulators -> relu -> bf16 -> H; the pair's two samples interleaved ----
+            for (int layer = 1; layer <= nmid; ++layer) {
+#pragma unroll
+              for (int ps = 0; ps < F6_PS; ++ps) {
+                const int nA = r * F6_SLOTS + ps * 2;
+                if (nA >= ng) continue;
+                const bool has_b = nA + 1 < ng;
+                const uint32_t sHA = sHbase + (ps * 2) * F6_TILE, sHB = sHA + F6_TILE;
+                const uint32_t tA = t_tg + ps * 128 + half * 32;
+                mbar_wait(bar_acc(g, ps), (pha >> ps) & 1u); pha ^= 1u << ps;   // this layer's accumulators are complete
+                tcgen05_fence_after();
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {                     // 2 x 16 columns per sample (G holds 32 registers)
+                  uint32_t ra[16], rb[16];
+                  f6_tmem_ld_32x16(tA + h2 * 16, ra);
+                  if (has_b) f6_tmem_ld_32x16(tA + 64 + h2 * 16, rb);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int c = 0; c < 2; ++c)
+                    sts128_u32(sHA + hoff[h2 * 2 + c],
+                               f6_pack_relu(__uint_as_float(ra[c * 8 + 0]), __uint_as_float(ra[c * 8 + 1])),
+                               f6_pack_relu(__uint_as_float(ra[c * 8 + 2]), __uint_as_float(ra[c * 8 + 3])),
+                               f6_pack_relu(__uint_as_float(ra[c * 8 + 4]), __uint_as_float(ra[c * 8 + 5])),
+                               f6_pack_relu(__uint_as_float(ra[c * 8 + 6]), __uint_as_float(ra[c * 8 + 7])));
+                  if (has_b) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                      sts128_u32(sHB + hoff[h2 * 2 + c],
+                                 f6_pack_relu(__uint_as_float(rb[c * 8 + 0]), __uint_as_float(rb[c * 8 + 1])),
+                                 f6_pack_relu(__uint_as_float(rb[c * 8 + 2]), __uint_as_float(rb[c * 8 + 3])),
+                                 f6_pack_relu(__uint_as_float(rb[c * 8 + 4]), __uint_as_float(rb[c * 8 + 5])),
+                                 f6_pack_relu(__uint_as_float(rb[c * 8 + 6]), __uint_as_float(rb[c * 8 + 7])));
+                  }
+                }
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                mbar_arrive(bar_ready(g, ps));
+              }
+            }
+            // ---- head logits -> softmax -> accumulate: half 0 takes the pair's first sample, half 1 the second ----
+#pragma unroll
+            for (int ps = 0; ps < F6_PS; ++ps) {
+              const int nA = r * F6_SLOTS + ps * 2;
+              if (nA >= ng) continue;
+              mbar_wait(bar_acc(g, ps), (pha >> ps) & 1u); pha ^= 1u << ps;
+              tcgen05_fence_after();
+              if (nA + half < ng) {
+                uint32_t hr[8];
+                f6_tmem_ld_32x8(t_tg + ps * 128 + half * 64, hr);
+                tmem_ld_wait();
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) if (c < C) mx = fmaxf(mx, __uint_as_float(hr[c]));
+                float e[CMAX], den = 0.f;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) { e[c] = (c < C) ? __expf(__uint_as_float(hr[c]) - mx) : 0.f; den += e[c]; }
+                const float inv = __fdividef(1.f, den);
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) { const float pr_ = e[c] * inv; s1[c] += pr_; s2[c] = fmaf(pr_, pr_, s2[c]); }
+              }
+            }
+          }
+          // ---- tile done: slot 0 may be overwritten by the next tile's G; combine the halves' sums ----
+          tcgen05_fence_before();
+          mbar_arrive(bar_free(g));
+          if (half == 1) {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) { scratch[(2 * c) * 128 + row] = s1[c]; scratch[(2 * c + 1) * 128 + row] = s2[c]; }
+          }
+          named_bar_sync(1 + g, F6_EPI);
+          if (half == 0) {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) { s1[c] += scratch[(2 * c) * 128 + row]; s2[c] += scratch[(2 * c + 1) * 128 + row]; }
+            if (pix < HW) {
+              float* o1 = slice_sums + ((int64_t)b * 2 + 0) * C * HW + pix;
+              float* o2 = slice_sums + ((int64_t)b * 2 + 1) * C * HW + pix;
+#pragma unroll
+              for (int c = 0; c < CMAX; ++c)
+                if (c < C) {
+                  if (n0 == 0) { o1[(int64_t)c * HW] = s1[c]; o2[(int64_t)c * HW] = s2[c]; }
+                  else { o1[(int64_t)c * HW] += s1[c]; o2[(int64_t)c * HW] += s2[c]; }
+                }
+            }
+          }
+          named_bar_sync(1 + g, F6_EPI);      // scratch consumed before the next tile's layer 0 rewrites H[0]
+        }
+      }
+    }
+    seg0 = seg1;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == F6_TG * 8) tmem_dealloc<512>(tmem_base);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 f6_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace pmu
+
+using namespace pmu;
+
+static int fcomb_v4_launch(const void* feat, const float* mu, const float* sigma,
+                                               const float* eps, const float* w0, const float* b0,
+                                               const float* wmid, const float* bmid, const float* wlast,
+                                               const float* blast, float* slice_sums, int B, int N, int L,
+                                               int C, int nl, int64_t HW, void* stream) {
+  auto fn = f6_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
+  CUtensorMap tmF;
+  cuuint64_t dims[2] = {(cuuint64_t)F6_F, (cuuint64_t)((int64_t)B * HW)};
+  cuuint64_t strides[1] = {(cuuint64_t)F6_F * 2};
+  cuuint32_t box[2] = {(cuuint32_t)F6_F, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&tmF, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(feat), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(features) failed: %d", (int)r); return PMU_ERR_CUDA; }
+
+  Fcomb6Params p;
+  p.N = N; p.L = L; p.C = C; p.nmid = nl - 2; p.HW = HW; p.B = B;
+  const int64_t tiles = (HW + 127) / 128, pps = (tiles + F6_TG - 1) / F6_TG;
+  const int64_t total = (int64_t)B * pps;
+  const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());     // one persistent CTA per SM
+  if (C <= 4) {
+    PMU_CUDA(cudaFuncSetAttribute(fcomb_tc6_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F6_SMEM));
+    fcomb_tc6_kernel<4><<<grid, F6_THREADS, F6_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid,
+                                                                            wlast, blast, slice_sums);
+  } else {
+    PMU_CUDA(cudaFuncSetAttribute(fcomb_tc6_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, F6_SMEM));
+    fcomb_tc6_kernel<8><<<grid, F6_THREADS, F6_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid,
+                                                                            wlast, blast, slice_sums);
+  }
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+// implemented in fcomb_tc.cu (register-chained mma.sync version, kept as the nmid > 2 path)
+extern "C" int pmu_fcomb_softmax_accum_bf16_mma(const void* feat, const float* mu, const float* sigma,
+                                                const float* eps, const float* w0, const float* b0,
+                                                const float* wmid, const float* bmid, const float* wlast,
+                                                const float* blast, float* slice_sums, int B, int N, int L,
+                                                int C, int nl, int64_t HW, void* stream);
+
+extern "C" int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, const float* sigma,
+                                            const float* eps, const float* w0, const float* b0,
+                                            const float* wmid, const float* bmid, const float* wlast,
+                                            const float* blast, float* slice_sums, int B, int N, int L,
+                                            int C, int nl, int64_t HW, void* stream) {
+  PMU_CHECK_ARG(feat && mu && sigma && eps && w0 && b0 && wlast && blast && slice_sums,
+                "pmu_fcomb_softmax_accum_bf16: null pointer");
+  PMU_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && HW > 0, "pmu_fcomb_softmax_accum_bf16: bad shape");
+  PMU_CHECK_ARG(nl >= 2 && (nl == 2 || (wmid && bmid)), "pmu_fcomb_softmax_accum_bf16: no_convs_fcomb >= 2; mid weights needed for > 2");
+  PMU_CHECK_SUPPORTED(L >= 1 && L <= F6_MAXL && C >= 1 && C <= F6_MAXC, "pmu_fcomb_softmax_accum_bf16: needs L <= 16, C <= 8 (got L=%d C=%d)", L, C);
+  const int nmid = nl - 2;
+  static int use_mma = -1;
+  if (use_mma < 0) { const char* e = getenv("PMU_FCOMB_MMA_SYNC"); use_mma = (e && atoi(e)) ? 1 : 0; }
+  if (nmid > 2 || use_mma || !aligned16(feat) || (int64_t)B * HW >= (1ll << 31))
+    return pmu_fcomb_softmax_accum_bf16_mma(feat, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums,
+                                            B, N, L, C, nl, HW, stream);
+  int cc_major = 0, dev = 0;
+  PMU_CUDA(cudaGetDevice(&dev));
+  PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  PMU_CHECK_SUPPORTED(cc_major == 10, "pmu_fcomb_softmax_accum_bf16: needs an sm_100 device; found cc %d.x", cc_major);
+
+  return fcomb_v4_launch(feat, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums, B, N, L, C, nl, HW, stream);
+}

@@ -197,12 +197,15 @@ def test_pool_head_transpose_bf16(ops):
     torch.testing.assert_close(torch.cat([mu, ls], 1).cpu(), ml, atol=1e-4, rtol=1e-4)
 
 
-@pytest.mark.parametrize("nl,N,C", [(4, 5, 3), (2, 1, 3), (3, 16, 2), (4, 20, 3), (5, 3, 3)])
-def test_fcomb_softmax_accum_bf16(ops, nl, N, C):
-    """Fused tensor-core fcomb vs the fp32 oracle: probabilities within the bf16 budget 2e-2."""
+@pytest.mark.parametrize("nl,N,C,B,H,W", [(4, 5, 3, 3, 20, 24), (2, 1, 3, 3, 20, 24), (3, 16, 2, 3, 20, 24),
+                                          (4, 20, 3, 3, 20, 24), (5, 3, 3, 3, 20, 24),
+                                          (4, 6, 3, 5, 96, 100),     # 190 tile pairs > 148 SMs: CTAs walk several
+                                          (3, 18, 4, 7, 72, 72)])    # pairs and cross slice boundaries; 2 sample groups
+def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W):
+    """Fused tensor-core fcomb vs the fp32 oracle: probabilities within the bf16 budget 2e-2.
+    HW = 480 is ragged against the 128-pixel tile."""
     sd = O.make_state_dict((64, 128), num_classes=C, latent_dim=6, no_convs_fcomb=nl, seed=10)
     g = _g(11)
-    B, H, W = 3, 20, 24                       # HW = 480: ragged vs the 512-pixel block
     feat = _bf(torch.relu(torch.randn(B, 64, H, W, generator=g)))
     mu = torch.randn(B, 6, generator=g)
     sigma = torch.rand(B, 6, generator=g) + 0.2

@@ -203,6 +203,60 @@ int pmu_dice_sums(const float* pred, const float* target, int64_t n, float* sums
 int pmu_argmax_dice_sums(const float* prob, const float* truth, int64_t X, int C, int64_t YZ,
                          float* sums, void* stream);
 
+/* ---- training step, fp32 NCHW parity mode (train.py:85-110) ---------- *
+ * What autograd does for the reference, as explicit kernels.  Data gradients of conv3x3 / conv1x1
+ * reuse pmu_conv3x3_f32 / pmu_conv1x1_f32 with transposed (+ flipped) weights.  `ws` is a caller-
+ * owned scratch of 2*C doubles.  Weight-gradient entry points ADD into dw (zero-fill first).   */
+
+/* nn.BatchNorm2d in training mode (+ReLU) (unet_parts.py:16-17, probabilistic_unet.py:39-40):
+ * mean/var[C] = batch statistics of y[B,C,HW] (biased variance); a = [relu](gamma*(y-mean)/sqrt(var+eps)+beta);
+ * run_mean/run_var (nullable) updated with `momentum` (unbiased variance), as torch does. */
+int pmu_bn_train_fwd_f32(const float* y, const float* gamma, const float* beta, float eps, int relu,
+                         float momentum, float* run_mean, float* run_var, float* mean, float* var,
+                         float* a, double* ws, int B, int C, int64_t HW, void* stream);
+/* backward of the above: da -> dy[B,C,HW], dgamma[C], dbeta[C] (overwritten; nullable). */
+int pmu_bn_train_bwd_f32(const float* da, const float* y, const float* mean, const float* var,
+                         const float* gamma, const float* beta, float eps, int relu, float* dy,
+                         float* dgamma, float* dbeta, double* ws, int B, int C, int64_t HW, void* stream);
+/* out[c] = sum_{b,p} x[b,c,p] (conv bias gradients); out[r] = sum_p x[r,p]. */
+int pmu_channel_sums_f32(const float* x, float* out, double* ws, int B, int C, int64_t HW, void* stream);
+int pmu_row_sums_f32(const float* x, float* out, int64_t rows, int64_t n, void* stream);
+/* dw[Cout,C0+C1,3,3] += sum_{b,h,w} dy[b,co,h,w] * cat(x0,x1)[b,ci,h+ky-1,w+kx-1]  (nn.Conv2d weight grad). */
+int pmu_conv3x3_wgrad_f32(const float* x0, int C0, const float* x1, int C1, const float* dy, float* dw,
+                          int B, int H, int W, int Cout, void* stream);
+/* dw[co*ldw + ci] += sum_{b,p} dy[b,co,p] * x[b,ci,p]  (1x1 conv weight grad; ldw >= Cin). */
+int pmu_conv1x1_wgrad_f32(const float* x, const float* dy, float* dw, int ldw, int B, int Cin, int Cout,
+                          int64_t HW, void* stream);
+/* MaxPool2d(2) / AvgPool2d(2,2,ceil_mode) backward: x[B,C,H,W] (max only), dy pooled -> dx[B,C,H,W]. */
+int pmu_pool2_bwd_f32(const float* x, const float* dy, float* dx, int B, int C, int H, int W, int mode,
+                      void* stream);
+/* nn.ConvTranspose2d(k=2,s=2) backward (unet_parts.py:52): dy[B,Cout,2H,2W], w[Cin,Cout,2,2]. */
+int pmu_convt2x2_dgrad_f32(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H,
+                           int W, void* stream);
+int pmu_convt2x2_wgrad_f32(const float* x, const float* dy, float* dw, int B, int Cin, int Cout, int H,
+                           int W, void* stream);
+/* dx = dy * (a > 0);  dst += src. */
+int pmu_relu_bwd_f32(const float* a, const float* dy, float* dx, int64_t n, void* stream);
+int pmu_add_f32(float* dst, const float* src, int64_t n, void* stream);
+/* d(sum CE)/dlogits * scale = scale * (softmax - onehot(target))   (probabilistic_unet.py:288,303-304). */
+int pmu_ce_bwd_f32(const float* logits, const float* target, float scale, float* dlogits, int B, int C,
+                   int64_t HW, void* stream);
+/* gradients of scale * sum_b KL(q||p) w.r.t. mu / log_sigma of both Gaussians (probabilistic_unet.py:272). */
+int pmu_kl_bwd_f32(const float* mu_q, const float* ls_q, const float* mu_p, const float* ls_p, float scale,
+                   float* dmu_q, float* dls_q, float* dmu_p, float* dls_p, int B, int L, void* stream);
+/* backward of pmu_gauss_head_f32 (probabilistic_unet.py:97-108): denc[B,C,h,w] overwritten; dw[2L,C], db[2L] += . */
+int pmu_gauss_head_bwd_f32(const float* enc, const float* w, const float* dmu, const float* dls, float* denc,
+                           float* dw, float* db, int B, int C, int h, int w_, int L, void* stream);
+/* Fcomb layer 0 split (probabilistic_unet.py:155-181): zb[b,co] = b0[co] + sum_l w0[co,F+l] z[b,l];
+ * backward from rs[b,co] = sum_p dh0[b,co,p]: dz[B,L] overwritten; dw0[:,F:], db0 += . */
+int pmu_fcomb_zbias_f32(const float* z, const float* w0, const float* b0, float* zb, int B, int F, int L,
+                        void* stream);
+int pmu_fcomb_zbias_bwd_f32(const float* rs, const float* z, const float* w0, float* dz, float* dw0,
+                            float* db0, int B, int F, int L, void* stream);
+/* y[b,co,p] = [relu](sum_ci w[co*ldw+ci] x[b,ci,p] + bias[b*bias_bstride+co])  (bias nullable). */
+int pmu_conv1x1_bb_f32(const float* x, const float* w, int ldw, const float* bias, int bias_bstride, float* y,
+                       int B, int Cin, int Cout, int64_t HW, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,23 @@ _SIG = {
     "pmu_kl_diag_gauss": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
     "pmu_dice_sums": (c_int, [_P, _P, c_int64, _P, _P]),
     "pmu_argmax_dice_sums": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P]),
+    "pmu_bn_train_fwd_f32": (c_int, [_P, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _P]),
+    "pmu_bn_train_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, c_int, c_int, c_int64, _P]),
+    "pmu_channel_sums_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int64, _P]),
+    "pmu_row_sums_f32": (c_int, [_P, _P, c_int64, c_int64, _P]),
+    "pmu_conv3x3_wgrad_f32": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "pmu_conv1x1_wgrad_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int64, _P]),
+    "pmu_pool2_bwd_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_convt2x2_dgrad_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_convt2x2_wgrad_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_relu_bwd_f32": (c_int, [_P, _P, _P, c_int64, _P]),
+    "pmu_add_f32": (c_int, [_P, _P, c_int64, _P]),
+    "pmu_ce_bwd_f32": (c_int, [_P, _P, c_float, _P, c_int, c_int, c_int64, _P]),
+    "pmu_kl_bwd_f32": (c_int, [_P, _P, _P, _P, c_float, _P, _P, _P, _P, c_int, c_int, _P]),
+    "pmu_gauss_head_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_fcomb_zbias_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "pmu_fcomb_zbias_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "pmu_conv1x1_bb_f32": (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
 }
 
 

@@ -15,9 +15,11 @@ these containers is ever called.  Execution goes PackedNet -> ops -> C-ABI.  The
 CPU / eager fallback: tensors must live on a CUDA device and the extension must be built.
 
 Differences from the (partly broken) reference, all listed in DESIGN.md:
-  * inference uses eval-mode BatchNorm (folded); the backward pass / train-mode BN kernels
-    are the next scope row — calling with autograd enabled on parameters
-    that require grad raises NotImplementedError instead of silently falling back to ATen.
+  * inference uses eval-mode BatchNorm (folded).  With autograd enabled on a ProbabilisticUnet in
+    train() mode, forward()/elbo() run the fp32 TRAINING path (train-mode BatchNorm, explicit
+    backward kernels, train_engine.py); combinations that path does not cover (bf16 precision,
+    eval-mode BN with gradients, a bare UNet) raise NotImplementedError instead of silently
+    falling back to ATen.
   * sample()/elbo()/reconstruct() accept keyword-only z= / eps= to inject latents (the
     reference has no such hook except sample_at); positional signatures are unchanged.
   * sample_at accepts [L] (reference behaviour, batch 1... broadcast) and [B,L].
@@ -33,6 +35,7 @@ import torch.nn as nn
 from torch.distributions import Independent, Normal
 
 from . import ops
+from . import train_engine
 from .engine import PackedNet
 
 
@@ -90,8 +93,8 @@ def _check_filters(num_filters: Sequence[int]):
 def _no_autograd(module: nn.Module, what: str):
     if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
         raise NotImplementedError(
-            f"{what}: backward / train-mode BatchNorm kernels are not built yet (SURVEY.md §8f rank 1). "
-            f"Call under torch.no_grad() (inference, eval-mode BN); there is no ATen fallback.")
+            f"{what}: this call has no backward kernels (the training path covers ProbabilisticUnet.forward(training=True) "
+            f"+ elbo() in train() mode, fp32). Call under torch.no_grad() for inference; there is no ATen fallback.")
 
 
 class _PackedMixin:
@@ -238,6 +241,20 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
     def _dist(self, mu, log_sigma):
         return Independent(Normal(loc=mu, scale=torch.exp(log_sigma)), 1)
 
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _fcomb_live(self):
+        """fcomb weights straight from the parameters (training: nothing is packed / folded)."""
+        convs = [m for m in self.fcomb.layers if isinstance(m, nn.Conv2d)]
+        F_ = convs[0].weight.shape[0]
+        last = self.fcomb.last_layer
+        return {"w0": convs[0].weight.detach().reshape(F_, -1), "b0": convs[0].bias.detach(),
+                "wmid": torch.stack([c.weight.detach().reshape(F_, F_) for c in convs[1:]]).contiguous() if len(convs) > 1 else None,
+                "bmid": torch.stack([c.bias.detach() for c in convs[1:]]).contiguous() if len(convs) > 1 else None,
+                "wlast": last.weight.detach().reshape(last.weight.shape[0], F_), "blast": last.bias.detach(),
+                "nl": 1 + len(convs), "F": F_, "L": convs[0].weight.shape[1] - F_, "C": last.weight.shape[0]}
+
     def _enter(self, what):
         _no_autograd(self, what)
         if self.training and not self._warned_train:
@@ -249,9 +266,29 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
     def forward(self, patch, segm, training=True):
         """probabilistic_unet.py:215-223: sets posterior_latent_space (if training),
         prior_latent_space, unet_features; returns None."""
+        patch = patch.contiguous().float()
+        self._step = None
+        if self._wants_grad():
+            # ---- training path: train-mode BatchNorm, activations recorded for the backward kernels ----
+            if not (self.training and training):
+                raise NotImplementedError("gradients are built for net.train() + forward(training=True) (what train.py "
+                                          "does); wrap inference in torch.no_grad()")
+            if self.precision != "fp32":
+                raise NotImplementedError("the training step is built for precision='fp32' (parity mode); bf16 training "
+                                          "(tcgen05 dgrad / wgrad) is the next scope row")
+            if segm is None:
+                raise ValueError("forward(training=True) needs segm for the posterior")
+            if patch.device.type != "cuda":
+                raise RuntimeError("pmu_b200 models run on CUDA only (no CPU fallback)")
+            st = train_engine.TrainStep(self, patch, segm.contiguous().float())
+            self._step = st
+            self._post, self._prior = (st.mu_q, st.ls_q), (st.mu_p, st.ls_p)
+            self.posterior_latent_space = self._dist(st.mu_q, st.ls_q)
+            self.prior_latent_space = self._dist(st.mu_p, st.ls_p)
+            self.unet_features = st.feat
+            return
         self._enter("ProbabilisticUnet.forward")
         pk = self.packed()
-        patch = patch.contiguous().float()
         if training:
             if segm is None:
                 raise ValueError("forward(training=True) needs segm for the posterior")
@@ -266,7 +303,9 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
     def sample(self, testing=False, *, z=None, eps=None):
         """probabilistic_unet.py:225-240: z ~ prior (rsample / sample) -> fcomb logits [B,C,H,W].
         Keyword-only z / eps inject the latent (z = mu + sigma*eps)."""
-        self._enter("ProbabilisticUnet.sample")
+        step = getattr(self, "_step", None)
+        if step is None:
+            self._enter("ProbabilisticUnet.sample")
         if z is None:
             if eps is not None:
                 z = self._prior[0] + torch.exp(self._prior[1]) * eps
@@ -275,6 +314,11 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             else:
                 z = self.prior_latent_space.sample()
         self.z_prior_sample = z
+        if step is not None:
+            # training step: the sample is only looked at (trainer.predict's return value never enters the loss,
+            # probunet_trainer.py:27-39) — computed from the live weights, detached
+            logits, _ = ops.fcomb_f32(self.unet_features, z.float()[:, None, :].contiguous(), self._fcomb_live())
+            return logits[:, 0]
         return self.packed().fcomb_logits(self.unet_features, z.float())
 
     def sample_at(self, z):
@@ -305,7 +349,9 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
     def elbo(self, segm, analytic_kl=True, reconstruct_posterior_mean=False, *, z=None, eps=None):
         """probabilistic_unet.py:281-308: -(sum CE + beta * mean_b KL); sets kl, reconstruction,
         reconstruction_loss."""
-        self._enter("ProbabilisticUnet.elbo")
+        step = getattr(self, "_step", None)
+        if step is None:
+            self._enter("ProbabilisticUnet.elbo")
         if self.n_classes == 1:
             raise NotImplementedError("num_classes == 1 ELBO is broken in the reference as well "
                                       "(probabilistic_unet.py:285-303, SURVEY.md App. B #8)")
@@ -313,8 +359,18 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             z_posterior = z
         elif eps is not None:
             z_posterior = self._post[0] + torch.exp(self._post[1]) * eps
+        elif step is not None:
+            # Normal.rsample() spelled out (loc + eps * scale with the same generator call), so eps is known to the backward
+            eps = torch.distributions.utils._standard_normal(self._post[0].shape, dtype=torch.float32, device=self._post[0].device)
+            z_posterior = self._post[0] + eps * torch.exp(self._post[1])
         else:
             z_posterior = self.posterior_latent_space.rsample()
+        if step is not None:
+            if reconstruct_posterior_mean:
+                z_posterior, eps = self._post[0], torch.zeros_like(self._post[0])
+            value = step.elbo(segm, z_posterior.float(), None if z is not None else eps, analytic_kl)
+            self.kl, self.reconstruction, self.reconstruction_loss = step.kl, step.logits, step.rec
+            return train_engine.elbo_with_grad(step, value, [p for p in self.parameters() if p.requires_grad])
         self.kl = torch.mean(self.kl_divergence(analytic=analytic_kl, calculate_posterior=False, z_posterior=z_posterior))
         self.reconstruction = self.reconstruct(use_posterior_mean=reconstruct_posterior_mean,
                                                calculate_posterior=False, z_posterior=z_posterior)

@@ -361,3 +361,161 @@ def argmax_dice_sums(prob, truth):
     lib, st = _prep(prob, truth, out)
     _launch(lib, "pmu_argmax_dice_sums", (_p(prob), _p(truth), X, C, YZ, _p(out), st,))
     return out.view(C - 1, 3)
+
+
+# ----------------------------------------------------------------------------- training step (fp32)
+def _ws(C, dev):
+    return torch.empty(2 * C, dtype=torch.float64, device=dev)
+
+
+def bn_train_fwd_f32(y, gamma, beta, eps, relu, momentum=0.1, run_mean=None, run_var=None):
+    """Train-mode BatchNorm2d (+ReLU): returns (a, mean, var); running stats updated in place."""
+    _f32(y, "y")
+    B, C, H, W = y.shape
+    mean = torch.empty(C, dtype=torch.float32, device=y.device)
+    var = torch.empty_like(mean)
+    a = torch.empty_like(y)
+    ws = _ws(C, y.device)
+    lib, st = _prep(y, gamma, beta, run_mean, run_var, mean, var, a, ws)
+    _launch(lib, "pmu_bn_train_fwd_f32", (_p(y), _p(gamma), _p(beta), float(eps), int(relu), float(momentum),
+                                        _p(run_mean), _p(run_var), _p(mean), _p(var), _p(a), _p(ws), B, C, H * W, st,))
+    return a, mean, var
+
+
+def bn_train_bwd_f32(da, y, mean, var, gamma, beta, eps, relu):
+    """-> (dy, dgamma, dbeta)."""
+    B, C, H, W = y.shape
+    dy = torch.empty_like(y)
+    dg = torch.empty(C, dtype=torch.float32, device=y.device)
+    db = torch.empty_like(dg)
+    ws = _ws(C, y.device)
+    lib, st = _prep(da, y, mean, var, gamma, beta, dy, dg, db, ws)
+    _launch(lib, "pmu_bn_train_bwd_f32", (_p(da), _p(y), _p(mean), _p(var), _p(gamma), _p(beta), float(eps), int(relu),
+                                        _p(dy), _p(dg), _p(db), _p(ws), B, C, H * W, st,))
+    return dy, dg, db
+
+
+def channel_sums_f32(x):
+    """[B,C,H,W] -> [C] sums over batch and pixels."""
+    B, C = x.shape[0], x.shape[1]
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = _ws(C, x.device)
+    lib, st = _prep(x, out, ws)
+    _launch(lib, "pmu_channel_sums_f32", (_p(x), _p(out), _p(ws), B, C, x.numel() // (B * C), st,))
+    return out
+
+
+def row_sums_f32(x, rows):
+    out = torch.empty(rows, dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, out)
+    _launch(lib, "pmu_row_sums_f32", (_p(x), _p(out), rows, x.numel() // rows, st,))
+    return out
+
+
+def conv3x3_wgrad_f32(x0, dy, dw, x1=None):
+    """dw[Cout,C0+C1,3,3] += weight gradient."""
+    B, C0, H, W = x0.shape
+    C1 = 0 if x1 is None else x1.shape[1]
+    Cout = dy.shape[1]
+    assert tuple(dw.shape) == (Cout, C0 + C1, 3, 3), dw.shape
+    lib, st = _prep(x0, x1, dy, dw)
+    _launch(lib, "pmu_conv3x3_wgrad_f32", (_p(x0), C0, _p(x1), C1, _p(dy), _p(dw), B, H, W, Cout, st,))
+
+
+def conv1x1_wgrad_f32(x, dy, dw, ldw=None):
+    B, Cin = x.shape[0], x.shape[1]
+    Cout = dy.shape[1]
+    lib, st = _prep(x, dy, dw)
+    _launch(lib, "pmu_conv1x1_wgrad_f32", (_p(x), _p(dy), _p(dw), int(ldw or Cin), B, Cin, Cout,
+                                         x.numel() // (B * Cin), st,))
+
+
+def pool2_bwd_f32(x, dy, mode):
+    B, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    lib, st = _prep(x, dy, dx)
+    _launch(lib, "pmu_pool2_bwd_f32", (_p(x), _p(dy), _p(dx), B, C, H, W, mode, st,))
+    return dx
+
+
+def convt2x2_dgrad_f32(dy, w):
+    B, Cout, H2, W2 = dy.shape
+    Cin = w.shape[0]
+    dx = torch.empty(B, Cin, H2 // 2, W2 // 2, dtype=torch.float32, device=dy.device)
+    lib, st = _prep(dy, w, dx)
+    _launch(lib, "pmu_convt2x2_dgrad_f32", (_p(dy), _p(w), _p(dx), B, Cin, Cout, H2 // 2, W2 // 2, st,))
+    return dx
+
+
+def convt2x2_wgrad_f32(x, dy, dw):
+    B, Cin, H, W = x.shape
+    Cout = dy.shape[1]
+    lib, st = _prep(x, dy, dw)
+    _launch(lib, "pmu_convt2x2_wgrad_f32", (_p(x), _p(dy), _p(dw), B, Cin, Cout, H, W, st,))
+
+
+def relu_bwd_f32(a, dy):
+    dx = torch.empty_like(dy)
+    lib, st = _prep(a, dy, dx)
+    _launch(lib, "pmu_relu_bwd_f32", (_p(a), _p(dy), _p(dx), dy.numel(), st,))
+    return dx
+
+
+def add_f32_(dst, src):
+    assert dst.shape == src.shape
+    lib, st = _prep(dst, src)
+    _launch(lib, "pmu_add_f32", (_p(dst), _p(src), dst.numel(), st,))
+    return dst
+
+
+def ce_bwd_f32(logits, target, scale):
+    B, C = logits.shape[0], logits.shape[1]
+    dl = torch.empty_like(logits)
+    lib, st = _prep(logits, target, dl)
+    _launch(lib, "pmu_ce_bwd_f32", (_p(logits), _p(target), float(scale), _p(dl), B, C, logits.numel() // (B * C), st,))
+    return dl
+
+
+def kl_bwd_f32(mu_q, ls_q, mu_p, ls_p, scale):
+    outs = [torch.empty_like(mu_q) for _ in range(4)]
+    lib, st = _prep(mu_q, ls_q, mu_p, ls_p, *outs)
+    _launch(lib, "pmu_kl_bwd_f32", (_p(mu_q), _p(ls_q), _p(mu_p), _p(ls_p), float(scale), *[_p(o) for o in outs],
+                                  mu_q.shape[0], mu_q.shape[1], st,))
+    return outs
+
+
+def gauss_head_bwd_f32(enc, w, dmu, dls, dw, db):
+    B, C, h, w_ = enc.shape
+    denc = torch.empty_like(enc)
+    lib, st = _prep(enc, w, dmu, dls, denc, dw, db)
+    _launch(lib, "pmu_gauss_head_bwd_f32", (_p(enc), _p(w), _p(dmu), _p(dls), _p(denc), _p(dw), _p(db), B, C, h, w_,
+                                          dmu.shape[1], st,))
+    return denc
+
+
+def fcomb_zbias_f32(z, w0, b0):
+    B, L = z.shape
+    F_ = w0.shape[0]
+    zb = torch.empty(B, F_, dtype=torch.float32, device=z.device)
+    lib, st = _prep(z, w0, b0, zb)
+    _launch(lib, "pmu_fcomb_zbias_f32", (_p(z), _p(w0), _p(b0), _p(zb), B, F_, L, st,))
+    return zb
+
+
+def fcomb_zbias_bwd_f32(rs, z, w0, dw0, db0):
+    B, L = z.shape
+    F_ = w0.shape[0]
+    dz = torch.empty_like(z)
+    lib, st = _prep(rs, z, w0, dz, dw0, db0)
+    _launch(lib, "pmu_fcomb_zbias_bwd_f32", (_p(rs), _p(z), _p(w0), _p(dz), _p(dw0), _p(db0), B, F_, L, st,))
+    return dz
+
+
+def conv1x1_bb_f32(x, w, ldw, bias, bias_bstride, Cin, Cout, relu):
+    """y[b,co] = [relu](sum_ci w[co*ldw+ci] x[b,ci] + bias[b*bias_bstride+co])."""
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    y = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, w, bias, y)
+    _launch(lib, "pmu_conv1x1_bb_f32", (_p(x), _p(w), int(ldw), _p(bias), int(bias_bstride), _p(y), B, Cin, Cout, H * W,
+                                      int(relu), st,))
+    return y

@@ -1,0 +1,282 @@
+"""Training step of ProbabilisticUnet through the CUDA kernels (fp32 NCHW parity mode).
+
+What the reference's training loop asks of autograd (train.py:85-110 via
+ProbUNetTrainer.predict / loss, trainer/probunet_trainer.py:27-39):
+
+    net.forward(imgs, masks, training=True)      # U-Net, prior, posterior — train-mode BatchNorm
+    loss = -net.elbo(masks)                       # z_q = rsample, fcomb, sum CE + beta * mean KL
+    loss.backward()                               # gradients of every parameter
+
+Here forward records what the backward kernels need (conv inputs, pre-BN outputs, batch
+statistics), and ``elbo`` returns a scalar attached to ONE autograd node (`_ElboFn`) whose
+backward runs the explicit backward kernels of csrc/train_f32.cu and hands each parameter its
+gradient — so ``loss.backward()``, gradient accumulation over ``acc_steps``,
+``clip_grad_value_`` and ``optim.SGD`` of train.py work unchanged.  No ATen kernel computes
+any of the arithmetic; torch owns memory and the [B, L]-sized reparameterisation glue.
+
+Layer backward formulas follow the torch ops the reference uses (nn.Conv2d, BatchNorm2d in
+training mode, ReLU, MaxPool2d(2), AvgPool2d(2,2,ceil_mode), ConvTranspose2d(k2,s2), torch.mean,
+CrossEntropyLoss(reduction none -> sum), kl_divergence of Independent Normals).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _d(t):
+    return t.detach()
+
+
+class _Tape:
+    """Gradients by parameter (id -> tensor); each parameter is written at most once per step."""
+
+    def __init__(self):
+        self.g: Dict[int, torch.Tensor] = {}
+
+    def put(self, p: nn.Parameter, g: torch.Tensor):
+        g = g.reshape(p.shape)
+        if id(p) in self.g:
+            ops.add_f32_(self.g[id(p)], g.contiguous())
+        else:
+            self.g[id(p)] = g
+
+
+# ------------------------------------------------------------------ conv3x3 + BN(train) + ReLU
+def _cbr_fwd(conv: nn.Conv2d, bn: nn.BatchNorm2d, x0, x1=None):
+    y = ops.conv3x3_f32(x0, _d(conv.weight), _d(conv.bias), relu=False, x1=x1)
+    a, mean, var = ops.bn_train_fwd_f32(y, _d(bn.weight), _d(bn.bias), bn.eps, True,
+                                        0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var)
+    bn.num_batches_tracked += 1
+    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var}
+
+
+def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
+    conv, bn = rec["conv"], rec["bn"]
+    dy, dg, db = ops.bn_train_bwd_f32(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True)
+    tape.put(bn.weight, dg)
+    tape.put(bn.bias, db)
+    dw = torch.zeros_like(_d(conv.weight))
+    ops.conv3x3_wgrad_f32(rec["x0"], dy, dw, rec["x1"])
+    tape.put(conv.weight, dw)
+    tape.put(conv.bias, ops.channel_sums_f32(dy))
+    if not need_dx:
+        return None, None
+    # data gradient = the same 3x3 kernel with the weights transposed (ci <-> co) and flipped
+    wt = _d(conv.weight).flip(2, 3).transpose(0, 1)
+    C0 = rec["x0"].shape[1]
+    dx0 = ops.conv3x3_f32(dy, wt[:C0].contiguous(), None, relu=False)
+    dx1 = ops.conv3x3_f32(dy, wt[C0:].contiguous(), None, relu=False) if rec["x1"] is not None else None
+    return dx0, dx1
+
+
+def _dconv_fwd(dc, x0, x1=None):
+    seq = dc.double_conv
+    a, r1 = _cbr_fwd(seq[0], seq[1], x0, x1)
+    b, r2 = _cbr_fwd(seq[3], seq[4], a)
+    return b, (r1, r2)
+
+
+def _dconv_bwd(recs, d, tape, need_dx=True):
+    d, _ = _cbr_bwd(recs[1], d, tape)
+    return _cbr_bwd(recs[0], d, tape, need_dx)
+
+
+# ------------------------------------------------------------------ U-Net (unet_model.py:31-54)
+def _unet_fwd(unet, x):
+    h, r = _dconv_fwd(unet.inc, x)
+    skips, recs = [h], [r]
+    for down in unet.down_blocks:
+        p = ops.pool2_f32(h, ops.POOL_MAX)
+        h, r = _dconv_fwd(down.maxpool_conv[1], p)
+        skips.append(h)
+        recs.append(r)
+    ups = []
+    n = len(unet.down_blocks)
+    for i, up in enumerate(unet.up_blocks):
+        skip = skips[n - 1 - i]
+        if skip.shape[2] != 2 * h.shape[2] or skip.shape[3] != 2 * h.shape[3]:
+            raise NotImplementedError("training needs H, W divisible by 2^levels (the F.pad branch of Up.forward, "
+                                      "unet_parts.py:58-62, is only built for inference)")
+        u = ops.convt2x2_f32(h, _d(up.up.weight), _d(up.up.bias))
+        h_in = h
+        h, r = _dconv_fwd(up.conv, skip, u)        # cat([skip, up]) as a two-source convolution
+        ups.append({"up": up, "h_in": h_in, "recs": r})
+    return h, {"skips": skips, "recs": recs, "ups": ups}
+
+
+def _unet_bwd(unet, st, dfeat, tape):
+    n = len(unet.down_blocks)
+    dskip: List[Optional[torch.Tensor]] = [None] * (n + 1)
+    d = dfeat
+    for i in reversed(range(len(st["ups"]))):
+        u = st["ups"][i]
+        ds, du = _dconv_bwd(u["recs"], d, tape)
+        dskip[n - 1 - i] = ds
+        up = u["up"].up
+        dw = torch.zeros_like(_d(up.weight))
+        ops.convt2x2_wgrad_f32(u["h_in"], du, dw)
+        tape.put(up.weight, dw)
+        tape.put(up.bias, ops.channel_sums_f32(du))
+        d = ops.convt2x2_dgrad_f32(du, _d(up.weight))
+    # d = gradient w.r.t. the deepest encoder map
+    for lvl in range(n, 0, -1):
+        if dskip[lvl] is not None:
+            ops.add_f32_(d, dskip[lvl])
+        d, _ = _dconv_bwd(st["recs"][lvl], d, tape)
+        d = ops.pool2_bwd_f32(st["skips"][lvl - 1], d, ops.POOL_MAX)
+    if dskip[0] is not None:
+        ops.add_f32_(d, dskip[0])
+    _dconv_bwd(st["recs"][0], d, tape, need_dx=False)
+
+
+# ------------------------------------------------------------------ prior / posterior (probabilistic_unet.py:11-114)
+def _gauss_fwd(net, x, segm=None):
+    layers = net.encoder.layers
+    nblk = len(net.num_filters)
+    h, recs, pool_in = x, [], []
+    for i in range(nblk):
+        if i > 0:
+            pool_in.append(h)
+            h = ops.pool2_f32(h, ops.POOL_AVG_CEIL)
+        a, r1 = _cbr_fwd(layers[7 * i], layers[7 * i + 1], h, segm if i == 0 else None)
+        h, r2 = _cbr_fwd(layers[7 * i + 3], layers[7 * i + 4], a)
+        recs.append((r1, r2))
+    cl = net.conv_layer
+    L = cl.weight.shape[0] // 2
+    mu, ls = ops.gauss_head_f32(h, _d(cl.weight).reshape(2 * L, -1), _d(cl.bias), L)
+    return mu, ls, {"enc": h, "recs": recs, "pool_in": pool_in}
+
+
+def _gauss_bwd(net, st, dmu, dls, tape):
+    cl = net.conv_layer
+    L = cl.weight.shape[0] // 2
+    dw = torch.zeros(2 * L, st["enc"].shape[1], dtype=torch.float32, device=dmu.device)
+    db = torch.zeros(2 * L, dtype=torch.float32, device=dmu.device)
+    d = ops.gauss_head_bwd_f32(st["enc"], _d(cl.weight).reshape(2 * L, -1), dmu.contiguous(), dls.contiguous(), dw, db)
+    tape.put(cl.weight, dw)
+    tape.put(cl.bias, db)
+    for i in reversed(range(len(st["recs"]))):
+        d, _ = _dconv_bwd(st["recs"][i], d, tape, need_dx=i > 0)
+        if i > 0:
+            d = ops.pool2_bwd_f32(st["pool_in"][i - 1], d, ops.POOL_AVG_CEIL)
+
+
+# ------------------------------------------------------------------ fcomb (probabilistic_unet.py:155-181)
+def _fcomb_convs(fc):
+    return [m for m in fc.layers if isinstance(m, nn.Conv2d)]
+
+
+def _fcomb_fwd(fc, feat, z):
+    convs = _fcomb_convs(fc)
+    F_ = convs[0].weight.shape[0]
+    L = convs[0].weight.shape[1] - F_
+    w0 = _d(convs[0].weight).reshape(F_, F_ + L)
+    zb = ops.fcomb_zbias_f32(z, w0, _d(convs[0].bias))
+    hs = [ops.conv1x1_bb_f32(feat, w0, F_ + L, zb, F_, F_, F_, True)]
+    for c in convs[1:]:
+        hs.append(ops.conv1x1_bb_f32(hs[-1], _d(c.weight).reshape(F_, F_), F_, _d(c.bias), 0, F_, F_, True))
+    last = fc.last_layer
+    C = last.weight.shape[0]
+    logits = ops.conv1x1_bb_f32(hs[-1], _d(last.weight).reshape(C, F_), F_, _d(last.bias), 0, F_, C, False)
+    return logits, {"feat": feat, "z": z, "hs": hs}
+
+
+def _fcomb_bwd(fc, st, dlogits, tape):
+    convs = _fcomb_convs(fc)
+    F_ = convs[0].weight.shape[0]
+    L = convs[0].weight.shape[1] - F_
+    last = fc.last_layer
+    C = last.weight.shape[0]
+    hs = st["hs"]
+    dw = torch.zeros(C, F_, dtype=torch.float32, device=dlogits.device)
+    ops.conv1x1_wgrad_f32(hs[-1], dlogits, dw)
+    tape.put(last.weight, dw)
+    tape.put(last.bias, ops.channel_sums_f32(dlogits))
+    d = ops.conv1x1_f32(dlogits, _d(last.weight).reshape(C, F_).t().contiguous(), None)
+    d = ops.relu_bwd_f32(hs[-1], d)
+    for j in range(len(convs) - 1, 0, -1):
+        c = convs[j]
+        dw = torch.zeros(F_, F_, dtype=torch.float32, device=d.device)
+        ops.conv1x1_wgrad_f32(hs[j - 1], d, dw)
+        tape.put(c.weight, dw)
+        tape.put(c.bias, ops.channel_sums_f32(d))
+        d = ops.conv1x1_f32(d, _d(c.weight).reshape(F_, F_).t().contiguous(), None)
+        d = ops.relu_bwd_f32(hs[j - 1], d)
+    # layer 0: weight [F, F+L] = [feature part | latent part]
+    w0 = _d(convs[0].weight).reshape(F_, F_ + L)
+    dw0 = torch.zeros(F_, F_ + L, dtype=torch.float32, device=d.device)
+    db0 = torch.zeros(F_, dtype=torch.float32, device=d.device)
+    ops.conv1x1_wgrad_f32(st["feat"], d, dw0, ldw=F_ + L)
+    B = d.shape[0]
+    rs = ops.row_sums_f32(d, B * F_)
+    dz = ops.fcomb_zbias_bwd_f32(rs, st["z"], w0, dw0, db0)
+    tape.put(convs[0].weight, dw0)
+    tape.put(convs[0].bias, db0)
+    dfeat = ops.conv1x1_f32(d, w0[:, :F_].t().contiguous(), None)
+    return dfeat, dz
+
+
+# ------------------------------------------------------------------ the step
+class TrainStep:
+    """State of one forward(training=True) of a ProbabilisticUnet; consumed by elbo() / backward."""
+
+    def __init__(self, net, patch: torch.Tensor, segm: torch.Tensor):
+        self.net = net
+        self.patch, self.segm = patch, segm
+        self.mu_q, self.ls_q, self.post = _gauss_fwd(net.posterior, patch, segm)
+        self.mu_p, self.ls_p, self.prior = _gauss_fwd(net.prior, patch)
+        self.feat, self.unet = _unet_fwd(net.unet, patch)
+        self.fc = None
+
+    def elbo(self, segm, z_q: torch.Tensor, eps: Optional[torch.Tensor], analytic_kl: bool):
+        net = self.net
+        if not analytic_kl:
+            raise NotImplementedError("training backward is built for the analytic KL (the reference's default, "
+                                      "probabilistic_unet.py:281)")
+        self.z_q, self.eps_q = z_q.contiguous(), eps
+        self.kl_b = ops.kl_diag_gauss(self.mu_q, self.ls_q, self.mu_p, self.ls_p)
+        self.logits, self.fc = _fcomb_fwd(net.fcomb, self.feat, self.z_q)
+        self.segm_t = segm.contiguous().float()
+        self.rec = ops.ce_sum(self.logits, self.segm_t)
+        self.kl = self.kl_b.mean()
+        return -(self.rec + net.beta * self.kl)
+
+    def backward(self, g: float) -> Dict[int, torch.Tensor]:
+        """g = d(loss)/d(elbo).  elbo = -(rec + beta * mean_b KL)."""
+        net, tape = self.net, _Tape()
+        B = self.mu_q.shape[0]
+        dlogits = ops.ce_bwd_f32(self.logits, self.segm_t, -g)
+        dfeat, dz = _fcomb_bwd(net.fcomb, self.fc, dlogits, tape)
+        dmu_q, dls_q, dmu_p, dls_p = ops.kl_bwd_f32(self.mu_q, self.ls_q, self.mu_p, self.ls_p, -g * net.beta / B)
+        if self.eps_q is not None:
+            # z_q = mu_q + exp(log_sigma_q) * eps  (rsample): [B, L]-sized glue
+            dmu_q = dmu_q + dz
+            dls_q = dls_q + dz * self.eps_q * torch.exp(self.ls_q)
+        _gauss_bwd(net.posterior, self.post, dmu_q, dls_q, tape)
+        _gauss_bwd(net.prior, self.prior, dmu_p, dls_p, tape)
+        _unet_bwd(net.unet, self.unet, dfeat, tape)
+        return tape.g
+
+
+class _ElboFn(torch.autograd.Function):
+    """One autograd node for the whole step: inputs = every parameter, output = elbo."""
+
+    @staticmethod
+    def forward(ctx, step: TrainStep, value: torch.Tensor, *params):
+        ctx.step = step
+        ctx.params = params
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.step.backward(float(g))
+        return (None, None) + tuple(grads.get(id(p)) for p in ctx.params)
+
+
+def elbo_with_grad(step: TrainStep, value: torch.Tensor, params):
+    return _ElboFn.apply(step, value, *params)

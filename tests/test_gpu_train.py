@@ -1,0 +1,239 @@
+"""GPU parity of the training step (fp32 NCHW): every backward kernel against torch autograd of
+the same op on the CPU, and the whole step (forward(training=True) + elbo + backward through the
+drop-in ProbabilisticUnet) against the gradients of the REAL reference (golden_grads.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pmu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pmu_b200
+    return pmu_b200.ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _close(got, ref, rtol=1e-4, what=""):
+    ref = ref.detach()
+    scale = max(float(ref.abs().max()), 1e-6)
+    err = float((got.detach().cpu() - ref).abs().max())
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("B,C,H,W,relu", [(3, 5, 9, 13, True), (2, 64, 16, 16, True), (4, 7, 8, 8, False)])
+def test_bn_train_fwd_bwd(ops, B, C, H, W, relu):
+    g = _g(1)
+    y = (torch.randn(B, C, H, W, generator=g) * 2 + 0.5).requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.3).requires_grad_(True)
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    a_ref = F.batch_norm(y, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+    if relu:
+        a_ref = F.relu(a_ref)
+    da = torch.randn(B, C, H, W, generator=g)
+    a_ref.backward(da)
+    rm_c, rv_c = rm.cuda(), rv.cuda()
+    a, mean, var = ops.bn_train_fwd_f32(y.detach().cuda(), gamma.detach().cuda(), beta.detach().cuda(), 1e-5, relu, 0.1, rm_c, rv_c)
+    _close(a, a_ref, 1e-5, "bn forward")
+    _close(rm_c, rm_ref, 1e-5, "running_mean")
+    _close(rv_c, rv_ref, 1e-5, "running_var")
+    dy, dg, db = ops.bn_train_bwd_f32(da.cuda(), y.detach().cuda(), mean, var, gamma.detach().cuda(), beta.detach().cuda(), 1e-5, relu)
+    _close(dy, y.grad, 2e-4, "bn dy")
+    _close(dg, gamma.grad, 1e-4, "bn dgamma")
+    _close(db, beta.grad, 1e-4, "bn dbeta")
+
+
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 1, 0, 4, 9, 13), (1, 5, 3, 7, 32, 48), (3, 16, 16, 33, 8, 8),
+                                               (2, 64, 0, 64, 20, 36), (2, 1, 1, 4, 16, 16)])
+def test_conv3x3_wgrad_dgrad(ops, B, C0, C1, Cout, H, W):
+    g = _g(2)
+    x = torch.randn(B, C0 + C1, H, W, generator=g).requires_grad_(True)
+    w = (torch.randn(Cout, C0 + C1, 3, 3, generator=g) * 0.2).requires_grad_(True)
+    b = torch.zeros(Cout, requires_grad=True)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    F.conv2d(x, w, b, padding=1).backward(dy)
+    x0 = x.detach()[:, :C0].contiguous().cuda()
+    x1 = x.detach()[:, C0:].contiguous().cuda() if C1 else None
+    dw = torch.zeros(Cout, C0 + C1, 3, 3, device="cuda")
+    ops.conv3x3_wgrad_f32(x0, dy.cuda(), dw, x1)
+    _close(dw, w.grad, 1e-4, "conv3x3 dw")
+    _close(ops.channel_sums_f32(dy.cuda()), b.grad, 1e-4, "conv3x3 db")
+    # data gradient through the forward kernel with transposed + flipped weights (what train_engine does)
+    wt = w.detach().flip(2, 3).transpose(0, 1).contiguous().cuda()
+    dx = ops.conv3x3_f32(dy.cuda(), wt, None, relu=False)
+    _close(dx, x.grad, 1e-4, "conv3x3 dx")
+
+
+@pytest.mark.parametrize("B,Cin,Cout,HW,ld", [(2, 70, 64, 480, 70), (3, 64, 3, 1000, 64), (1, 64, 64, 128, 70)])
+def test_conv1x1_wgrad_and_bb(ops, B, Cin, Cout, HW, ld):
+    g = _g(3)
+    x = torch.randn(B, Cin, HW, 1, generator=g)
+    dy = torch.randn(B, Cout, HW, 1, generator=g)
+    ref = torch.einsum("bop,bip->oi", dy[..., 0], x[..., 0])
+    dw = torch.zeros(Cout, ld, device="cuda")
+    ops.conv1x1_wgrad_f32(x.cuda(), dy.cuda(), dw, ldw=ld)
+    _close(dw[:, :Cin], ref, 1e-4, "conv1x1 dw")
+    assert float(dw[:, Cin:].abs().max()) == 0.0 if ld > Cin else True
+    # per-(batch, channel) bias forward
+    w = torch.randn(Cout, ld, generator=g) * 0.2
+    bias = torch.randn(B, Cout, generator=g)
+    y = ops.conv1x1_bb_f32(x.cuda(), w.cuda(), ld, bias.cuda(), Cout, Cin, Cout, True)
+    yref = F.relu(torch.einsum("oi,bip->bop", w[:, :Cin], x[..., 0]) + bias[:, :, None])
+    _close(y[..., 0], yref, 1e-5, "conv1x1 bb")
+    _close(ops.row_sums_f32(dy.cuda(), B * Cout), dy.sum((2, 3)).reshape(-1), 1e-5, "row sums")
+
+
+@pytest.mark.parametrize("mode,H,W", [(0, 8, 12), (1, 8, 12), (1, 7, 9)])
+def test_pool2_bwd(ops, mode, H, W):
+    g = _g(4)
+    x = torch.randn(2, 3, H, W, generator=g)
+    x[0, 0, :2, :2] = 0.0                     # a tie: the gradient goes to the first maximum (torch)
+    x.requires_grad_(True)
+    y = F.max_pool2d(x, 2) if mode == 0 else F.avg_pool2d(x, 2, 2, 0, ceil_mode=True)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    dx = ops.pool2_bwd_f32(x.detach().cuda(), dy.cuda(), mode)
+    _close(dx, x.grad, 1e-6, "pool bwd")
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 8, 4, 5, 7), (1, 64, 32, 8, 8), (3, 33, 17, 4, 6)])
+def test_convt2x2_bwd(ops, B, Cin, Cout, H, W):
+    g = _g(5)
+    x = torch.randn(B, Cin, H, W, generator=g).requires_grad_(True)
+    w = (torch.randn(Cin, Cout, 2, 2, generator=g) * 0.3).requires_grad_(True)
+    b = torch.zeros(Cout, requires_grad=True)
+    dy = torch.randn(B, Cout, 2 * H, 2 * W, generator=g)
+    F.conv_transpose2d(x, w, b, stride=2).backward(dy)
+    dx = ops.convt2x2_dgrad_f32(dy.cuda(), w.detach().cuda())
+    _close(dx, x.grad, 1e-4, "convT dx")
+    dw = torch.zeros(Cin, Cout, 2, 2, device="cuda")
+    ops.convt2x2_wgrad_f32(x.detach().cuda(), dy.cuda(), dw)
+    _close(dw, w.grad, 1e-4, "convT dw")
+
+
+def test_ce_kl_head_relu_bwd(ops):
+    g = _g(6)
+    B, C, H, W, L = 3, 3, 10, 12, 6
+    logits = torch.randn(B, C, H, W, generator=g).requires_grad_(True)
+    tgt = torch.randint(0, C, (B, 1, H, W), generator=g).float()
+    (F.cross_entropy(logits, tgt.long().squeeze(1), reduction="sum") * -0.5).backward()
+    _close(ops.ce_bwd_f32(logits.detach().cuda(), tgt.cuda(), -0.5), logits.grad, 1e-5, "ce bwd")
+    # KL
+    ps = [torch.randn(B, L, generator=g).requires_grad_(True) for _ in range(4)]
+    kl = O.kl_diag_gauss(*ps).sum() * 0.7
+    kl.backward()
+    outs = ops.kl_bwd_f32(*[p.detach().cuda() for p in ps], 0.7)
+    for o, p, n in zip(outs, ps, ("mu_q", "ls_q", "mu_p", "ls_p")):
+        _close(o, p.grad, 1e-5, "kl " + n)
+    # Gaussian head
+    Cc, h, w_ = 40, 4, 6
+    enc = torch.randn(B, Cc, h, w_, generator=g).requires_grad_(True)
+    hw_ = (torch.randn(2 * L, Cc, generator=g) * 0.2).requires_grad_(True)
+    hb = torch.randn(2 * L, generator=g).requires_grad_(True)
+    out = F.conv2d(enc.mean(2, keepdim=True).mean(3, keepdim=True), hw_[:, :, None, None], hb)[:, :, 0, 0]
+    dmu, dls = torch.randn(B, L, generator=g), torch.randn(B, L, generator=g)
+    out.backward(torch.cat([dmu, dls], 1))
+    dw = torch.zeros(2 * L, Cc, device="cuda")
+    db = torch.zeros(2 * L, device="cuda")
+    denc = ops.gauss_head_bwd_f32(enc.detach().cuda(), hw_.detach().cuda(), dmu.cuda(), dls.cuda(), dw, db)
+    _close(denc, enc.grad, 1e-5, "head denc")
+    _close(dw, hw_.grad, 1e-5, "head dw")
+    _close(db, hb.grad, 1e-5, "head db")
+    # relu bwd / add
+    a = F.relu(torch.randn(1000, generator=g))
+    d = torch.randn(1000, generator=g)
+    assert torch.equal(ops.relu_bwd_f32(a.cuda(), d.cuda()).cpu(), d * (a > 0))
+    acc = d.clone().cuda()
+    ops.add_f32_(acc, a.cuda())
+    assert torch.equal(acc.cpu(), d + a)
+
+
+def _load_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "golden_grads.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _grad_scale(g, k):
+    scale = float(np.abs(g[k]).max())
+    if k.endswith(".bias") and k[:-4] + "weight" in g:      # zero-gradient conv biases in front of BN: see test_oracle_golden
+        scale = max(scale, float(np.abs(g[k[:-4] + "weight"]).max()))
+    return max(scale, 1e-3)
+
+
+def test_training_step_matches_reference_gradients(ops, golden_dir):
+    """The drop-in ProbabilisticUnet stepped like train.py:85-97 (predict -> loss -> backward) gives the
+    REAL reference's gradients, losses and BatchNorm running statistics."""
+    import pmu_b200
+    g = _load_golden(golden_dir)
+    net = pmu_b200.ProbabilisticUnet(input_channels=1, num_classes=3, num_filters=[4, 8, 16, 32, 64], latent_dim=6,
+                                     no_convs_fcomb=4, beta=10)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")}
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    x, segm = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["segm"]).cuda()
+    net.forward(x, segm, training=True)
+    masks_pred = net.sample(testing=False)                       # trainer.predict's return value
+    assert masks_pred.shape == (3, 3, 32, 48) and not masks_pred.requires_grad
+    elbo = net.elbo(segm, eps=torch.from_numpy(g["eps_q"]).cuda())
+    assert elbo.requires_grad
+    np.testing.assert_allclose(float(elbo), float(g["elbo"]), rtol=2e-5)
+    np.testing.assert_allclose(float(net.kl), float(g["kl"]), rtol=2e-4)
+    np.testing.assert_allclose(float(net.reconstruction_loss), float(g["rec"]), rtol=2e-5)
+    loss = -elbo
+    loss.backward()
+    named = dict(net.named_parameters())
+    n = 0
+    for k, ref in g.items():
+        if not k.startswith("grad/"):
+            continue
+        got = named[k[5:]].grad
+        assert got is not None, k
+        err = float((got.cpu() - torch.from_numpy(ref)).abs().max())
+        assert err <= 1e-3 * _grad_scale(g, k) + 1e-5, f"{k}: err {err:.3e} scale {_grad_scale(g, k):.3e}"
+        n += 1
+    assert n > 100
+    assert named["unet.outc.conv.weight"].grad is None            # discarded layer (unet_model.py:40-54)
+    post = net.state_dict()
+    for k, ref in g.items():
+        if k.startswith("post/"):
+            np.testing.assert_allclose(post[k[5:]].cpu().numpy(), ref, rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+def test_training_loop_reduces_loss(ops):
+    """train.py's inner loop verbatim on the drop-in model: SGD + momentum, grad accumulation, value clipping."""
+    import pmu_b200
+    torch.manual_seed(0)
+    trainer = pmu_b200.ProbUNetTrainer("cuda", n_channels=1, n_classes=3, latent_dim=6, beta=10)
+    net = trainer.net
+    optimizer = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9)
+    vol, lab = O.phantom(32, seed=3)
+    imgs = torch.from_numpy(O.plane_slices(vol, 0, 8, 4)).cuda()
+    masks = torch.from_numpy(lab[8:12, None].astype(np.float32)).cuda()
+    net.train()
+    losses = []
+    acc_steps = 2
+    optimizer.zero_grad()
+    for it in range(12):
+        trainer.predict(imgs, masks)
+        loss = trainer.loss(imgs, masks, None) / acc_steps
+        loss.backward()
+        losses.append(float(loss))
+        if (it + 1) % acc_steps == 0:
+            torch.nn.utils.clip_grad_value_(net.parameters(), 0.1)
+            optimizer.step()
+            optimizer.zero_grad()
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-2:]) < 0.9 * np.mean(losses[:2]), losses

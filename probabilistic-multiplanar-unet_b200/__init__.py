@@ -9,5 +9,6 @@ from .engine import PackedNet  # noqa: F401
 from .model import ProbabilisticUnet, UNet  # noqa: F401
 from .multiplanar import MultiPlanarPredictor, padded_dims, reduce_accumulators, shard_slices  # noqa: F401
 from .trainer import ProbUNetTrainer  # noqa: F401
+from .train_dp import allreduce_gradients, dp_train_step  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,60 @@
+"""Data-parallel training step: one process per GPU, gradients summed over NCCL (NVLink / NVSwitch).
+
+The reference trains on one device (train.py); BASELINE config 4 asks for the batch-64 step split over
+8 GPUs.  The loss is  sum_b CE_b + beta * mean_b KL_b  (probabilistic_unet.py:294-308): the CE part
+ADDS over shards, the KL part AVERAGES.  Each rank therefore steps its shard with
+``net.kl_world_size = world`` (the local KL term is weighted beta / world) and the gradients are
+SUM-reduced — the result is exactly the gradient of the global objective evaluated with per-rank
+BatchNorm statistics (standard data parallelism; the reference has no SyncBN either).
+
+One exchange per step: the gradients are flattened into a few large buckets so the all-reduce cost
+is launch latency + bytes / NVLink bandwidth (275 MB of fp32 gradients for the trainer model).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 128 << 20) -> int:
+    """SUM-all-reduce ``p.grad`` of every parameter that has one, in flat buckets.  Every rank must hold
+    gradients for the same parameters (true for the ELBO step: the set is fixed by the architecture).
+    Returns the number of collectives issued."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    buckets: List[List[torch.Tensor]] = [[]]
+    size = 0
+    for g in grads:
+        nbytes = g.numel() * g.element_size()
+        if buckets[-1] and (size + nbytes > bucket_bytes or g.dtype != buckets[-1][0].dtype):
+            buckets.append([])
+            size = 0
+        buckets[-1].append(g)
+        size += nbytes
+    for b in buckets:
+        flat = torch._utils._flatten_dense_tensors(b)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        for g, synced in zip(b, torch._utils._unflatten_dense_tensors(flat, b)):
+            g.copy_(synced)
+    return len(buckets)
+
+
+def dp_train_step(trainer, imgs, masks, optimizer, acc_steps: int = 1, clip_value: Optional[float] = 0.1,
+                  group=None, step_now: bool = True):
+    """train.py:85-110 for one shard: predict -> loss / acc_steps -> backward -> (all-reduce, clip, SGD step).
+    Returns the local loss (sum over ranks of the local losses == the global loss)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    trainer.net.kl_world_size = world
+    trainer.predict(imgs, masks)
+    loss = trainer.loss(imgs, masks, None) / acc_steps
+    loss.backward()
+    if step_now:
+        allreduce_gradients(trainer.net.parameters(), group)
+        if clip_value is not None:
+            torch.nn.utils.clip_grad_value_(trainer.net.parameters(), clip_value)
+        optimizer.step()
+        optimizer.zero_grad()
+    return loss.detach()

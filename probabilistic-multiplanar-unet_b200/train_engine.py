@@ -233,6 +233,10 @@ class TrainStep:
         self.feat, self.unet = _unet_fwd(net.unet, patch)
         self.fc = None
 
+    def _beta(self) -> float:
+        # data parallel: the KL term averages over the GLOBAL batch (train_dp.py)
+        return float(self.net.beta) / float(getattr(self.net, "kl_world_size", 1))
+
     def elbo(self, segm, z_q: torch.Tensor, eps: Optional[torch.Tensor], analytic_kl: bool):
         net = self.net
         if not analytic_kl:
@@ -244,7 +248,7 @@ class TrainStep:
         self.segm_t = segm.contiguous().float()
         self.rec = ops.ce_sum(self.logits, self.segm_t)
         self.kl = self.kl_b.mean()
-        return -(self.rec + net.beta * self.kl)
+        return -(self.rec + self._beta() * self.kl)
 
     def backward(self, g: float) -> Dict[int, torch.Tensor]:
         """g = d(loss)/d(elbo).  elbo = -(rec + beta * mean_b KL)."""
@@ -252,7 +256,7 @@ class TrainStep:
         B = self.mu_q.shape[0]
         dlogits = ops.ce_bwd_f32(self.logits, self.segm_t, -g)
         dfeat, dz = _fcomb_bwd(net.fcomb, self.fc, dlogits, tape)
-        dmu_q, dls_q, dmu_p, dls_p = ops.kl_bwd_f32(self.mu_q, self.ls_q, self.mu_p, self.ls_p, -g * net.beta / B)
+        dmu_q, dls_q, dmu_p, dls_p = ops.kl_bwd_f32(self.mu_q, self.ls_q, self.mu_p, self.ls_p, -g * self._beta() / B)
         if self.eps_q is not None:
             # z_q = mu_q + exp(log_sigma_q) * eps  (rsample): [B, L]-sized glue
             dmu_q = dmu_q + dz

@@ -146,6 +146,61 @@ def test_sharded_accumulators_reduce_over_gloo():
     assert err < 1e-6
 
 
+def _gloo_grad_worker(rank, world, port, ret):
+    """Data-parallel training exchange (train_dp.py) on 2 gloo ranks: every rank differentiates its
+    half batch of the ORACLE objective with the KL term weighted beta / world, gradients are
+    SUM-all-reduced in buckets; rank 0 compares with the single-process gradient of
+    sum_b CE + beta * mean_b KL evaluated with the same per-shard BatchNorm statistics."""
+    import torch.distributed as dist
+    from pmu_b200.train_dp import allreduce_gradients
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    beta = 10.0
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(4, 1, 16, 16, generator=g)
+    segm = torch.randint(0, 3, (4, 1, 16, 16), generator=g).float()
+    eps = torch.randn(4, 6, generator=g)
+
+    def params(seed=0):
+        sd = O.make_state_dict((4, 8), num_classes=3, latent_dim=6, no_convs_fcomb=3, seed=seed)
+        ps = {k: torch.nn.Parameter(v.clone()) for k, v in sd.items() if v.dtype == torch.float32 and "running_" not in k
+              and "outc" not in k}
+        full = dict(sd); full.update(ps)
+        return ps, full
+
+    ps, sd = params()
+    sl = slice(rank * 2, rank * 2 + 2)
+    r = O.elbo(sd, x[sl], segm[sl], eps[sl], beta=beta / world, bn_train=True)
+    (-r["elbo"]).backward()
+    n_coll = allreduce_gradients(ps.values(), bucket_bytes=4096)      # small buckets: several collectives
+    if rank == 0:
+        ps1, sd1 = params()
+        total = 0
+        for rr in range(world):
+            s2 = slice(rr * 2, rr * 2 + 2)
+            o = O.elbo(sd1, x[s2], segm[s2], eps[s2], beta=beta, bn_train=True)
+            total = total + o["reconstruction_loss"] + beta * o["kl"] / world
+        total.backward()
+        err = max(float((ps[k].grad - ps1[k].grad).abs().max()) / max(float(ps1[k].grad.abs().max()), 1e-3) for k in ps)
+        ret.put((err, n_coll))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_over_gloo():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_grad_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, n_coll = ret.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-4, err
+    assert n_coll > 1
+
+
 def test_nifti_roundtrip(tmp_path):
     from pmu_b200 import nifti_io
     v = np.random.default_rng(0).random((5, 6, 7))

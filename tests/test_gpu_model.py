@@ -69,10 +69,25 @@ def test_small_model_vs_reference_golden(pmu, golden_dir):
         np.testing.assert_allclose(unet(x).cpu().numpy(), g["eval/unet_out"], **tol)
 
 
-def test_autograd_is_refused_loudly(pmu):
+def test_unsupported_autograd_is_refused_loudly(pmu):
+    """Gradients exist for train() + forward(training=True) in fp32 (test_gpu_train.py); every other
+    combination raises instead of silently running ATen or eval-mode BatchNorm."""
+    x, m = torch.rand(1, 1, 8, 8, device="cuda"), torch.zeros(1, 1, 8, 8, device="cuda")
     net = pmu.ProbabilisticUnet(1, 3, [4, 8], 2, 2).cuda()
-    with pytest.raises(NotImplementedError):
-        net.forward(torch.zeros(1, 1, 8, 8, device="cuda"), torch.zeros(1, 1, 8, 8, device="cuda"))
+    net.eval()
+    with pytest.raises(NotImplementedError):          # eval-mode BatchNorm with gradients
+        net.forward(x, m)
+    net.train()
+    with pytest.raises(NotImplementedError):          # training=False with gradients
+        net.forward(x, m, training=False)
+    net.set_precision("bf16")
+    with pytest.raises(NotImplementedError):          # bf16 training: next scope row
+        net.forward(x, m)
+    with pytest.raises(NotImplementedError):          # the bare U-Net has no backward path
+        pmu.UNet(1, 3, [4, 8]).cuda()(x)
+    net.set_precision("fp32")
+    net.forward(x, m)                                  # the supported combination
+    assert net.elbo(m).requires_grad
 
 
 @pytest.fixture(scope="module")

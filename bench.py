@@ -282,8 +282,46 @@ def run_ours(args):
         V = float(D) ** 3
         if "pmu_slice_gather" in tot:
             gb = P * V * 8.0 * world_frac / 1e9          # read 4 B + write 4 B per voxel per plane
-            hbm_kernels["slice_gather"] = {"achieved": gb / (tot["pmu_slice_gather"]["ms"] * 1e-3), "unit": "GB/s",
-                                           "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
+            in_step = gb / (tot["pmu_slice_gather"]["ms"] * 1e-3)
+            # The in-step figure brackets every ~10-25 us launch with its own event pair, so it mostly measures
+            # launch gaps.  Kernel throughput: whole-plane gathers of all three planes replayed back to back from
+            # a CUDA graph, rotating over 4 volumes + 4 outputs (256 MB + 256 MB >> the 126 MB L2), one event pair
+            # around the whole region.
+            try:
+                vols = [vol] + [vol.clone() for _ in range(3)]
+                outs = [torch.empty(D, 1, D, D, dtype=torch.float32, device=vol.device) for _ in range(4)]
+                mx = ops.plane_max(vol)
+                offs = [0, D, 2 * D]
+
+                def gather_round():
+                    for i in range(4):
+                        for p in range(3):
+                            ops.slice_gather(vols[i], p, 0, D, slice_max_in=mx[offs[p]:offs[p] + D].contiguous(), out=outs[(i + p) % 4])
+                gather_round(); torch.cuda.synchronize()
+                gs = torch.cuda.Stream()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(gs):
+                    gather_round()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(graph, stream=gs):
+                        gather_round()
+                    graph.replay(); torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 10
+                    e0.record(gs)
+                    for _ in range(reps):
+                        graph.replay()
+                    e1.record(gs); torch.cuda.synchronize()
+                gbm = reps * 4 * 3 * V * 8.0 / 1e9
+                ach = gbm / (e0.elapsed_time(e1) * 1e-3)
+                hbm_kernels["slice_gather"] = {"achieved": ach, "unit": "GB/s", "peak": peaks["hbm_gbs"], "algorithmic_gb": gb,
+                                               "how": "CUDA-graph replay of 120 whole-plane launches over 4 volumes (working set 512 MB > L2), "
+                                                      "normalisation fused, one event pair",
+                                               "in_step_event_pairs_gbs": in_step}
+                del vols, outs
+            except Exception as ex:  # noqa
+                hbm_kernels["slice_gather"] = {"achieved": in_step, "unit": "GB/s", "peak": peaks["hbm_gbs"], "algorithmic_gb": gb,
+                                               "how": "per-launch event pairs inside the step (graph microbench failed: %s)" % str(ex)[:120]}
         if "pmu_scatter_accum" in tot:
             gb = P * V * 2 * 3 * 4.0 * 3.0 * world_frac / 1e9  # read sums + RMW (read+write) accumulators, 2*C floats/voxel
             hbm_kernels["scatter_accum"] = {"achieved": gb / (tot["pmu_scatter_accum"]["ms"] * 1e-3), "unit": "GB/s",

@@ -257,6 +257,16 @@ int pmu_fcomb_zbias_bwd_f32(const float* rs, const float* z, const float* w0, fl
 int pmu_conv1x1_bb_f32(const float* x, const float* w, int ldw, const float* bias, int bias_bstride, float* y,
                        int B, int Cin, int Cout, int64_t HW, int relu, void* stream);
 
+/* ---- training step, bf16 tensor-core mode ------------------------------------------------- */
+/* fp32 NCHW [B,C,H,W] -> bf16 NHWC [B,H,W,C] (operand cast for the tensor-core convolutions). */
+int pmu_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream);
+/* tcgen05 weight gradient of conv3x3 pad 1 (ntaps = 9) / conv1x1 (ntaps = 1):
+ * dw fp32 [Cout][ntaps][C0+C1] += sum_{b,h,w} dy[b,h,w,co] * cat(x0,x1)[b,h+ky-1,w+kx-1,ci]   (tap = ky*3+kx)
+ * x0 bf16 [B,H,W,C0], x1 (nullable) bf16 [B,H,W,C1], dy bf16 [B,H,W,Cout]; channels multiples of 64.
+ * The reduction over pixels is split across CTAs; partials are added with fp32 atomics (zero-fill dw). */
+int pmu_conv_wgrad_bf16(const void* x0, int C0, const void* x1, int C1, const void* dy, float* dw, int B,
+                        int H, int W, int Cout, int ntaps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,6 +216,34 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, 
   }
 }
 
+// ---------------------------------------------------------------------------------
+// [B][C][HW] fp32 -> [B][HW][C] bf16 through a 64 px x 64 ch shared tile (training: the tensor-core
+// convolutions of the bf16 training mode take NHWC bf16 operands; BatchNorm etc. stay fp32 NCHW)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t HW, int C) {
+  __shared__ float tile[64][65];     // [channel][pixel]
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = t + 256 * k;  // 0..4095
+    const int cc = idx >> 6, pp = idx & 63;
+    tile[cc][pp] = (p0 + pp < HW && c0 + cc < C) ? __ldg(x + ((int64_t)b * C + c0 + cc) * HW + p0 + pp) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = t + 256 * k;  // 0..2047
+    const int pp = idx >> 5, c2 = (idx & 31) * 2;
+    if (p0 + pp < HW && c0 + c2 < C)
+      *reinterpret_cast<__nv_bfloat162*>(y + ((int64_t)b * HW + p0 + pp) * C + c0 + c2) =
+          __floats2bfloat162_rn(tile[c2][pp], tile[c2 + 1][pp]);
+  }
+}
+
 }  // namespace pmu
 
 using namespace pmu;
@@ -266,6 +294,16 @@ extern "C" int pmu_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, 
   const int64_t HW = (int64_t)H * W;
   dim3 grid((unsigned)cdiv64(HW, 64), cdiv(C, 64), B);
   nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, HW, C);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream) {
+  PMU_CHECK_ARG(x && y && B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0, "pmu_nchw_f32_to_nhwc_bf16: bad arguments");
+  PMU_CHECK_SUPPORTED(C % 2 == 0, "pmu_nchw_f32_to_nhwc_bf16: C must be even");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)cdiv64(HW, 64), cdiv(C, 64), B);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), HW, C);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

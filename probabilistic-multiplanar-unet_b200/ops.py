@@ -519,3 +519,26 @@ def conv1x1_bb_f32(x, w, ldw, bias, bias_bstride, Cin, Cout, relu):
     _launch(lib, "pmu_conv1x1_bb_f32", (_p(x), _p(w), int(ldw), _p(bias), int(bias_bstride), _p(y), B, Cin, Cout, H * W,
                                       int(relu), st,))
     return y
+
+
+# ----------------------------------------------------------------------------- training step (bf16 tensor-core mode)
+def nchw_f32_to_nhwc_bf16(x):
+    _f32(x, "x")
+    B, C, H, W = x.shape
+    y = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=x.device)
+    lib, st = _prep(x, y)
+    _launch(lib, "pmu_nchw_f32_to_nhwc_bf16", (_p(x), _p(y), B, H, W, C, st,))
+    return y
+
+
+def conv_wgrad_bf16(x0, dy, dw, x1=None, ntaps=9):
+    """dw fp32 [Cout, ntaps, C0+C1] += tcgen05 weight gradient; x0/x1/dy bf16 NHWC."""
+    _bf16(x0, "x0"); _bf16(x1, "x1"); _bf16(dy, "dy"); _f32(dw, "dw")
+    B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    Cout = dy.shape[3]
+    assert tuple(dw.shape) == (Cout, ntaps, C0 + C1), dw.shape
+    lib, st = _prep(x0, x1, dy, dw)
+    global _META
+    _META = {"flops": 2.0 * B * H * W * Cout * ntaps * (C0 + C1)}
+    _launch(lib, "pmu_conv_wgrad_bf16", (_p(x0), C0, _p(x1), C1, _p(dy), _p(dw), B, H, W, Cout, int(ntaps), st,))

@@ -237,3 +237,47 @@ def test_training_loop_reduces_loss(ops):
             optimizer.zero_grad()
     assert all(np.isfinite(losses))
     assert np.mean(losses[-2:]) < 0.9 * np.mean(losses[:2]), losses
+
+
+# --------------------------------------------------------------------------- bf16 tensor-core training mode
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def test_nchw_f32_to_nhwc_bf16(ops):
+    x = torch.randn(3, 70, 9, 13, generator=_g(20))
+    y = ops.nchw_f32_to_nhwc_bf16(x.cuda())
+    assert torch.equal(y.cpu(), _nhwc(x).to(torch.bfloat16))
+    assert torch.equal(ops.nhwc_bf16_to_nchw_f32(y).cpu(), _bf(x))
+
+
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W,ntaps", [
+    (2, 64, 0, 64, 16, 16, 9),        # Cin = 64: the two units of an M tile are two taps; 9 units -> odd pair count
+    (1, 128, 0, 64, 32, 32, 9),
+    (3, 64, 64, 128, 16, 16, 9),      # two-source (skip concat), N = 128
+    (2, 128, 0, 256, 8, 8, 9),        # N = 256; brick spans two images
+    (5, 256, 0, 256, 4, 4, 9),        # brick spans 8 images, ragged batch
+    (2, 64, 0, 128, 24, 40, 9),       # partial tiles
+    (2, 128, 0, 64, 16, 16, 1),       # 1x1
+])
+def test_conv_wgrad_bf16_tcgen05(ops, B, C0, C1, Cout, H, W, ntaps):
+    """tcgen05 weight gradient (MN-major operands, split-K atomics) vs torch autograd on the same
+    bf16-rounded operands: fp32 accumulation on both sides, so the tolerance is the summation order."""
+    g = _g(21)
+    Cin = C0 + C1
+    x = _bf(torch.randn(B, Cin, H, W, generator=g)).requires_grad_(False)
+    dy = _bf(torch.randn(B, Cout, H, W, generator=g))
+    k = 3 if ntaps == 9 else 1
+    w = torch.zeros(Cout, Cin, k, k, requires_grad=True)
+    F.conv2d(x, w, None, padding=k // 2).backward(dy)
+    ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, ntaps, Cin)          # [co][tap][ci]
+    xn = _nhwc(x).to(torch.bfloat16).cuda()
+    x0 = xn[..., :C0].contiguous()
+    x1 = xn[..., C0:].contiguous() if C1 else None
+    dw = torch.zeros(Cout, ntaps, Cin, device="cuda")
+    ops.conv_wgrad_bf16(x0, _nhwc(dy).to(torch.bfloat16).cuda(), dw, x1, ntaps)
+    _close(dw, ref, 2e-4, "tcgen05 wgrad")

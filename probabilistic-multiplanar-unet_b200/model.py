@@ -273,9 +273,9 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             if not (self.training and training):
                 raise NotImplementedError("gradients are built for net.train() + forward(training=True) (what train.py "
                                           "does); wrap inference in torch.no_grad()")
-            if self.precision != "fp32":
-                raise NotImplementedError("the training step is built for precision='fp32' (parity mode); bf16 training "
-                                          "(tcgen05 dgrad / wgrad) is the next scope row")
+            if self.precision == "bf16" and (any(f % 64 for f in self.num_filters) or patch.shape[2] % 16 or patch.shape[3] % 16):
+                raise NotImplementedError("bf16 training needs channel counts that are multiples of 64 and H, W divisible "
+                                          "by 16 (tcgen05 / TMA tiles); use precision='fp32' for this model")
             if segm is None:
                 raise ValueError("forward(training=True) needs segm for the posterior")
             if patch.device.type != "cuda":

@@ -1,4 +1,5 @@
-"""Training step of ProbabilisticUnet through the CUDA kernels (fp32 NCHW parity mode).
+"""Training step of ProbabilisticUnet through the CUDA kernels: fp32 NCHW parity mode and the bf16
+tensor-core mode (precision="bf16": every convolution GEMM — forward, dgrad, wgrad — on tcgen05).
 
 What the reference's training loop asks of autograd (train.py:85-110 via
 ProbUNetTrainer.predict / loss, trainer/probunet_trainer.py:27-39):
@@ -47,12 +48,46 @@ class _Tape:
 
 
 # ------------------------------------------------------------------ conv3x3 + BN(train) + ReLU
+# bf16 tensor-core mode: BatchNorm / ReLU / pooling stay fp32 NCHW (batch statistics in fp32); the three
+# GEMMs of every convolution — forward, data gradient, weight gradient — run on tcgen05 with bf16 NHWC
+# operands (conv_tc.cu forward kernel twice, wgrad_tc.cu), bracketed by layout casts.
+_BF16 = {"on": False, "cache": {}}
+# Self-check hook (tests / debugging): when CHECK_LOG is a list, every tcgen05 dgrad / wgrad of the step is
+# recomputed by the fp32 CUDA-core kernel on the SAME operands and (kind, Cin, Cout, H, relative L2 deviation)
+# is appended — the deviation is then pure bf16 operand rounding (~3e-3).
+CHECK_LOG = None
+
+
+def _to_bf16_nhwc(t):
+    """bf16 NHWC copy of an fp32 NCHW activation, cached per step (skips / pooled maps feed several GEMMs)."""
+    c = _BF16["cache"]
+    k = id(t)
+    if k not in c:
+        c[k] = (t, ops.nchw_f32_to_nhwc_bf16(t))      # keep t alive so id() stays unique
+    return c[k][1]
+
+
+def _tc_ok(conv):
+    return _BF16["on"] and conv.weight.shape[0] % 64 == 0 and conv.weight.shape[1] % 64 == 0
+
+
 def _cbr_fwd(conv: nn.Conv2d, bn: nn.BatchNorm2d, x0, x1=None):
-    y = ops.conv3x3_f32(x0, _d(conv.weight), _d(conv.bias), relu=False, x1=x1)
+    tc = _tc_ok(conv) and x0.shape[1] % 64 == 0 and (x1 is None or x1.shape[1] % 64 == 0)
+    if tc:
+        w = _d(conv.weight)
+        wpack = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()     # [Cout][tap][Cin]
+        yb = ops.conv_gemm_bf16(_to_bf16_nhwc(x0), wpack, _d(conv.bias), w.shape[0], 9, False,
+                                x1=None if x1 is None else _to_bf16_nhwc(x1))
+        y = ops.nhwc_bf16_to_nchw_f32(yb)
+        if CHECK_LOG is not None:
+            ref = ops.conv3x3_f32(x0, w, _d(conv.bias), relu=False, x1=x1)
+            CHECK_LOG.append(("fwd", w.shape[1], w.shape[0], y.shape[2], float((y - ref).norm() / ref.norm())))
+    else:
+        y = ops.conv3x3_f32(x0, _d(conv.weight), _d(conv.bias), relu=False, x1=x1)
     a, mean, var = ops.bn_train_fwd_f32(y, _d(bn.weight), _d(bn.bias), bn.eps, True,
                                         0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var)
     bn.num_batches_tracked += 1
-    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var}
+    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var, "tc": tc}
 
 
 def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
@@ -60,15 +95,41 @@ def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
     dy, dg, db = ops.bn_train_bwd_f32(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True)
     tape.put(bn.weight, dg)
     tape.put(bn.bias, db)
-    dw = torch.zeros_like(_d(conv.weight))
+    tape.put(conv.bias, ops.channel_sums_f32(dy))
+    w = _d(conv.weight)
+    Cout, Cin = w.shape[0], w.shape[1]
+    C0 = rec["x0"].shape[1]
+    if rec["tc"]:
+        dyb = ops.nchw_f32_to_nhwc_bf16(dy)
+        x0b = _to_bf16_nhwc(rec["x0"])
+        x1b = None if rec["x1"] is None else _to_bf16_nhwc(rec["x1"])
+        dwp = torch.zeros(Cout, 9, Cin, dtype=torch.float32, device=dy.device)
+        ops.conv_wgrad_bf16(x0b, dyb, dwp, x1b, 9)
+        tape.put(conv.weight, dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous())
+        if CHECK_LOG is not None:
+            ref = torch.zeros_like(w)
+            ops.conv3x3_wgrad_f32(rec["x0"], dy, ref, rec["x1"])
+            got = dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+            CHECK_LOG.append(("wgrad", Cin, Cout, dy.shape[2], float((got - ref).norm() / ref.norm())))
+        if not need_dx:
+            return None, None
+        # data gradient: the forward tcgen05 kernel with W transposed (ci <-> co) and flipped, [ci][tap][co]
+        wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).to(torch.bfloat16)
+        dx0 = ops.nhwc_bf16_to_nchw_f32(ops.conv_gemm_bf16(dyb, wt[:C0].contiguous(), None, C0, 9, False))
+        if CHECK_LOG is not None:
+            ref = ops.conv3x3_f32(dy, w.flip(2, 3).transpose(0, 1)[:C0].contiguous(), None, relu=False)
+            CHECK_LOG.append(("dgrad", Cin, Cout, dy.shape[2], float((dx0 - ref).norm() / ref.norm())))
+        dx1 = None
+        if rec["x1"] is not None:
+            dx1 = ops.nhwc_bf16_to_nchw_f32(ops.conv_gemm_bf16(dyb, wt[C0:].contiguous(), None, Cin - C0, 9, False))
+        return dx0, dx1
+    dw = torch.zeros_like(w)
     ops.conv3x3_wgrad_f32(rec["x0"], dy, dw, rec["x1"])
     tape.put(conv.weight, dw)
-    tape.put(conv.bias, ops.channel_sums_f32(dy))
     if not need_dx:
         return None, None
     # data gradient = the same 3x3 kernel with the weights transposed (ci <-> co) and flipped
-    wt = _d(conv.weight).flip(2, 3).transpose(0, 1)
-    C0 = rec["x0"].shape[1]
+    wt = w.flip(2, 3).transpose(0, 1)
     dx0 = ops.conv3x3_f32(dy, wt[:C0].contiguous(), None, relu=False)
     dx1 = ops.conv3x3_f32(dy, wt[C0:].contiguous(), None, relu=False) if rec["x1"] is not None else None
     return dx0, dx1
@@ -228,6 +289,19 @@ class TrainStep:
     def __init__(self, net, patch: torch.Tensor, segm: torch.Tensor):
         self.net = net
         self.patch, self.segm = patch, segm
+        self.bf16 = net.precision == "bf16"
+        self._mode(True)
+        try:
+            self._forward(net, patch, segm)
+        finally:
+            self._mode(False)
+
+    def _mode(self, on: bool):
+        _BF16["on"] = on and self.bf16
+        if not on:
+            _BF16["cache"] = {}
+
+    def _forward(self, net, patch, segm):
         self.mu_q, self.ls_q, self.post = _gauss_fwd(net.posterior, patch, segm)
         self.mu_p, self.ls_p, self.prior = _gauss_fwd(net.prior, patch)
         self.feat, self.unet = _unet_fwd(net.unet, patch)
@@ -252,6 +326,13 @@ class TrainStep:
 
     def backward(self, g: float) -> Dict[int, torch.Tensor]:
         """g = d(loss)/d(elbo).  elbo = -(rec + beta * mean_b KL)."""
+        self._mode(True)
+        try:
+            return self._backward(g)
+        finally:
+            self._mode(False)
+
+    def _backward(self, g: float) -> Dict[int, torch.Tensor]:
         net, tape = self.net, _Tape()
         B = self.mu_q.shape[0]
         dlogits = ops.ce_bwd_f32(self.logits, self.segm_t, -g)

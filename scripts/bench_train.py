@@ -13,7 +13,8 @@ from oracle import pmu_oracle as O
 B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 8
 steps = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 3
 torch.manual_seed(0)
-trainer = pmu_b200.ProbUNetTrainer("cuda", n_channels=1, n_classes=3, latent_dim=6, beta=10)
+PREC = "bf16" if "--bf16" in sys.argv else "fp32"
+trainer = pmu_b200.ProbUNetTrainer("cuda", n_channels=1, n_classes=3, latent_dim=6, beta=10, precision=PREC)
 net = trainer.net.train()
 opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
 vol, lab = O.phantom(256, seed=3)
@@ -38,7 +39,7 @@ ms = e0.elapsed_time(e1) / steps
 # backward = dgrad + wgrad ~ 2 x forward of the differentiated part
 fwd = 96.18 + 2 * 33.90 + 2 * 1.69
 flop = B * (fwd + 2 * (fwd - 1.69)) * 1e9
-print(f"train step B={B} x 256x256 fp32: {ms:.1f} ms/step, {B / ms * 1e3:.2f} slices/s, {flop / ms / 1e9:.1f} TFLOP/s (useful), loss {float(loss):.1f}")
+print(f"train step B={B} x 256x256 {PREC}: {ms:.1f} ms/step, {B / ms * 1e3:.2f} slices/s, {flop / ms / 1e9:.1f} TFLOP/s (useful), loss {float(loss):.1f}")
 ops.PROFILE = []
 step(); torch.cuda.synchronize()
 tot = collections.defaultdict(float)

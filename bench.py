@@ -266,9 +266,12 @@ def run_ours(args):
         if dom[0] == "pmu_conv_gemm_bf16":
             c = dom[1]
             ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
-            roof = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": ach,
+            tk = [traffic[k] for k in ("conv_tc_kernel", "conv_rs_kernel") if k in traffic]
+            tr = (sum(t["dram_bytes"] for t in tk) / max(1, sum(t["launches_captured"] for t in tk))) if tk else None
+            roof = {"kernel": "conv_tc_kernel + conv_rs_kernel (tcgen05 implicit GEMM, generic and row-shift variants)",
+                    "bound": "tensor", "achieved": ach,
                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                    "traffic": (traffic.get("conv_tc_kernel") or {}).get("dram_bytes_per_launch"),
+                    "traffic": tr,
                     "traffic_note": "dram__bytes_read+write per launch, mean over the conv launches of one ncu --set full "
                                     "capture (profiles/); algorithmic bytes per launch (in+out+weights) = "
                                     f"{c.get('bytes', 0.0) / max(c['n'], 1):.3e}",

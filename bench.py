@@ -142,7 +142,8 @@ def run_reference(args):
     spp = 1            # one slice per plane per step keeps K+W steps within minutes on few cores
     rates = []
     for i in range(args.warmup + args.steps):
-        v, dt, cores, n_done = cpu_reference_rate(D, N, spp)
+        # all host threads, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+        v, dt, cores, n_done = cpu_reference_rate(D, N, spp, threads=os.cpu_count())
         if i >= args.warmup:
             rates.append((v, dt))
     tot_t = sum(dt for _, dt in rates)
@@ -357,7 +358,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores, n_done = cpu_reference_rate(D, N, args.cpu_slices_per_plane)
+        v, dt, cores, n_done = cpu_reference_rate(D, N, args.cpu_slices_per_plane, threads=os.cpu_count())
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n_done} of {3 * D} slices ({args.cpu_slices_per_plane} equally spaced per plane), "
                                   f"forward once + {N} x fcomb + softmax + accumulate, {dt:.1f} s of CPU time, extrapolated"}

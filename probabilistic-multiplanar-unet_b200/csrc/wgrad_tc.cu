@@ -102,7 +102,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    if (elect_one()) {      // single provably-active thread: descriptors stay in uniform registers
       uint32_t kc = 0;
       for (int kb = kb_lo; kb < kb_hi; ++kb, ++kc) {
         int t = kb;
@@ -129,7 +129,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (elect_one()) {      // single provably-active thread: descriptors stay in uniform registers
       constexpr uint32_t idesc = umma_idesc_bf16_mn(128, N);
       uint32_t kc = 0;
       for (int kb = kb_lo; kb < kb_hi; ++kb, ++kc) {

@@ -29,7 +29,8 @@ def step():
     opt.step(); opt.zero_grad()
     return loss
 
-step(); torch.cuda.synchronize()
+for _ in range(3): step()          # warm-up: module load, allocator, lazy cudaFuncSetAttribute (iteration 1 is still 8x slower)
+torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps): loss = step()

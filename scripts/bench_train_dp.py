@@ -22,7 +22,8 @@ s0 = 40 + rank * B
 imgs = torch.from_numpy(O.plane_slices(vol, 0, s0, B)).cuda()
 masks = torch.from_numpy(lab[s0:s0 + B, None].astype(np.float32)).cuda()
 steps = 3
-pmu_b200.dp_train_step(trainer, imgs, masks, opt)
+for _ in range(3):
+    pmu_b200.dp_train_step(trainer, imgs, masks, opt)
 torch.cuda.synchronize(); dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()

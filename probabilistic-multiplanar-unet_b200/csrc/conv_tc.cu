@@ -461,10 +461,14 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1u;
             mbar_wait(bar_empty + s * 8, ph ^ 1u);
             const uint32_t sa = smem_base + L::RING_OFF + s * L::STAGE_BYTES;
-            mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
             // rows h0-1 .. h0+16, pixels w0+dx-1 .. +7; out-of-image rows / pixels are zero-filled = conv padding
-            if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx - 1, h0 - 1, b0);
-            else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx - 1, h0 - 1, b0);
+            if (p.debug & 2) {           // experiment: no activation loads
+              mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES - L::BOX_BYTES);
+            } else {
+              mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+              if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx - 1, h0 - 1, b0);
+              else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx - 1, h0 - 1, b0);
+            }
             if (!RESB) {
 #pragma unroll
               for (int dy = 0; dy < 3; ++dy)

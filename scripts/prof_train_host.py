@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, pmu_b200
 from oracle import pmu_oracle as O
-B = 8
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 torch.manual_seed(0)
 trainer = pmu_b200.ProbUNetTrainer("cuda", n_channels=1, n_classes=3, latent_dim=6, beta=10, precision="bf16")
 net = trainer.net.train()

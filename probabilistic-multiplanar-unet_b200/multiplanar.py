@@ -96,6 +96,11 @@ class MultiPlanarPredictor:
         self.L = self.net.fcomb["L"]
 
     # ------------------------------------------------------------------
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
     def _to_device_volume(self, vol) -> torch.Tensor:
         if isinstance(vol, np.ndarray):
             vol = torch.from_numpy(np.ascontiguousarray(vol, dtype=np.float32))
@@ -107,9 +112,12 @@ class MultiPlanarPredictor:
             vol = big
         return vol.contiguous()
 
-    def accumulate(self, vol: torch.Tensor, eps: torch.Tensor, acc: torch.Tensor, only_plane: Optional[int] = None) -> int:
+    def accumulate(self, vol: torch.Tensor, eps: torch.Tensor, acc: torch.Tensor, only_plane: Optional[int] = None,
+                   plane0_last: bool = False, on_slab=None) -> int:
         """Run this rank's slices and add their sums into acc [2,X,C,Y,Z]; returns #slices done.
-        only_plane restricts the pass to one view (per-view volumes of eval.py:176-190)."""
+        only_plane restricts the pass to one view (per-view volumes of eval.py:176-190).
+        plane0_last processes the x-slicing view after the others, so that after every plane-0 batch the voxels
+        of that x-slab are complete; on_slab(x0, x1) is then called (streaming finalise + device->host copy)."""
         dims = tuple(vol.shape)
         net, N = self.net, self.n_samples
         my = shard_slices(dims, self.planes, self.rank, self.world)
@@ -119,7 +127,10 @@ class MultiPlanarPredictor:
         maxes = ops.plane_max(vol) if exact else None
         offs = (0, dims[0], dims[0] + dims[1])
         done = 0
-        for pi, p in enumerate(self.planes):
+        order = list(enumerate(self.planes))
+        if plane0_last:
+            order = [(pi, p) for pi, p in order if p != 0] + [(pi, p) for pi, p in order if p == 0]
+        for pi, p in order:
             if p not in my or (only_plane is not None and p != only_plane):
                 continue
             s_lo, s_hi = my[p]
@@ -142,15 +153,22 @@ class MultiPlanarPredictor:
                 sums = net.fcomb_sums(feat, mu, sigma, eps[pi, s0:s0 + ns].contiguous())
                 ops.scatter_accum_(sums, p, s0, dims, acc[0], acc[1])
                 done += ns
+                if on_slab is not None and p == 0:
+                    on_slab(s0, s0 + ns)
         return done
 
     @torch.no_grad()
     def predict(self, vol, eps: Optional[torch.Tensor] = None, seed: int = 4321, want_labels: bool = False,
-                keep_sums: bool = False, per_plane: bool = False) -> Dict[str, torch.Tensor]:
+                keep_sums: bool = False, per_plane: bool = False, host_out: Optional[Dict[str, torch.Tensor]] = None
+                ) -> Dict[str, torch.Tensor]:
         """vol: [d0,d1,d2] fp32 (numpy / CPU / CUDA).  eps: [P, D, N, L] standard-normal draws
         (host or device); generated on the device from `seed` when omitted.  Returns mean / var
         [x,C,y,z], entropy [x,y,z] (valid on rank 0 when world_size > 1).  per_plane=True also
-        returns "plane_means": the per-view probability volumes volume1/2/3 of eval.py:176-190."""
+        returns "plane_means": the per-view probability volumes volume1/2/3 of eval.py:176-190.
+        host_out = {"mean", "var", "entropy"[, "labels"]} of PINNED host tensors: the results are also delivered to
+        the host; on one GPU the x-slicing view runs last, every finished x-slab is finalised and copied out on a
+        side stream while the next slice batch computes (the 470 MB device->host copy of a 256^3 result leaves
+        the critical path), and the call returns with the copies complete on the current stream."""
         if self.interp != "exact" and not self.identity_grid:
             raise NotImplementedError("voxel fusion (scatter back onto the voxel lattice) is defined for the standard "
                                       "axis-aligned grids; arbitrary resampling grids are available through "
@@ -176,6 +194,32 @@ class MultiPlanarPredictor:
                     plane_means.append(ops.fuse_finalize(pacc[0], pacc[1], float(N), want_var=False, want_entropy=False)[0])
                 acc += pacc
             out["plane_means"] = plane_means
+        elif host_out is not None and self.world == 1 and 0 in self.planes:
+            # streaming path: finalise + copy out x-slabs as the last view completes them
+            mean = torch.empty_like(acc[0])
+            var = torch.empty_like(acc[0])
+            ent = torch.empty(dims, dtype=torch.float32, device=self.device)
+            lab = torch.empty(dims, dtype=torch.uint8, device=self.device) if want_labels else None
+            main, side = torch.cuda.current_stream(self.device), self._side_stream()
+            keys = [("mean", mean), ("var", var), ("entropy", ent)] + ([("labels", lab)] if want_labels else [])
+
+            def on_slab(x0, x1):
+                ops.fuse_finalize(acc[0][x0:x1], acc[1][x0:x1], float(P * N), want_labels=want_labels,
+                                  out=(mean[x0:x1], var[x0:x1], ent[x0:x1], None if lab is None else lab[x0:x1]))
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for k, t in keys:
+                        if k in host_out:
+                            host_out[k][x0:x1].copy_(t[x0:x1], non_blocking=True)
+
+            self.accumulate(vol, eps, acc, plane0_last=True, on_slab=on_slab)
+            main.wait_stream(side)
+            out.update(mean=mean, var=var, entropy=ent)
+            if want_labels:
+                out["labels"] = lab
+            if keep_sums:
+                out["S1"], out["S2"] = acc[0], acc[1]
+            return out
         else:
             self.accumulate(vol, eps, acc)
             reduce_accumulators(acc, self.world, self.group, dst=0)
@@ -184,6 +228,10 @@ class MultiPlanarPredictor:
             out.update(mean=mean, var=var, entropy=ent)
             if want_labels:
                 out["labels"] = lab
+            if host_out is not None:
+                for k in ("mean", "var", "entropy", "labels"):
+                    if k in host_out and k in out:
+                        host_out[k].copy_(out[k], non_blocking=True)
         if keep_sums:
             out["S1"], out["S2"] = acc[0], acc[1]
         return out

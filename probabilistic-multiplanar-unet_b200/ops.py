@@ -309,13 +309,17 @@ def scatter_accum_(slice_sums, plane, s0, dims, S1, S2):
     _launch(lib, "pmu_scatter_accum", (_p(slice_sums), int(plane), int(s0), int(ns), _dims(dims), int(C), _p(S1), _p(S2), st,))
 
 
-def fuse_finalize(S1, S2, count, want_var=True, want_entropy=True, want_labels=False):
+def fuse_finalize(S1, S2, count, want_var=True, want_entropy=True, want_labels=False, out=None):
+    """out = (mean, var, entropy, labels) writes into caller tensors (x-slabs of the full outputs)."""
     _f32(S1, "S1"); _f32(S2, "S2")
     X, C, Y, Z = S1.shape
-    mean = torch.empty_like(S1)
-    var = torch.empty_like(S1) if want_var else None
-    ent = torch.empty(X, Y, Z, dtype=torch.float32, device=S1.device) if want_entropy else None
-    lab = torch.empty(X, Y, Z, dtype=torch.uint8, device=S1.device) if want_labels else None
+    if out is not None:
+        mean, var, ent, lab = out
+    else:
+        mean = torch.empty_like(S1)
+        var = torch.empty_like(S1) if want_var else None
+        ent = torch.empty(X, Y, Z, dtype=torch.float32, device=S1.device) if want_entropy else None
+        lab = torch.empty(X, Y, Z, dtype=torch.uint8, device=S1.device) if want_labels else None
     lib, st = _prep(S1, S2, mean, var, ent, lab)
     _launch(lib, "pmu_fuse_finalize", (_p(S1), _p(S2), float(count), _dims((X, Y, Z)), C, _p(mean), _p(var), _p(ent),
                                      _p(lab), st,))

@@ -179,6 +179,17 @@ def test_multiplanar_properties_and_sharding(pmu, trainer_sd):
     # determinism: same inputs, same bits
     out2 = one.predict(vol, eps=eps)
     assert torch.equal(out2["mean"], mean)
+    # streaming host output: the x-slicing view runs last, finished x-slabs are finalised and copied to pinned host
+    # memory on a side stream — same results up to the fp32 summation order of the three views
+    host = {"mean": torch.empty(D, 3, D, D).pin_memory(), "var": torch.empty(D, 3, D, D).pin_memory(),
+            "entropy": torch.empty(D, D, D).pin_memory(), "labels": torch.empty(D, D, D, dtype=torch.uint8).pin_memory()}
+    out3 = one.predict(vol, eps=eps, host_out=host, want_labels=True)
+    torch.cuda.current_stream().synchronize()
+    torch.testing.assert_close(out3["mean"], mean, atol=1e-6, rtol=0)
+    torch.testing.assert_close(out3["var"], var, atol=1e-6, rtol=0)
+    torch.testing.assert_close(out3["entropy"], ent, atol=1e-5, rtol=0)
+    for k in host:
+        assert torch.equal(host[k], out3[k].cpu()), k
 
 
 def test_fitted_model_dice(pmu, golden_dir):

@@ -225,7 +225,7 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 
 // NHWC = false: enc[B][C][hw];  NHWC = true: enc[B][hw][C]
 template <typename T, bool NHWC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gauss_head_kernel(const T* __restrict__ enc, const float* __restrict__ w, const float* __restrict__ bvec,
                   float* __restrict__ mu, float* __restrict__ log_sigma, int C, int hw, int L) {
   extern __shared__ float mean_s[];  // [C]
@@ -238,6 +238,31 @@ gauss_head_kernel(const T* __restrict__ enc, const float* __restrict__ w, const 
       for (int i = lane; i < hw; i += 32) s += to_f32<T>(p[i]);
       s = warp_sum(s);
       if (lane == 0) mean_s[c] = s * inv;
+    }
+  } else if (sizeof(T) == 2 && C % 8 == 0 && blockDim.x % (C / 8) == 0) {
+    // bf16 NHWC: thread = (8-channel group, pixel group); 128-bit loads, `pg` pixel groups reduced through smem
+    // (deterministic order; a block per slice streams its 0.5 MB at full per-SM bandwidth instead of 2 B per thread)
+    const int groups = C / 8, pgs = blockDim.x / groups;
+    const int cg = threadIdx.x % groups, pg = threadIdx.x / groups;
+    float* part = mean_s + C;          // [pgs][C]
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const uint4* p = reinterpret_cast<const uint4*>(enc + (int64_t)b * hw * C) + cg;
+#pragma unroll 4
+    for (int i = pg; i < hw; i += pgs) {
+      const uint4 v = __ldg(p + (int64_t)i * groups);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[2 * j] += __low2float(h[j]); acc[2 * j + 1] += __high2float(h[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[pg * C + cg * 8 + j] = acc[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int g = 0; g < pgs; ++g) s += part[g * C + c];
+      mean_s[c] = s * inv;
     }
   } else {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -471,8 +496,23 @@ extern "C" int pmu_gauss_head_bf16(const void* enc, const float* w, const float*
                                    float* log_sigma, int B, int C, int h, int w_, int L, void* stream) {
   PMU_CHECK_ARG(enc && w && b && mu && log_sigma, "pmu_gauss_head_bf16: null pointer");
   PMU_CHECK_ARG(B > 0 && C > 0 && h > 0 && w_ > 0 && L > 0 && C <= 12288, "pmu_gauss_head_bf16: bad shape");
-  gauss_head_kernel<__nv_bfloat16, true><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(enc), w, b, mu, log_sigma, C, h * w_, L);
+  // vector path: threads = (C/8 channel groups) x (pixel groups), as many pixel groups as fit 1024 threads
+  PMU_CHECK_ARG(aligned16(enc), "pmu_gauss_head_bf16: enc must be 16-byte aligned");
+  int threads = 256;
+  size_t smem = C * sizeof(float);
+  if (C % 8 == 0) {
+    const int groups = C / 8;
+    if (groups <= 1024) {
+      int pgs = std::max(1, std::min(1024 / groups, h * w_));
+      while (pgs > 1 && (groups * pgs) % 32) --pgs;
+      if ((groups * pgs) % 32 == 0) threads = groups * pgs;
+    }
+    if (threads % groups == 0) smem = (size_t)(1 + threads / groups) * C * sizeof(float);   // the kernel takes the vector path
+  }
+  auto kern = gauss_head_kernel<__nv_bfloat16, true>;
+  if (smem > 48 * 1024) PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B, threads, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(enc), w, b, mu, log_sigma, C,
+                                                  h * w_, L);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

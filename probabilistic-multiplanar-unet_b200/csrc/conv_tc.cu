@@ -522,6 +522,198 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------
+// First layer (Cin = 1 -> 64) on the tensor cores.  The CUDA-core stencil (layers_bf16.cu) needs 576 FMAs per pixel
+// and ran at 2.2 TB/s of output; here the 3x3 neighbourhood of every pixel is laid out as ONE K-major operand row
+// (im2col in shared memory, built by four producer warps from a staged fp32 patch) and the 9-tap contraction is two
+// K = 16 UMMAs per 128-pixel tile: k = 0..8 the bf16 high parts of the nine taps, k = 9..17 their bf16 low parts
+// (x = hi + lo keeps the fp32 input's precision; the weight row repeats the nine weights for both), the rest zero.
+// The kernel is then bound by its 128 B / pixel of output, written by the shared TMA-store epilogue.
+// ------------------------------------------------------------------------------------
+constexpr int CF_THREADS = 448;           // warp 1: MMA issuer, warps 2..5 / 6..9: epilogue groups 0 / 1, warps 10..13: im2col producers
+struct ConvFirstSmem {
+  static constexpr int A_BYTES = TC_BM * 128;                 // [128 px][64 k] bf16 rows of 128 B (k < 32 used), x2
+  static constexpr int W_OFF = 2 * A_BYTES;                   // [64 couts][64 k]
+  static constexpr int STG_OFF = W_OFF + 64 * 128;            // one staging tile per epilogue group
+  static constexpr int PATCH_OFF = STG_OFF + 2 * TC_BM * 128; // fp32 (8+2) x (16+2) input patch, x2
+  static constexpr int PATCH_FLOATS = 192;
+  static constexpr int BAR_OFF = PATCH_OFF + 2 * PATCH_FLOATS * 4;   // a_full[2], a_empty[2], tfull[2], tempty[2]
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + 8 * 8;
+  static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;
+  static constexpr int DYN_BYTES = BIAS_OFF + 64 * 4;
+};
+
+__global__ void __launch_bounds__(CF_THREADS, 2)
+conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmY, const ConvTcParams p, const float* __restrict__ x,
+                     const float* __restrict__ w, const float* __restrict__ bias) {
+  using L = ConvFirstSmem;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const uint32_t bar_afull = smem_base + L::BAR_OFF, bar_aempty = bar_afull + 16, bar_tfull = bar_aempty + 16,
+                 bar_tempty = bar_tfull + 16;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem_raw + L::TMEM_PTR_OFF);
+  float* bias_s = reinterpret_cast<float*>(smem_raw + L::BIAS_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmY);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_afull + a * 8, 128); mbar_init(bar_aempty + a * 8, 1);
+      mbar_init(bar_tfull + a * 8, 1); mbar_init(bar_tempty + a * 8, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(smem_base + L::TMEM_PTR_OFF);
+  // zero the operand tiles (k >= 18 must read as zero), then the weight tile: row co = [w(9) | w(9) | 0...]
+  for (int i = threadIdx.x; i < (L::STG_OFF) / 16; i += CF_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 18; i += CF_THREADS) {
+    const int co = i / 18, k = i % 18;
+    const uint32_t off = (uint32_t)(co * 128 + ((((k >> 3) ^ (co & 7)) & 7) << 4) + (k & 7) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(smem_raw + L::W_OFF + off) = __float2bfloat16(__ldg(w + co * 9 + (k % 9)));
+  }
+  for (int i = threadIdx.x; i < 64; i += CF_THREADS) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, 64);
+      const uint64_t bdesc = umma_smem_desc_sw128(smem_base + L::W_OFF);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+        mbar_wait(bar_afull + s * 8, ph);
+        mbar_wait(bar_tempty + s * 8, ph ^ 1u);
+        tcgen05_fence_after();
+        const uint64_t adesc = umma_smem_desc_sw128(smem_base + s * L::A_BYTES);
+        umma_bf16(tmem_base + s * 64, adesc, bdesc, idesc, 0u);
+        umma_bf16(tmem_base + s * 64, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_commit(bar_aempty + s * 8);
+        umma_commit(bar_tfull + s * 8);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2 && warp < 10) {
+    // =========================== epilogue: two groups of four warps, group e owns TMEM stage e ===========================
+    // (the MMA is two instructions per tile, so the epilogue IS the critical path: tiles alternate between the groups)
+    const int e = (warp - 2) >> 2;
+    const int eg = threadIdx.x - 64 - e * 128;       // 0..127
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                     // tile row == pixel of the 16 x 8 brick
+    const uint32_t stg = smem_base + L::STG_OFF + e * (TC_BM * 128);
+    const uint32_t stg_row = stg + m * 128;
+    const uint32_t tmem_d = tmem_base + e * 64 + ((uint32_t)(q * 32) << 16);
+    const uint32_t bs_addr = smem_u32(bias_s);
+    uint32_t k = 0;
+    for (int tile = blockIdx.x + e * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, ++k) {
+      int m_tile = tile;
+      const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
+      const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
+      const int b0 = m_tile;
+      if (eg == 0) tma_store_wait_read0();           // the previous store of this group has finished reading the staging tile
+      named_bar_sync(1 + 2 * e, 128);
+      mbar_wait(bar_tfull + e * 8, k & 1u);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_d + (uint32_t)(half * 32), r);
+        tmem_ld_wait();
+        if (half == 1) { tcgen05_fence_before(); mbar_arrive(bar_tempty + e * 8); }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = lds128_f4(bs_addr + (half * 32 + 4 * j) * 4);
+          if (p.relu) {
+            pk[2 * j] = add_pack_bf16x2<true>(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b4.x, b4.y);
+            pk[2 * j + 1] = add_pack_bf16x2<true>(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b4.z, b4.w);
+          } else {
+            pk[2 * j] = add_pack_bf16x2<false>(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b4.x, b4.y);
+            pk[2 * j + 1] = add_pack_bf16x2<false>(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b4.z, b4.w);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128_u32(stg_row + ((((half * 4 + j) ^ (m & 7)) & 7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2 + 2 * e, 128);
+      if (eg == 0) { tma_store_4d(&tmY, stg, 0, w0, h0, b0); tma_store_commit(); }
+    }
+    if (eg == 0) tma_store_wait_all();
+  } else if (warp >= 10) {
+    // =========================== im2col producers (128 threads, thread = tile row) ===========================
+    const int m = threadIdx.x - 320;
+    const int tx = m % p.TW, ty = m / p.TW;
+    const int PW = p.TW + 2, PH = p.TH + 2;
+    const int64_t HW = (int64_t)p.H * p.W;
+    // the patch of tile i+1 is loaded into registers while tile i is built: the global-load latency (~1.5k cycles
+    // per tile when exposed) was what bounded this kernel, not the epilogue
+    auto load_patch = [&](int tile, float (&v)[2]) {
+      int m_tile = tile;
+      const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
+      const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
+      const int b0 = m_tile;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int e = m + 128 * j;
+        const int r = e / PW, c = e % PW;
+        const int gy = h0 - 1 + r, gx = w0 - 1 + c;
+        v[j] = (e < PH * PW && tile < total_tiles && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+                   ? __ldg(x + (int64_t)b0 * HW + (int64_t)gy * p.W + gx) : 0.f;
+      }
+    };
+    float nxt[2];
+    load_patch(blockIdx.x, nxt);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+      mbar_wait(bar_aempty + s * 8, ph ^ 1u);            // the UMMAs that read this A buffer are done
+      float* patch = reinterpret_cast<float*>(smem_raw + L::PATCH_OFF) + s * L::PATCH_FLOATS;
+      patch[m] = nxt[0];
+      if (m + 128 < PH * PW) patch[m + 128] = nxt[1];
+      load_patch(tile + gridDim.x, nxt);                 // in flight during the build below
+      named_bar_sync(5, 128);
+      // k = 0..8: bf16(x_tap); k = 9..17: bf16(x_tap - hi)
+      __nv_bfloat16 kv[24];
+#pragma unroll
+      for (int t9 = 0; t9 < 9; ++t9) {
+        const float v = patch[(ty + t9 / 3) * PW + tx + t9 % 3];
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        kv[t9] = hi;
+        kv[9 + t9] = __float2bfloat16(v - __bfloat162float(hi));
+      }
+#pragma unroll
+      for (int j = 18; j < 24; ++j) kv[j] = __float2bfloat16(0.f);
+      const uint32_t arow = smem_base + s * L::A_BYTES + m * 128;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h2 = __halves2bfloat162(kv[c * 8 + 2 * j], kv[c * 8 + 2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        sts128_u32(arow + (((c ^ (m & 7)) & 7) << 4), pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_afull + s * 8);
+      named_bar_sync(5, 128);                              // patch[s ^ ...] reuse: everyone done reading before the next fill
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------
 // host side: tensor-map encoding through the driver entry point (no libcuda link)
 // ------------------------------------------------------------------------------------
@@ -614,6 +806,31 @@ static int conv_variant() {
     v = e ? atoi(e) : -1;
   }
   return v;
+}
+
+// Cin = 1, Cout = 64, W >= 16, H >= 8: tensor-core first layer; returns PMU_ERR_UNSUPPORTED otherwise (the caller
+// falls back to the CUDA-core stencil of layers_bf16.cu)
+int conv_first_tc_launch(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int relu,
+                         cudaStream_t st) {
+  int cc_major = 0, dev = 0;
+  PMU_CUDA(cudaGetDevice(&dev));
+  PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major != 10 || W < 16 || H < 8 || !get_encode_fn()) return PMU_ERR_UNSUPPORTED;
+  ConvTcParams p;
+  p.B = B; p.H = H; p.W = W; p.C0 = 64; p.C1 = 0; p.Cout = 64; p.ntaps = 9; p.relu = relu;
+  p.pool_mode = -1; p.debug = 0; p.tma_store = 1;
+  p.TW = 16; p.TH = 8; p.TB = 1;
+  p.tiles_w = cdiv(W, 16); p.tiles_h = cdiv(H, 8); p.tiles_b = B; p.n_tiles = 1;
+  const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * B;
+  if (tiles >= (1ll << 31)) return PMU_ERR_UNSUPPORTED;
+  CUtensorMap ym;
+  int rc = make_act_map(&ym, y, B, H, W, 64, 16, 8, 1);
+  if (rc) return rc;
+  PMU_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvFirstSmem::DYN_BYTES));
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
+  conv_first_tc_kernel<<<grid, CF_THREADS, ConvFirstSmem::DYN_BYTES, st>>>(ym, p, x, w, bias);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
 }
 
 }  // namespace pmu

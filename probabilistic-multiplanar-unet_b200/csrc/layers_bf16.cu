@@ -246,6 +246,10 @@ nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, 
 
 }  // namespace pmu
 
+namespace pmu {
+int conv_first_tc_launch(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int relu,
+                         cudaStream_t st);   // conv_tc.cu
+}
 using namespace pmu;
 
 extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const float* w, const float* bias,
@@ -254,6 +258,13 @@ extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const fl
   PMU_CHECK_SUPPORTED(Cin >= 1 && Cin <= 2 && (Cin == 1 || x1), "pmu_conv3x3_first_bf16: Cin must be 1, or 2 with x1 (got %d)", Cin);
   PMU_CHECK_SUPPORTED(Cout % 8 == 0 && Cout <= 128, "pmu_conv3x3_first_bf16: Cout must be a multiple of 8, <= 128 (got %d)", Cout);
   PMU_CHECK_ARG(aligned16(y), "pmu_conv3x3_first_bf16: y must be 16-byte aligned");
+  // tensor-core path (conv_tc.cu): im2col rows in shared memory, two K = 16 UMMAs per 128 pixels, TMA-store epilogue
+  static int use_tc = -1;
+  if (use_tc < 0) { const char* e = getenv("PMU_FIRST_TC"); use_tc = e ? atoi(e) : 1; }
+  if (use_tc && Cin == 1 && Cout == 64) {
+    const int rc = conv_first_tc_launch(x0, w, bias, y, B, H, W, relu, (cudaStream_t)stream);
+    if (rc != PMU_ERR_UNSUPPORTED) return rc;
+  }
   const int groups = Cout / 8;
   if (Cin == 1 && W % 4 == 0 && 256 % groups == 0 && aligned16(x0) && (int64_t)B * H * (W / 4) < (1ll << 31)) {
     const int64_t quads = (int64_t)B * H * (W / 4);

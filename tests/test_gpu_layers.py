@@ -93,10 +93,13 @@ def _nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize("Cin", [1, 2])
-def test_first_conv_bf16(ops, Cin):
+@pytest.mark.parametrize("Cin,B,H,W", [(1, 3, 16, 24), (2, 3, 16, 24), (1, 2, 40, 56), (1, 5, 8, 16), (1, 1, 64, 64),
+                                        (1, 2, 6, 12)])       # last: below the tensor-core tile -> CUDA-core stencil
+def test_first_conv_bf16(ops, Cin, B, H, W):
+    """Cin = 1 with W >= 16, H >= 8 runs the tcgen05 first layer (im2col rows in smem, input split into bf16 hi + lo);
+    everything else the CUDA-core stencil."""
     g = _g(5)
-    x = torch.rand(3, Cin, 16, 24, generator=g)
+    x = torch.rand(B, Cin, H, W, generator=g)
     w = torch.randn(64, Cin, 3, 3, generator=g) * 0.3
     b = torch.randn(64, generator=g) * 0.1
     ref = F.relu(F.conv2d(x, w, b, padding=1))

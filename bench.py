@@ -197,16 +197,22 @@ def run_ours(args):
             return ops.fuse_finalize(acc[0], acc[1], float(P * N))
         return None
 
+    # e2e leg: the public call with host buffers.  N = 1: results stream to rank 0's pinned buffers x-slab by x-slab
+    # behind the last view.  N > 1: slab-sharded outputs (reduce-scatter along x) — every rank
+    # finalises its x-slab and copies it to its own pinned buffers, so the 470 MB of results leave over N PCIe links.
+    slab = world > 1 and D % world == 0
+    pred_e2e = pred if not slab else pmu_b200.MultiPlanarPredictor(
+        sd, dev, precision=args.precision, n_samples=N, slice_batch=args.slice_batch, interp=args.interp, rank=rank,
+        world_size=world, output="slab")
     host_out = None
-    if rank == 0:
-        host_out = {"mean": torch.empty(D, 3, D, D, dtype=torch.float32).pin_memory(),
-                    "var": torch.empty(D, 3, D, D, dtype=torch.float32).pin_memory(),
-                    "entropy": torch.empty(D, D, D, dtype=torch.float32).pin_memory()}
+    if rank == 0 or slab:
+        Dx = D // world if slab else D
+        host_out = {"mean": torch.empty(Dx, 3, D, D, dtype=torch.float32).pin_memory(),
+                    "var": torch.empty(Dx, 3, D, D, dtype=torch.float32).pin_memory(),
+                    "entropy": torch.empty(Dx, D, D, dtype=torch.float32).pin_memory()}
 
     def step_e2e():
-        # H2D of the pinned volume and D2H of the step's results (mean / var / entropy into pinned host tensors)
-        # both inside the public call; on one GPU the D2H streams out x-slab by x-slab behind the last view
-        pred.predict(vol_host, eps=eps, host_out=host_out if rank == 0 else None)
+        pred_e2e.predict(vol_host, eps=eps, host_out=host_out)
 
     def barrier():
         if world > 1:
@@ -370,8 +376,11 @@ def run_ours(args):
                                        f"[64,128,256,512,1024] C=3 L=6 fcomb=4, mean/var/entropy fusion",
                            "slice_batch": args.slice_batch, "parallelism": f"slice-sharded x{world} + 1 reduce",
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
-                "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * D ** 3),
-                        "d2h_bytes_per_step": int(4 * D ** 3 * 7), "ms_per_step": ms_e2e / args.steps},
+                "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(4 * D ** 3) * world,          # every rank uploads the volume
+                        "d2h_bytes_per_step": int(4 * D ** 3 * 7),              # mean + var (3 classes each) + entropy, whole job
+                        "ms_per_step": ms_e2e / args.steps,
+                        "outputs": "x-slab per rank (reduce-scatter)" if slab else "rank 0 (streamed behind the last view)" if world == 1 else "rank 0"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels,
                 "kernel_time_shares": shares, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))

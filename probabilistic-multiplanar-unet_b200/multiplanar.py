@@ -71,13 +71,35 @@ def reduce_accumulators(acc: torch.Tensor, world: int, group=None, dst: Optional
     return acc
 
 
+def reduce_scatter_accumulators(acc: torch.Tensor, rank: int, world: int, group=None):
+    """Slab-sharded form of the exchange step: every rank ends up with the SUM of its own x-slab
+    [2, X/world, C, Y, Z] of the accumulators — `ncclReduceScatter` along x, one call per moment (Σp, Σp² are two
+    contiguous [X, ...] tensors), so that each rank finalises and delivers only its slab.  X must be divisible by
+    world.  Backends without reduce-scatter (gloo in the CPU tests) fall back to all-reduce + slicing."""
+    X = acc.shape[1]
+    if X % world:
+        raise ValueError(f"slab-sharded output needs X = {X} divisible by world = {world}")
+    xs = X // world
+    if world <= 1:
+        return acc, (0, X)
+    import torch.distributed as dist
+    out = torch.empty((2, xs) + tuple(acc.shape[2:]), dtype=acc.dtype, device=acc.device)
+    if dist.get_backend(group) == "nccl":
+        for j in range(2):
+            dist.reduce_scatter_tensor(out[j], acc[j], op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        out.copy_(acc[:, rank * xs:(rank + 1) * xs])
+    return out, (rank * xs, (rank + 1) * xs)
+
+
 class MultiPlanarPredictor:
     """3-plane, N-sample probabilistic prediction of a volume on the current CUDA device."""
 
     def __init__(self, state_dict, device="cuda", precision: str = "bf16", n_samples: int = 16,
                  planes: Sequence[int] = (0, 1, 2), slice_batch: int = 32, interp: str = "exact",
                  affines: Optional[Dict[int, Sequence[float]]] = None, out_hw: Optional[Tuple[int, int]] = None,
-                 rank: int = 0, world_size: int = 1, process_group=None):
+                 rank: int = 0, world_size: int = 1, process_group=None, output: str = "rank0"):
         if hasattr(state_dict, "state_dict"):
             state_dict = state_dict.state_dict()
         self.device = torch.device(device)
@@ -92,6 +114,10 @@ class MultiPlanarPredictor:
         self.identity_grid = all(list(map(float, affines[p])) == plane_affine(p) for p in self.planes)
         self.interp, self.affines, self.out_hw = interp, affines, out_hw
         self.rank, self.world, self.group = int(rank), int(world_size), process_group
+        if output not in ("rank0", "slab"):
+            raise ValueError("output must be 'rank0' (one reduce, results on rank 0) or 'slab' (reduce-scatter along x, "
+                             "every rank keeps its x-slab)")
+        self.output = output
         self.C = self.net.fcomb["C"]
         self.L = self.net.fcomb["L"]
 
@@ -163,7 +189,8 @@ class MultiPlanarPredictor:
                 ) -> Dict[str, torch.Tensor]:
         """vol: [d0,d1,d2] fp32 (numpy / CPU / CUDA).  eps: [P, D, N, L] standard-normal draws
         (host or device); generated on the device from `seed` when omitted.  Returns mean / var
-        [x,C,y,z], entropy [x,y,z] (valid on rank 0 when world_size > 1).  per_plane=True also
+        [x,C,y,z], entropy [x,y,z] (valid on rank 0 when world_size > 1; with output="slab" every rank gets its
+        own x-slab, "x_range" = (x0, x1), from a reduce-scatter instead of a reduce).  per_plane=True also
         returns "plane_means": the per-view probability volumes volume1/2/3 of eval.py:176-190.
         host_out = {"mean", "var", "entropy"[, "labels"]} of PINNED host tensors: the results are also delivered to
         the host; on one GPU the x-slicing view runs last, every finished x-slab is finalised and copied out on a
@@ -219,6 +246,21 @@ class MultiPlanarPredictor:
                 out["labels"] = lab
             if keep_sums:
                 out["S1"], out["S2"] = acc[0], acc[1]
+            return out
+        elif self.output == "slab" and self.world > 1:
+            # slab-sharded outputs: reduce-scatter along x, every rank finalises (and copies out) its own x-slab
+            self.accumulate(vol, eps, acc)
+            mine, (x0, x1) = reduce_scatter_accumulators(acc, self.rank, self.world, self.group)
+            mean, var, ent, lab = ops.fuse_finalize(mine[0], mine[1], float(P * N), want_labels=want_labels)
+            out.update(mean=mean, var=var, entropy=ent, x_range=(x0, x1))
+            if want_labels:
+                out["labels"] = lab
+            if host_out is not None:
+                for k in ("mean", "var", "entropy", "labels"):
+                    if k in host_out and k in out:
+                        host_out[k][: x1 - x0].copy_(out[k], non_blocking=True)
+            if keep_sums:
+                out["S1"], out["S2"] = mine[0], mine[1]
             return out
         else:
             self.accumulate(vol, eps, acc)

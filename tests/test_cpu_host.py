@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 import pmu_b200
 from oracle import pmu_oracle as O
 from pmu_b200 import _lib
-from pmu_b200.multiplanar import padded_dims, reduce_accumulators, shard_slices
+from pmu_b200.multiplanar import padded_dims, reduce_accumulators, reduce_scatter_accumulators, shard_slices
 
 
 def test_library_loads_and_exports_header_symbols():
@@ -120,13 +120,22 @@ def _gloo_worker(rank, world, port, dims, ret):
             full = torch.zeros_like(per_slice[p][:, j])
             full[a:b] = per_slice[p][a:b, j]
             acc[j] += O.scatter_plane(p, full)
+    ref = torch.zeros_like(acc)
+    for p in range(3):
+        for j in range(2):
+            ref[j] += O.scatter_plane(p, per_slice[p][:, j])
+    # slab-sharded exchange (reduce-scatter along x; gloo takes the all-reduce fallback): every rank owns its x-slab
+    err_slab = 0.0
+    if dims[0] % world == 0:
+        mine, (x0, x1) = reduce_scatter_accumulators(acc.clone(), rank, world, None)
+        err_slab = float((mine - ref[:, x0:x1]).abs().max())
+        assert (x1 - x0) * world == dims[0]
     reduce_accumulators(acc, world, None, dst=0)
+    errs = [torch.tensor([err_slab])]
+    gathered = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(gathered, errs[0])
     if rank == 0:
-        ref = torch.zeros_like(acc)
-        for p in range(3):
-            for j in range(2):
-                ref[j] += O.scatter_plane(p, per_slice[p][:, j])
-        ret.put(float((acc - ref).abs().max()))
+        ret.put(max(float((acc - ref).abs().max()), max(float(g) for g in gathered)))
     dist.destroy_process_group()
 
 
@@ -136,7 +145,7 @@ def test_sharded_accumulators_reduce_over_gloo():
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, (5, 6, 7), ret)) for r in range(2)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, (6, 5, 7), ret)) for r in range(2)]
     for p in procs:
         p.start()
     err = ret.get(timeout=120)

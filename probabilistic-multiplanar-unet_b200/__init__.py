@@ -7,6 +7,7 @@ from . import _lib, nifti_io, ops  # noqa: F401
 from .dice_loss import dice_coeff, volume_dice  # noqa: F401
 from .engine import PackedNet  # noqa: F401
 from .model import ProbabilisticUnet, UNet  # noqa: F401
+from .mri_dataset import MRI_Dataset, view_affine  # noqa: F401
 from .multiplanar import (MultiPlanarPredictor, padded_dims, reduce_accumulators, reduce_scatter_accumulators,  # noqa: F401
                           shard_slices)
 from .trainer import ProbUNetTrainer  # noqa: F401

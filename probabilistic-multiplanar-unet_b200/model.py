@@ -329,6 +329,23 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             z = z.unsqueeze(0).expand(self.unet_features.shape[0], -1)
         return self.packed().fcomb_logits(self.unet_features, z.contiguous())
 
+    def sample_grid(self, n_preds: int = 3, sigma_scale: float = 1.0, axes=(0, 1)):
+        """Latent-grid sweep of visualize_sampling.py:21-31 in ONE fcomb launch: for every slice of the last forward(),
+        z[i, j] = mu with z[axes[0]] = i * sigma_scale * sigma[axes[0]] + mu[axes[0]] and likewise axes[1] for j,
+        i, j in range(-(n_preds // 2), n_preds // 2 + 1).  Returns (logits [B, G, G, C, H, W], z [B, G, G, L]);
+        the reference loops G*G full `predict(slice, mask, z=z)` calls (each a whole U-Net pass) for the same result."""
+        self._enter("ProbabilisticUnet.sample_grid")
+        mu, sigma = self._prior[0].float(), torch.exp(self._prior[1]).float()
+        steps = torch.arange(-(n_preds // 2), n_preds // 2 + 1, device=mu.device, dtype=torch.float32)
+        G = steps.numel()
+        z = mu[:, None, None, :].repeat(1, G, G, 1)
+        a0, a1 = axes
+        z[:, :, :, a0] = steps[None, :, None] * sigma_scale * sigma[:, None, None, a0] + mu[:, None, None, a0]
+        z[:, :, :, a1] = steps[None, None, :] * sigma_scale * sigma[:, None, None, a1] + mu[:, None, None, a1]
+        B = z.shape[0]
+        logits = self.packed().fcomb_logits(self.unet_features, z.reshape(B, G * G, -1))
+        return logits.reshape(B, G, G, *logits.shape[2:]), z
+
     def reconstruct(self, use_posterior_mean=False, calculate_posterior=False, z_posterior=None):
         """probabilistic_unet.py:251-262."""
         self._enter("ProbabilisticUnet.reconstruct")

@@ -53,3 +53,22 @@ class ProbUNetTrainer(Trainer):
         s = ops.argmax_dice_sums(masks_pred.contiguous().float(), true_masks.contiguous().float().reshape(B, H, W))
         d = (2.0 * s[:, 0] + 1e-6) / (s[:, 1] + s[:, 2] + 1e-6)
         return d.cpu().numpy()
+
+    def mask_to_image(self, masks, prediction=False):
+        """probunet_trainer.py:62-92: class indices -> RGB [B,3,H,W] (0 black, 1 blue, 2 green, 3 red); predictions are
+        arg-maxed first.  One table lookup on the masks' device instead of the reference's per-pixel Python loop."""
+        if self.net.n_classes == 1:
+            return (masks >= 0.5).float() if prediction else masks
+        colors = torch.tensor([[0., 0., 0.], [0., 0., 1.], [0., 1., 0.], [1., 0., 0.]], device=masks.device)
+        idx = torch.argmax(masks, dim=1) if prediction else masks.squeeze(1).long()
+        return colors[idx].permute(0, 3, 1, 2)
+
+    def latent_grid(self, imgs, true_masks, n_preds=3, sigma_scale=1.0, axes=(0, 1)):
+        """visualize_sampling.py:11-31: the n_preds x n_preds grid of predictions around the prior mean — one network
+        pass and one fcomb launch (ProbabilisticUnet.sample_grid).  Returns (images [B,G,G,3,H,W], logits, z)."""
+        with torch.no_grad():
+            self.net.forward(imgs, true_masks, training=False)
+            logits, z = self.net.sample_grid(n_preds, sigma_scale, axes)
+        B, G = logits.shape[0], logits.shape[1]
+        img = self.mask_to_image(logits.reshape(B * G * G, *logits.shape[3:]), prediction=True)
+        return img.reshape(B, G, G, *img.shape[1:]), logits, z

@@ -183,6 +183,109 @@ class MultiPlanarPredictor:
                     on_slab(s0, s0 + ns)
         return done
 
+    # ------------------------------------------------------------------ pipelined serving path
+    @torch.no_grad()
+    def submit(self, vol_host: torch.Tensor, eps: torch.Tensor, host_out: Dict[str, torch.Tensor],
+               want_labels: bool = False, depth: int = 2) -> int:
+        """Asynchronous predict for a stream of volumes: enqueue one volume and return a ticket at once.
+
+        vol_host: PINNED fp32 host tensor [d0,d1,d2] (already cubic / padded); eps: device tensor [P, D, N, L];
+        host_out: PINNED host tensors {"mean", "var", "entropy"[, "labels"]} — the whole volume on one GPU, this rank's
+        x-slab with output="slab", rank 0 only with output="rank0".  `wait(ticket)` (or `wait()` for everything
+        submitted) blocks the host until the results are in host_out.
+
+        Three streams: the host->device copy of volume k+1 runs on a copy stream while volume k computes on the current
+        stream, and the device->host copies of volume k's results run on a second copy stream behind the next volume's
+        kernels.  `depth` slots of device buffers (volume, accumulators, outputs) rotate; a slot is rewritten only after
+        the compute that read it / the copy-out that drained it has finished (CUDA events, no host synchronisation).
+        Same kernels, same results as predict(host_out=...) — only the scheduling differs."""
+        if self.interp != "exact" and not self.identity_grid:
+            raise NotImplementedError("voxel fusion is defined for the standard axis-aligned grids")
+        if not (isinstance(vol_host, torch.Tensor) and vol_host.dtype == torch.float32 and vol_host.is_pinned()):
+            raise ValueError("submit() takes a pinned fp32 host tensor (torch.Tensor.pin_memory())")
+        dims = tuple(vol_host.shape)
+        if padded_dims(dims) != dims:
+            raise ValueError("submit() takes an already padded volume (pad_dimensions); use predict() otherwise")
+        P, N = len(self.planes), self.n_samples
+        slab = self.output == "slab" and self.world > 1
+        if slab and dims[0] % self.world:
+            raise ValueError(f"slab-sharded output needs X = {dims[0]} divisible by world = {self.world}")
+        pipe = getattr(self, "_pipe", None)
+        if pipe is None or pipe["dims"] != dims or pipe["depth"] != depth or pipe["labels"] != want_labels:
+            self.wait()
+            dev = self.device
+            xs = dims[0] // self.world if slab else dims[0]
+            mine = self.rank == 0 or slab
+            slots = []
+            for _ in range(depth):
+                s = {"vol": torch.empty(dims, dtype=torch.float32, device=dev),
+                     "acc": torch.empty(2, dims[0], self.C, dims[1], dims[2], dtype=torch.float32, device=dev),
+                     "in": torch.cuda.Event(), "compute": None, "out": None}
+                if mine:
+                    s["mean"] = torch.empty(xs, self.C, dims[1], dims[2], dtype=torch.float32, device=dev)
+                    s["var"] = torch.empty_like(s["mean"])
+                    s["entropy"] = torch.empty(xs, dims[1], dims[2], dtype=torch.float32, device=dev)
+                    s["labels"] = torch.empty(xs, dims[1], dims[2], dtype=torch.uint8, device=dev) if want_labels else None
+                slots.append(s)
+            pipe = self._pipe = {"dims": dims, "depth": depth, "labels": want_labels, "slots": slots, "k": 0,
+                                 "h2d": torch.cuda.Stream(dev), "pending": {}}
+        k = pipe["k"]
+        pipe["k"] = k + 1
+        s = pipe["slots"][k % depth]
+        main, h2d, d2h = torch.cuda.current_stream(self.device), pipe["h2d"], self._side_stream()
+        # ---- copy-in on its own stream (waits for the compute that last read this slot's volume) ----
+        if s["compute"] is not None:
+            h2d.wait_event(s["compute"])
+        with torch.cuda.stream(h2d):
+            s["vol"].copy_(vol_host, non_blocking=True)
+            s["in"].record(h2d)
+        main.wait_event(s["in"])
+        if s["out"] is not None:
+            main.wait_event(s["out"])                     # the slot's outputs have left for the host
+        acc = s["acc"]
+        acc.zero_()
+        keys = [k_ for k_ in ("mean", "var", "entropy", "labels") if k_ in host_out and s.get(k_) is not None]
+
+        def copy_out(x0, x1):
+            d2h.wait_stream(main)
+            with torch.cuda.stream(d2h):
+                for k_ in keys:
+                    host_out[k_][x0:x1].copy_(s[k_][x0:x1], non_blocking=True)
+
+        if self.world == 1 and 0 in self.planes:
+            def on_slab(x0, x1):
+                ops.fuse_finalize(acc[0][x0:x1], acc[1][x0:x1], float(P * N), want_labels=want_labels,
+                                  out=(s["mean"][x0:x1], s["var"][x0:x1], s["entropy"][x0:x1],
+                                       None if s["labels"] is None else s["labels"][x0:x1]))
+                copy_out(x0, x1)
+            self.accumulate(s["vol"], eps, acc, plane0_last=True, on_slab=on_slab)
+        else:
+            self.accumulate(s["vol"], eps, acc)
+            if slab:
+                part, _ = reduce_scatter_accumulators(acc, self.rank, self.world, self.group)
+            else:
+                reduce_accumulators(acc, self.world, self.group, dst=0)
+                part = acc
+            if self.rank == 0 or slab:
+                ops.fuse_finalize(part[0], part[1], float(P * N), want_labels=want_labels,
+                                  out=(s["mean"], s["var"], s["entropy"], s["labels"]))
+                copy_out(0, s["mean"].shape[0])
+        s["compute"] = torch.cuda.Event()
+        s["compute"].record(main)
+        s["out"] = torch.cuda.Event()
+        s["out"].record(d2h)
+        pipe["pending"][k] = s["out"]
+        return k
+
+    def wait(self, ticket: Optional[int] = None) -> None:
+        """Block the host until `ticket`'s results (default: everything submitted) are complete in host memory."""
+        pipe = getattr(self, "_pipe", None)
+        if pipe is None:
+            return
+        for k in sorted(pipe["pending"]):
+            if ticket is None or k <= ticket:
+                pipe["pending"].pop(k).synchronize()
+
     @torch.no_grad()
     def predict(self, vol, eps: Optional[torch.Tensor] = None, seed: int = 4321, want_labels: bool = False,
                 keep_sums: bool = False, per_plane: bool = False, host_out: Optional[Dict[str, torch.Tensor]] = None

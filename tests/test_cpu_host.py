@@ -222,3 +222,48 @@ def test_nifti_roundtrip(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "bad.nii").write_bytes(b"x" * 400)
         nifti_io.load(str(tmp_path / "bad.nii"))
+
+
+def test_view_affine_frames():
+    """Host logic of the generalised views: standard axes give the oracle's identity grids; any other vector gives an
+    orthonormal right-handed frame centred on the volume, with unit spacing."""
+    import pmu_b200
+    dims = (40, 48, 56)
+    for p in range(3):
+        aff, hw, n = pmu_b200.view_affine(np.eye(3, dtype=int)[p], dims)
+        assert np.array_equal(np.array(aff, np.float32), O.identity_affine(p))
+        assert n == dims[p] and hw == tuple(d for a, d in enumerate(dims) if a != p)
+    for view in [(1, 1, 0), (1, 2, 3), (-1, 0.5, 0.25), (0, 0, 2)]:
+        aff, hw, n = pmu_b200.view_affine(view, dims)
+        A = np.array(aff, np.float64)
+        nn, u, v = A[3:6], A[6:9], A[9:12]
+        np.testing.assert_allclose([nn @ nn, u @ u, v @ v], 1.0, atol=1e-6)
+        np.testing.assert_allclose([nn @ u, nn @ v, u @ v], 0.0, atol=1e-6)
+        np.testing.assert_allclose(np.cross(nn, u), v, atol=1e-6)
+        np.testing.assert_allclose(nn, np.array(view, float) / np.linalg.norm(view), atol=1e-6)
+        assert hw == (56, 56) and n == 56
+        np.testing.assert_allclose(A[:3] + (n - 1) / 2.0 * (nn + u + v), (np.array(dims) - 1) / 2.0, atol=1e-4)
+    with pytest.raises(ValueError):
+        pmu_b200.view_affine((0, 0, 0), dims)
+
+
+def test_dataset_and_pipeline_refuse_cpu():
+    import pmu_b200
+    with pytest.raises(RuntimeError):
+        pmu_b200.MRI_Dataset(None, None, 3, device="cpu", volumes={"a": (np.zeros((4, 4, 4)), np.zeros((4, 4, 4)))})
+
+
+@pytest.mark.parametrize("name", ["golden_cfg2_lattice.npz", "golden_cfg3_lattice.npz"])
+def test_fullsize_lattice_fixtures_are_consistent(golden_dir, name):
+    """The whole-volume oracle runs behind the full-size GPU tests: probabilities sum to one, population variance and
+    natural-log entropy are inside their ranges, the checksums agree with the lattice's scale."""
+    g = np.load(os.path.join(golden_dir, name))
+    n = len(range(int(g["offset"]), int(g["D"]), int(g["step"])))
+    assert g["mean"].shape == (n, n, n, 3) and g["var"].shape == (n, n, n, 3) and g["entropy"].shape == (n, n, n)
+    np.testing.assert_allclose(g["mean"].sum(-1), 1.0, atol=1e-5)
+    assert g["var"].min() >= 0 and g["var"].max() <= 0.25
+    assert g["entropy"].min() >= 0 and g["entropy"].max() <= np.log(3) + 1e-6
+    p = np.clip(g["mean"], 1e-12, 1)
+    np.testing.assert_allclose(-(p * np.log(p)).sum(-1), g["entropy"], atol=1e-5)
+    np.testing.assert_allclose(g["mean_sum"].sum(), float(g["D"]) ** 3, rtol=1e-6)
+    assert int(g["labels_hist"].sum()) == int(g["D"]) ** 3

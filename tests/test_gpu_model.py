@@ -269,3 +269,137 @@ def test_eval_entry_point(pmu, tmp_path):
     out = pred.predict(vol, seed=1, per_plane=True)
     avg = (out["plane_means"][0] + out["plane_means"][1] + out["plane_means"][2]) / 3.0
     torch.testing.assert_close(out["mean"], avg, atol=1e-6, rtol=1e-5)
+
+
+def test_pipelined_submit_matches_predict(pmu, trainer_sd):
+    """submit()/wait(): a stream of different volumes through two buffer slots and three CUDA streams gives, for every
+    volume, the bits of the one-at-a-time predict(host_out=...) call (same kernels, only the scheduling differs)."""
+    D, N = 32, 2
+    one = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=16)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(5)).cuda()
+    vols = [torch.from_numpy(O.phantom(D, seed=20 + i)[0]).pin_memory() for i in range(5)]
+
+    def outs():
+        return {"mean": torch.empty(D, 3, D, D).pin_memory(), "var": torch.empty(D, 3, D, D).pin_memory(),
+                "entropy": torch.empty(D, D, D).pin_memory(), "labels": torch.empty(D, D, D, dtype=torch.uint8).pin_memory()}
+
+    want = []
+    for v in vols:
+        h = outs()
+        one.predict(v, eps=eps, host_out=h, want_labels=True)
+        torch.cuda.synchronize()
+        want.append({k: t.clone() for k, t in h.items()})
+    got = [outs() for _ in vols]
+    tickets = [one.submit(v, eps, got[i], want_labels=True) for i, v in enumerate(vols)]
+    assert tickets == list(range(5))
+    one.wait(tickets[1])
+    for k in want[0]:
+        assert torch.equal(got[0][k], want[0][k]) and torch.equal(got[1][k], want[1][k]), k
+    one.wait()
+    for i in range(5):
+        for k in want[i]:
+            assert torch.equal(got[i][k], want[i][k]), (i, k)
+    with pytest.raises(ValueError):
+        one.submit(torch.zeros(D, D, D), eps, got[0])                      # not pinned
+    with pytest.raises(ValueError):
+        one.submit(torch.zeros(D, D, D - 1).pin_memory(), eps, got[0])     # needs padding -> predict()
+
+
+# a single view's N-sample mean carries the bf16 noise of ONE network pass (the fused mean averages three): with the
+# random-init trainer model (logits +-5, sigma up to 6) the worst of ~10^5 pixels of a full-size slice sits at 2.0-2.3e-2
+# (scripts/diag_bf16_error.py: all of it is the 1.1 % rms error of the bf16 U-Net features; p99.9 = 1e-2)
+BF16_VIEW_TOL = 3e-2
+
+
+def _spot_check_planes(out, ref, spots, N, tol):
+    """per-view probability volumes (eval.py:176-190 layout [x,C,y,z]) against the oracle's per-slice sums."""
+    worst, errs = 0.0, []
+    for p, s0 in spots.items():
+        want = ref["per_slice"][p][0] / float(N)                          # [ns, C, H, W]
+        pm = out["plane_means"][p]
+        for i in range(want.shape[0]):
+            s = s0 + i
+            got = {0: pm[s], 1: pm[:, :, s, :].permute(1, 0, 2), 2: pm[:, :, :, s].permute(1, 0, 2)}[p].cpu()
+            e = (got - want[i]).abs()
+            worst = max(worst, float(e.max()))
+            errs.append(e.flatten())
+    assert worst < tol, f"per-view probabilities off by {worst}"
+    return worst, torch.cat(errs)
+
+
+def _check_lattice(out, golden_dir, name, tol, ent_tol):
+    """FUSED voxel-space outputs at the configuration's real size against the oracle's whole-volume run, sampled on
+    a voxel lattice (tests/golden/make_golden_fullsize.py), + whole-volume checksums."""
+    g = np.load(os.path.join(golden_dir, name))
+    D, step, off = int(g["D"]), int(g["step"]), int(g["offset"])
+    idx = torch.arange(off, D, step, device="cuda")
+    lat = lambda v: v[idx][:, :, idx][:, :, :, idx]
+    mean, var = lat(out["mean"]).permute(0, 2, 3, 1).cpu().numpy(), lat(out["var"]).permute(0, 2, 3, 1).cpu().numpy()
+    ent = out["entropy"][idx][:, idx][:, :, idx].cpu().numpy()
+    e_mean, e_var, e_ent = np.abs(mean - g["mean"]).max(), np.abs(var - g["var"]).max(), np.abs(ent - g["entropy"]).max()
+    assert e_mean < tol and e_var < tol and e_ent < ent_tol, (e_mean, e_var, e_ent)
+    V = float(D) ** 3
+    got_sum = out["mean"].double().sum((0, 2, 3)).cpu().numpy()
+    assert np.abs(got_sum - g["mean_sum"]).max() / V < tol / 10          # mean error over the volume << worst voxel
+    assert abs(float(out["entropy"].double().sum()) - float(g["entropy_sum"])) / V < ent_tol / 10
+    return e_mean, e_var, e_ent
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config2_full_size(pmu, trainer_sd, golden_dir, precision):
+    """BASELINE config 2 at its full size (128^3, 3 planes x 8 samples, mean / variance fusion): the fused outputs on a
+    16^3 voxel lattice against the oracle's whole-volume run, whole slices of every view against the oracle (two per
+    view), and the size-independent properties."""
+    D, N = 128, 8
+    vol, _ = O.phantom(D, seed=1234)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    spots = {0: 40, 1: 77, 2: 126}
+    ref = O.multiplanar_predict(vol, trainer_sd, eps, N, batch=2, slice_ranges={p: (s, s + 2) for p, s in spots.items()},
+                                return_per_slice=True)
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision=precision, n_samples=N, slice_batch=64)
+    out = pred.predict(vol, eps=eps, per_plane=True, keep_sums=True)
+    fp32 = precision == "fp32"
+    _check_lattice(out, golden_dir, "golden_cfg2_lattice.npz", FP32_PROB_TOL if fp32 else BF16_PROB_TOL, 1e-3 if fp32 else 6e-2)
+    _, errs = _spot_check_planes(out, ref, spots, N, FP32_PROB_TOL if fp32 else BF16_VIEW_TOL)
+    if not fp32:
+        assert float(errs.quantile(0.999)) < BF16_PROB_TOL and float(errs.mean()) < 4e-3
+    mean, var, ent = out["mean"], out["var"], out["entropy"]
+    torch.testing.assert_close(mean.sum(1), torch.ones_like(mean[:, 0]), atol=1e-4, rtol=0)
+    torch.testing.assert_close(out["S1"].sum(1), torch.full_like(mean[:, 0], 3.0 * N), atol=1e-3, rtol=0)
+    torch.testing.assert_close(mean, (out["plane_means"][0] + out["plane_means"][1] + out["plane_means"][2]) / 3,
+                               atol=1e-6, rtol=0)                        # eval.py:193 avg_volume
+    assert float(var.min()) >= 0.0 and float(var.max()) <= 0.25 + 1e-6
+    assert float(ent.min()) >= 0.0 and float(ent.max()) <= np.log(3) + 1e-5
+
+
+def test_config3_full_size(pmu, trainer_sd, golden_dir):
+    """BASELINE config 3 at its full size (256^3, 3 planes x 16 samples, trilinear resampling on the standard grids,
+    bf16): fused outputs on a 16^3 voxel lattice against the oracle's whole-volume run, one whole slice per view
+    against the oracle, properties, and the sharded run (4 emulated ranks) adding up to the single-rank accumulators."""
+    D, N = 256, 16
+    vol, _ = O.phantom(D, seed=1234)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    spots = {0: 100, 1: 3, 2: 255}
+    ref = O.multiplanar_predict(vol, trainer_sd, eps, N, batch=1, slice_ranges={p: (s, s + 1) for p, s in spots.items()},
+                                return_per_slice=True)
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=64, interp="trilinear")
+    epsd = eps.cuda()
+    out = pred.predict(vol, eps=epsd, per_plane=True, keep_sums=True)
+    _check_lattice(out, golden_dir, "golden_cfg3_lattice.npz", BF16_PROB_TOL, 6e-2)
+    _, errs = _spot_check_planes(out, ref, spots, N, BF16_VIEW_TOL)
+    assert float(errs.quantile(0.999)) < BF16_PROB_TOL and float(errs.mean()) < 4e-3
+    mean = out["mean"]
+    torch.testing.assert_close(mean.sum(1), torch.ones_like(mean[:, 0]), atol=1e-4, rtol=0)
+    torch.testing.assert_close(out["S1"].sum(1), torch.full_like(mean[:, 0], 3.0 * N), atol=2e-3, rtol=0)
+    assert float(out["var"].min()) >= 0.0 and float(out["entropy"].max()) <= np.log(3) + 1e-5
+    S1 = out["S1"].clone()
+    del out
+    v = torch.from_numpy(vol).cuda()
+    tot = torch.zeros(2, D, 3, D, D, device="cuda")
+    done = 0
+    for r in range(4):
+        pr = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=64, interp="trilinear",
+                                      rank=r, world_size=4)
+        done += pr.accumulate(v, epsd, tot)
+    assert done == 3 * D
+    torch.testing.assert_close(tot[0], S1, atol=1e-4, rtol=0)

@@ -256,6 +256,16 @@ def run_ours(args):
     launches = ops.LAUNCHES - l0
     clocks = sampler.finish() if sampler else None
 
+    if args.timed_only:
+        # profiling aid (ncu launch list / captures of the timed step's kernels): skip the e2e legs and the per-kernel
+        # instrumentation, print the resident number only
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                              "gpu_launches": launches, "note": "--timed-only (profiling aid): warm-up + timed resident steps only"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     step_e2e_sync()                                             # warm the e2e paths (pinned buffers, allocator)
     ms_e2e_sync = timed(step_e2e_sync, args.steps)
     run_e2e(2)
@@ -422,6 +432,7 @@ def main():
                     help="slice resampling onto the three standard plane grids (BASELINE configs[2]: trilinear)")
     ap.add_argument("--cpu-slices-per-plane", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timed-only", action="store_true", help="profiling aid: only the warm-up and the timed resident steps")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

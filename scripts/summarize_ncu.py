@@ -12,7 +12,7 @@ if os.path.exists(lc):
         tot[k][0] += 1; tot[k][1] += float(row["Metric Value"])
     s = sum(v[1] for v in tot.values())
     with open(f"profiles/{tag}_launch_summary.txt", "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --timed-only\n")
         f.write(f"# per-kernel totals over the whole run (cold-cache, serialised: compare SHARES); total {s/1e6:.2f} ms, {sum(v[0] for v in tot.values())} launches\n")
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{v[1]/1e6:10.3f} ms {100*v[1]/s:6.2f}%  n={v[0]:5d}  avg={v[1]/v[0]/1e3:9.1f} us  {k}\n")
@@ -24,9 +24,18 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm_
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_lsu.sum"]
-for rep in glob.glob("gpurun_out/prof_*.ncu-rep"):
+def raw_csv(rep):
+    """raw page of a report: the CSV made on the GPU box if it is there (large reports do not travel), else ncu -i."""
+    pre = rep[:-8] + ".raw.csv"
+    if os.path.exists(pre):
+        return open(pre).read()
+    return subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
+REPS = sorted(set(glob.glob("gpurun_out/prof_*.ncu-rep")) | {f[:-8] + ".ncu-rep" for f in glob.glob("gpurun_out/prof_*.raw.csv")})
+for rep in REPS:
     name = os.path.basename(rep)[:-8]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = raw_csv(rep)
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3:
         continue
@@ -47,8 +56,8 @@ traffic = {}
 def _num(x):
     try: return float(x.replace(",", ""))
     except Exception: return None
-for rep in glob.glob("gpurun_out/prof_*.ncu-rep"):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+for rep in REPS:
+    raw = raw_csv(rep)
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3: continue
     hdr, units = rows[0], rows[1]

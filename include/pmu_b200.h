@@ -218,6 +218,12 @@ int pmu_bn_train_fwd_f32(const float* y, const float* gamma, const float* beta, 
 int pmu_bn_train_bwd_f32(const float* da, const float* y, const float* mean, const float* var,
                          const float* gamma, const float* beta, float eps, int relu, float* dy,
                          float* dgamma, float* dbeta, double* ws, int B, int C, int64_t HW, void* stream);
+/* the same + dbias[C] (nullable) = sum_{b,p} dy[b,c,p], the bias gradient of the nn.Conv2d in front of the BatchNorm
+ * (unet_parts.py:15-16), accumulated while dy is written; ws = 3*C doubles when dbias is given. */
+int pmu_bn_train_bwd_bias_f32(const float* da, const float* y, const float* mean, const float* var,
+                              const float* gamma, const float* beta, float eps, int relu, float* dy,
+                              float* dgamma, float* dbeta, float* dbias, double* ws, int B, int C, int64_t HW,
+                              void* stream);
 /* out[c] = sum_{b,p} x[b,c,p] (conv bias gradients); out[r] = sum_p x[r,p]. */
 int pmu_channel_sums_f32(const float* x, float* out, double* ws, int B, int C, int64_t HW, void* stream);
 int pmu_row_sums_f32(const float* x, float* out, int64_t rows, int64_t n, void* stream);

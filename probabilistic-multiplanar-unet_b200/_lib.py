@@ -51,6 +51,7 @@ _SIG = {
     "pmu_argmax_dice_sums": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P]),
     "pmu_bn_train_fwd_f32": (c_int, [_P, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _P]),
     "pmu_bn_train_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, c_int, c_int, c_int64, _P]),
+    "pmu_bn_train_bwd_bias_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _P]),
     "pmu_channel_sums_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int64, _P]),
     "pmu_row_sums_f32": (c_int, [_P, _P, c_int64, c_int64, _P]),
     "pmu_conv3x3_wgrad_f32": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),

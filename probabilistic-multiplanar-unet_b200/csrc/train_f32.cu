@@ -35,19 +35,34 @@ __device__ __forceinline__ void block_sum2(float& a, float& b) {
 }
 
 // ------------------------------------------------------------------------------------
-// BatchNorm2d training forward.  stats: per channel sum / sum of squares over (B, HW).
-// grid (chunks, C); acc = fp64 [C][2].
+// BatchNorm2d training forward / backward.  Every kernel walks rows (b, c) of HW contiguous floats, so there is no
+// integer division in the inner loops, and with HW % 4 == 0 (VEC) every access is a 128-bit load / store.
+// Per-channel reductions: grid (chunks over HW, C), a block loops over the batch; block partials (fp32) are added to
+// fp64 accumulators acc[C][2] with atomics.
 // ------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float* __restrict__ y, int B, int C, int64_t HW, int64_t chunk, double* __restrict__ acc) {
   const int c = blockIdx.y;
-  const int64_t total = (int64_t)B * HW;
-  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = (lo + chunk < total) ? lo + chunk : total;
+  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = (lo + chunk < HW) ? lo + chunk : HW;
   float s = 0.f, ss = 0.f;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
-    const int64_t b = i / HW, p = i - b * HW;
-    const float v = __ldg(y + (b * C + c) * HW + p);
-    s += v; ss = fmaf(v, v, ss);
+  for (int b = 0; b < B; ++b) {
+    const float* row = y + ((int64_t)b * C + c) * HW;
+    if (VEC) {
+#pragma unroll 4
+      for (int64_t p = lo + threadIdx.x * 4; p < hi; p += 1024) {
+        const float4 v = ld4(row + p);
+        s += (v.x + v.y) + (v.z + v.w);
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+      }
+    } else {
+      for (int64_t p = lo + threadIdx.x; p < hi; p += 256) {
+        const float v = __ldg(row + p);
+        s += v; ss = fmaf(v, v, ss);
+      }
+    }
   }
   block_sum2(s, ss);
   if (threadIdx.x == 0) { atomicAdd(acc + 2 * c, (double)s); atomicAdd(acc + 2 * c + 1, (double)ss); }
@@ -68,6 +83,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double
   if (run_var) run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(n > 1 ? v * n / (n - 1) : v);
 }
 // a = [relu](gamma * (y - mean) * rsqrt(var + eps) + beta); grid (B*C, chunks over HW)
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ var,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
@@ -77,12 +93,18 @@ bn_act_kernel(const float* __restrict__ y, const float* __restrict__ mean, const
   const float m = __ldg(mean + c), g = __ldg(gamma + c), bt = __ldg(beta + c);
   const float* src = y + (int64_t)bc * HW;
   float* dst = a + (int64_t)bc * HW;
-  for (int64_t p = (int64_t)blockIdx.y * 256 + threadIdx.x; p < HW; p += (int64_t)gridDim.y * 256) {
-    float v = (src[p] - m) * inv * g + bt;
-    dst[p] = relu ? fmaxf(v, 0.f) : v;
+  auto f = [&](float x) { const float v = (x - m) * inv * g + bt; return relu ? fmaxf(v, 0.f) : v; };
+  if (VEC) {
+    for (int64_t p = ((int64_t)blockIdx.y * 256 + threadIdx.x) * 4; p < HW; p += (int64_t)gridDim.y * 1024) {
+      const float4 v = ld4(src + p);
+      *reinterpret_cast<float4*>(dst + p) = make_float4(f(v.x), f(v.y), f(v.z), f(v.w));
+    }
+  } else {
+    for (int64_t p = (int64_t)blockIdx.y * 256 + threadIdx.x; p < HW; p += (int64_t)gridDim.y * 256) dst[p] = f(src[p]);
   }
 }
 // backward, pass 1: dz = da * (z > 0) with z recomputed from y; acc[c] += {sum dz, sum dz * xhat}
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -90,27 +112,39 @@ bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ y, 
   const int c = blockIdx.y;
   const float inv = 1.f / sqrtf(__ldg(var + c) + eps);
   const float m = __ldg(mean + c), g = __ldg(gamma + c), bt = __ldg(beta + c);
-  const int64_t total = (int64_t)B * HW;
-  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = (lo + chunk < total) ? lo + chunk : total;
+  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = (lo + chunk < HW) ? lo + chunk : HW;
   float s1 = 0.f, s2 = 0.f;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
-    const int64_t b = i / HW, p = i - b * HW;
-    const int64_t o = (b * C + c) * HW + p;
-    const float xh = (__ldg(y + o) - m) * inv;
-    float d = __ldg(da + o);
+  auto f = [&](float yv, float d) {
+    const float xh = (yv - m) * inv;
     if (relu && !(xh * g + bt > 0.f)) d = 0.f;
     s1 += d; s2 = fmaf(d, xh, s2);
+  };
+  for (int b = 0; b < B; ++b) {
+    const int64_t base = ((int64_t)b * C + c) * HW;
+    if (VEC) {
+#pragma unroll 2
+      for (int64_t p = lo + threadIdx.x * 4; p < hi; p += 1024) {
+        const float4 yv = ld4(y + base + p), d = ld4(da + base + p);
+        f(yv.x, d.x); f(yv.y, d.y); f(yv.z, d.z); f(yv.w, d.w);
+      }
+    } else {
+      for (int64_t p = lo + threadIdx.x; p < hi; p += 256) f(__ldg(y + base + p), __ldg(da + base + p));
+    }
   }
   block_sum2(s1, s2);
   if (threadIdx.x == 0) { atomicAdd(acc + 2 * c, (double)s1); atomicAdd(acc + 2 * c + 1, (double)s2); }
 }
 // backward, pass 2: dy = gamma * inv * (dz - mean(dz) - xhat * mean(dz * xhat)); also writes
-// dgamma = sum dz * xhat, dbeta = sum dz (block (0, c-th row of b == 0) does it)
+// dgamma = sum dz * xhat, dbeta = sum dz (block (0, c-th row of b == 0) does it).  bias_acc (nullable, fp64 [C],
+// zero-filled): += sum of the dy values this block wrote — the bias gradient of the convolution in front of the
+// BatchNorm (mathematically zero; autograd's value is the rounding residue of exactly this sum).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float eps, int relu, const double* __restrict__ acc, double n, float* __restrict__ dy,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int64_t HW) {
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ bias_acc, int C,
+                    int64_t HW) {
   const int bc = blockIdx.x, c = bc % C;
   const float inv = 1.f / sqrtf(__ldg(var + c) + eps);
   const float m = __ldg(mean + c), g = __ldg(gamma + c), bt = __ldg(beta + c);
@@ -120,20 +154,35 @@ bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ y, c
     if (dgamma) dgamma[c] = (float)acc[2 * c + 1];
   }
   const int64_t base = (int64_t)bc * HW;
-  for (int64_t p = (int64_t)blockIdx.y * 256 + threadIdx.x; p < HW; p += (int64_t)gridDim.y * 256) {
-    const float xh = (y[base + p] - m) * inv;
-    float d = da[base + p];
+  float sb = 0.f, zero = 0.f;
+  auto f = [&](float yv, float d) {
+    const float xh = (yv - m) * inv;
     if (relu && !(xh * g + bt > 0.f)) d = 0.f;
-    dy[base + p] = g * inv * (d - m1 - xh * m2);
+    const float r = g * inv * (d - m1 - xh * m2);
+    sb += r;
+    return r;
+  };
+  if (VEC) {
+    for (int64_t p = ((int64_t)blockIdx.y * 256 + threadIdx.x) * 4; p < HW; p += (int64_t)gridDim.y * 1024) {
+      const float4 yv = ld4(y + base + p), d = ld4(da + base + p);
+      *reinterpret_cast<float4*>(dy + base + p) = make_float4(f(yv.x, d.x), f(yv.y, d.y), f(yv.z, d.z), f(yv.w, d.w));
+    }
+  } else {
+    for (int64_t p = (int64_t)blockIdx.y * 256 + threadIdx.x; p < HW; p += (int64_t)gridDim.y * 256)
+      dy[base + p] = f(y[base + p], da[base + p]);
+  }
+  if (bias_acc) {
+    block_sum2(sb, zero);
+    if (threadIdx.x == 0) atomicAdd(bias_acc + c, (double)sb);
   }
 }
 
 // ------------------------------------------------------------------------------------
-// per-channel sums over (B, HW): conv bias gradients.  grid (chunks, C); acc fp64 [C][2] (slot 0)
+// per-channel sums over (B, HW): conv bias gradients.  acc fp64 [C][2] (slot 0) or a plain fp64 [C] (stride 1)
 // ------------------------------------------------------------------------------------
-__global__ void channel_sum_finalize_kernel(const double* __restrict__ acc, int C, float* __restrict__ out) {
+__global__ void channel_sum_finalize_kernel(const double* __restrict__ acc, int stride, int C, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) out[c] = (float)acc[2 * c];
+  if (c < C) out[c] = (float)acc[stride * c];
 }
 // per-row sums: out[r] = sum_p x[r][p]   (rows = B*C); one block per row
 __global__ void __launch_bounds__(256)
@@ -528,14 +577,16 @@ static inline unsigned ew_grid(int64_t n) { return (unsigned)std::min<int64_t>(c
 
 using namespace pmu;
 
-// split (B*HW) into chunks so that chunks * C blocks fill the machine a few times over
-static void stat_chunks(int B, int C, int64_t HW, int64_t* chunk, int* nchunks) {
-  const int64_t total = (int64_t)B * HW;
+// split HW into chunks (multiples of 1024 = 256 threads x float4) so that chunks * C blocks fill the machine a few times over
+static void stat_chunks(int C, int64_t HW, int64_t* chunk, int* nchunks) {
   int64_t want = std::max<int64_t>(1, (8ll * sm_count() + C - 1) / C);
-  int64_t ch = std::max<int64_t>(2048, cdiv64(total, want));
-  ch = ((ch + 255) / 256) * 256;
+  int64_t ch = std::max<int64_t>(1024, cdiv64(HW, want));
+  ch = ((ch + 1023) / 1024) * 1024;
   *chunk = ch;
-  *nchunks = (int)cdiv64(total, ch);
+  *nchunks = (int)cdiv64(HW, ch);
+}
+static inline bool rows_vec(int64_t HW, const void* a, const void* b = nullptr, const void* c = nullptr) {
+  return HW % 4 == 0 && aligned16(a) && (!b || aligned16(b)) && (!c || aligned16(c));
 }
 
 extern "C" int pmu_bn_train_fwd_f32(const float* y, const float* gamma, const float* beta, float eps, int relu,
@@ -546,14 +597,47 @@ extern "C" int pmu_bn_train_fwd_f32(const float* y, const float* gamma, const fl
   cudaStream_t st = (cudaStream_t)stream;
   PMU_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
   int64_t chunk; int nch;
-  stat_chunks(B, C, HW, &chunk, &nch);
-  bn_stats_kernel<<<dim3(nch, C), 256, 0, st>>>(y, B, C, HW, chunk, ws);
+  stat_chunks(C, HW, &chunk, &nch);
+  const bool vec = rows_vec(HW, y, a);
+  if (vec) bn_stats_kernel<true><<<dim3(nch, C), 256, 0, st>>>(y, B, C, HW, chunk, ws);
+  else bn_stats_kernel<false><<<dim3(nch, C), 256, 0, st>>>(y, B, C, HW, chunk, ws);
   PMU_LAUNCH_CHECK();
   bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, C, (double)B * (double)HW, mean, var, run_mean, run_var, momentum);
   PMU_LAUNCH_CHECK();
-  const unsigned gx = (unsigned)std::min<int64_t>(cdiv64(HW, 256), 64);
-  bn_act_kernel<<<dim3(B * C, gx), 256, 0, st>>>(y, mean, var, gamma, beta, eps, relu, a, C, HW);
+  const unsigned gx = (unsigned)std::min<int64_t>(cdiv64(HW, vec ? 1024 : 256), 64);
+  if (vec) bn_act_kernel<true><<<dim3(B * C, gx), 256, 0, st>>>(y, mean, var, gamma, beta, eps, relu, a, C, HW);
+  else bn_act_kernel<false><<<dim3(B * C, gx), 256, 0, st>>>(y, mean, var, gamma, beta, eps, relu, a, C, HW);
   PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_bn_train_bwd_bias_f32(const float* da, const float* y, const float* mean, const float* var,
+                                         const float* gamma, const float* beta, float eps, int relu, float* dy,
+                                         float* dgamma, float* dbeta, float* dbias, double* ws, int B, int C,
+                                         int64_t HW, void* stream) {
+  PMU_CHECK_ARG(da && y && mean && var && gamma && beta && dy && ws, "pmu_bn_train_bwd_f32: null pointer");
+  PMU_CHECK_ARG(B > 0 && C > 0 && C <= 65535 && HW > 0 && (int64_t)B * C < (1ll << 31), "pmu_bn_train_bwd_f32: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  PMU_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (dbias ? 3 : 2) * C, st));
+  int64_t chunk; int nch;
+  stat_chunks(C, HW, &chunk, &nch);
+  const bool vec = rows_vec(HW, da, y, dy);
+  if (vec) bn_bwd_reduce_kernel<true><<<dim3(nch, C), 256, 0, st>>>(da, y, mean, var, gamma, beta, eps, relu, B, C, HW, chunk, ws);
+  else bn_bwd_reduce_kernel<false><<<dim3(nch, C), 256, 0, st>>>(da, y, mean, var, gamma, beta, eps, relu, B, C, HW, chunk, ws);
+  PMU_LAUNCH_CHECK();
+  const unsigned gx = (unsigned)std::min<int64_t>(cdiv64(HW, vec ? 1024 : 256), 64);
+  double* bias_acc = dbias ? ws + 2 * (size_t)C : nullptr;
+  if (vec)
+    bn_bwd_apply_kernel<true><<<dim3(B * C, gx), 256, 0, st>>>(da, y, mean, var, gamma, beta, eps, relu, ws,
+                                                              (double)B * (double)HW, dy, dgamma, dbeta, bias_acc, C, HW);
+  else
+    bn_bwd_apply_kernel<false><<<dim3(B * C, gx), 256, 0, st>>>(da, y, mean, var, gamma, beta, eps, relu, ws,
+                                                               (double)B * (double)HW, dy, dgamma, dbeta, bias_acc, C, HW);
+  PMU_LAUNCH_CHECK();
+  if (dbias) {
+    channel_sum_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(bias_acc, 1, C, dbias);
+    PMU_LAUNCH_CHECK();
+  }
   return PMU_OK;
 }
 
@@ -561,19 +645,7 @@ extern "C" int pmu_bn_train_bwd_f32(const float* da, const float* y, const float
                                     const float* gamma, const float* beta, float eps, int relu, float* dy,
                                     float* dgamma, float* dbeta, double* ws, int B, int C, int64_t HW,
                                     void* stream) {
-  PMU_CHECK_ARG(da && y && mean && var && gamma && beta && dy && ws, "pmu_bn_train_bwd_f32: null pointer");
-  PMU_CHECK_ARG(B > 0 && C > 0 && C <= 65535 && HW > 0 && (int64_t)B * C < (1ll << 31), "pmu_bn_train_bwd_f32: bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
-  PMU_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-  int64_t chunk; int nch;
-  stat_chunks(B, C, HW, &chunk, &nch);
-  bn_bwd_reduce_kernel<<<dim3(nch, C), 256, 0, st>>>(da, y, mean, var, gamma, beta, eps, relu, B, C, HW, chunk, ws);
-  PMU_LAUNCH_CHECK();
-  const unsigned gx = (unsigned)std::min<int64_t>(cdiv64(HW, 256), 64);
-  bn_bwd_apply_kernel<<<dim3(B * C, gx), 256, 0, st>>>(da, y, mean, var, gamma, beta, eps, relu, ws,
-                                                      (double)B * (double)HW, dy, dgamma, dbeta, C, HW);
-  PMU_LAUNCH_CHECK();
-  return PMU_OK;
+  return pmu_bn_train_bwd_bias_f32(da, y, mean, var, gamma, beta, eps, relu, dy, dgamma, dbeta, nullptr, ws, B, C, HW, stream);
 }
 
 extern "C" int pmu_channel_sums_f32(const float* x, float* out, double* ws, int B, int C, int64_t HW, void* stream) {
@@ -581,10 +653,11 @@ extern "C" int pmu_channel_sums_f32(const float* x, float* out, double* ws, int 
   cudaStream_t st = (cudaStream_t)stream;
   PMU_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
   int64_t chunk; int nch;
-  stat_chunks(B, C, HW, &chunk, &nch);
-  bn_stats_kernel<<<dim3(nch, C), 256, 0, st>>>(x, B, C, HW, chunk, ws);
+  stat_chunks(C, HW, &chunk, &nch);
+  if (rows_vec(HW, x)) bn_stats_kernel<true><<<dim3(nch, C), 256, 0, st>>>(x, B, C, HW, chunk, ws);
+  else bn_stats_kernel<false><<<dim3(nch, C), 256, 0, st>>>(x, B, C, HW, chunk, ws);
   PMU_LAUNCH_CHECK();
-  channel_sum_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, C, out);
+  channel_sum_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, 2, C, out);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

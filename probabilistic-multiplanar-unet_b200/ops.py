@@ -386,17 +386,18 @@ def bn_train_fwd_f32(y, gamma, beta, eps, relu, momentum=0.1, run_mean=None, run
     return a, mean, var
 
 
-def bn_train_bwd_f32(da, y, mean, var, gamma, beta, eps, relu):
-    """-> (dy, dgamma, dbeta)."""
+def bn_train_bwd_f32(da, y, mean, var, gamma, beta, eps, relu, want_dbias=False):
+    """-> (dy, dgamma, dbeta) [+ dbias = channel sums of dy, the bias gradient of the conv in front, fused]."""
     B, C, H, W = y.shape
     dy = torch.empty_like(y)
     dg = torch.empty(C, dtype=torch.float32, device=y.device)
     db = torch.empty_like(dg)
-    ws = _ws(C, y.device)
+    dbias = torch.empty_like(dg) if want_dbias else None
+    ws = torch.empty(3 * C, dtype=torch.float64, device=y.device)
     lib, st = _prep(da, y, mean, var, gamma, beta, dy, dg, db, ws)
-    _launch(lib, "pmu_bn_train_bwd_f32", (_p(da), _p(y), _p(mean), _p(var), _p(gamma), _p(beta), float(eps), int(relu),
-                                        _p(dy), _p(dg), _p(db), _p(ws), B, C, H * W, st,))
-    return dy, dg, db
+    _launch(lib, "pmu_bn_train_bwd_bias_f32", (_p(da), _p(y), _p(mean), _p(var), _p(gamma), _p(beta), float(eps), int(relu),
+                                             _p(dy), _p(dg), _p(db), _p(dbias), _p(ws), B, C, H * W, st,))
+    return (dy, dg, db, dbias) if want_dbias else (dy, dg, db)
 
 
 def channel_sums_f32(x):

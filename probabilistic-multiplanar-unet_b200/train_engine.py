@@ -92,10 +92,11 @@ def _cbr_fwd(conv: nn.Conv2d, bn: nn.BatchNorm2d, x0, x1=None):
 
 def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
     conv, bn = rec["conv"], rec["bn"]
-    dy, dg, db = ops.bn_train_bwd_f32(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True)
+    dy, dg, db, dcb = ops.bn_train_bwd_f32(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True,
+                                           want_dbias=True)
     tape.put(bn.weight, dg)
     tape.put(bn.bias, db)
-    tape.put(conv.bias, ops.channel_sums_f32(dy))
+    tape.put(conv.bias, dcb)
     w = _d(conv.weight)
     Cout, Cin = w.shape[0], w.shape[1]
     C0 = rec["x0"].shape[1]
@@ -163,7 +164,18 @@ def _unet_fwd(unet, x):
         if skip.shape[2] != 2 * h.shape[2] or skip.shape[3] != 2 * h.shape[3]:
             raise NotImplementedError("training needs H, W divisible by 2^levels (the F.pad branch of Up.forward, "
                                       "unet_parts.py:58-62, is only built for inference)")
-        u = ops.convt2x2_f32(h, _d(up.up.weight), _d(up.up.bias))
+        wt = _d(up.up.weight)                                   # [Cin, Cout, 2, 2]
+        if _BF16["on"] and wt.shape[0] % 64 == 0 and wt.shape[1] % 64 == 0:
+            # transposed convolution on tcgen05: one K tap, N = 4 * Cout (the four output phases share one A load)
+            wpack = wt.permute(2, 3, 1, 0).reshape(4 * wt.shape[1], wt.shape[0]).to(torch.bfloat16).contiguous()
+            ub = ops.conv_gemm_bf16(_to_bf16_nhwc(h), wpack, _d(up.up.bias), wt.shape[1], 4, False)
+            u = ops.nhwc_bf16_to_nchw_f32(ub)
+            _BF16["cache"][id(u)] = (u, ub)                    # the decoder convolution reads the bf16 NHWC form
+            if CHECK_LOG is not None:
+                ref = ops.convt2x2_f32(h, wt, _d(up.up.bias))
+                CHECK_LOG.append(("convt", wt.shape[0], wt.shape[1], u.shape[2], float((u - ref).norm() / ref.norm())))
+        else:
+            u = ops.convt2x2_f32(h, wt, _d(up.up.bias))
         h_in = h
         h, r = _dconv_fwd(up.conv, skip, u)        # cat([skip, up]) as a two-source convolution
         ups.append({"up": up, "h_in": h_in, "recs": r})

@@ -13,7 +13,8 @@ imgs = torch.from_numpy(O.plane_slices(vol, 0, 100, B)).cuda()
 masks = torch.from_numpy(lab[100:100 + B, None].astype(np.float32)).cuda()
 def T():
     torch.cuda.synchronize(); return time.perf_counter()
-for it in range(4):
+NIT = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+for it in range(NIT):
     t0 = T(); net.forward(imgs, masks, training=True)
     t1 = T(); s = net.sample(testing=False)
     t2 = T(); loss = -net.elbo(masks)
@@ -23,6 +24,8 @@ for it in range(4):
     t6 = T()
     print(f"it {it}: forward {1e3*(t1-t0):.1f}  sample {1e3*(t2-t1):.1f}  elbo {1e3*(t3-t2):.1f}  backward {1e3*(t4-t3):.1f}  clip {1e3*(t5-t4):.1f}  sgd {1e3*(t6-t5):.1f}  total {1e3*(t6-t0):.1f} ms")
 print("alloc retries:", torch.cuda.memory_stats().get("num_alloc_retries"), " peak GB:", torch.cuda.max_memory_allocated() / 1e9)
+if '--no-profiler' in sys.argv:
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     trainer.predict(imgs, masks); loss = trainer.loss(imgs, masks, None); loss.backward(); torch.cuda.synchronize()

@@ -32,7 +32,8 @@ def _close(got, ref, rtol=1e-4, what=""):
     assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
 
 
-@pytest.mark.parametrize("B,C,H,W,relu", [(3, 5, 9, 13, True), (2, 64, 16, 16, True), (4, 7, 8, 8, False)])
+@pytest.mark.parametrize("B,C,H,W,relu", [(3, 5, 9, 13, True), (2, 64, 16, 16, True), (4, 7, 8, 8, False),
+                                          (2, 3, 96, 100, True), (3, 2, 130, 130, True), (2, 4, 128, 256, False)])
 def test_bn_train_fwd_bwd(ops, B, C, H, W, relu):
     g = _g(1)
     y = (torch.randn(B, C, H, W, generator=g) * 2 + 0.5).requires_grad_(True)
@@ -54,6 +55,13 @@ def test_bn_train_fwd_bwd(ops, B, C, H, W, relu):
     _close(dy, y.grad, 2e-4, "bn dy")
     _close(dg, gamma.grad, 1e-4, "bn dgamma")
     _close(db, beta.grad, 1e-4, "bn dbeta")
+    # fused bias gradient of the convolution in front: the channel sums of dy (mathematically zero: rounding residue)
+    dy2, dg2, db2, dcb = ops.bn_train_bwd_f32(da.cuda(), y.detach().cuda(), mean, var, gamma.detach().cuda(),
+                                              beta.detach().cuda(), 1e-5, relu, want_dbias=True)
+    assert torch.equal(dy2, dy) and torch.equal(dg2, dg) and torch.equal(db2, db)
+    want = dy.double().sum((0, 2, 3)).float()
+    assert float((dcb - want).abs().max()) <= 1e-6 * max(1.0, float(dy.abs().max())) * 4
+    assert torch.allclose(ops.channel_sums_f32(dy), want, atol=1e-5 * float(dy.abs().sum((0, 2, 3)).max()), rtol=0)
 
 
 @pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 1, 0, 4, 9, 13), (1, 5, 3, 7, 32, 48), (3, 16, 16, 33, 8, 8),
@@ -315,6 +323,7 @@ def test_bf16_training_step(ops):
         assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
     kinds = {k: [r for r in log if r[0] == k] for k in ("fwd", "dgrad", "wgrad")}
     assert len(kinds["fwd"]) == 35 and len(kinds["wgrad"]) == 35 and len(kinds["dgrad"]) == 35, {k: len(v) for k, v in kinds.items()}
+    assert len([r for r in log if r[0] == "convt"]) == 4          # the four transposed convolutions of the decoder
     worst = max(log, key=lambda r: r[4])
     assert worst[4] < 1e-2, worst
     assert abs(vals["bf16"][2] - vals["fp32"][2]) <= 2e-2 * abs(vals["fp32"][2]), vals

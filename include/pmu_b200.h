@@ -266,6 +266,10 @@ int pmu_conv1x1_bb_f32(const float* x, const float* w, int ldw, const float* bia
 /* ---- training step, bf16 tensor-core mode ------------------------------------------------- */
 /* fp32 NCHW [B,C,H,W] -> bf16 NHWC [B,H,W,C] (operand cast for the tensor-core convolutions). */
 int pmu_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream);
+/* space-to-depth: x bf16 NHWC [B,2H,2W,C] -> y bf16 NHWC [B,H,W,4C], y[b,h,w,(i*2+j)*C+c] = x[b,2h+i,2w+j,c] (C % 8 == 0).
+ * With it the data / weight gradients of nn.ConvTranspose2d(k=2, s=2) (unet_parts.py:52) are 1x1 GEMMs:
+ * pmu_conv_gemm_bf16(ntaps = 1, K = 4*Cout) and pmu_conv_wgrad_bf16(ntaps = 1, N = 4*Cout). */
+int pmu_s2d_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* tcgen05 weight gradient of conv3x3 pad 1 (ntaps = 9) / conv1x1 (ntaps = 1):
  * dw fp32 [Cout][ntaps][C0+C1] += sum_{b,h,w} dy[b,h,w,co] * cat(x0,x1)[b,h+ky-1,w+kx-1,ci]   (tap = ky*3+kx)
  * x0 bf16 [B,H,W,C0], x1 (nullable) bf16 [B,H,W,C1], dy bf16 [B,H,W,Cout]; channels multiples of 64.

@@ -67,6 +67,7 @@ _SIG = {
     "pmu_fcomb_zbias_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "pmu_fcomb_zbias_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "pmu_nchw_f32_to_nhwc_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "pmu_s2d_nhwc_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pmu_conv_wgrad_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_conv1x1_bb_f32": (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
 }

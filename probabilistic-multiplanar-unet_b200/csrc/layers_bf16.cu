@@ -309,6 +309,36 @@ extern "C" int pmu_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, 
   return PMU_OK;
 }
 
+// space-to-depth of a bf16 NHWC map: dst[b,h,w,(i*2+j)*C + c] = src[b,2h+i,2w+j,c]  (16-byte vectors; C % 8 == 0).
+// The gradient of a k2 s2 transposed convolution reads its output-side tensor exactly in this order, which turns its
+// data and weight gradients into plain 1x1 GEMMs with K (resp. N) = 4*C (nn.ConvTranspose2d backward, unet_parts.py:52).
+namespace pmu {
+__global__ void __launch_bounds__(256)
+s2d_nhwc_bf16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int C8, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int c = (int)(i % C8);
+    int64_t r = i / C8;
+    const int ij = (int)(r & 3); r >>= 2;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int64_t b = r / H;
+    const int64_t sp = (b * 2 * H + 2 * h + (ij >> 1)) * (2 * (int64_t)W) + 2 * w + (ij & 1);
+    dst[i] = __ldg(src + sp * C8 + c);
+  }
+}
+}  // namespace pmu
+
+extern "C" int pmu_s2d_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  PMU_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0, "pmu_s2d_nhwc_bf16: bad arguments");
+  PMU_CHECK_SUPPORTED(C % 8 == 0 && aligned16(x) && aligned16(y), "pmu_s2d_nhwc_bf16: C must be a multiple of 8, pointers 16-byte aligned");
+  const int64_t total = (int64_t)B * H * W * 4 * (C / 8);
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 32);
+  pmu::s2d_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
+                                                                   H, W, C / 8, total);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
 extern "C" int pmu_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream) {
   PMU_CHECK_ARG(x && y && B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0, "pmu_nchw_f32_to_nhwc_bf16: bad arguments");
   PMU_CHECK_SUPPORTED(C % 2 == 0, "pmu_nchw_f32_to_nhwc_bf16: C must be even");

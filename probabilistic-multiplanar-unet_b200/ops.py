@@ -536,6 +536,18 @@ def nchw_f32_to_nhwc_bf16(x):
     return y
 
 
+def s2d_nhwc_bf16(x):
+    """bf16 NHWC [B,2H,2W,C] -> [B,H,W,4C] with channel order (i, j, c): y[b,h,w,(i*2+j)*C+c] = x[b,2h+i,2w+j,c]."""
+    _bf16(x, "x")
+    B, H2, W2, C = x.shape
+    if H2 % 2 or W2 % 2:
+        raise RuntimeError("s2d_nhwc_bf16 needs even H and W")
+    y = torch.empty(B, H2 // 2, W2 // 2, 4 * C, dtype=torch.bfloat16, device=x.device)
+    lib, st = _prep(x, y)
+    _launch(lib, "pmu_s2d_nhwc_bf16", (_p(x), _p(y), B, H2 // 2, W2 // 2, C, st,))
+    return y
+
+
 def conv_wgrad_bf16(x0, dy, dw, x1=None, ntaps=9):
     """dw fp32 [Cout, ntaps, C0+C1] += tcgen05 weight gradient; x0/x1/dy bf16 NHWC."""
     _bf16(x0, "x0"); _bf16(x1, "x1"); _bf16(dy, "dy"); _f32(dw, "dw")

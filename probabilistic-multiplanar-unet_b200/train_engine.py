@@ -122,7 +122,9 @@ def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
             CHECK_LOG.append(("dgrad", Cin, Cout, dy.shape[2], float((dx0 - ref).norm() / ref.norm())))
         dx1 = None
         if rec["x1"] is not None:
-            dx1 = ops.nhwc_bf16_to_nchw_f32(ops.conv_gemm_bf16(dyb, wt[C0:].contiguous(), None, Cin - C0, 9, False))
+            dx1b = ops.conv_gemm_bf16(dyb, wt[C0:].contiguous(), None, Cin - C0, 9, False)
+            dx1 = ops.nhwc_bf16_to_nchw_f32(dx1b)
+            _BF16["cache"][id(dx1)] = (dx1, dx1b)               # the transposed-convolution backward reads the bf16 form
         return dx0, dx1
     dw = torch.zeros_like(w)
     ops.conv3x3_wgrad_f32(rec["x0"], dy, dw, rec["x1"])
@@ -191,11 +193,30 @@ def _unet_bwd(unet, st, dfeat, tape):
         ds, du = _dconv_bwd(u["recs"], d, tape)
         dskip[n - 1 - i] = ds
         up = u["up"].up
-        dw = torch.zeros_like(_d(up.weight))
-        ops.convt2x2_wgrad_f32(u["h_in"], du, dw)
-        tape.put(up.weight, dw)
+        wt = _d(up.weight)                                      # [Cin, Cout, 2, 2]
+        Cin, Co = wt.shape[0], wt.shape[1]
         tape.put(up.bias, ops.channel_sums_f32(du))
-        d = ops.convt2x2_dgrad_f32(du, _d(up.weight))
+        if _BF16["on"] and Cin % 64 == 0 and Co % 64 == 0:
+            # transposed-convolution backward on tcgen05: space-to-depth of du turns both gradients into 1x1 GEMMs
+            D = ops.s2d_nhwc_bf16(_to_bf16_nhwc(du))            # [B, H, W, (i, j, co)]
+            xb = _to_bf16_nhwc(u["h_in"])
+            dwp = torch.zeros(4 * Co, 1, Cin, dtype=torch.float32, device=du.device)
+            ops.conv_wgrad_bf16(xb, D, dwp, None, 1)            # dwp[(i,j,co)][ci] = sum_pix D * x
+            dw = dwp.reshape(2, 2, Co, Cin).permute(3, 2, 0, 1).contiguous()
+            tape.put(up.weight, dw)
+            wd = wt.permute(0, 2, 3, 1).reshape(Cin, 4 * Co).to(torch.bfloat16).contiguous()       # [ci][(i,j,co)]
+            d = ops.nhwc_bf16_to_nchw_f32(ops.conv_gemm_bf16(D, wd, None, Cin, 1, False))
+            if CHECK_LOG is not None:
+                ref = torch.zeros_like(wt)
+                ops.convt2x2_wgrad_f32(u["h_in"], du, ref)
+                CHECK_LOG.append(("convt_wgrad", Cin, Co, du.shape[2], float((dw - ref).norm() / ref.norm())))
+                ref = ops.convt2x2_dgrad_f32(du, wt)
+                CHECK_LOG.append(("convt_dgrad", Cin, Co, du.shape[2], float((d - ref).norm() / ref.norm())))
+        else:
+            dw = torch.zeros_like(wt)
+            ops.convt2x2_wgrad_f32(u["h_in"], du, dw)
+            tape.put(up.weight, dw)
+            d = ops.convt2x2_dgrad_f32(du, wt)
     # d = gradient w.r.t. the deepest encoder map
     for lvl in range(n, 0, -1):
         if dskip[lvl] is not None:

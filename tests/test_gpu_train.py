@@ -291,6 +291,28 @@ def test_conv_wgrad_bf16_tcgen05(ops, B, C0, C1, Cout, H, W, ntaps):
     _close(dw, ref, 2e-4, "tcgen05 wgrad")
 
 
+def test_space_to_depth_and_convt_backward_as_gemms(ops):
+    """pmu_s2d_nhwc_bf16 (bit-exact data movement) and the ConvTranspose2d(k2, s2) backward built on it: data gradient
+    = 1x1 tcgen05 GEMM with K = 4*Cout, weight gradient = 1x1 tcgen05 wgrad with N = 4*Cout, vs torch autograd on
+    the same bf16-rounded operands."""
+    g = _g(40)
+    B, Cin, Co, H, W = 2, 128, 64, 8, 16
+    x = _bf(torch.randn(B, Cin, H, W, generator=g)).requires_grad_(True)
+    w = _bf(torch.randn(Cin, Co, 2, 2, generator=g) * 0.1).requires_grad_(True)
+    du = _bf(torch.randn(B, Co, 2 * H, 2 * W, generator=g))
+    F.conv_transpose2d(x, w, None, stride=2).backward(du)
+    dub = _nhwc(du).to(torch.bfloat16).cuda()
+    D = ops.s2d_nhwc_bf16(dub)
+    want = dub.cpu().reshape(B, H, 2, W, 2, Co).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, 4 * Co)
+    assert torch.equal(D.cpu(), want)
+    wd = w.detach().permute(0, 2, 3, 1).reshape(Cin, 4 * Co).to(torch.bfloat16).contiguous().cuda()
+    dx = ops.nhwc_bf16_to_nchw_f32(ops.conv_gemm_bf16(D, wd, None, Cin, 1, False))
+    _close(dx, x.grad, 1e-2, "convT dgrad as a 1x1 GEMM")                    # output rounded to bf16
+    dwp = torch.zeros(4 * Co, 1, Cin, device="cuda")
+    ops.conv_wgrad_bf16(_nhwc(x.detach()).to(torch.bfloat16).cuda(), D, dwp, None, 1)
+    _close(dwp.reshape(2, 2, Co, Cin).permute(3, 2, 0, 1), w.grad, 2e-4, "convT wgrad as a 1x1 wgrad")
+
+
 def test_bf16_training_step(ops):
     """Trainer architecture [64..1024] in the bf16 tensor-core training mode (tcgen05 forward / dgrad / wgrad,
     fp32 BatchNorm).  Every tensor-core GEMM of a real step is recomputed by the fp32 kernels on the SAME
@@ -323,7 +345,8 @@ def test_bf16_training_step(ops):
         assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
     kinds = {k: [r for r in log if r[0] == k] for k in ("fwd", "dgrad", "wgrad")}
     assert len(kinds["fwd"]) == 35 and len(kinds["wgrad"]) == 35 and len(kinds["dgrad"]) == 35, {k: len(v) for k, v in kinds.items()}
-    assert len([r for r in log if r[0] == "convt"]) == 4          # the four transposed convolutions of the decoder
+    for kind in ("convt", "convt_wgrad", "convt_dgrad"):         # the four transposed convolutions of the decoder
+        assert len([r for r in log if r[0] == kind]) == 4, kind
     worst = max(log, key=lambda r: r[4])
     assert worst[4] < 1e-2, worst
     assert abs(vals["bf16"][2] - vals["fp32"][2]) <= 2e-2 * abs(vals["fp32"][2]), vals

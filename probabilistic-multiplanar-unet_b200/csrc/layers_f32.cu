@@ -444,10 +444,15 @@ extern "C" int pmu_conv3x3_f32(const float* x0, int C0, const float* x1, int C1,
   return PMU_OK;
 }
 
+// implemented in train_f32.cu: the register-tiled 1x1 kernel (per-batch bias variant; bias_bstride = 0 -> shared bias)
+extern "C" int pmu_conv1x1_bb_f32(const float* x, const float* w, int ldw, const float* bias, int bias_bstride, float* y,
+                                  int B, int Cin, int Cout, int64_t HW, int relu, void* stream);
+
 extern "C" int pmu_conv1x1_f32(const float* x, const float* w, const float* bias, float* y, int B,
                                int Cin, int Cout, int64_t HW, int relu, void* stream) {
   PMU_CHECK_ARG(x && w && y && B > 0 && Cin > 0 && Cout > 0 && HW > 0, "pmu_conv1x1_f32: bad arguments");
   PMU_CHECK_ARG(B <= 65535, "pmu_conv1x1_f32: batch too large");
+  if (Cin <= 1536) return pmu_conv1x1_bb_f32(x, w, Cin, bias, 0, y, B, Cin, Cout, HW, relu, stream);
   dim3 grid((unsigned)cdiv64(HW, 256), cdiv(Cout, 8), B);
   conv1x1_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, Cin, Cout, HW, relu);
   PMU_LAUNCH_CHECK();

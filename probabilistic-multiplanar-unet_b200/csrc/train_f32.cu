@@ -545,29 +545,59 @@ __global__ void fcomb_zbias_bwd_kernel(const float* __restrict__ rs, const float
     db0[co] += s;
   }
 }
-// y[b,co,p] = [relu](sum_ci w[co*ldw + ci] x[b,ci,p] + bias[b*bias_bstride + co]); thread per pixel, 8 couts per pass
+// y[b,co,p] = [relu](sum_ci w[co*ldw + ci] x[b,ci,p] + bias[b*bias_bstride + co]).
+// Register tile: 4 consecutive pixels x 8 couts per thread.  The 8 x Cin weight slab of the block sits in shared memory
+// as [ci][8], so one ci step is ONE 128-bit global load (4 pixels) + TWO 128-bit broadcast shared loads for 32 FMAs
+// (the thread-per-pixel version issued 9 loads per 8 FMAs and was bound by the load/store unit).  The sum over ci keeps
+// its sequential fmaf order, so results are bit-identical with the previous kernel.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 conv1x1_bb_kernel(const float* __restrict__ x, const float* __restrict__ w, int ldw, const float* __restrict__ bias,
                   int bias_bstride, float* __restrict__ y, int Cin, int Cout, int64_t HW, int relu) {
+  extern __shared__ float ws[];                       // [Cin][8]
   const int b = blockIdx.z, co0 = blockIdx.y * 8;
-  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int i = threadIdx.x; i < Cin * 8; i += 256) {
+    const int ci = i >> 3, c = i & 7;
+    ws[i] = (co0 + c < Cout) ? __ldg(w + (int64_t)(co0 + c) * ldw + ci) : 0.f;
+  }
+  __syncthreads();
+  const int64_t p = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (p >= HW) return;
-  float acc[8];
+  float acc[4][8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
   const float* xp = x + (int64_t)b * Cin * HW + p;
+  const int npx = (HW - p < 4) ? (int)(HW - p) : 4;
   for (int ci = 0; ci < Cin; ++ci) {
-    const float v = __ldg(xp + (int64_t)ci * HW);
+    float v[4];
+    if (VEC) {
+      const float4 t = *reinterpret_cast<const float4*>(xp + (int64_t)ci * HW);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (co0 + c < Cout) acc[c] = fmaf(v, __ldg(w + (int64_t)(co0 + c) * ldw + ci), acc[c]);
+      for (int q = 0; q < 4; ++q) v[q] = (q < npx) ? __ldg(xp + (int64_t)ci * HW + q) : 0.f;
+    }
+    const float4 wa = *reinterpret_cast<const float4*>(ws + ci * 8), wb = *reinterpret_cast<const float4*>(ws + ci * 8 + 4);
+    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = fmaf(v[q], wv[c], acc[q][c]);
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    if (co0 + c < Cout) {
-      float v = acc[c] + (bias ? __ldg(bias + (int64_t)b * bias_bstride + co0 + c) : 0.f);
-      y[((int64_t)b * Cout + co0 + c) * HW + p] = relu ? fmaxf(v, 0.f) : v;
-    }
+    if (co0 + c >= Cout) continue;
+    const float bv = bias ? __ldg(bias + (int64_t)b * bias_bstride + co0 + c) : 0.f;
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { o[q] = acc[q][c] + bv; if (relu) o[q] = fmaxf(o[q], 0.f); }
+    float* yp = y + ((int64_t)b * Cout + co0 + c) * HW + p;
+    if (VEC) *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (q < npx) yp[q] = o[q];
   }
 }
 
@@ -669,11 +699,89 @@ extern "C" int pmu_row_sums_f32(const float* x, float* out, int64_t rows, int64_
   return PMU_OK;
 }
 
+namespace pmu {
+// conv3x3 weight gradient for the 1- and 2-channel input layers (inc.c1 of the U-Net, the first layers of the prior /
+// posterior encoders): the 32 x 32 (co x ci) tile of the general kernel would waste 15/16 of its ci lanes there.
+// grid (chunks, Cout): a block owns one output channel and a range of pixel quads over all images; a thread walks quads
+// (4 consecutive pixels of a row: one 128-bit dy load, 3 x 6 x-taps per input channel) with 9 * CIN running sums in
+// registers; block reduction, then one fp32 atomicAdd per weight (same accumulation contract as the general kernel).
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv3x3_wgrad_smallcin_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                              const float* __restrict__ dy, float* __restrict__ dw, int H, int W, int Cout,
+                              int64_t quads, int64_t quads_per_block) {
+  const int co = blockIdx.y;
+  const int W4 = W >> 2;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t lo = (int64_t)blockIdx.x * quads_per_block;
+  const int64_t hi = (lo + quads_per_block < quads) ? lo + quads_per_block : quads;
+  float acc[CIN][3][3];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[c][k / 3][k % 3] = 0.f;
+  for (int64_t q = lo + threadIdx.x; q < hi; q += 256) {
+    const int w0 = (int)(q % W4) * 4;
+    const int64_t r = q / W4;
+    const int h = (int)(r % H);
+    const int64_t b = r / H;
+    const float4 d4 = *reinterpret_cast<const float4*>(dy + (b * Cout + co) * HW + (int64_t)h * W + w0);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float* xs = (c < C0) ? x0 + (b * C0 + c) * HW : x1 + (b * C1 + (c - C0)) * HW;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int hh = h + ky - 1;
+        float v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int ww = w0 + j - 1;
+          v[j] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xs + (int64_t)hh * W + ww) : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[c][ky][kx] = fmaf(d[j], v[j + kx], acc[c][ky][kx]);
+      }
+    }
+  }
+  __shared__ float red[8][CIN * 9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float v = warp_sum(acc[c][k / 3][k % 3]);
+      if (lane == 0) red[warp][c * 9 + k] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < CIN * 9) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
+    atomicAdd(dw + (int64_t)co * CIN * 9 + threadIdx.x, v);       // dw[co][ci][ky][kx], ci * 9 + ky * 3 + kx
+  }
+}
+}  // namespace pmu
+
 extern "C" int pmu_conv3x3_wgrad_f32(const float* x0, int C0, const float* x1, int C1, const float* dy, float* dw,
                                      int B, int H, int W, int Cout, void* stream) {
   PMU_CHECK_ARG(x0 && dy && dw && (C1 == 0 || x1), "pmu_conv3x3_wgrad_f32: null pointer");
   PMU_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && C1 >= 0, "pmu_conv3x3_wgrad_f32: bad shape");
   const int Cin = C0 + C1;
+  if (Cin <= 2 && W % 4 == 0 && aligned16(dy) && Cout <= 65535) {
+    const int64_t quads = (int64_t)B * H * (W / 4);
+    const int64_t want = std::max<int64_t>(1, cdiv64(8ll * sm_count(), Cout));
+    const int64_t qpb = std::max<int64_t>(256, cdiv64(quads, want));
+    const dim3 grid((unsigned)cdiv64(quads, qpb), Cout);
+    if (Cin == 1)
+      conv3x3_wgrad_smallcin_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, dy, dw, H, W, Cout, quads, qpb);
+    else
+      conv3x3_wgrad_smallcin_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, dy, dw, H, W, Cout, quads, qpb);
+    PMU_LAUNCH_CHECK();
+    return PMU_OK;
+  }
   const int tiles_x = cdiv(W, WG_TW), tiles_y = cdiv(H, WG_TH);
   const int gx = cdiv(Cout, WG_CO) * cdiv(Cin, WG_CI);
   const int units = B * tiles_x * tiles_y;
@@ -844,8 +952,13 @@ extern "C" int pmu_fcomb_zbias_bwd_f32(const float* rs, const float* z, const fl
 extern "C" int pmu_conv1x1_bb_f32(const float* x, const float* w, int ldw, const float* bias, int bias_bstride, float* y,
                                   int B, int Cin, int Cout, int64_t HW, int relu, void* stream) {
   PMU_CHECK_ARG(x && w && y && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && HW > 0 && ldw >= Cin, "pmu_conv1x1_bb_f32: bad argument");
-  conv1x1_bb_kernel<<<dim3((unsigned)cdiv64(HW, 256), cdiv(Cout, 8), B), 256, 0, (cudaStream_t)stream>>>(
-      x, w, ldw, bias, bias_bstride, y, Cin, Cout, HW, relu);
+  PMU_CHECK_SUPPORTED(Cin <= 1536, "pmu_conv1x1_bb_f32: Cin <= 1536 (the 8 x Cin weight slab is staged in 48 KB of shared memory)");
+  const dim3 grid((unsigned)cdiv64(HW, 1024), cdiv(Cout, 8), B);
+  const size_t smem = (size_t)Cin * 8 * sizeof(float);
+  if (HW % 4 == 0 && aligned16(x) && aligned16(y))
+    conv1x1_bb_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, ldw, bias, bias_bstride, y, Cin, Cout, HW, relu);
+  else
+    conv1x1_bb_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, ldw, bias, bias_bstride, y, Cin, Cout, HW, relu);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

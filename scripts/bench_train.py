@@ -31,11 +31,15 @@ def step():
 
 for _ in range(3): step()          # warm-up: module load, allocator, lazy cudaFuncSetAttribute (iteration 1 is still 8x slower)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(steps): loss = step()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / steps
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+evs[0].record()
+for i in range(steps):
+    loss = step()
+    evs[i + 1].record()
+torch.cuda.synchronize()
+per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+ms = evs[0].elapsed_time(evs[steps]) / steps
+print("per-step ms:", " ".join(f"{t:.1f}" for t in per), f"| median {sorted(per)[len(per) // 2]:.1f}  mean {ms:.1f}")
 # FLOPs: forward 96.2 (unet) + 2 x 33.9 (prior, posterior) + 2 x 1.69 (fcomb: sample + reconstruction) GFLOP per 256^2 slice;
 # backward = dgrad + wgrad ~ 2 x forward of the differentiated part
 fwd = 96.18 + 2 * 33.90 + 2 * 1.69

@@ -224,3 +224,25 @@ def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W, ts_mode, monkeypatch):
     err = (got - ref).abs().max().item() / N
     assert err < 2e-2, f"mean-prob err {err}"
     torch.testing.assert_close(got[:, 0].sum(1), torch.full((B, H, W), float(N)), atol=1e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,relu", [(2, 64, 64, 64, 72, True), (3, 3, 64, 33, 31, False), (1, 64, 3, 40, 40, False),
+                                                 (2, 70, 13, 17, 20, True), (1, 9, 11, 1, 3, False)])
+def test_conv1x1_register_tiled(ops, B, Cin, Cout, H, W, relu):
+    """The 4-pixel x 8-cout register-tiled 1x1 kernel (vector and ragged paths, cout / pixel tails, weight row
+    stride, per-batch bias) against torch."""
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, generator=g) * 0.3
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w[:, :, None, None], b)
+    got = ops.conv1x1_f32(x.cuda(), w.cuda(), b.cuda(), relu=relu).cpu()
+    torch.testing.assert_close(got, F.relu(ref) if relu else ref, atol=2e-5, rtol=1e-5)
+    ld = Cin + 5
+    wl = torch.zeros(Cout, ld)
+    wl[:, :Cin] = w
+    wl[:, Cin:] = 99.0                                           # must never be read
+    bb = torch.randn(B, Cout, generator=g)
+    got = ops.conv1x1_bb_f32(x.reshape(B, Cin, H * W, 1).cuda(), wl.cuda(), ld, bb.cuda(), Cout, Cin, Cout, relu).cpu()
+    ref = F.conv2d(x, w[:, :, None, None]) + bb[:, :, None, None]
+    torch.testing.assert_close(got.reshape(B, Cout, H, W), F.relu(ref) if relu else ref, atol=2e-5, rtol=1e-5)

@@ -65,7 +65,8 @@ def test_bn_train_fwd_bwd(ops, B, C, H, W, relu):
 
 
 @pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 1, 0, 4, 9, 13), (1, 5, 3, 7, 32, 48), (3, 16, 16, 33, 8, 8),
-                                               (2, 64, 0, 64, 20, 36), (2, 1, 1, 4, 16, 16)])
+                                               (2, 64, 0, 64, 20, 36), (2, 1, 1, 4, 16, 16),
+                                               (3, 1, 0, 64, 40, 72), (2, 2, 0, 5, 7, 12), (1, 1, 1, 64, 64, 64)])
 def test_conv3x3_wgrad_dgrad(ops, B, C0, C1, Cout, H, W):
     g = _g(2)
     x = torch.randn(B, C0 + C1, H, W, generator=g).requires_grad_(True)

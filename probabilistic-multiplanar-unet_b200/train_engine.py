@@ -359,11 +359,17 @@ class TrainStep:
 
     def backward(self, g: float) -> Dict[int, torch.Tensor]:
         """g = d(loss)/d(elbo).  elbo = -(rec + beta * mean_b KL)."""
+        if self.unet is None:
+            raise RuntimeError("this forward's activations were released by its first backward (one backward per "
+                               "forward; retain_graph is not supported)")
         self._mode(True)
         try:
             return self._backward(g)
         finally:
             self._mode(False)
+            # the recorded activations are dead now (one backward per forward, like autograd without retain_graph):
+            # drop them at once instead of when the caller's loss tensor goes out of scope
+            self.post = self.prior = self.unet = self.fc = self.logits = None
 
     def _backward(self, g: float) -> Dict[int, torch.Tensor]:
         net, tape = self.net, _Tape()

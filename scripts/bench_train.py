@@ -29,14 +29,23 @@ def step():
     opt.step(); opt.zero_grad()
     return loss
 
-for _ in range(3): step()          # warm-up: module load, allocator, lazy cudaFuncSetAttribute (iteration 1 is still 8x slower)
+for _ in range(6): step()          # warm-up (the caching allocator still issues one cudaMalloc at step 5): module load, allocator, lazy cudaFuncSetAttribute (iteration 1 is still 8x slower)
 torch.cuda.synchronize()
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+import gc
+if "--gc-off" in sys.argv:
+    gc.disable()
+mallocs, host = [], []
 evs[0].record()
 for i in range(steps):
+    m0, t0 = torch.cuda.memory_stats().get("num_device_alloc", 0), time.perf_counter()
     loss = step()
     evs[i + 1].record()
+    mallocs.append(torch.cuda.memory_stats().get("num_device_alloc", 0) - m0)
+    host.append(1e3 * (time.perf_counter() - t0))
 torch.cuda.synchronize()
+print("cudaMalloc calls per step:", mallocs, "| host ms per step:", " ".join(f"{t:.1f}" for t in host),
+      "| reserved GB", round(torch.cuda.memory_reserved() / 1e9, 2))
 per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
 ms = evs[0].elapsed_time(evs[steps]) / steps
 print("per-step ms:", " ".join(f"{t:.1f}" for t in per), f"| median {sorted(per)[len(per) // 2]:.1f}  mean {ms:.1f}")

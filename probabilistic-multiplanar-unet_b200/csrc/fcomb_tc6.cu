@@ -527,7 +527,8 @@ extern "C" int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, c
 
   // TS-mode variant (activations resident in tensor memory, fcomb_ts.cu); PMU_FCOMB_TS=0 selects the SS version above
   // (read per call so a test can flip it; both variants are bound by the TMEM read of the fp32 accumulators —
-  //  96 KB per tile-sample — and time the same, 25.5 ms per volume; the SS version is the default)
+  //  68 KB per tile-sample — and time the same, 25.5 ms per volume; the SS version is the default).  PMU_FCOMB_TS=2 is
+  //  the TS form with f16 hidden layers and packed 16-bit accumulator read-back: an unmeasured experiment, see fcomb_ts.cu)
   const char* ts_env = getenv("PMU_FCOMB_TS");
   if (ts_env && atoi(ts_env))
     return pmu_fcomb_softmax_accum_bf16_ts(feat, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums, B, N, L, C,

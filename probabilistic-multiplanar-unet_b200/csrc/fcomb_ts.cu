@@ -15,7 +15,16 @@
 //   * softmax of slot s is done by column quarter s (one thread per pixel), partial sums combined
 //     through shared memory at the end of the tile.
 // Replaces Fcomb.forward / softmax / the sample loop (probabilistic_unet.py:155-181, eval.py:146-157).
+//
+// F16 = true (PMU_FCOMB_TS=2, EXPERIMENT, not the default): the per-sample hidden layers run f16 x f16 -> f16.  A dense
+// UMMA keeps an f16 accumulator in the low half of a 32-bit TMEM column; `tcgen05.ld ... .pack::16b` returns two
+// adjacent columns per register, which is already the packed A-operand layout of the next layer: the epilogue of a
+// hidden layer is ld (8 registers) -> max.f16x2 with 0 -> st.  If the TMEM read port is paced by the bytes delivered
+// to the register file (64 B/clk, see fcomb_tc6.cu) this halves the dominant cost; if it is paced by the columns
+// touched it changes nothing.  Layer 0 (G = W0f f, bf16 features, fp32 accumulate, exact fp32 bias) and the logits
+// (fp32 accumulate) are unchanged; the hidden activations carry 11 significand bits instead of 8.
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include "pmu_common.cuh"
 #include "sm100_ptx.cuh"
@@ -54,6 +63,43 @@ struct FcombTsParams {
 
 __device__ __forceinline__ void ft_st_bf16(uint8_t* tile, int row, int k, float v) {
   *reinterpret_cast<__nv_bfloat16*>(tile + (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2)) = __float2bfloat16(v);
+}
+template <bool F16>
+__device__ __forceinline__ void ft_st_w(uint8_t* tile, int row, int k, float v) {   // weight / bias element of a per-sample layer
+  if constexpr (F16)
+    *reinterpret_cast<__half*>(tile + (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2)) = __float2half_rn(v);
+  else
+    ft_st_bf16(tile, row, k, v);
+}
+template <bool F16>
+__device__ __forceinline__ float ft_round_w(float v) {
+  if constexpr (F16) return __half2float(__float2half_rn(v));
+  else return __bfloat162float(__float2bfloat16(v));
+}
+// relu(a + b) of two fp32 pairs -> packed f16x2
+__device__ __forceinline__ uint32_t ft_add_pack_relu_h(float a0, float a1, float b0, float b1) {
+  uint32_t d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
+      "mov.b64 ra, {%1, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {lo, hi}, rd;\n\t"
+      "cvt.rn.relu.f16x2.f32 %0, hi, lo;\n\t}"
+      : "=r"(d) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+  return d;
+}
+__device__ __forceinline__ uint32_t ft_relu_h2(uint32_t v) {
+  uint32_t d;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(0u));
+  return d;
+}
+// 32 lanes x 16 columns holding one f16 each (low half) -> 8 registers of f16x2 (column 2j low, 2j + 1 high)
+__device__ __forceinline__ void ft_tmem_ld16_pack(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+// kind::f16 instruction descriptor, f16 x f16 operands (formats 0), accumulator f16 (D format 0) or fp32 (1)
+__host__ __device__ constexpr uint32_t ft_idesc_f16(int M, int N, bool acc_f32) {
+  return ((acc_f32 ? 1u : 0u) << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ uint32_t ft_pack_relu(float lo, float hi) {
   uint32_t d;
@@ -110,7 +156,7 @@ __device__ __forceinline__ void ft_issue_layer(uint32_t tX, uint32_t tY, uint32_
   ft_umma_ts(tX, tY + 32, umma_smem_desc_sw128(b_tile), idesc, 1u);
 }
 
-template <int CMAX>
+template <int CMAX, bool F16>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, const float* __restrict__ mu,
                 const float* __restrict__ sigma, const float* __restrict__ eps, const float* __restrict__ w0,
@@ -145,20 +191,20 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
   for (int i = tid; i < FT_F * FT_F; i += FT_THREADS) {
     const int o = i >> 6, k = i & 63;
     ft_st_bf16(sgen + FT_OFF_W0, o, k, __ldg(w0 + (int64_t)o * (FT_F + L) + k));
-    for (int m = 0; m < nmid; ++m) ft_st_bf16(sgen + FT_OFF_WM + m * FT_WT, o, k, __ldg(wmid + (int64_t)m * FT_F * FT_F + i));
+    for (int m = 0; m < nmid; ++m) ft_st_w<F16>(sgen + FT_OFF_WM + m * FT_WT, o, k, __ldg(wmid + (int64_t)m * FT_F * FT_F + i));
   }
-  for (int i = tid; i < C * FT_F; i += FT_THREADS) ft_st_bf16(sgen + FT_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
+  for (int i = tid; i < C * FT_F; i += FT_THREADS) ft_st_w<F16>(sgen + FT_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
   for (int i = tid; i < nmid * FT_F; i += FT_THREADS) {
     const float bv = __ldg(bmid + i);
-    const float bh = __bfloat162float(__float2bfloat16(bv));
-    ft_st_bf16(sgen + FT_OFF_BMT + (i >> 6) * FT_WT, i & 63, 0, bh);
-    ft_st_bf16(sgen + FT_OFF_BMT + (i >> 6) * FT_WT, i & 63, 1, bv - bh);
+    const float bh = ft_round_w<F16>(bv);
+    ft_st_w<F16>(sgen + FT_OFF_BMT + (i >> 6) * FT_WT, i & 63, 0, bh);
+    ft_st_w<F16>(sgen + FT_OFF_BMT + (i >> 6) * FT_WT, i & 63, 1, bv - bh);
   }
   for (int i = tid; i < C; i += FT_THREADS) {
     const float bv = __ldg(blast + i);
-    const float bh = __bfloat162float(__float2bfloat16(bv));
-    ft_st_bf16(sgen + FT_OFF_BLT, i, 0, bh);
-    ft_st_bf16(sgen + FT_OFF_BLT, i, 1, bv - bh);
+    const float bh = ft_round_w<F16>(bv);
+    ft_st_w<F16>(sgen + FT_OFF_BLT, i, 0, bh);
+    ft_st_w<F16>(sgen + FT_OFF_BLT, i, 1, bv - bh);
   }
   float* zb_s = reinterpret_cast<float*>(sgen + FT_OFF_ZB);
   float* scr = reinterpret_cast<float*>(sgen + FT_OFF_SCR);
@@ -174,7 +220,7 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
   const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
   if (warp < 16 && cq == 0) {
     // the constant K extension of every slot's A operand: k = 64, 65 -> 1.0 (bf16 pair), k = 66..79 -> 0
-    const uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const uint32_t ones[8] = {F16 ? 0x3C003C00u : 0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // (1.0, 1.0) as f16 / bf16 pairs
 #pragma unroll
     for (int s = 0; s < FT_SLOTS; ++s) ft_tmem_st8(tmem_base + lane_off + s * FT_SLOT_COLS + 64 + 32, ones);
     ft_tmem_st_wait();
@@ -217,7 +263,9 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
         // uniform registers; `lane == 0` costs a 12-instruction waterfall (ELECT / R2UR.BROADCAST / BRA.U.ANY) per UMMA.
         // elect.sync over the full warp always picks the same lane, so the per-thread barrier phases persist.
         if (elect_one()) {
-          constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64), idesc16 = umma_idesc_bf16(128, 16);
+          constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);                                   // layer 0: bf16 features
+          constexpr uint32_t idesc_mid = F16 ? ft_idesc_f16(128, 64, false) : umma_idesc_bf16(128, 64);
+          constexpr uint32_t idesc16 = F16 ? ft_idesc_f16(128, 16, true) : umma_idesc_bf16(128, 16);
           const uint32_t sW0 = sbase + FT_OFF_W0, sWM = sbase + FT_OFF_WM, sWL = sbase + FT_OFF_WL;
           const uint32_t sBM = sbase + FT_OFF_BMT, sBL = sbase + FT_OFF_BLT;
           bool f_in_flight = false;
@@ -253,7 +301,7 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
                   const uint32_t tX = tmem_base + s * FT_SLOT_COLS, tY = tX + 64;
                   mbar_wait(bar_ready(s), (phr >> s) & 1u); phr ^= 1u << s;
                   tcgen05_fence_after();
-                  if (layer <= nmid) ft_issue_layer(tX, tY, sWM + (layer - 1) * FT_WT, sBM + (layer - 1) * FT_WT, idesc64);
+                  if (layer <= nmid) ft_issue_layer(tX, tY, sWM + (layer - 1) * FT_WT, sBM + (layer - 1) * FT_WT, idesc_mid);
                   else ft_issue_layer(tX, tY, sWL, sBL, idesc16);
                   umma_commit(bar_acc(s));
                 }
@@ -288,8 +336,13 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 z = ft_lds128f(zb + j * 16);
-                pk[2 * j] = ft_add_pack_relu(__uint_as_float(G[4 * j]), __uint_as_float(G[4 * j + 1]), z.x, z.y);
-                pk[2 * j + 1] = ft_add_pack_relu(__uint_as_float(G[4 * j + 2]), __uint_as_float(G[4 * j + 3]), z.z, z.w);
+                if constexpr (F16) {
+                  pk[2 * j] = ft_add_pack_relu_h(__uint_as_float(G[4 * j]), __uint_as_float(G[4 * j + 1]), z.x, z.y);
+                  pk[2 * j + 1] = ft_add_pack_relu_h(__uint_as_float(G[4 * j + 2]), __uint_as_float(G[4 * j + 3]), z.z, z.w);
+                } else {
+                  pk[2 * j] = ft_add_pack_relu(__uint_as_float(G[4 * j]), __uint_as_float(G[4 * j + 1]), z.x, z.y);
+                  pk[2 * j + 1] = ft_add_pack_relu(__uint_as_float(G[4 * j + 2]), __uint_as_float(G[4 * j + 3]), z.z, z.w);
+                }
               }
               ft_tmem_st8(tbase + s * FT_SLOT_COLS + 64 + cq * 8, pk);
               ft_tmem_st_wait();
@@ -304,11 +357,19 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
                 if (r * FT_SLOTS + s >= ng) continue;
                 mbar_wait(bar_acc(s), (pha >> s) & 1u); pha ^= 1u << s;
                 tcgen05_fence_after();
-                uint32_t rr[16], pk[8];
-                ft_tmem_ld16(tbase + s * FT_SLOT_COLS + cq * 16, rr);
-                tmem_ld_wait();
+                uint32_t pk[8];
+                if constexpr (F16) {
+                  ft_tmem_ld16_pack(tbase + s * FT_SLOT_COLS + cq * 16, pk);
+                  tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) pk[j] = ft_pack_relu(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
+                  for (int j = 0; j < 8; ++j) pk[j] = ft_relu_h2(pk[j]);
+                } else {
+                  uint32_t rr[16];
+                  ft_tmem_ld16(tbase + s * FT_SLOT_COLS + cq * 16, rr);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) pk[j] = ft_pack_relu(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
+                }
                 ft_tmem_st8(tbase + s * FT_SLOT_COLS + 64 + cq * 8, pk);
                 ft_tmem_st_wait();
                 tcgen05_fence_before();
@@ -406,15 +467,15 @@ extern "C" int pmu_fcomb_softmax_accum_bf16_ts(const void* feat, const float* mu
   const int64_t tiles = (HW + 127) / 128;
   const int64_t total = (int64_t)B * tiles;
   const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
-  if (C <= 4) {
-    PMU_CUDA(cudaFuncSetAttribute(fcomb_ts_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-    fcomb_ts_kernel<4><<<grid, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast,
-                                                                          blast, slice_sums);
-  } else {
-    PMU_CUDA(cudaFuncSetAttribute(fcomb_ts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-    fcomb_ts_kernel<8><<<grid, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast,
-                                                                          blast, slice_sums);
-  }
-  PMU_LAUNCH_CHECK();
-  return PMU_OK;
+  // PMU_FCOMB_TS=2 (the dispatcher in fcomb_tc6.cu only comes here for a non-zero value): f16 hidden layers (experiment)
+  const char* ts_env = getenv("PMU_FCOMB_TS");
+  const bool f16 = ts_env && atoi(ts_env) == 2;
+  auto launch = [&](auto kern) -> int {
+    PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    kern<<<grid, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums);
+    PMU_LAUNCH_CHECK();
+    return PMU_OK;
+  };
+  if (C <= 4) return f16 ? launch(fcomb_ts_kernel<4, true>) : launch(fcomb_ts_kernel<4, false>);
+  return f16 ? launch(fcomb_ts_kernel<8, true>) : launch(fcomb_ts_kernel<8, false>);
 }

@@ -7,7 +7,12 @@ import torch.nn.functional as F
 
 from oracle import pmu_oracle as O
 
+import os
+
 pytestmark = pytest.mark.gpu
+# kernel variants that are not the default path and have not been measured yet: opt in with PMU_TEST_EXPERIMENTAL=1
+EXPERIMENTAL = pytest.mark.skipif(os.environ.get("PMU_TEST_EXPERIMENTAL") != "1",
+                                  reason="experimental kernel variant (set PMU_TEST_EXPERIMENTAL=1)")
 
 
 @pytest.fixture(scope="module")
@@ -204,11 +209,12 @@ def test_pool_head_transpose_bf16(ops):
                                           (4, 20, 3, 3, 20, 24), (5, 3, 3, 3, 20, 24),
                                           (4, 6, 3, 5, 96, 100),     # 190 tile pairs > 148 SMs: CTAs walk several
                                           (3, 18, 4, 7, 72, 72)])    # pairs and cross slice boundaries; 2 sample groups
-@pytest.mark.parametrize("ts_mode", ["0", "1"])
+@pytest.mark.parametrize("ts_mode", ["0", "1", pytest.param("2", marks=EXPERIMENTAL)])
 def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W, ts_mode, monkeypatch):
     """Fused tensor-core fcomb vs the fp32 oracle: probabilities within the bf16 budget 2e-2.
     HW = 480 is ragged against the 128-pixel tile.  ts_mode 1 = activations resident in tensor memory
-    (TS-form UMMAs, fcomb_ts.cu), 0 = through shared memory (fcomb_tc6.cu, the default)."""
+    (TS-form UMMAs, fcomb_ts.cu), 0 = through shared memory (fcomb_tc6.cu, the default), 2 = TS form with f16
+    hidden layers and packed 16-bit accumulator read-back (experiment, PMU_TEST_EXPERIMENTAL=1)."""
     monkeypatch.setenv("PMU_FCOMB_TS", ts_mode)
     sd = O.make_state_dict((64, 128), num_classes=C, latent_dim=6, no_convs_fcomb=nl, seed=10)
     g = _g(11)

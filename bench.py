@@ -38,6 +38,12 @@ METRIC = "volumes/sec (256^3, 3 planes x 16 samples)"
 UNIT = "volumes/s"
 
 
+def workload(D, N, interp):
+    """config.workload — the SAME string on both arms (the reference arm's sampling is described in its cpu_baseline)."""
+    return (f"{D}^3 fp32 volume, 3 planes x {N} z-samples, {interp} resampling on the standard plane grids, trainer model "
+            f"[64,128,256,512,1024] C=3 L=6 fcomb=4, mean/var/entropy fusion")
+
+
 def load_traffic():
     """DRAM bytes per launch of our kernels from the last committed `ncu --set full` capture
     (profiles/*_traffic.json, written by scripts/summarize_ncu.py)."""
@@ -153,9 +159,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(len(rates), 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"{D}^3 volume, 3 planes x {N} samples, trainer model [64..1024]; each step = "
-                                   f"{3 * spp} slices (one per plane) through the oracle port of the reference CPU path, "
-                                   f"extrapolated to {3 * D} slices"},
+            "config": {"workload": workload(D, N, args.interp),
+                       "sampling": f"each step = {3 * spp} slices (one per plane) through the oracle port of the reference "
+                                   f"CPU path (fp32, batch 1 like eval.py:105), extrapolated to {3 * D} slices; on the "
+                                   f"standard plane grids {args.interp} resampling is exact slicing, which the port does"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{3 * spp} of {3 * D} slices per step, forward once + {N} x fcomb + softmax + accumulate"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,7 +212,8 @@ def run_ours(args):
     slab = world > 1 and D % world == 0
     pred_e2e = pred if not slab else pmu_b200.MultiPlanarPredictor(
         sd, dev, precision=args.precision, n_samples=N, slice_batch=args.slice_batch, interp=args.interp, rank=rank,
-        world_size=world, output="slab")
+        world_size=world, output="slab", upload=args.e2e_upload)
+
     def pinned_outputs():
         if not (rank == 0 or slab):
             return {}
@@ -270,6 +278,36 @@ def run_ours(args):
     ms_e2e_sync = timed(step_e2e_sync, args.steps)
     run_e2e(2)
     ms_e2e = timed(lambda: run_e2e(args.steps), 1)
+
+    phases = None
+    if args.e2e_phases:
+        # where the e2e leg's time goes when all ranks hit the host at once: each phase alone, max over ranks
+        dvol = torch.empty_like(vol)
+        Dx = D // world if slab else D
+        dres = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_outs[0].items()}
+
+        def ph_h2d():
+            dvol.copy_(vol_host, non_blocking=True)
+
+        def ph_d2h():
+            for k, v in dres.items():
+                host_outs[0][k].copy_(v, non_blocking=True)
+
+        def ph_slab():
+            acc.zero_()
+            pred_e2e.accumulate(vol, eps, acc)
+            if slab:
+                part, _ = pmu_b200.reduce_scatter_accumulators(acc, rank, world, None)
+            else:
+                part = pmu_b200.reduce_accumulators(acc, world, None, dst=0)
+            if slab or rank == 0:
+                ops.fuse_finalize(part[0], part[1], float(P * N))
+
+        phases = {}
+        for name, fn in (("h2d_volume", ph_h2d), ("d2h_results", ph_d2h), ("resident_step_with_exchange", ph_slab)):
+            fn()
+            phases[name] = timed(fn, args.steps) / args.steps
+        del dvol, dres
 
     # ---- per-kernel roofline: one instrumented step, CUDA events around every C-ABI call ----
     roof, hbm_kernels, shares = None, {}, {}
@@ -397,12 +435,12 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": f"{D}^3 fp32 volume, 3 planes x {N} z-samples, {args.interp} resampling on the standard plane grids, trainer model "
-                                       f"[64,128,256,512,1024] C=3 L=6 fcomb=4, mean/var/entropy fusion",
+                "config": {"workload": workload(D, N, args.interp),
                            "slice_batch": args.slice_batch, "parallelism": f"slice-sharded x{world} + 1 reduce",
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": int(4 * D ** 3) * world,          # every rank uploads the volume
+                        # every rank uploads the volume (--e2e-upload broadcast: rank 0 alone, then NVLink)
+                        "h2d_bytes_per_step": int(4 * D ** 3) * (1 if (slab and args.e2e_upload == "broadcast") else world),
                         "d2h_bytes_per_step": int(4 * D ** 3 * 7),              # mean + var (3 classes each) + entropy, whole job
                         "ms_per_step": ms_e2e / args.steps,
                         "how": "MultiPlanarPredictor.submit()/wait(): pinned host volume in, pinned host mean/var/entropy out, "
@@ -410,7 +448,8 @@ def run_ours(args):
                                "results complete in host memory before the timed region ends",
                         "sync_ms_per_step": ms_e2e_sync / args.steps,
                         "sync_note": "MultiPlanarPredictor.predict(host_out=...): one volume at a time, no overlap across steps",
-                        "outputs": "x-slab per rank (reduce-scatter)" if slab else "rank 0 (streamed behind the last view)" if world == 1 else "rank 0"},
+                        "outputs": "x-slab per rank (reduce-scatter)" if slab else "rank 0 (streamed behind the last view)" if world == 1 else "rank 0",
+                        **({"upload": args.e2e_upload} if slab else {}), **({"phases_ms": phases} if phases else {})},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels,
                 "kernel_time_shares": shares, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
@@ -433,6 +472,12 @@ def main():
     ap.add_argument("--cpu-slices-per-plane", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: only the warm-up and the timed resident steps")
+    ap.add_argument("--e2e-upload", default="each", choices=["each", "broadcast"],
+                    help="N > 1 e2e leg: every rank uploads the volume over its own PCIe link (default), or rank 0 uploads "
+                         "once and broadcasts over NVLink (experiment)")
+    ap.add_argument("--e2e-phases", action="store_true",
+                    help="diagnostic: also time the e2e leg's host->device copy, device->host copy and resident slab step "
+                         "on their own (all ranks at once), reported under e2e.phases_ms")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

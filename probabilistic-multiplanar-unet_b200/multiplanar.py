@@ -99,7 +99,8 @@ class MultiPlanarPredictor:
     def __init__(self, state_dict, device="cuda", precision: str = "bf16", n_samples: int = 16,
                  planes: Sequence[int] = (0, 1, 2), slice_batch: int = 32, interp: str = "exact",
                  affines: Optional[Dict[int, Sequence[float]]] = None, out_hw: Optional[Tuple[int, int]] = None,
-                 rank: int = 0, world_size: int = 1, process_group=None, output: str = "rank0"):
+                 rank: int = 0, world_size: int = 1, process_group=None, output: str = "rank0",
+                 upload: str = "each"):
         if hasattr(state_dict, "state_dict"):
             state_dict = state_dict.state_dict()
         self.device = torch.device(device)
@@ -118,6 +119,10 @@ class MultiPlanarPredictor:
             raise ValueError("output must be 'rank0' (one reduce, results on rank 0) or 'slab' (reduce-scatter along x, "
                              "every rank keeps its x-slab)")
         self.output = output
+        if upload not in ("each", "broadcast"):
+            raise ValueError("upload must be 'each' (every rank copies the volume from its own host buffer) or 'broadcast' "
+                             "(submit(): rank 0 copies it once, the other ranks receive it over NVLink)")
+        self.upload = upload
         self.C = self.net.fcomb["C"]
         self.L = self.net.fcomb["L"]
 
@@ -189,7 +194,9 @@ class MultiPlanarPredictor:
                want_labels: bool = False, depth: int = 2) -> int:
         """Asynchronous predict for a stream of volumes: enqueue one volume and return a ticket at once.
 
-        vol_host: PINNED fp32 host tensor [d0,d1,d2] (already cubic / padded); eps: device tensor [P, D, N, L];
+        vol_host: PINNED fp32 host tensor [d0,d1,d2] (already cubic / padded) — with upload="broadcast" and
+        world_size > 1 only rank 0's buffer is read (one PCIe upload, then one NCCL broadcast over NVLink; the other
+        ranks pass a tensor of the same shape, or a torch.Size / tuple of dims); eps: device tensor [P, D, N, L];
         host_out: PINNED host tensors {"mean", "var", "entropy"[, "labels"]} — the whole volume on one GPU, this rank's
         x-slab with output="slab", rank 0 only with output="rank0".  `wait(ticket)` (or `wait()` for everything
         submitted) blocks the host until the results are in host_out.
@@ -201,9 +208,11 @@ class MultiPlanarPredictor:
         Same kernels, same results as predict(host_out=...) — only the scheduling differs."""
         if self.interp != "exact" and not self.identity_grid:
             raise NotImplementedError("voxel fusion is defined for the standard axis-aligned grids")
-        if not (isinstance(vol_host, torch.Tensor) and vol_host.dtype == torch.float32 and vol_host.is_pinned()):
+        bcast = self.upload == "broadcast" and self.world > 1
+        reads_host = not bcast or self.rank == 0
+        if reads_host and not (isinstance(vol_host, torch.Tensor) and vol_host.dtype == torch.float32 and vol_host.is_pinned()):
             raise ValueError("submit() takes a pinned fp32 host tensor (torch.Tensor.pin_memory())")
-        dims = tuple(vol_host.shape)
+        dims = tuple(vol_host.shape) if isinstance(vol_host, torch.Tensor) else tuple(int(d) for d in vol_host)
         if padded_dims(dims) != dims:
             raise ValueError("submit() takes an already padded volume (pad_dimensions); use predict() otherwise")
         P, N = len(self.planes), self.n_samples
@@ -237,7 +246,13 @@ class MultiPlanarPredictor:
         if s["compute"] is not None:
             h2d.wait_event(s["compute"])
         with torch.cuda.stream(h2d):
-            s["vol"].copy_(vol_host, non_blocking=True)
+            if reads_host:
+                s["vol"].copy_(vol_host, non_blocking=True)
+            if bcast:
+                # issued from the copy stream: NCCL orders the broadcast behind the upload, and the compute stream only
+                # waits for the slot's "in" event (same collective order on every rank: broadcast k, exchange k, ...)
+                import torch.distributed as dist
+                dist.broadcast(s["vol"], group=self.group, group_src=0)
             s["in"].record(h2d)
         main.wait_event(s["in"])
         if s["out"] is not None:

@@ -45,6 +45,7 @@ struct ConvTcParams {
   int pool_mode;      // -1 none; PMU_POOL_MAX / PMU_POOL_AVG_CEIL: also emit the 2x2-pooled map
   int debug;          // experiments only (PMU_CONV_DEBUG): bit0 = no global stores, bit1 = no A loads
   int tma_store;      // full-resolution output leaves through the smem staging tile + TMA tensor stores
+  int pool_split;     // experiment (PMU_POOL_SPLIT=1): host-side selector of the PSPLIT kernel instantiations
 };
 
 template <int BN, int STAGES, int NSTG = 1>
@@ -96,7 +97,7 @@ struct EpiCtx {
   float* bias_s;
 };
 
-template <int BN, int NSTG>
+template <int BN, int NSTG, bool PSPLIT = false>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCtx& e, const CUtensorMap* tmY0p,
                                               const CUtensorMap* tmY1p, const CUtensorMap* tmY2p,
                                               const CUtensorMap* tmY3p, const float* __restrict__ bias,
@@ -196,7 +197,53 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(dt + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
-        if (p.pool_mode == PMU_POOL_MAX) {
+        if (PSPLIT && p.pool_mode >= 0) {
+          // Halving exchange over the window lanes {l, l^1, l^TW, l^(1|TW)}.  The butterfly below leaves the whole pooled
+          // row in all four lanes and lets one of them write 64 B: 32 shuffles + 32 max per 32 channels and thread.  Here
+          // a lane keeps half of its channels per step and sends the other half: step 1 (lane ^ 1) 8 registers, step 2
+          // (lane ^ TW) 4 registers (8 fp32 sums for the average) — 12 (16) shuffles — and every lane ends up with 8
+          // channels of the pooled pixel, which it writes itself (16 B each; the four lanes' pieces are contiguous).
+          // Same arithmetic as below: max is exact; the average adds (a + b) + (c + d) in fp32 and rounds once.
+          const bool odd = (lane & 1) != 0, up = (lane & p.TW) != 0;
+          uint32_t o4[4];
+          if (p.pool_mode == PMU_POOL_MAX) {
+            uint32_t k8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t send = odd ? pk[j] : pk[j + 8], keep = odd ? pk[j + 8] : pk[j];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+              __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv));
+              k8[j] = *reinterpret_cast<uint32_t*>(&a);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t send = up ? k8[j] : k8[j + 4], keep = up ? k8[j + 4] : k8[j];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, p.TW);
+              __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv));
+              o4[j] = *reinterpret_cast<uint32_t*>(&a);
+            }
+          } else {
+            float lo8[8], hi8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t send = odd ? pk[j] : pk[j + 8], keep = odd ? pk[j + 8] : pk[j];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+              const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&keep), c = *reinterpret_cast<const __nv_bfloat162*>(&recv);
+              lo8[j] = __low2float(a) + __low2float(c);
+              hi8[j] = __high2float(a) + __high2float(c);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float slo = up ? lo8[j] : lo8[j + 4], shi = up ? hi8[j] : hi8[j + 4];
+              const float klo = up ? lo8[j + 4] : lo8[j], khi = up ? hi8[j + 4] : hi8[j];
+              const float lo = klo + __shfl_xor_sync(0xffffffffu, slo, p.TW), hi = khi + __shfl_xor_sync(0xffffffffu, shi, p.TW);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
+              o4[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          }
+          if (valid)    // a window never straddles the image edge (even H, W; bricks start at even coordinates)
+            *reinterpret_cast<uint4*>(dstp + c0 + (odd ? 16 : 0) + (up ? 8 : 0)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        } else if (p.pool_mode == PMU_POOL_MAX) {
           // max of bf16-rounded values == bf16 rounding of the max (monotonic): exact, packed
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -220,7 +267,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
             pk[j] = *reinterpret_cast<uint32_t*>(&h2);
           }
         }
-        if (pool_writer) {
+        if (!PSPLIT && pool_writer) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(dstp + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -253,7 +300,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
 // current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
 // setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
-template <int BN, int STAGES, int MINB, int NSTG>
+template <int BN, int STAGES, int MINB, int NSTG, bool PSPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0,
@@ -367,7 +414,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else {
     // =========================== epilogue (warps 2..5) ===========================
     EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
-    conv_epilogue<BN, NSTG>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
+    conv_epilogue<BN, NSTG, PSPLIT>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -402,7 +449,7 @@ struct ConvRsSmem {
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int STAGES, bool RESB>
+template <int BN, int STAGES, bool RESB, bool PSPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0, const ConvTcParams p,
@@ -515,7 +562,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   } else {
     EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
-    conv_epilogue<BN, 1>(p, ec, &tmY0, &tmY0, &tmY0, &tmY0, bias, y, y_pool, total_tiles, warp, lane);
+    conv_epilogue<BN, 1, PSPLIT>(p, ec, &tmY0, &tmY0, &tmY0, &tmY0, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -760,13 +807,13 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN, int STAGES, int MINB, int NSTG = 1>
+template <int BN, int STAGES, int MINB, int NSTG = 1, bool PSPLIT = false>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm, const CUtensorMap* ym,
                           const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
                           cudaStream_t st) {
   using L = ConvTcSmem<BN, STAGES, NSTG>;
   static_assert(MINB * (L::DYN_BYTES + 1024) <= 228 * 1024 && L::DYN_BYTES <= 227 * 1024, "shared memory budget");
-  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG>;
+  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, PSPLIT>;
   PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
   grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
   kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, ym[0], ym[1], ym[2], ym[3], p, bias,
@@ -818,7 +865,7 @@ int conv_first_tc_launch(const float* x, const float* w, const float* bias, void
   if (cc_major != 10 || W < 16 || H < 8 || !get_encode_fn()) return PMU_ERR_UNSUPPORTED;
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = 64; p.C1 = 0; p.Cout = 64; p.ntaps = 9; p.relu = relu;
-  p.pool_mode = -1; p.debug = 0; p.tma_store = 1;
+  p.pool_mode = -1; p.debug = 0; p.tma_store = 1; p.pool_split = 0;
   p.TW = 16; p.TH = 8; p.TB = 1;
   p.tiles_w = cdiv(W, 16); p.tiles_h = cdiv(H, 8); p.tiles_b = B; p.n_tiles = 1;
   const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * B;
@@ -858,6 +905,7 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   p.B = B; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout; p.ntaps = ntaps; p.relu = relu;
   p.pool_mode = y_pool ? pool_mode : -1;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMU_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  { const char* e = getenv("PMU_POOL_SPLIT"); p.pool_split = (e && atoi(e)) ? 1 : 0; }   // read per call: tests flip it
   p.TW = std::min(16, pow2ceil(W));
   p.TH = std::min(TC_BM / p.TW, pow2ceil(H));
   p.TB = TC_BM / (p.TW * p.TH);
@@ -925,6 +973,11 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
       PMU_LAUNCH_CHECK();
       return PMU_OK;
     };
+    // PMU_POOL_SPLIT=1 (experiment): pooling epilogue with the halving exchange, on the tile configurations the
+    // pooled layers of the network use
+    const bool psplit = p.pool_split && p.pool_mode >= 0;
+    if (psplit && BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, true, true>, ConvRsSmem<64, 6, true>::DYN_BYTES);
+    if (psplit && BN == 128) return launch_rs(conv_rs_kernel<128, 3, false, true>, ConvRsSmem<128, 3, false>::DYN_BYTES);
     if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, true>, ConvRsSmem<64, 6, true>::DYN_BYTES);
     if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, false>, ConvRsSmem<64, 4, false>::DYN_BYTES);
     return launch_rs(conv_rs_kernel<128, 3, false>, ConvRsSmem<128, 3, false>::DYN_BYTES);
@@ -933,6 +986,8 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
     if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
     return launch_conv_tc<64, 4, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   }
+  if (BN == 256 && p.pool_split && p.pool_mode >= 0)
+    return launch_conv_tc<256, 4, 1, 2, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   if (BN == 256) return launch_conv_tc<256, 4, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   if (BN == 128) return launch_conv_tc<128, 6, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   return launch_conv_tc<64, 8, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);

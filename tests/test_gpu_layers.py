@@ -156,9 +156,14 @@ def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W):
 
 
 @pytest.mark.parametrize("B,C0,Cout,H,W,mode", [(2, 64, 64, 32, 48, 0), (1, 128, 128, 16, 16, 1), (3, 64, 128, 8, 16, 0),
-                                                  (2, 64, 64, 24, 40, 1)])
-def test_conv_gemm_pool_bf16(ops, B, C0, Cout, H, W, mode):
-    """Fused pooling epilogue: y identical to the unfused conv, y_pool == pool(y)."""
+                                                  (2, 64, 64, 24, 40, 1),
+                                                  pytest.param(2, 128, 256, 16, 32, 0, marks=EXPERIMENTAL),   # BN = 256 tiles
+                                                  pytest.param(2, 128, 256, 16, 32, 1, marks=EXPERIMENTAL)])
+@pytest.mark.parametrize("split", ["0", pytest.param("1", marks=EXPERIMENTAL)])
+def test_conv_gemm_pool_bf16(ops, B, C0, Cout, H, W, mode, split, monkeypatch):
+    """Fused pooling epilogue: y identical to the unfused conv, y_pool == pool(y).  split = 1: the halving-exchange
+    variant of the pooling epilogue (PMU_POOL_SPLIT=1, experiment) must give bit-identical pooled maps."""
+    monkeypatch.setenv("PMU_POOL_SPLIT", split)
     g = _g(12)
     x = _nhwc(_bf(torch.randn(B, C0, H, W, generator=g))).to(torch.bfloat16).cuda()
     w = _bf(torch.randn(Cout, C0, 3, 3, generator=g) * (2.0 / (9 * C0)) ** 0.5)
@@ -169,6 +174,10 @@ def test_conv_gemm_pool_bf16(ops, B, C0, Cout, H, W, mode):
     assert torch.equal(y, y_ref)
     _, yp2 = ops.conv_gemm_pool_bf16(x, wpack, b, Cout, True, mode, want_full=False)
     assert torch.equal(yp, yp2)
+    if split == "1":
+        monkeypatch.setenv("PMU_POOL_SPLIT", "0")
+        _, yp0 = ops.conv_gemm_pool_bf16(x, wpack, b, Cout, True, mode)
+        assert torch.equal(yp, yp0)
     yn = y.float().permute(0, 3, 1, 2)
     if mode == 0:
         assert torch.equal(yp.float(), _nhwc(F.max_pool2d(yn, 2)))

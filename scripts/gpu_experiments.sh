@@ -1,0 +1,20 @@
+#!/bin/bash
+# One-GPU A/B run of the opt-in kernel variants that were written without GPU time:
+#   1. their parity tests (PMU_TEST_EXPERIMENTAL=1 un-skips them),
+#   2. the resident step (bench.py --timed-only) with each switch on its own and with all of them.
+# Usage: gpurun --timeout 900 -- 'bash scripts/gpu_experiments.sh'
+mkdir -p gpurun_out; rm -f gpurun_out/exp_*.log gpurun_out/exp_rc.txt
+PMU_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_layers.py -m gpu -q --no-header -rf \
+  -k "fcomb_softmax_accum_bf16 or conv_gemm_pool_bf16" > gpurun_out/exp_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/exp_rc.txt
+B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --timed-only"
+run() {   # name, env assignments...
+  local name=$1; shift
+  env "$@" timeout 300 $B > gpurun_out/exp_$name.log 2>&1; echo "$name rc=$? $(tail -1 gpurun_out/exp_$name.log | cut -c1-160)" >> gpurun_out/exp_rc.txt
+}
+run default PMU_NOOP=1
+run fcomb_ts PMU_FCOMB_TS=1
+run fcomb_ts_f16 PMU_FCOMB_TS=2
+run pool_split PMU_POOL_SPLIT=1
+run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1
+run default_again PMU_NOOP=1
+cat gpurun_out/exp_rc.txt; tail -12 gpurun_out/exp_tests.log

@@ -17,4 +17,7 @@ run fcomb_ts_f16 PMU_FCOMB_TS=2
 run pool_split PMU_POOL_SPLIT=1
 run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1
 run default_again PMU_NOOP=1
+# slice batch: the 16x16 layers (Cout = 1024) run 512 tiles = 3.46 waves of 148 SMs at batch 64 (13 % tail), 6.9 at 128
+B="$B --slice-batch 128"; run batch128 PMU_NOOP=1
+B="${B/--slice-batch 128/--slice-batch 256}"; run batch256 PMU_NOOP=1
 cat gpurun_out/exp_rc.txt; tail -12 gpurun_out/exp_tests.log

@@ -430,14 +430,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // 8-row swizzle group == one image row and the three dy taps of that dx are the SAME box read through
 // descriptors offset by dy * 1024 B: 3 A loads per 64-channel chunk instead of 9 (A traffic / 2.7).
 // A stage = one A box + the three weight taps (dy = 0..2) of that dx: 12 UMMAs per stage.
-// RESB (Cin == 64, Cout == 64): all nine weight taps (72 KB) stay resident in smem for the whole
-// kernel and only A streams (18 KB per 384 MMA cycles).
+// RESB = number of resident 64-channel weight chunks (0 = weights stream with the A boxes).  RESB = 1 (Cin == 64,
+// Cout == 64): all nine weight taps (72 KB) stay resident in smem for the whole kernel and only A streams (18 KB
+// per 384 MMA cycles).  RESB = 2 (Cin == 128, Cout == 64 — the decoder's skip-concat layer at full resolution;
+// experiment, PMU_CONV_RES128=1): 144 KB of weights resident, a 3-stage A ring.
 // ------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool RESB>
+template <int BN, int STAGES, int RESB>
 struct ConvRsSmem {
   static constexpr int W_TAP = BN * 128;                           // one tap, one 64-channel chunk: [BN][64] bf16
   static constexpr int BOX_BYTES = 18 * 8 * 128;                   // 18,432
-  static constexpr int WRES_BYTES = RESB ? 9 * W_TAP : 0;          // resident weights
+  static constexpr int WRES_BYTES = 9 * RESB * W_TAP;              // resident weights: [tap][chunk][BN][64]
   static constexpr int STAGE_BYTES = BOX_BYTES + (RESB ? 0 : 3 * W_TAP);
   static constexpr int RING_OFF = WRES_BYTES;
   static constexpr int STG_OFF = RING_OFF + STAGES * STAGE_BYTES;
@@ -449,7 +451,7 @@ struct ConvRsSmem {
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int STAGES, bool RESB, bool PSPLIT = false>
+template <int BN, int STAGES, int RESB, bool PSPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0, const ConvTcParams p,
@@ -490,9 +492,11 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
-      if (RESB) {   // the nine weight taps, once
+      if (RESB) {   // the nine weight taps (all RESB chunks of each), once
         mbar_arrive_expect_tx(bar_wfull, L::WRES_BYTES);
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem_base + tap * L::W_TAP, &tmW, bar_wfull, tap * Cin, 0);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int rc = 0; rc < RESB; ++rc)
+            tma_load_2d(smem_base + (tap * RESB + rc) * L::W_TAP, &tmW, bar_wfull, tap * Cin + rc * TC_BK, 0);
       }
       uint32_t kc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -546,7 +550,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int dy = 0; dy < 3; ++dy) {
               // tap (dy, dx): image rows dy .. dy+15 of the box = +dy swizzle groups of 8 rows (1024 B each)
               const uint64_t adesc = umma_smem_desc_sw128(sa + dy * 1024);
-              const uint64_t bdesc = umma_smem_desc_sw128(RESB ? smem_base + (dy * 3 + dx) * L::W_TAP
+              const uint64_t bdesc = umma_smem_desc_sw128(RESB ? smem_base + ((dy * 3 + dx) * RESB + (RESB > 1 ? ch : 0)) * L::W_TAP
                                                                : sa + L::BOX_BYTES + dy * L::W_TAP);
 #pragma unroll
               for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
@@ -976,11 +980,15 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
     // PMU_POOL_SPLIT=1 (experiment): pooling epilogue with the halving exchange, on the tile configurations the
     // pooled layers of the network use
     const bool psplit = p.pool_split && p.pool_mode >= 0;
-    if (psplit && BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, true, true>, ConvRsSmem<64, 6, true>::DYN_BYTES);
-    if (psplit && BN == 128) return launch_rs(conv_rs_kernel<128, 3, false, true>, ConvRsSmem<128, 3, false>::DYN_BYTES);
-    if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, true>, ConvRsSmem<64, 6, true>::DYN_BYTES);
-    if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, false>, ConvRsSmem<64, 4, false>::DYN_BYTES);
-    return launch_rs(conv_rs_kernel<128, 3, false>, ConvRsSmem<128, 3, false>::DYN_BYTES);
+    if (psplit && BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, 1, true>, ConvRsSmem<64, 6, 1>::DYN_BYTES);
+    if (psplit && BN == 128) return launch_rs(conv_rs_kernel<128, 3, 0, true>, ConvRsSmem<128, 3, 0>::DYN_BYTES);
+    if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, 1>, ConvRsSmem<64, 6, 1>::DYN_BYTES);
+    // PMU_CONV_RES128=1 (experiment): weights of the 128 -> 64 layer resident too (144 KB), 3-stage A ring
+    { const char* e = getenv("PMU_CONV_RES128");
+      if (e && atoi(e) && BN == 64 && Cin == 128 && Cout == 64)
+        return launch_rs(conv_rs_kernel<64, 3, 2>, ConvRsSmem<64, 3, 2>::DYN_BYTES); }
+    if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, 0>, ConvRsSmem<64, 4, 0>::DYN_BYTES);
+    return launch_rs(conv_rs_kernel<128, 3, 0>, ConvRsSmem<128, 3, 0>::DYN_BYTES);
   }
   if (variant == 1 || (variant == -1 && BN != 256)) {
     if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);

@@ -5,7 +5,7 @@
 # Usage: gpurun --timeout 900 -- 'bash scripts/gpu_experiments.sh'
 mkdir -p gpurun_out; rm -f gpurun_out/exp_*.log gpurun_out/exp_rc.txt
 PMU_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_layers.py -m gpu -q --no-header -rf \
-  -k "fcomb_softmax_accum_bf16 or conv_gemm_pool_bf16" > gpurun_out/exp_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/exp_rc.txt
+  -k "fcomb_softmax_accum_bf16 or conv_gemm_pool_bf16 or resident_weights_128" > gpurun_out/exp_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/exp_rc.txt
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --timed-only"
 run() {   # name, env assignments...
   local name=$1; shift
@@ -15,7 +15,8 @@ run default PMU_NOOP=1
 run fcomb_ts PMU_FCOMB_TS=1
 run fcomb_ts_f16 PMU_FCOMB_TS=2
 run pool_split PMU_POOL_SPLIT=1
-run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1
+run res128 PMU_CONV_RES128=1
+run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1 PMU_CONV_RES128=1
 run default_again PMU_NOOP=1
 # slice batch: the 16x16 layers (Cout = 1024) run 512 tiles = 3.46 waves of 148 SMs at batch 64 (13 % tail), 6.9 at 128
 B="$B --slice-batch 128"; run batch128 PMU_NOOP=1

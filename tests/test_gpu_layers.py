@@ -143,6 +143,25 @@ def test_conv_gemm_bf16_3x3(ops, B, C0, C1, Cout, H, W):
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
 
 
+@EXPERIMENTAL
+@pytest.mark.parametrize("B,C0,C1,H,W", [(2, 64, 64, 24, 40), (3, 128, 0, 64, 72), (1, 64, 64, 256, 256)])
+def test_conv_rs_resident_weights_128(ops, B, C0, C1, H, W, monkeypatch):
+    """PMU_CONV_RES128=1 (experiment): the 128 -> 64 row-shift layer with all 18 weight boxes resident in shared memory
+    must give bit-identical outputs to the streaming variant (same UMMA order per accumulator)."""
+    g = _g(16)
+    Cin, Cout = C0 + C1, 64
+    x0 = _nhwc(_bf(torch.randn(B, C0, H, W, generator=g))).to(torch.bfloat16).cuda()
+    x1 = _nhwc(_bf(torch.randn(B, C1, H, W, generator=g))).to(torch.bfloat16).cuda() if C1 else None
+    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5)
+    b = (torch.randn(Cout, generator=g) * 0.1).cuda()
+    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(torch.bfloat16).contiguous().cuda()
+    monkeypatch.setenv("PMU_CONV_RES128", "0")
+    ref = ops.conv_gemm_bf16(x0, wpack, b, Cout, 9, True, x1)
+    monkeypatch.setenv("PMU_CONV_RES128", "1")
+    got = ops.conv_gemm_bf16(x0, wpack, b, Cout, 9, True, x1)
+    assert torch.equal(got, ref)
+
+
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 128, 64, 8, 8), (1, 1024, 512, 4, 4), (3, 256, 128, 16, 12)])
 def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W):
     g = _g(7)

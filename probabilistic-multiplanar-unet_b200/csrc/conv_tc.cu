@@ -433,7 +433,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // RESB = number of resident 64-channel weight chunks (0 = weights stream with the A boxes).  RESB = 1 (Cin == 64,
 // Cout == 64): all nine weight taps (72 KB) stay resident in smem for the whole kernel and only A streams (18 KB
 // per 384 MMA cycles).  RESB = 2 (Cin == 128, Cout == 64 — the decoder's skip-concat layer at full resolution;
-// experiment, PMU_CONV_RES128=1): 144 KB of weights resident, a 3-stage A ring.
+// experiment, PMU_CONV_RES128=1): 144 KB of weights resident, a 3-stage A ring; the same switch keeps the nine
+// 16 KB taps of the 64 -> 128 layers resident (BN = 128, RESB = 1).
 // ------------------------------------------------------------------------------------
 template <int BN, int STAGES, int RESB>
 struct ConvRsSmem {
@@ -986,7 +987,9 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
     // PMU_CONV_RES128=1 (experiment): weights of the 128 -> 64 layer resident too (144 KB), 3-stage A ring
     { const char* e = getenv("PMU_CONV_RES128");
       if (e && atoi(e) && BN == 64 && Cin == 128 && Cout == 64)
-        return launch_rs(conv_rs_kernel<64, 3, 2>, ConvRsSmem<64, 3, 2>::DYN_BYTES); }
+        return launch_rs(conv_rs_kernel<64, 3, 2>, ConvRsSmem<64, 3, 2>::DYN_BYTES);
+      if (e && atoi(e) && BN == 128 && Cin == 64 && Cout == 128 && !psplit)     // 64 -> 128: nine 16 KB taps resident
+        return launch_rs(conv_rs_kernel<128, 3, 1>, ConvRsSmem<128, 3, 1>::DYN_BYTES); }
     if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, 0>, ConvRsSmem<64, 4, 0>::DYN_BYTES);
     return launch_rs(conv_rs_kernel<128, 3, 0>, ConvRsSmem<128, 3, 0>::DYN_BYTES);
   }

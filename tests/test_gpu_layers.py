@@ -144,12 +144,13 @@ def test_conv_gemm_bf16_3x3(ops, B, C0, C1, Cout, H, W):
 
 
 @EXPERIMENTAL
-@pytest.mark.parametrize("B,C0,C1,H,W", [(2, 64, 64, 24, 40), (3, 128, 0, 64, 72), (1, 64, 64, 256, 256)])
-def test_conv_rs_resident_weights_128(ops, B, C0, C1, H, W, monkeypatch):
-    """PMU_CONV_RES128=1 (experiment): the 128 -> 64 row-shift layer with all 18 weight boxes resident in shared memory
-    must give bit-identical outputs to the streaming variant (same UMMA order per accumulator)."""
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 64, 64, 64, 24, 40), (3, 128, 0, 64, 64, 72), (1, 64, 64, 64, 256, 256),
+                                              (2, 64, 0, 128, 32, 40), (1, 64, 0, 128, 128, 128)])
+def test_conv_rs_resident_weights_128(ops, B, C0, C1, Cout, H, W, monkeypatch):
+    """PMU_CONV_RES128=1 (experiment): the 128 -> 64 (and 64 -> 128) row-shift layers with all weight boxes resident in
+    shared memory must give bit-identical outputs to the streaming variant (same UMMA order per accumulator)."""
     g = _g(16)
-    Cin, Cout = C0 + C1, 64
+    Cin = C0 + C1
     x0 = _nhwc(_bf(torch.randn(B, C0, H, W, generator=g))).to(torch.bfloat16).cuda()
     x1 = _nhwc(_bf(torch.randn(B, C1, H, W, generator=g))).to(torch.bfloat16).cuda() if C1 else None
     w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5)

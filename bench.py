@@ -199,8 +199,11 @@ def run_ours(args):
     acc = torch.zeros(2, D, 3, D, D, dtype=torch.float32, device=dev)
 
     def step_resident():
-        acc.zero_()
-        pred.accumulate(vol, eps, acc)
+        if args.graph:
+            pred.accumulate_graphed(vol, eps, acc)          # zero + slice pass, one CUDA-graph launch
+        else:
+            acc.zero_()
+            pred.accumulate(vol, eps, acc)
         pmu_b200.reduce_accumulators(acc, world, None, dst=0)
         if rank == 0:
             return ops.fuse_finalize(acc[0], acc[1], float(P * N))
@@ -212,7 +215,7 @@ def run_ours(args):
     slab = world > 1 and D % world == 0
     pred_e2e = pred if not slab else pmu_b200.MultiPlanarPredictor(
         sd, dev, precision=args.precision, n_samples=N, slice_batch=args.slice_batch, interp=args.interp, rank=rank,
-        world_size=world, output="slab", upload=args.e2e_upload)
+        world_size=world, output="slab", upload=args.e2e_upload, graph=args.graph)
 
     def pinned_outputs():
         if not (rank == 0 or slab):
@@ -436,7 +439,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": workload(D, N, args.interp),
-                           "slice_batch": args.slice_batch, "parallelism": f"slice-sharded x{world} + 1 reduce",
+                           "slice_batch": args.slice_batch, **({"cuda_graph": True} if args.graph else {}), "parallelism": f"slice-sharded x{world} + 1 reduce",
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                         # every rank uploads the volume (--e2e-upload broadcast: rank 0 alone, then NVLink)
@@ -472,6 +475,8 @@ def main():
     ap.add_argument("--cpu-slices-per-plane", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: only the warm-up and the timed resident steps")
+    ap.add_argument("--graph", action="store_true",
+                    help="experiment: replay the slice pass of a volume as one CUDA graph (resident step; e2e leg for N > 1)")
     ap.add_argument("--e2e-upload", default="each", choices=["each", "broadcast"],
                     help="N > 1 e2e leg: every rank uploads the volume over its own PCIe link (default), or rank 0 uploads "
                          "once and broadcasts over NVLink (experiment)")

@@ -6,6 +6,8 @@
 mkdir -p gpurun_out; rm -f gpurun_out/exp_*.log gpurun_out/exp_rc.txt
 PMU_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_layers.py -m gpu -q --no-header -rf \
   -k "fcomb_softmax_accum_bf16 or conv_gemm_pool_bf16 or resident_weights_128" > gpurun_out/exp_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/exp_rc.txt
+PMU_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q --no-header -rf \
+  -k "accumulate_graphed" > gpurun_out/exp_tests_graph.log 2>&1; echo "graph test rc=$?" >> gpurun_out/exp_rc.txt
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --timed-only"
 run() {   # name, env assignments...
   local name=$1; shift
@@ -18,6 +20,7 @@ run pool_split PMU_POOL_SPLIT=1
 run res128 PMU_CONV_RES128=1
 run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1 PMU_CONV_RES128=1
 run default_again PMU_NOOP=1
+B0="$B"; B="$B --graph"; run graph PMU_NOOP=1; B="$B0"
 # slice batch: the 16x16 layers (Cout = 1024) run 512 tiles = 3.46 waves of 148 SMs at batch 64 (13 % tail), 6.9 at 128
 B="$B --slice-batch 128"; run batch128 PMU_NOOP=1
 B="${B/--slice-batch 128/--slice-batch 256}"; run batch256 PMU_NOOP=1

@@ -271,6 +271,27 @@ def test_eval_entry_point(pmu, tmp_path):
     torch.testing.assert_close(out["mean"], avg, atol=1e-6, rtol=1e-5)
 
 
+@pytest.mark.skipif(os.environ.get("PMU_TEST_EXPERIMENTAL") != "1", reason="experimental path (set PMU_TEST_EXPERIMENTAL=1)")
+def test_accumulate_graphed_matches_eager(pmu, trainer_sd):
+    """accumulate_graphed(): the slice pass of a volume replayed as one CUDA graph gives the bits of the eager pass, for
+    a second volume written into the same buffer too (the graph is captured once per buffer triple)."""
+    D, N = 32, 2
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=16)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(5)).cuda()
+    vol = torch.empty(D, D, D, device="cuda")
+    acc = torch.empty(2, D, 3, D, D, device="cuda")
+    for i in range(3):
+        v = torch.from_numpy(O.phantom(D, seed=40 + i)[0]).cuda()
+        want = torch.zeros_like(acc)
+        n_want = pred.accumulate(v, eps, want)
+        vol.copy_(v)
+        n_got = pred.accumulate_graphed(vol, eps, acc)
+        torch.cuda.synchronize()
+        assert n_got == n_want == 3 * D
+        assert torch.equal(acc, want), i
+    assert len(pred._graphs) == 1
+
+
 def test_pipelined_submit_matches_predict(pmu, trainer_sd):
     """submit()/wait(): a stream of different volumes through two buffer slots and three CUDA streams gives, for every
     volume, the bits of the one-at-a-time predict(host_out=...) call (same kernels, only the scheduling differs)."""

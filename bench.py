@@ -472,7 +472,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--interp", default="trilinear", choices=["exact", "nearest", "trilinear"],
                     help="slice resampling onto the three standard plane grids (BASELINE configs[2]: trilinear)")
-    ap.add_argument("--cpu-slices-per-plane", type=int, default=8)
+    ap.add_argument("--cpu-slices-per-plane", type=int, default=32,
+                    help="cpu_baseline sample: equally spaced slices per plane (32 -> 96 of 768 slices, ~10 s on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: only the warm-up and the timed resident steps")
     ap.add_argument("--graph", action="store_true",

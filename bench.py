@@ -11,7 +11,8 @@ variance / entropy fusion.  One "step" = one whole volume.
 
   value : volumes/s, volume + latents resident in HBM, outputs left in HBM (CUDA events, max
           over ranks).  N > 1: the slice list of ONE volume is sharded over the ranks and the
-          accumulators are sum-reduced to rank 0 ("scaling": "strong").
+          accumulators are reduce-scattered along x, every rank finalising its x-slab
+          ("scaling": "strong"; --resident-output rank0: sum-reduced to rank 0).
   e2e   : same metric through the public API with the volume in pinned host memory and mean / var /
           entropy read back to pinned host memory, every step: MultiPlanarPredictor.submit()/wait()
           (copies of neighbouring volumes overlap compute); sync_ms_per_step is the one-at-a-time
@@ -198,12 +199,20 @@ def run_ours(args):
     eps = torch.randn(P, D, N, 6, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)
     acc = torch.zeros(2, D, 3, D, D, dtype=torch.float32, device=dev)
 
+    # N > 1: the one exchange step is a reduce-scatter of the accumulators along x — every rank finalises its own x-slab
+    # and the outputs stay slab-sharded in HBM (the path predict(output="slab") takes).
+    # --resident-output rank0 sum-reduces everything to rank 0 instead (what rounds 1a-1d measured).
+    slab_res = world > 1 and D % world == 0 and args.resident_output == "slab"
+
     def step_resident():
         if args.graph:
             pred.accumulate_graphed(vol, eps, acc)          # zero + slice pass, one CUDA-graph launch
         else:
             acc.zero_()
             pred.accumulate(vol, eps, acc)
+        if slab_res:
+            part, _ = pmu_b200.reduce_scatter_accumulators(acc, rank, world, None)
+            return ops.fuse_finalize(part[0], part[1], float(P * N))
         pmu_b200.reduce_accumulators(acc, world, None, dst=0)
         if rank == 0:
             return ops.fuse_finalize(acc[0], acc[1], float(P * N))
@@ -402,7 +411,7 @@ def run_ours(args):
             hbm_kernels["scatter_accum"] = {"achieved": gb / (tot["pmu_scatter_accum"]["ms"] * 1e-3), "unit": "GB/s",
                                             "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
         if "pmu_fuse_finalize" in tot:
-            gb = V * 52.0 / 1e9
+            gb = V * 52.0 * (world_frac if slab_res else 1.0) / 1e9      # rank 0's x-slab with slab-sharded outputs
             hbm_kernels["fuse_finalize"] = {"achieved": gb / (tot["pmu_fuse_finalize"]["ms"] * 1e-3), "unit": "GB/s",
                                             "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
         # the general resampling kernel (TMA-staged brick) on an oblique grid, timed on its own: the
@@ -439,7 +448,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": workload(D, N, args.interp),
-                           "slice_batch": args.slice_batch, **({"cuda_graph": True} if args.graph else {}), "parallelism": f"slice-sharded x{world} + 1 reduce",
+                           "slice_batch": args.slice_batch, **({"cuda_graph": True} if args.graph else {}), "parallelism": f"slice-sharded x{world} + 1 " + ("reduce-scatter along x (x-slab outputs per rank)" if slab_res else "reduce"),
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                         # every rank uploads the volume (--e2e-upload broadcast: rank 0 alone, then NVLink)
@@ -476,6 +485,9 @@ def main():
                     help="cpu_baseline sample: equally spaced slices per plane (32 -> 96 of 768 slices, ~10 s on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: only the warm-up and the timed resident steps")
+    ap.add_argument("--resident-output", default="slab", choices=["slab", "rank0"],
+                    help="N > 1, resident step: reduce-scatter the accumulators along x and let every rank finalise its x-slab "
+                         "(default), or sum-reduce them to rank 0")
     ap.add_argument("--graph", action="store_true",
                     help="experiment: replay the slice pass of a volume as one CUDA graph (resident step; e2e leg for N > 1)")
     ap.add_argument("--e2e-upload", default="each", choices=["each", "broadcast"],

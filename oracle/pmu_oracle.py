@@ -361,6 +361,18 @@ def argmax_dice(prob: torch.Tensor, truth: torch.Tensor, k: int) -> float:
 # Data plane out: softmax, reassembly, fusion  (eval.py:157,162-193 + App. A 5-7)
 # ----------------------------------------------------------------------------
 
+def eval_sample_loop(draws: Sequence[torch.Tensor], literal: bool = True) -> torch.Tensor:
+    """The per-slice sample loop + softmax of eval.py:145-157 on the logit maps `draws` that five stochastic
+    ProbUNetTrainer.predict calls returned.  literal=True is what the file computes: the `+` on eval.py:152 discards its
+    result, so pred_masks = draws[0] / len(draws) and probs = softmax(draws[0] / 5, dim=1).
+    literal=False is the evident intent — softmax of the MEAN logits.  (The build's N-sample fusion averages
+    probabilities, App. A step 5; this function exists to pin row a20 of SURVEY.md §8 against the reference.)"""
+    n = len(draws)
+    pred = draws[0].clone() if literal else torch.stack(list(draws)).sum(0)
+    pred = pred / n
+    return torch.softmax(pred, dim=1)
+
+
 def scatter_plane(view: int, per_slice: torch.Tensor) -> torch.Tensor:
     """[S,C,H,W] per-slice maps of one view -> [x,C,y,z] volume.  view 0: as is
     (eval.py:176); view 1: permute(2,1,0,3) (eval.py:182); view 2: permute(2,1,3,0)

@@ -318,6 +318,15 @@ def kl_diag_gauss(mu_q, log_sigma_q, mu_p, log_sigma_p) -> torch.Tensor:
     return (0.5 * (var_ratio + t1 - 1 - torch.log(var_ratio))).sum(1)
 
 
+def kl_monte_carlo(mu_q, log_sigma_q, mu_p, log_sigma_p, z) -> torch.Tensor:
+    """One-sample estimate log q(z) - log p(z) -> [B] (probabilistic_unet.py:274-278, kl_divergence(analytic=False)):
+    log N(z; mu, sigma) summed over the latent dim = sum_l [ -((z-mu)/sigma)^2 / 2 - log sigma - log sqrt(2 pi) ]
+    (Independent(Normal(mu, exp(log_sigma)), 1).log_prob); the 2 pi terms cancel in the difference."""
+    def log_prob(mu, ls):
+        return (-0.5 * ((z - mu) / torch.exp(ls)) ** 2 - ls).sum(1)
+    return log_prob(mu_q, log_sigma_q) - log_prob(mu_p, log_sigma_p)
+
+
 def ce_sum(logits: torch.Tensor, segm: torch.Tensor) -> torch.Tensor:
     """CrossEntropyLoss(reduction none) summed over batch and pixels
     (probabilistic_unet.py:288,300-304).  segm: float [B,1,H,W] integer labels."""

@@ -7,7 +7,7 @@ mkdir -p gpurun_out; rm -f gpurun_out/exp_*.log gpurun_out/exp_rc.txt
 PMU_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_layers.py -m gpu -q --no-header -rf \
   -k "fcomb_softmax_accum_bf16 or conv_gemm_pool_bf16 or resident_weights_128" > gpurun_out/exp_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/exp_rc.txt
 PMU_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q --no-header -rf \
-  -k "accumulate_graphed" > gpurun_out/exp_tests_graph.log 2>&1; echo "graph test rc=$?" >> gpurun_out/exp_rc.txt
+  -k "accumulate_graphed or mc_kl" > gpurun_out/exp_tests_graph.log 2>&1; echo "graph test rc=$?" >> gpurun_out/exp_rc.txt
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --timed-only"
 run() {   # name, env assignments...
   local name=$1; shift

@@ -69,6 +69,31 @@ def test_small_model_vs_reference_golden(pmu, golden_dir):
         np.testing.assert_allclose(unet(x).cpu().numpy(), g["eval/unet_out"], **tol)
 
 
+@pytest.mark.skipif(os.environ.get("PMU_TEST_EXPERIMENTAL") != "1", reason="written without GPU time (set PMU_TEST_EXPERIMENTAL=1)")
+def test_small_model_mc_kl_and_posterior_mean(pmu, golden_dir):
+    """The less-travelled arguments of the drop-in API against the REAL reference (golden_small_extra.npz): the
+    Monte-Carlo KL, the ELBO built on it, and the posterior-mean reconstruction — which the reference itself cannot
+    compute (`.loc` on the Independent wrapper raises), so it is checked against the reference's fcomb at z = mu_q."""
+    z = np.load(os.path.join(golden_dir, "golden_small.npz"))
+    g = {k: z[k] for k in z.files}
+    e = np.load(os.path.join(golden_dir, "golden_small_extra.npz"))
+    sd = {k[3:]: _t(v) for k, v in g.items() if k.startswith("sd/")}
+    net = pmu.ProbabilisticUnet(1, 3, [4, 8, 16, 32, 64], latent_dim=6, no_convs_fcomb=4, beta=10)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x, segm, zq = _t(g["x"]).cuda(), _t(g["segm"]).cuda(), _t(g["eval/z_q"]).cuda()
+    with torch.no_grad():
+        net.forward(x, segm, training=True)
+        np.testing.assert_allclose(net.kl_divergence(analytic=False, z_posterior=zq).cpu().numpy(), e["kl_mc"], rtol=1e-4, atol=1e-4)
+        val = net.elbo(segm, analytic_kl=False, z=zq)
+        np.testing.assert_allclose(float(net.kl), float(e["elbo_mc_kl"]), rtol=1e-4)
+        np.testing.assert_allclose(float(net.reconstruction_loss), float(e["elbo_mc_rec"]), rtol=1e-4)
+        np.testing.assert_allclose(float(val), float(e["elbo_mc"]), rtol=1e-4)
+        rec = net.reconstruct(use_posterior_mean=True)
+        want = O.fcomb(sd, _t(g["eval/features"]), _t(g["eval/mu_q"]))
+        np.testing.assert_allclose(rec.cpu().numpy(), want.numpy(), rtol=1e-4, atol=2e-5)
+
+
 def test_unsupported_autograd_is_refused_loudly(pmu):
     """Gradients exist for train() + forward(training=True) in fp32 (test_gpu_train.py); every other
     combination raises instead of silently running ATen or eval-mode BatchNorm."""

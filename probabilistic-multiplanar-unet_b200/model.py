@@ -212,6 +212,20 @@ class Fcomb(nn.Module):
                 _orth_(m)
 
 
+def latent_grid_z(mu: torch.Tensor, sigma: torch.Tensor, n_preds: int = 3, sigma_scale: float = 1.0, axes=(0, 1)) -> torch.Tensor:
+    """The z list of visualize_sampling.py:21-26 for every slice: mu, sigma [B, L] -> z [B, G, G, L] with
+    z[b, i, j] = mu[b] except z[axes[0]] = s_i * sigma_scale * sigma[axes[0]] + mu[axes[0]] and z[axes[1]] likewise with
+    s_j; s = -(n_preds // 2) .. n_preds // 2.  (The reference scales sigma by 40 first, visualize_sampling.py:78, and
+    walks z_0 over rows, z_1 over columns.)  Pure tensor code on mu's device."""
+    steps = torch.arange(-(n_preds // 2), n_preds // 2 + 1, device=mu.device, dtype=torch.float32)
+    G = steps.numel()
+    z = mu[:, None, None, :].repeat(1, G, G, 1)
+    a0, a1 = axes
+    z[:, :, :, a0] = steps[None, :, None] * sigma_scale * sigma[:, None, None, a0] + mu[:, None, None, a0]
+    z[:, :, :, a1] = steps[None, None, :] * sigma_scale * sigma[:, None, None, a1] + mu[:, None, None, a1]
+    return z
+
+
 class ProbabilisticUnet(nn.Module, _PackedMixin):
     """Drop-in for model/probabilistic_unet/probabilistic_unet.py:184-308."""
 
@@ -336,14 +350,8 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
         i, j in range(-(n_preds // 2), n_preds // 2 + 1).  Returns (logits [B, G, G, C, H, W], z [B, G, G, L]);
         the reference loops G*G full `predict(slice, mask, z=z)` calls (each a whole U-Net pass) for the same result."""
         self._enter("ProbabilisticUnet.sample_grid")
-        mu, sigma = self._prior[0].float(), torch.exp(self._prior[1]).float()
-        steps = torch.arange(-(n_preds // 2), n_preds // 2 + 1, device=mu.device, dtype=torch.float32)
-        G = steps.numel()
-        z = mu[:, None, None, :].repeat(1, G, G, 1)
-        a0, a1 = axes
-        z[:, :, :, a0] = steps[None, :, None] * sigma_scale * sigma[:, None, None, a0] + mu[:, None, None, a0]
-        z[:, :, :, a1] = steps[None, None, :] * sigma_scale * sigma[:, None, None, a1] + mu[:, None, None, a1]
-        B = z.shape[0]
+        z = latent_grid_z(self._prior[0].float(), torch.exp(self._prior[1]).float(), n_preds, sigma_scale, axes)
+        B, G = z.shape[0], z.shape[1]
         logits = self.packed().fcomb_logits(self.unet_features, z.reshape(B, G * G, -1))
         return logits.reshape(B, G, G, *logits.shape[2:]), z
 

@@ -16,6 +16,7 @@ run() {   # name, env assignments...
 run default PMU_NOOP=1
 run fcomb_ts PMU_FCOMB_TS=1
 run fcomb_ts_f16 PMU_FCOMB_TS=2
+run fcomb_ss_f16 PMU_FCOMB_F16=1
 run pool_split PMU_POOL_SPLIT=1
 run res128 PMU_CONV_RES128=1
 run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1 PMU_CONV_RES128=1

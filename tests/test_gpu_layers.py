@@ -238,13 +238,14 @@ def test_pool_head_transpose_bf16(ops):
                                           (4, 20, 3, 3, 20, 24), (5, 3, 3, 3, 20, 24),
                                           (4, 6, 3, 5, 96, 100),     # 190 tile pairs > 148 SMs: CTAs walk several
                                           (3, 18, 4, 7, 72, 72)])    # pairs and cross slice boundaries; 2 sample groups
-@pytest.mark.parametrize("ts_mode", ["0", "1", pytest.param("2", marks=EXPERIMENTAL)])
+@pytest.mark.parametrize("ts_mode", ["0", "1", pytest.param("2", marks=EXPERIMENTAL), pytest.param("0+f16", marks=EXPERIMENTAL)])
 def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W, ts_mode, monkeypatch):
     """Fused tensor-core fcomb vs the fp32 oracle: probabilities within the bf16 budget 2e-2.
     HW = 480 is ragged against the 128-pixel tile.  ts_mode 1 = activations resident in tensor memory
     (TS-form UMMAs, fcomb_ts.cu), 0 = through shared memory (fcomb_tc6.cu, the default), 2 = TS form with f16
     hidden layers and packed 16-bit accumulator read-back (experiment, PMU_TEST_EXPERIMENTAL=1)."""
-    monkeypatch.setenv("PMU_FCOMB_TS", ts_mode)
+    monkeypatch.setenv("PMU_FCOMB_TS", ts_mode.split("+")[0])
+    monkeypatch.setenv("PMU_FCOMB_F16", "1" if ts_mode.endswith("+f16") else "0")     # "0+f16": SS form with f16 layers
     sd = O.make_state_dict((64, 128), num_classes=C, latent_dim=6, no_convs_fcomb=nl, seed=10)
     g = _g(11)
     feat = _bf(torch.relu(torch.randn(B, 64, H, W, generator=g)))

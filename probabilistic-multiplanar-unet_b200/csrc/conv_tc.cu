@@ -48,15 +48,21 @@ struct ConvTcParams {
   int pool_split;     // experiment (PMU_POOL_SPLIT=1): host-side selector of the PSPLIT kernel instantiations
 };
 
-template <int BN, int STAGES, int NSTG = 1>
+// RESW > 0 (experiment, PMU_CONVT_RESW=1): the layer's whole weight matrix — RESW k-blocks of [BN][64] — is loaded
+// once per CTA and stays resident; only the activation boxes stream through the ring.  For a single-N-tile layer with a
+// short K (the 128 -> 64 transposed convolution: N = 4 * 64 = 256, K = 128) the generic kernel re-fetches 64 KB of
+// weights from L2 for every 128-pixel tile, as much as the tile writes.
+template <int BN, int STAGES, int NSTG = 1, int RESW = 0>
 struct ConvTcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_OFF = STAGES * STAGE_BYTES;            // output staging tile [128 px][64 ch] bf16, 128B swizzle
+  static constexpr int WRES_BYTES = RESW * B_BYTES;
+  static constexpr int RING_OFF = WRES_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + (RESW ? 0 : B_BYTES);
+  static constexpr int STG_OFF = RING_OFF + STAGES * STAGE_BYTES; // output staging tile [128 px][64 ch] bf16, 128B swizzle
   static constexpr int STG_BYTES = TC_BM * 128;                    // x NSTG buffers
-  static constexpr int BAR_OFF = STG_OFF + NSTG * STG_BYTES;             // full[S], empty[S], tmem_full[2], tmem_empty[2]
-  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int BAR_OFF = STG_OFF + NSTG * STG_BYTES;             // full[S], empty[S], tmem_full[2], tmem_empty[2][, wfull]
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4 + (RESW ? 1 : 0)) * 8;
   static constexpr int BIAS_OFF = ((TMEM_PTR_OFF + 4 + 15) / 16) * 16;   // BN floats
   static constexpr int TOTAL = BIAS_OFF + BN * 4;
   static constexpr int DYN_BYTES = TOTAL;            // base is 1024 B aligned (__align__ + runtime check)
@@ -300,7 +306,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
 // current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
 // setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
-template <int BN, int STAGES, int MINB, int NSTG, bool PSPLIT = false>
+template <int BN, int STAGES, int MINB, int NSTG, bool PSPLIT = false, int RESW = 0>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0,
@@ -308,7 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmY3, const ConvTcParams p,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                __nv_bfloat16* __restrict__ y_pool) {
-  using L = ConvTcSmem<BN, STAGES, NSTG>;
+  using L = ConvTcSmem<BN, STAGES, NSTG, RESW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   uint8_t* smem_gen = smem_raw;
@@ -317,6 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const uint32_t bar_tfull = bar_empty + STAGES * 8;   // [2] accumulator stage ready for the epilogue
   const uint32_t bar_tempty = bar_tfull + 2 * 8;       // [2] accumulator stage drained by the epilogue
+  const uint32_t bar_wfull = bar_tempty + 2 * 8;       // RESW only: resident weights have landed
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TMEM_PTR_OFF);
   float* bias_s = reinterpret_cast<float*>(smem_gen + L::BIAS_OFF);
 
@@ -340,6 +347,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(bar_tfull + a * 8, 1);
       mbar_init(bar_tempty + a * 8, 128);   // every epilogue thread arrives
     }
+    if (RESW) mbar_init(bar_wfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(smem_base + L::TMEM_PTR_OFF);
@@ -351,6 +359,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
+      if (RESW) {   // the whole weight matrix, once (the launcher guarantees one N tile and k_iters <= RESW)
+        mbar_arrive_expect_tx(bar_wfull, (uint32_t)k_iters * L::B_BYTES);
+        for (int it = 0; it < k_iters; ++it) tma_load_2d(smem_base + it * L::B_BYTES, &tmW, bar_wfull, it * TC_BK, 0);
+      }
       uint32_t kc = 0;   // k-block counter over the whole tile sequence
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
@@ -367,16 +379,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int c = (it - tap * kc_per_tap) * TC_BK;   // channel offset inside the concatenated K
           int dy = 0, dx = 0;
           if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+          const uint32_t sa = smem_base + L::RING_OFF + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
-          if (p.debug & 2) {
+          if (!RESW && (p.debug & 2)) {
             mbar_arrive_expect_tx(bar_full + s * 8, L::B_BYTES);
           } else {
             mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
             if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
             else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
           }
-          tma_load_2d(sb, &tmW, bar_full + s * 8, tap * Cin + c, n0);
+          if (!RESW) tma_load_2d(sb, &tmW, bar_full + s * 8, tap * Cin + c, n0);
         }
       }
     }
@@ -385,6 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // one elected thread runs the whole issue loop: nothing but barrier polls between MMAs
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      if (RESW) { mbar_wait(bar_wfull, 0); tcgen05_fence_after(); }
       uint32_t kc = 0, iter = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
@@ -396,9 +409,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t ph = (kc / STAGES) & 1u;
           mbar_wait(bar_full + s * 8, ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+          const uint32_t sa = smem_base + L::RING_OFF + s * L::STAGE_BYTES;
           const uint64_t adesc = umma_smem_desc_sw128(sa);
-          const uint64_t bdesc = umma_smem_desc_sw128(sa + L::A_BYTES);
+          const uint64_t bdesc = umma_smem_desc_sw128(RESW ? smem_base + it * L::B_BYTES : sa + L::A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             // +32 B per UMMA_K inside the 128 B swizzle row: start-address field += 2
@@ -812,13 +825,13 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN, int STAGES, int MINB, int NSTG = 1, bool PSPLIT = false>
+template <int BN, int STAGES, int MINB, int NSTG = 1, bool PSPLIT = false, int RESW = 0>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm, const CUtensorMap* ym,
                           const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
                           cudaStream_t st) {
-  using L = ConvTcSmem<BN, STAGES, NSTG>;
+  using L = ConvTcSmem<BN, STAGES, NSTG, RESW>;
   static_assert(MINB * (L::DYN_BYTES + 1024) <= 228 * 1024 && L::DYN_BYTES <= 227 * 1024, "shared memory budget");
-  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, PSPLIT>;
+  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, PSPLIT, RESW>;
   PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
   grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
   kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, ym[0], ym[1], ym[2], ym[3], p, bias,
@@ -997,6 +1010,9 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
     if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
     return launch_conv_tc<64, 4, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   }
+  { const char* e = getenv("PMU_CONVT_RESW");      // experiment: resident weights for a one-N-tile transposed convolution
+    if (e && atoi(e) && BN == 256 && ntaps == 4 && Ntot == 256 && Cin <= 128)
+      return launch_conv_tc<256, 6, 1, 2, false, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st); }
   if (BN == 256 && p.pool_split && p.pool_mode >= 0)
     return launch_conv_tc<256, 4, 1, 2, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   if (BN == 256) return launch_conv_tc<256, 4, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);

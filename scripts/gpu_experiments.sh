@@ -5,7 +5,7 @@
 # Usage: gpurun --timeout 900 -- 'bash scripts/gpu_experiments.sh'
 mkdir -p gpurun_out; rm -f gpurun_out/exp_*.log gpurun_out/exp_rc.txt
 PMU_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_layers.py -m gpu -q --no-header -rf \
-  -k "fcomb_softmax_accum_bf16 or conv_gemm_pool_bf16 or resident_weights_128" > gpurun_out/exp_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/exp_rc.txt
+  -k "fcomb_softmax_accum_bf16 or conv_gemm_pool_bf16 or resident_weights" > gpurun_out/exp_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/exp_rc.txt
 PMU_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q --no-header -rf \
   -k "accumulate_graphed or mc_kl" > gpurun_out/exp_tests_graph.log 2>&1; echo "graph test rc=$?" >> gpurun_out/exp_rc.txt
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --timed-only"
@@ -19,7 +19,8 @@ run fcomb_ts_f16 PMU_FCOMB_TS=2
 run fcomb_ss_f16 PMU_FCOMB_F16=1
 run pool_split PMU_POOL_SPLIT=1
 run res128 PMU_CONV_RES128=1
-run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1 PMU_CONV_RES128=1
+run convt_resw PMU_CONVT_RESW=1
+run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1 PMU_CONV_RES128=1 PMU_CONVT_RESW=1
 run default_again PMU_NOOP=1
 B0="$B"; B="$B --graph"; run graph PMU_NOOP=1; B="$B0"
 # slice batch: the 16x16 layers (Cout = 1024) run 512 tiles = 3.46 waves of 148 SMs at batch 64 (13 % tail), 6.9 at 128

@@ -163,6 +163,24 @@ def test_conv_rs_resident_weights_128(ops, B, C0, C1, Cout, H, W, monkeypatch):
     assert torch.equal(got, ref)
 
 
+@EXPERIMENTAL
+@pytest.mark.parametrize("B,Cin,H,W", [(2, 128, 8, 8), (3, 128, 128, 128), (5, 64, 24, 40)])
+def test_convt_resident_weights(ops, B, Cin, H, W, monkeypatch):
+    """PMU_CONVT_RESW=1 (experiment): the one-N-tile transposed convolution (Cout = 64, N = 256) with its whole weight
+    matrix resident in shared memory gives the bits of the streaming kernel."""
+    g = _g(17)
+    Cout = 64
+    x = _nhwc(_bf(torch.randn(B, Cin, H, W, generator=g))).to(torch.bfloat16).cuda()
+    w = _bf(torch.randn(Cin, Cout, 2, 2, generator=g) * (1.0 / Cin) ** 0.5)
+    b = (torch.randn(Cout, generator=g) * 0.1).cuda()
+    wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(torch.bfloat16).contiguous().cuda()
+    monkeypatch.setenv("PMU_CONVT_RESW", "0")
+    ref = ops.conv_gemm_bf16(x, wpack, b, Cout, 4, False)
+    monkeypatch.setenv("PMU_CONVT_RESW", "1")
+    got = ops.conv_gemm_bf16(x, wpack, b, Cout, 4, False)
+    assert torch.equal(got, ref)
+
+
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 128, 64, 8, 8), (1, 1024, 512, 4, 4), (3, 256, 128, 16, 12)])
 def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W):
     g = _g(7)

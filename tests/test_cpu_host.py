@@ -267,3 +267,35 @@ def test_fullsize_lattice_fixtures_are_consistent(golden_dir, name):
     np.testing.assert_allclose(-(p * np.log(p)).sum(-1), g["entropy"], atol=1e-5)
     np.testing.assert_allclose(g["mean_sum"].sum(), float(g["D"]) ** 3, rtol=1e-6)
     assert int(g["labels_hist"].sum()) == int(g["D"]) ** 3
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/pmu_b200.h against the ctypes table of _lib.py: same parameter count and the same
+    class of type per position (pointer / int / int64_t / float) — a drifted binding corrupts arguments silently."""
+    import ctypes
+    import re
+    from pmu_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"\b(?:const\s+char\s*\*|int)\s+(pmu_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert sorted(n for n, _ in protos) == _lib.header_symbols()
+    assert sorted(_lib._SIG) == _lib.header_symbols()            # the table binds exactly what the header declares
+
+    def kind_of_c(param):
+        param = param.strip()
+        if "*" in param or "[" in param:
+            return "ptr"
+        t = param.rsplit(" ", 1)[0].replace("const", "").strip()
+        return {"int": "int", "int32_t": "int", "int64_t": "int64", "float": "float"}[t]
+
+    def kind_of_ctypes(t):
+        if t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "_type_") and not isinstance(t._type_, str):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_int32: "int", ctypes.c_int64: "int64", ctypes.c_float: "float"}[t]
+
+    for name, params in protos:
+        plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        _, args = _lib._SIG[name]
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        for i, (p, a) in enumerate(zip(plist, args)):
+            assert kind_of_c(p) == kind_of_ctypes(a), (name, i, p.strip(), a)

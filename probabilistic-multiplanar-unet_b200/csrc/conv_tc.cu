@@ -300,13 +300,99 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
   if (p.tma_store && et == 0) tma_store_wait_all();
 }
 
+// Epilogue variant for the one-N-tile transposed convolution (Cout = 64, N = 4 * 64; experiment, PMU_CONVT_PAIR=1).
+// The shared epilogue stores every phase (i, j) through its own strided tensor map: 128 scattered 128-byte pieces per
+// store (pixel stride 256 B) — measured, that layer runs at ~6400 cycles per tile with nothing saturated (L2 28 %,
+// DRAM 44 %, tensor pipe 16 %): it waits for its stores.  Here the two column parities j = 0, 1 of one output-row parity i
+// are staged INTERLEAVED, staging row = (tb, ty, 2 * tx + j), so that one tensor store per i writes 2 * TW * 128 B = 4 KB
+// contiguous runs of the output row 2 * h + i: half as many stores, each over whole rows.
+template <int NSTG>
+__device__ __forceinline__ void convt_pair_epilogue(const ConvTcParams& p, const EpiCtx& e, const CUtensorMap* tmP0,
+                                                    const CUtensorMap* tmP1, const float* __restrict__ bias,
+                                                    int total_tiles, int warp, int lane) {
+  constexpr int BN = 256, PAIR_BYTES = 2 * TC_BM * 128, NPAIR = NSTG / 2;
+  static_assert(NSTG >= 2 && NSTG % 2 == 0, "pair staging buffers are two 16 KB tiles each");
+  const uint32_t smem_base = e.smem_base, bar_tfull = e.bar_tfull, bar_tempty = e.bar_tempty, tmem_base = e.tmem_base;
+  float* bs = e.bias_s;
+  const int et = threadIdx.x - 64;   // 0..127
+  const int q = warp & 3;
+  const int m = q * 32 + lane;
+  const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
+  uint32_t iter = 0, pair_count = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
+    int m_tile = tile;                               // one N tile
+    const int w0 = (m_tile % p.tiles_w) * p.TW; m_tile /= p.tiles_w;
+    const int h0 = (m_tile % p.tiles_h) * p.TH; m_tile /= p.tiles_h;
+    const int b0 = m_tile * p.TB;
+    named_bar_sync(4, 128);          // every warp is done reading the previous tile's bias
+    for (int i = et; i < BN; i += 128) bs[i] = bias ? __ldg(bias + i % p.Cout) : 0.f;
+    named_bar_sync(1, 128);          // bias visible
+    mbar_wait(bar_tfull + as * 8, aph);
+    tcgen05_fence_after();
+    const uint32_t tmem_d = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int i2 = 0; i2 < 2; ++i2) {                 // output row parity
+      const uint32_t stg = smem_base + e.stg_off + (pair_count % NPAIR) * PAIR_BYTES;
+      // the store that used this pair buffer must have finished READING it before it is rewritten
+      if (et == 0) { if (NPAIR > 1) tma_store_wait_read1(); else tma_store_wait_read0(); }
+      named_bar_sync(2, 128);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {                  // output column parity: GEMM columns [(2 i + j) * 64, +64)
+        const int row = (tb * p.TH + ty) * (2 * p.TW) + 2 * tx + j;
+        const uint32_t stg_row = stg + (uint32_t)row * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = (i2 * 2 + j) * 64 + half * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_d + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (c0 + 32 >= BN) {       // last TMEM read of this accumulator stage
+            tcgen05_fence_before();
+            mbar_arrive(bar_tempty + as * 8);
+          }
+          uint32_t pk[16];
+          const uint32_t bs_addr = smem_u32(bs) + (uint32_t)c0 * 4;
+          if (p.relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 b4 = lds128_f4(bs_addr + k * 16);
+              pk[2 * k] = add_pack_bf16x2<true>(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), b4.x, b4.y);
+              pk[2 * k + 1] = add_pack_bf16x2<true>(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]), b4.z, b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 b4 = lds128_f4(bs_addr + k * 16);
+              pk[2 * k] = add_pack_bf16x2<false>(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), b4.x, b4.y);
+              pk[2 * k + 1] = add_pack_bf16x2<false>(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]), b4.z, b4.w);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            sts128_u32(stg_row + ((((half * 4 + k) ^ (row & 7)) & 7) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        }
+      }
+      fence_proxy_async_smem();      // staging writes (generic proxy) -> visible to the TMA engine
+      named_bar_sync(3, 128);
+      if (et == 0 && !(p.debug & 1)) {
+        // box {64 ch, 2 TW output pixels, TH rows of parity i2, TB}: rows 2 h + i2, pixels 2 w0 .. 2 w0 + 2 TW - 1
+        tma_store_4d(i2 ? tmP1 : tmP0, stg, 0, 2 * w0, h0, b0);
+        tma_store_commit();
+      }
+      ++pair_count;
+    }
+  }
+  if (et == 0) tma_store_wait_all();
+}
+
 // Persistent kernel: one CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x,
 // N-tile fastest so concurrently running CTAs share activation bricks in L2).  The smem ring
 // keeps running across tiles (the producer prefetches the next tile's operands while the
 // current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
 // setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
-template <int BN, int STAGES, int MINB, int NSTG, bool PSPLIT = false, int RESW = 0>
+template <int BN, int STAGES, int MINB, int NSTG, bool PSPLIT = false, int RESW = 0, bool TPAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0,
@@ -427,7 +513,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else {
     // =========================== epilogue (warps 2..5) ===========================
     EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
-    conv_epilogue<BN, NSTG, PSPLIT>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
+    if constexpr (TPAIR) convt_pair_epilogue<NSTG>(p, ec, &tmY0, &tmY1, bias, total_tiles, warp, lane);
+    else conv_epilogue<BN, NSTG, PSPLIT>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -825,13 +912,13 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN, int STAGES, int MINB, int NSTG = 1, bool PSPLIT = false, int RESW = 0>
+template <int BN, int STAGES, int MINB, int NSTG = 1, bool PSPLIT = false, int RESW = 0, bool TPAIR = false>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm, const CUtensorMap* ym,
                           const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
                           cudaStream_t st) {
   using L = ConvTcSmem<BN, STAGES, NSTG, RESW>;
   static_assert(MINB * (L::DYN_BYTES + 1024) <= 228 * 1024 && L::DYN_BYTES <= 227 * 1024, "shared memory budget");
-  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, PSPLIT, RESW>;
+  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, PSPLIT, RESW, TPAIR>;
   PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
   grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
   kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, ym[0], ym[1], ym[2], ym[3], p, bias,
@@ -855,6 +942,22 @@ static int make_convt_out_map(CUtensorMap* m, void* y, int B, int H, int W, int 
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(convT output phase %d) failed: %d", ij, (int)r); return PMU_ERR_CUDA; }
+  return PMU_OK;
+}
+
+// rows of parity i of the ConvTranspose2d output y[B][2H][2W][Cout] as a [B][H][2W][Cout] tensor (row stride = two
+// output rows): one box {64 ch, 2 TW, TH, TB} covers both column parities of a tile (convt_pair_epilogue)
+static int make_convt_pair_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int i, int TW, int TH, int TB) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
+  char* base = reinterpret_cast<char*>(y) + (int64_t)i * 2 * W * Cout * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)(2 * W), (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)2 * (2 * W) * Cout * 2, (cuuint64_t)(2 * H) * (2 * W) * Cout * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(2 * TW), (cuuint32_t)TH, (cuuint32_t)TB};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(convT output rows of parity %d) failed: %d", i, (int)r); return PMU_ERR_CUDA; }
   return PMU_OK;
 }
 
@@ -1010,6 +1113,14 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
     if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
     return launch_conv_tc<64, 4, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   }
+  { const char* e = getenv("PMU_CONVT_PAIR");      // experiment: resident weights + paired-phase stores (Cout = 64 only)
+    if (e && atoi(e) && BN == 256 && ntaps == 4 && Cout == 64 && Cin <= 128 && y && p.tma_store) {
+      for (int i = 0; i < 2; ++i) {
+        const int rc = make_convt_pair_map(&ym[i], y, B, H, W, Cout, i, p.TW, p.TH, p.TB);
+        if (rc) return rc;
+      }
+      return launch_conv_tc<256, 5, 1, 4, false, 2, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+    } }
   { const char* e = getenv("PMU_CONVT_RESW");      // experiment: resident weights for a one-N-tile transposed convolution
     if (e && atoi(e) && BN == 256 && ntaps == 4 && Ntot == 256 && Cin <= 128)
       return launch_conv_tc<256, 6, 1, 2, false, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st); }

@@ -24,12 +24,13 @@ run fcomb_ss_f16 PMU_FCOMB_F16=1
 run pool_split PMU_POOL_SPLIT=1
 run res128 PMU_CONV_RES128=1
 run convt_resw PMU_CONVT_RESW=1
-run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1 PMU_CONV_RES128=1 PMU_CONVT_RESW=1
+run convt_pair PMU_CONVT_PAIR=1
+run all PMU_FCOMB_TS=2 PMU_POOL_SPLIT=1 PMU_CONV_RES128=1 PMU_CONVT_PAIR=1
 run default_again PMU_NOOP=1
 B0="$B"; B="$B --graph"; run graph PMU_NOOP=1; B="$B0"
 # per-layer A/B of the conv variants (median of 5 per layer, CUDA events)
 timeout 200 python scripts/time_convs.py > gpurun_out/exp_convs_default.log 2>&1; echo "time_convs default rc=$?" >> gpurun_out/exp_rc.txt
-PMU_POOL_SPLIT=1 PMU_CONV_RES128=1 PMU_CONVT_RESW=1 timeout 200 python scripts/time_convs.py > gpurun_out/exp_convs_variants.log 2>&1; echo "time_convs variants rc=$?" >> gpurun_out/exp_rc.txt
+PMU_POOL_SPLIT=1 PMU_CONV_RES128=1 PMU_CONVT_PAIR=1 timeout 200 python scripts/time_convs.py > gpurun_out/exp_convs_variants.log 2>&1; echo "time_convs variants rc=$?" >> gpurun_out/exp_rc.txt
 paste -d'|' <(cut -c1-62 gpurun_out/exp_convs_default.log) <(cut -c41-62 gpurun_out/exp_convs_variants.log) > gpurun_out/exp_convs_ab.txt
 # slice batch: the 16x16 layers (Cout = 1024) run 512 tiles = 3.46 waves of 148 SMs at batch 64 (13 % tail), 6.9 at 128
 B="$B --slice-batch 128"; run batch128 PMU_NOOP=1

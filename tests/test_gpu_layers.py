@@ -164,10 +164,13 @@ def test_conv_rs_resident_weights_128(ops, B, C0, C1, Cout, H, W, monkeypatch):
 
 
 @EXPERIMENTAL
-@pytest.mark.parametrize("B,Cin,H,W", [(2, 128, 8, 8), (3, 128, 128, 128), (5, 64, 24, 40)])
-def test_convt_resident_weights(ops, B, Cin, H, W, monkeypatch):
+@pytest.mark.parametrize("B,Cin,H,W", [(2, 128, 8, 8), (3, 128, 128, 128), (5, 64, 24, 40), (9, 128, 4, 4), (2, 128, 20, 12)])
+@pytest.mark.parametrize("flag", ["PMU_CONVT_RESW", "PMU_CONVT_PAIR"])
+def test_convt_resident_weights(ops, B, Cin, H, W, flag, monkeypatch):
     """PMU_CONVT_RESW=1 (experiment): the one-N-tile transposed convolution (Cout = 64, N = 256) with its whole weight
-    matrix resident in shared memory gives the bits of the streaming kernel."""
+    matrix resident in shared memory gives the bits of the streaming kernel.  PMU_CONVT_PAIR=1 adds the paired-phase
+    epilogue (both column parities of an output row staged interleaved, one tensor store per row parity): same bits;
+    the cases cover partial tiles, bricks that span several images (4 x 4) and non-power-of-two extents."""
     g = _g(17)
     Cout = 64
     x = _nhwc(_bf(torch.randn(B, Cin, H, W, generator=g))).to(torch.bfloat16).cuda()
@@ -175,8 +178,9 @@ def test_convt_resident_weights(ops, B, Cin, H, W, monkeypatch):
     b = (torch.randn(Cout, generator=g) * 0.1).cuda()
     wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(torch.bfloat16).contiguous().cuda()
     monkeypatch.setenv("PMU_CONVT_RESW", "0")
+    monkeypatch.setenv("PMU_CONVT_PAIR", "0")
     ref = ops.conv_gemm_bf16(x, wpack, b, Cout, 4, False)
-    monkeypatch.setenv("PMU_CONVT_RESW", "1")
+    monkeypatch.setenv(flag, "1")
     got = ops.conv_gemm_bf16(x, wpack, b, Cout, 4, False)
     assert torch.equal(got, ref)
 

@@ -260,7 +260,9 @@ def test_pool_head_transpose_bf16(ops):
                                           (4, 20, 3, 3, 20, 24), (5, 3, 3, 3, 20, 24),
                                           (4, 6, 3, 5, 96, 100),     # 190 tile pairs > 148 SMs: CTAs walk several
                                           (3, 18, 4, 7, 72, 72)])    # pairs and cross slice boundaries; 2 sample groups
-@pytest.mark.parametrize("ts_mode", ["0", "1", pytest.param("2", marks=EXPERIMENTAL), pytest.param("0+f16", marks=EXPERIMENTAL)])
+@pytest.mark.parametrize("ts_mode", [pytest.param("0", id="ss"), pytest.param("1", id="ts"),
+                                     pytest.param("2", marks=EXPERIMENTAL, id="tshalf"),
+                                     pytest.param("0+f16", marks=EXPERIMENTAL, id="sshalf")])
 def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W, ts_mode, monkeypatch):
     """Fused tensor-core fcomb vs the fp32 oracle: probabilities within the bf16 budget 2e-2.
     HW = 480 is ragged against the 128-pixel tile.  ts_mode 1 = activations resident in tensor memory

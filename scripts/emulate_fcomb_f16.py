@@ -1,0 +1,64 @@
+"""CPU emulation of the numerics of the f16 fcomb variants (PMU_FCOMB_TS=2 / PMU_FCOMB_F16=1) against today's bf16 path,
+both measured against fp32 on the same bf16 features: layer 0 as in the kernels (bf16 feature GEMM with fp32 accumulate +
+exact fp32 per-sample bias), hidden layers with bf16 or f16 operands; "f16 accumulate" rounds the running sum to f16 after
+every K = 16 step and adds the bias in f16 — a worst case for what the tensor core does.
+
+    python scripts/emulate_fcomb_f16.py
+
+Result with the trainer-seeded fcomb weights, 20 000 pixels, |z| ~ 3 sigma (max / p99.9 / mean abs error of the softmax):
+    bf16 operands, fp32 accumulate (today)               1.1e-02 / 7.7e-03 / 1.1e-03
+    f16 operands, fp32 accumulate                        4.5e-03 / 2.8e-03 / 3.7e-04
+    f16 operands, f16 accumulate (worst-case rounding)   5.1e-03 / 2.9e-03 / 3.9e-04
+so the f16 variants sit well inside the 2e-2 budget — 11 significand bits in the hidden activations instead of 8."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import pmu_oracle as O  # noqa: E402  (a diagnostic script, like bench.py's cpu_baseline leg)
+
+
+def r16(t, kind):
+    return t.to(torch.bfloat16 if kind == "bf16" else torch.float16).float()
+
+
+def main():
+    sd = O.make_state_dict(seed=0)
+    g = torch.Generator().manual_seed(1)
+    P = 20000
+    featb = (torch.relu(torch.randn(P, 64, generator=g)) * 2.0).to(torch.bfloat16).float()
+    z = torch.randn(P, 6, generator=g) * 3
+    W0, b0 = sd["fcomb.layers.0.weight"][:, :, 0, 0], sd["fcomb.layers.0.bias"]
+    mids = [(sd[f"fcomb.layers.{i}.weight"][:, :, 0, 0], sd[f"fcomb.layers.{i}.bias"]) for i in (2, 4)]
+    W3, b3 = sd["fcomb.last_layer.weight"][:, :, 0, 0], sd["fcomb.last_layer.bias"]
+    h = torch.relu(torch.cat([featb, z], 1) @ W0.t() + b0)
+    for W, b in mids:
+        h = torch.relu(h @ W.t() + b)
+    ref = torch.softmax(h @ W3.t() + b3, 1)
+
+    def mlp(kind, acc16):
+        G = featb @ r16(W0[:, :64], "bf16").t()
+        h = r16(torch.relu(G + z @ W0[:, 64:].t() + b0), kind)
+        for W, b in mids:
+            Wq = r16(W, kind)
+            if acc16:
+                acc = torch.zeros(P, 64)
+                for k in range(0, 64, 16):
+                    acc = r16(acc + h[:, k:k + 16] @ Wq[:, k:k + 16].t(), "f16")
+                acc = r16(acc + r16(b, "f16"), "f16")
+            else:
+                acc = h @ Wq.t() + b
+            h = r16(torch.relu(acc), kind)
+        return torch.softmax(h @ r16(W3, kind).t() + b3, 1)
+
+    for name, kind, a16 in (("bf16 operands, fp32 accumulate (today)", "bf16", False),
+                            ("f16 operands, fp32 accumulate", "f16", False),
+                            ("f16 operands, f16 accumulate (worst-case rounding)", "f16", True)):
+        e = (mlp(kind, a16) - ref).abs()
+        p999 = e.flatten().kthvalue(int(e.numel() * 0.999)).values
+        print(f"{name:52s} max {e.max():.1e}  p99.9 {p999:.1e}  mean {e.mean():.1e}")
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,7 @@ timeout 600 ncu --set full --clock-control none -k regex:conv_tc_kernel\|conv_rs
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fcomb_tc6 -s 1 -c 1 -o gpurun_out/prof_fcomb $B > gpurun_out/ncu_fcomb.log 2>&1; echo "ncu-fcomb rc=$?" >> gpurun_out/rc.txt
 timeout 300 ncu --set full --clock-control none -k regex:gather_\|scatter_\|finalize_\|gauss_head -c 10 -o gpurun_out/prof_gather $B > gpurun_out/ncu_gather.log 2>&1; echo "ncu-gather rc=$?" >> gpurun_out/rc.txt
 if [ "$1" == "train" ]; then
-timeout 600 ncu --set full --clock-control none -k regex:wgrad_tc_kernel -s 4 -c 6 -o gpurun_out/prof_wgrad python scripts/bench_train.py 8 1 --bf16 > gpurun_out/ncu_wgrad.log 2>&1; echo "ncu-wgrad rc=$?" >> gpurun_out/rc.txt
+timeout 600 ncu --set full --clock-control none -k regex:wgrad_tc_kernel -s 4 -c 6 -o gpurun_out/prof_wgrad python tests/tools/bench_train.py 8 1 --bf16 > gpurun_out/ncu_wgrad.log 2>&1; echo "ncu-wgrad rc=$?" >> gpurun_out/rc.txt
 fi
 for r in gpurun_out/prof_*.ncu-rep; do ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null; done
 ls -la gpurun_out/*.ncu-rep gpurun_out/*.raw.csv

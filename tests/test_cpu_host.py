@@ -48,6 +48,14 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+    # the entry points and the helper scripts stay oracle-free too: only tests/ (incl. tests/tools/), smoke() and
+    # bench.py's cpu_baseline / --impl reference legs may touch it
+    others = [os.path.join(root, f) for f in ("eval.py", "predict.py", "pmu_b200/__init__.py")]
+    others += [os.path.join(root, "scripts", f) for f in os.listdir(os.path.join(root, "scripts"))]
+    for f in others:
+        if os.path.isfile(f) and f.endswith((".py", ".sh", ".cu")):
+            src = open(f).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
 
 
 def test_state_dict_schema_matches_reference():

@@ -353,7 +353,7 @@ def test_pipelined_submit_matches_predict(pmu, trainer_sd):
 
 # a single view's N-sample mean carries the bf16 noise of ONE network pass (the fused mean averages three): with the
 # random-init trainer model (logits +-5, sigma up to 6) the worst of ~10^5 pixels of a full-size slice sits at 2.0-2.3e-2
-# (scripts/diag_bf16_error.py: all of it is the 1.1 % rms error of the bf16 U-Net features; p99.9 = 1e-2)
+# (tests/tools/diag_bf16_error.py: all of it is the 1.1 % rms error of the bf16 U-Net features; p99.9 = 1e-2)
 BF16_VIEW_TOL = 3e-2
 
 

@@ -1,9 +1,9 @@
 """Training-step timing (BASELINE config 4 shape, fp32 parity mode): B slices of 256x256 through
 ProbUNetTrainer.predict -> loss -> backward (+ clip + SGD step), CUDA events, plus the per-entry-point
 breakdown and the oracle (torch CPU autograd) on a smaller batch for the same step.
-usage: python scripts/bench_train.py [B] [steps] [--cpu]"""
+usage: python tests/tools/bench_train.py [B] [steps] [--cpu]"""
 import os, sys, time, collections
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import pmu_b200

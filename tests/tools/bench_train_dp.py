@@ -2,7 +2,7 @@
 mode, one process per GPU, gradients SUM-all-reduced over NCCL in buckets (pmu_b200.train_dp).  Launch with
 torchrun.  Prints ms/step (max over ranks, CUDA events) and checks that all ranks hold identical weights after."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import torch.distributed as dist

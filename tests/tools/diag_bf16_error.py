@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pmu_oracle as O  # noqa: E402
 import pmu_b200  # noqa: E402
 from pmu_b200.engine import PackedNet  # noqa: E402

@@ -3,7 +3,7 @@ both measured against fp32 on the same bf16 features: layer 0 as in the kernels 
 exact fp32 per-sample bias), hidden layers with bf16 or f16 operands; "f16 accumulate" rounds the running sum to f16 after
 every K = 16 step and adds the bias in f16 — a worst case for what the tensor core does.
 
-    python scripts/emulate_fcomb_f16.py
+    python tests/tools/emulate_fcomb_f16.py
 
 Result with the trainer-seeded fcomb weights, 20 000 pixels, |z| ~ 3 sigma (max / p99.9 / mean abs error of the softmax):
     bf16 operands, fp32 accumulate (today)               1.1e-02 / 7.7e-03 / 1.1e-03
@@ -15,8 +15,8 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import pmu_oracle as O  # noqa: E402  (a diagnostic script, like bench.py's cpu_baseline leg)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import pmu_oracle as O  # noqa: E402  (tests/ may use the oracle)
 
 
 def r16(t, kind):

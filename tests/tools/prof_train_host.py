@@ -1,6 +1,6 @@
 """Where does the wall time of a bf16 training step go?  Phase timings with synchronisation + torch profiler top ops."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, pmu_b200
 from oracle import pmu_oracle as O
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8

@@ -10,16 +10,24 @@ This is a *restatement* (plain torch-CPU / numpy, fp32) of the reference
 function cites the reference file:line it follows (paths relative to
 ``Probabilistic-Multiplanar-Unet/`` in the reference tree).
 
-Parity pin: the reference has no tests and no golden vectors of its own
-(SURVEY.md §4/§8c), so the pin is manufactured: ``tests/golden/make_golden.py``
-imports the *real* reference modules (``model/``, ``dice_loss.py``) in the build
-container and stores their outputs on seeded inputs under ``tests/golden/``;
-``tests/test_oracle_golden.py`` checks this restatement against those vectors.
-The data-plane half (slicing / normalisation / reassembly, ``utils/mri_dataset.py``
-and ``eval.py``) is not importable in the reference (missing modules, syntax
-error at eval.py:137-138) and is therefore "parity unpinned" by the reference;
-it is pinned only by construction (numpy indexing identities) and by the
-build-defined spec in SURVEY.md Appendix A.
+Parity pin — PINNED against the reference's own code run in the build container.  The reference has no
+tests and no golden vectors of its own, so the vectors are generated from the REAL
+reference and committed under ``tests/golden/`` together with the scripts that made them;
+``tests/test_oracle_golden.py`` checks this restatement against every one of them:
+  * model half — ``make_golden.py`` / ``make_golden_small_extra.py`` / ``make_golden_trainer_api.py`` /
+    ``make_golden_grads.py`` import the real ``model/``, ``dice_loss.py`` and ``trainer/`` modules (two import shims,
+    SURVEY App. C): forward / sample_at / reconstruct / analytic and Monte-Carlo KL / ELBO in eval- and train-mode
+    BatchNorm, the trainer architecture, ``ProbUNetTrainer.predict / eval / loss / mask_to_image``, ``dice_coeff``,
+    and every parameter gradient of ``loss.backward()``;
+  * data-plane half — ``utils/mri_dataset.py`` is executed unmodified with stub ``nibabel`` / ``utils.dataset``
+    modules (its only unmet imports) by ``make_golden_dataplane.py``: index map, ``pad_dimensions``,
+    ``sample_slice``, ``preprocess``, ``__getitem__`` match bit for bit; ``eval.py`` cannot be parsed as a whole
+    (syntax error at :137-138), so its ``dice``, ``slices_to_volume``, reassembly / fusion statements and the
+    per-slice sample loop are exec'd verbatim by line range (``make_golden_dataplane.py``,
+    ``make_golden_sampleloop.py``); the latent-grid loop of ``visualize_sampling.py:21-31`` likewise
+    (``make_golden_latent_grid.py``).
+Build-defined and therefore WITHOUT a reference counterpart (SURVEY.md Appendix A is their spec): N-sample
+averaging of probabilities, per-voxel variance and entropy, nearest / trilinear resampling onto arbitrary grids.
 """
 from __future__ import annotations
 

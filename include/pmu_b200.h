@@ -83,9 +83,11 @@ int pmu_slice_gather(const float* vol, const int32_t dims[3], int plane, int s0,
                      const float* slice_max_in, float* slice_max_out,
                      float* out, void* stream);
 
-/* In-place x/max per slice (same fp64 divide), slices [ns][hw], slice_max [ns]. */
+/* In-place x/max per slice (same fp64 divide), slices [ns][hw], slice_max [ns]:
+ * MRI_Dataset.preprocess, mri_dataset.py:109-110 (x / np.max(x) if the max is not 0). */
 int pmu_slice_normalize(float* slices, const float* slice_max, int ns, int64_t hw, void* stream);
 
+/* p[0..n) = value (the -inf pre-fill of the max buffers above; no reference counterpart). */
 int pmu_fill_f32(float* p, float value, int64_t n, void* stream);
 
 /* ---- fp32 NCHW layer ops (parity mode, CUDA cores) ----------------------- */
@@ -106,8 +108,8 @@ int pmu_conv1x1_f32(const float* x, const float* w, const float* bias, float* y,
 int pmu_convt2x2_f32(const float* x, const float* w, const float* bias, float* y, int B,
                      int Cin, int Cout, int H, int W, int Ho, int Wo, int padT, int padL,
                      void* stream);
-/* 2x2 stride-2 pooling; MAX floors the output size, AVG_CEIL ceils it and divides
- * by the number of in-bounds taps. */
+/* 2x2 stride-2 pooling; MAX floors the output size (nn.MaxPool2d(2), unet_parts.py:33), AVG_CEIL ceils it and
+ * divides by the number of in-bounds taps (nn.AvgPool2d(2, 2, 0, ceil_mode=True), probabilistic_unet.py:36). */
 int pmu_pool2_f32(const float* x, float* y, int B, int C, int H, int W, int mode, void* stream);
 /* AxisAlignedConvGaussian head (probabilistic_unet.py:97-108): mean over H then W of
  * enc[B,C,h,w], 1x1 conv w[2L,C]+b -> mu[B,L], log_sigma[B,L]. */
@@ -132,7 +134,9 @@ int pmu_fcomb_f32(const float* feat, const float* z, const float* w0, const floa
 int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const float* w, const float* bias,
                            void* y, int B, int H, int W, int Cin, int Cout, int relu, void* stream);
 
-/* tcgen05/TMEM implicit-GEMM convolution, TMA-fed (sm_100a only).
+/* tcgen05/TMEM implicit-GEMM convolution, TMA-fed (sm_100a only): every nn.Conv2d 3x3 + BatchNorm2d + ReLU of
+ * DoubleConv / Encoder (unet_parts.py:15-20, probabilistic_unet.py:38-45), the cat of Up.forward (unet_parts.py:65-66)
+ * as a two-source K loop, and nn.ConvTranspose2d k2 s2 (unet_parts.py:52).
  *  ntaps = 9: conv3x3 pad 1 over cat(x0[B,H,W,C0], x1[B,H,W,C1]) (x1 nullable);
  *             wpack bf16 [Cout][9][C0+C1] (tap = ky*3+kx); y bf16 [B,H,W,Cout].
  *  ntaps = 4: ConvTranspose2d k2 s2: x0[B,H,W,C0]; wpack bf16 [4*Cout][C0]
@@ -152,12 +156,13 @@ int pmu_conv_gemm_pool_bf16(const void* x0, int C0, const void* x1, int C1, cons
                             const float* bias, void* y, void* y_pool, int pool_mode, int B, int H,
                             int W, int Cout, int relu, void* stream);
 
+/* 2x2 pooling on bf16 NHWC (unet_parts.py:33 / probabilistic_unet.py:36), for shapes the fused epilogue does not take. */
 int pmu_pool2_bf16(const void* x, void* y, int B, int H, int W, int C, int mode, void* stream);
-/* enc bf16 NHWC [B,h,w,C]; w fp32 [2L,C]; outputs fp32. */
+/* AxisAlignedConvGaussian head on bf16 NHWC (probabilistic_unet.py:97-108): enc [B,h,w,C]; w fp32 [2L,C]; outputs fp32. */
 int pmu_gauss_head_bf16(const void* enc, const float* w, const float* b, float* mu,
                         float* log_sigma, int B, int C, int h, int w_, int L, void* stream);
-/* bf16 NHWC [B,H,W,C] -> fp32 NCHW [B,C,H,W] (hands unet_features back to the
- * reference-facing API in its own layout). */
+/* bf16 NHWC [B,H,W,C] -> fp32 NCHW [B,C,H,W]: hands unet_features back to the reference-facing API in the layout
+ * ProbabilisticUnet.forward leaves it in (probabilistic_unet.py:222). */
 int pmu_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, void* stream);
 
 /* K3+K4 fused: fcomb over N samples with tensor-core MLP, softmax, and per-pixel
@@ -175,7 +180,8 @@ int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, const float*
 /* ---- K4: softmax + scatter-accumulate + finalise (data plane out) -------- *
  * replaces eval.py:157 (softmax), :176-190 (cat/permute), :193 (fusion)      */
 
-/* Unfused variant: logits fp32 [B,N,C,HW] -> slice_sums [B,2,C,HW] (overwritten). */
+/* Unfused variant: softmax over C (eval.py:157) of logits fp32 [B,N,C,HW], summed over the N samples of the loop
+ * eval.py:146-154 -> slice_sums [B,2,C,HW] = (sum p, sum p^2), overwritten. */
 int pmu_softmax_accum(const float* logits, float* slice_sums, int B, int N, int C, int64_t HW,
                       void* stream);
 /* S1/S2 [x][C][y][z] += slice_sums[b][0/1][C][H][W] for slices s0..s0+ns of `plane`:
@@ -214,7 +220,8 @@ int pmu_argmax_dice_sums(const float* prob, const float* truth, int64_t X, int C
 int pmu_bn_train_fwd_f32(const float* y, const float* gamma, const float* beta, float eps, int relu,
                          float momentum, float* run_mean, float* run_var, float* mean, float* var,
                          float* a, double* ws, int B, int C, int64_t HW, void* stream);
-/* backward of the above: da -> dy[B,C,HW], dgamma[C], dbeta[C] (overwritten; nullable). */
+/* backward of the above (what loss.backward(), train.py:95, does for unet_parts.py:16-17): da -> dy[B,C,HW],
+ * dgamma[C], dbeta[C] (overwritten; nullable). */
 int pmu_bn_train_bwd_f32(const float* da, const float* y, const float* mean, const float* var,
                          const float* gamma, const float* beta, float eps, int relu, float* dy,
                          float* dgamma, float* dbeta, double* ws, int B, int C, int64_t HW, void* stream);
@@ -224,16 +231,20 @@ int pmu_bn_train_bwd_bias_f32(const float* da, const float* y, const float* mean
                               const float* gamma, const float* beta, float eps, int relu, float* dy,
                               float* dgamma, float* dbeta, float* dbias, double* ws, int B, int C, int64_t HW,
                               void* stream);
-/* out[c] = sum_{b,p} x[b,c,p] (conv bias gradients); out[r] = sum_p x[r,p]. */
+/* out[c] = sum_{b,p} x[b,c,p] (bias gradients of nn.Conv2d, unet_parts.py:15,18,73; probabilistic_unet.py:137-146);
+ * out[r] = sum_p x[r,p] (per-slice sums for the Fcomb layer-0 split below). */
 int pmu_channel_sums_f32(const float* x, float* out, double* ws, int B, int C, int64_t HW, void* stream);
 int pmu_row_sums_f32(const float* x, float* out, int64_t rows, int64_t n, void* stream);
-/* dw[Cout,C0+C1,3,3] += sum_{b,h,w} dy[b,co,h,w] * cat(x0,x1)[b,ci,h+ky-1,w+kx-1]  (nn.Conv2d weight grad). */
+/* dw[Cout,C0+C1,3,3] += sum_{b,h,w} dy[b,co,h,w] * cat(x0,x1)[b,ci,h+ky-1,w+kx-1]: weight gradient of the 3x3
+ * nn.Conv2d layers (unet_parts.py:15,18; probabilistic_unet.py:38,43). */
 int pmu_conv3x3_wgrad_f32(const float* x0, int C0, const float* x1, int C1, const float* dy, float* dw,
                           int B, int H, int W, int Cout, void* stream);
-/* dw[co*ldw + ci] += sum_{b,p} dy[b,co,p] * x[b,ci,p]  (1x1 conv weight grad; ldw >= Cin). */
+/* dw[co*ldw + ci] += sum_{b,p} dy[b,co,p] * x[b,ci,p]: weight gradient of the 1x1 nn.Conv2d layers (Fcomb,
+ * probabilistic_unet.py:137-146; OutConv, unet_parts.py:73); ldw >= Cin. */
 int pmu_conv1x1_wgrad_f32(const float* x, const float* dy, float* dw, int ldw, int B, int Cin, int Cout,
                           int64_t HW, void* stream);
-/* MaxPool2d(2) / AvgPool2d(2,2,ceil_mode) backward: x[B,C,H,W] (max only), dy pooled -> dx[B,C,H,W]. */
+/* MaxPool2d(2) (unet_parts.py:33) / AvgPool2d(2,2,ceil_mode) (probabilistic_unet.py:36) backward: x[B,C,H,W] (max
+ * only), dy pooled -> dx[B,C,H,W]. */
 int pmu_pool2_bwd_f32(const float* x, const float* dy, float* dx, int B, int C, int H, int W, int mode,
                       void* stream);
 /* nn.ConvTranspose2d(k=2,s=2) backward (unet_parts.py:52): dy[B,Cout,2H,2W], w[Cin,Cout,2,2]. */
@@ -241,7 +252,8 @@ int pmu_convt2x2_dgrad_f32(const float* dy, const float* w, float* dx, int B, in
                            int W, void* stream);
 int pmu_convt2x2_wgrad_f32(const float* x, const float* dy, float* dw, int B, int Cin, int Cout, int H,
                            int W, void* stream);
-/* dx = dy * (a > 0);  dst += src. */
+/* dx = dy * (a > 0) (nn.ReLU backward, probabilistic_unet.py:138,143);  dst += src (gradient fan-in of the skip
+ * connections, unet_model.py:49-52). */
 int pmu_relu_bwd_f32(const float* a, const float* dy, float* dx, int64_t n, void* stream);
 int pmu_add_f32(float* dst, const float* src, int64_t n, void* stream);
 /* d(sum CE)/dlogits * scale = scale * (softmax - onehot(target))   (probabilistic_unet.py:288,303-304). */
@@ -259,12 +271,14 @@ int pmu_fcomb_zbias_f32(const float* z, const float* w0, const float* b0, float*
                         void* stream);
 int pmu_fcomb_zbias_bwd_f32(const float* rs, const float* z, const float* w0, float* dz, float* dw0,
                             float* db0, int B, int F, int L, void* stream);
-/* y[b,co,p] = [relu](sum_ci w[co*ldw+ci] x[b,ci,p] + bias[b*bias_bstride+co])  (bias nullable). */
+/* y[b,co,p] = [relu](sum_ci w[co*ldw+ci] x[b,ci,p] + bias[b*bias_bstride+co])  (bias nullable): the 1x1 layers of
+ * Fcomb (probabilistic_unet.py:137-146) with a per-slice bias — layer 0 after the split above — and their data gradients. */
 int pmu_conv1x1_bb_f32(const float* x, const float* w, int ldw, const float* bias, int bias_bstride, float* y,
                        int B, int Cin, int Cout, int64_t HW, int relu, void* stream);
 
 /* ---- training step, bf16 tensor-core mode ------------------------------------------------- */
-/* fp32 NCHW [B,C,H,W] -> bf16 NHWC [B,H,W,C] (operand cast for the tensor-core convolutions). */
+/* fp32 NCHW [B,C,H,W] -> bf16 NHWC [B,H,W,C]: operand cast for the tensor-core convolutions of the training step
+ * (the reference keeps NCHW fp32 throughout, train.py:85-110). */
 int pmu_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream);
 /* space-to-depth: x bf16 NHWC [B,2H,2W,C] -> y bf16 NHWC [B,H,W,4C], y[b,h,w,(i*2+j)*C+c] = x[b,2h+i,2w+j,c] (C % 8 == 0).
  * With it the data / weight gradients of nn.ConvTranspose2d(k=2, s=2) (unet_parts.py:52) are 1x1 GEMMs:
@@ -273,7 +287,8 @@ int pmu_s2d_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* 
 /* tcgen05 weight gradient of conv3x3 pad 1 (ntaps = 9) / conv1x1 (ntaps = 1):
  * dw fp32 [Cout][ntaps][C0+C1] += sum_{b,h,w} dy[b,h,w,co] * cat(x0,x1)[b,h+ky-1,w+kx-1,ci]   (tap = ky*3+kx)
  * x0 bf16 [B,H,W,C0], x1 (nullable) bf16 [B,H,W,C1], dy bf16 [B,H,W,Cout]; channels multiples of 64.
- * The reduction over pixels is split across CTAs; partials are added with fp32 atomics (zero-fill dw). */
+ * The reduction over pixels is split across CTAs; partials are added with fp32 atomics (zero-fill dw).
+ * Weight gradient of the nn.Conv2d layers of unet_parts.py:15,18 / probabilistic_unet.py:38,43 in loss.backward() (train.py:95). */
 int pmu_conv_wgrad_bf16(const void* x0, int C0, const void* x1, int C1, const void* dy, float* dw, int B,
                         int H, int W, int Cout, int ntaps, void* stream);
 

@@ -307,3 +307,19 @@ def test_ctypes_signatures_match_the_header():
         assert len(plist) == len(args), (name, len(plist), len(args))
         for i, (p, a) in enumerate(zip(plist, args)):
             assert kind_of_c(p) == kind_of_ctypes(a), (name, i, p.strip(), a)
+
+
+def test_every_compute_entry_point_cites_the_reference():
+    """include/pmu_b200.h: the comment in front of every compute prototype names the reference file (file:line) whose
+    arithmetic it replaces; housekeeping entry points (error string, version, device, fill) have no counterpart."""
+    import re
+    from pmu_b200 import _lib
+    src = open(_lib.HEADER_PATH).read()
+    tokens = re.findall(r"/\*.*?\*/|\b(?:const\s+char\s*\*|int)\s+pmu_[a-z0-9_]+\s*\([^)]*\)\s*;", src, flags=re.S)
+    last, missing = "", []
+    for t in tokens:
+        if t.startswith("/*"):
+            last = t
+        elif not re.search(r"[a-z_]+\.py:\d+", last):
+            missing.append(re.search(r"(pmu_[a-z0-9_]+)", t).group(1))
+    assert set(missing) <= {"pmu_last_error", "pmu_version", "pmu_device_info", "pmu_set_device", "pmu_fill_f32"}, missing

@@ -175,6 +175,18 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    if not os.path.exists(os.path.join(ROOT, "probabilistic-multiplanar-unet_b200", "libpmu_b200.so")):
+        # fresh checkout: the CUDA library is a git-ignored build product.  Rank 0 of the node compiles it, the others wait
+        # for the file (no CPU path exists to fall back to: without the library the import below raises).
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__
+            __graft_entry__.build()
+        else:
+            pkg, t_end = os.path.join(ROOT, "probabilistic-multiplanar-unet_b200"), time.time() + 900
+            while time.time() < t_end and not (os.path.exists(os.path.join(pkg, "libpmu_b200.so"))
+                                               and os.path.exists(os.path.join(pkg, "build", "stamp.txt"))):
+                time.sleep(2)
+            time.sleep(1)             # the stamp is written after the link step
     import pmu_b200
     from pmu_b200 import ops
     from pmu_b200.synthetic import phantom_volume, trainer_state_dict

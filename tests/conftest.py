@@ -12,6 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The CUDA library is a build product (git-ignored).  A fresh checkout has none: compile it once (nvcc cross-compiles
+    for sm_100a without a GPU) instead of failing every test on a missing file.  The product itself never builds or
+    falls back on its own — pmu_b200._lib.load() raises when the library is absent."""
+    lib = os.path.join(ROOT, "probabilistic-multiplanar-unet_b200", "libpmu_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")

@@ -323,3 +323,15 @@ def test_every_compute_entry_point_cites_the_reference():
         elif not re.search(r"[a-z_]+\.py:\d+", last):
             missing.append(re.search(r"(pmu_[a-z0-9_]+)", t).group(1))
     assert set(missing) <= {"pmu_last_error", "pmu_version", "pmu_device_info", "pmu_set_device", "pmu_fill_f32"}, missing
+
+
+def test_missing_library_raises_loudly(monkeypatch, tmp_path):
+    """The product never builds or falls back on its own: with no libpmu_b200.so, loading — and therefore every op —
+    raises a RuntimeError that says how to build it."""
+    from pmu_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libpmu_b200.so"))
+    with pytest.raises(RuntimeError, match="not built|not found"):
+        _lib.load()
+    with pytest.raises(RuntimeError):
+        _lib.check(-1, "anything")          # even error reporting needs the library

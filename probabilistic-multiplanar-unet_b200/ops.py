@@ -286,6 +286,14 @@ def fcomb_softmax_accum_bf16(feat, mu, sigma, eps, fw, out=None):
     if out is None:
         out = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=feat.device)
     lib, st = _prep(feat, mu, sigma, eps, out)
+    global _META
+    nmid = nl - 2
+    # algorithmic work: shared layer-0 GEMM once per pixel, hidden layers + head per sample; and the
+    # accumulator read-back that bounds the kernel: G once, one 64-column fp32 tile per hidden layer
+    # and the 8 head columns per sample
+    _META = {"flops": 2.0 * B * H * W * (64 * 64 + N * (nmid * 64 * 64 + 64 * C)),
+             "bytes": 2.0 * B * H * W * 64 + 4.0 * out.numel(),
+             "tmem_read_bytes": 4.0 * B * H * W * (64 + N * (nmid * 64 + 8))}
     _launch(lib, "pmu_fcomb_softmax_accum_bf16", (_p(feat), _p(mu), _p(sigma), _p(eps), _p(fw["w0"]), _p(fw["b0"]),
                                                 _p(fw["wmid"]), _p(fw["bmid"]), _p(fw["wlast"]), _p(fw["blast"]),
                                                 _p(out), B, N, L, C, nl, H * W, st,))

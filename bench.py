@@ -436,6 +436,11 @@ def run_ours(args):
             gb = P * V * 2 * 3 * 4.0 * 3.0 * world_frac / 1e9  # read sums + RMW (read+write) accumulators, 2*C floats/voxel
             hbm_kernels["scatter_accum"] = {"achieved": gb / (tot["pmu_scatter_accum"]["ms"] * 1e-3), "unit": "GB/s",
                                             "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
+        if "pmu_conv3x3_first_bf16" in tot:
+            # the two 1 -> 64 first layers (U-Net and prior): 4 B in + 128 B (64 bf16 channels) out per pixel, output-bound
+            gb = 2.0 * P * V * (4.0 + 128.0) * world_frac / 1e9
+            hbm_kernels["first_conv"] = {"achieved": gb / (tot["pmu_conv3x3_first_bf16"]["ms"] * 1e-3), "unit": "GB/s",
+                                         "peak": peaks["hbm_gbs"], "algorithmic_gb": gb}
         if "pmu_fuse_finalize" in tot:
             gb = V * 52.0 * (world_frac if slab_res else 1.0) / 1e9      # rank 0's x-slab with slab-sharded outputs
             hbm_kernels["fuse_finalize"] = {"achieved": gb / (tot["pmu_fuse_finalize"]["ms"] * 1e-3), "unit": "GB/s",

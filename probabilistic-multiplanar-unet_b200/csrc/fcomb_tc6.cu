@@ -570,6 +570,11 @@ extern "C" int pmu_fcomb_softmax_accum_bf16_ts(const void* feat, const float* mu
                                                const float* w0, const float* b0, const float* wmid, const float* bmid,
                                                const float* wlast, const float* blast, float* slice_sums, int B, int N,
                                                int L, int C, int nl, int64_t HW, void* stream);
+// implemented in fcomb_ts2.cu (TS form, two independent slot groups)
+extern "C" int pmu_fcomb_softmax_accum_bf16_ts2(const void* feat, const float* mu, const float* sigma, const float* eps,
+                                                const float* w0, const float* b0, const float* wmid, const float* bmid,
+                                                const float* wlast, const float* blast, float* slice_sums, int B, int N,
+                                                int L, int C, int nl, int64_t HW, void* stream);
 // implemented in fcomb_tc.cu (register-chained mma.sync version, kept as the nmid > 2 path)
 extern "C" int pmu_fcomb_softmax_accum_bf16_mma(const void* feat, const float* mu, const float* sigma,
                                                 const float* eps, const float* w0, const float* b0,
@@ -603,6 +608,9 @@ extern "C" int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, c
   //  68 KB per tile-sample — and time the same, 25.5 ms per volume; the SS version is the default).  PMU_FCOMB_TS=2 is
   //  the TS form with f16 hidden layers and packed 16-bit accumulator read-back: an unmeasured experiment, see fcomb_ts.cu)
   const char* ts_env = getenv("PMU_FCOMB_TS");
+  if (ts_env && atoi(ts_env) == 3)
+    return pmu_fcomb_softmax_accum_bf16_ts2(feat, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums, B, N, L, C,
+                                            nl, HW, stream);
   if (ts_env && atoi(ts_env))
     return pmu_fcomb_softmax_accum_bf16_ts(feat, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums, B, N, L, C,
                                            nl, HW, stream);

@@ -1,0 +1,446 @@
+// K3 + K4 fused — the fcomb MLP over N latent samples with its hidden activations RESIDENT IN TENSOR
+// MEMORY (TS-form UMMAs: A operand from TMEM, B = weights from shared memory), softmax, per-pixel
+// sum / sum-of-squares.  Per-sample logits never reach HBM.
+//
+// Replaces Fcomb.forward (probabilistic_unet.py:155-181) called once per sample from
+// ProbabilisticUnet.sample (:225-240), the softmax of eval.py:157 and the sample loop of
+// eval.py:146-154.
+//
+// What the round-2 measurements said about the two earlier tcgen05 versions (both ~1130 cycles per 128-pixel
+// tile-sample, tensor pipe ~32 % busy):
+//   * the TMEM read port is NOT the limit: scripts/tmem_ld_bench.cu measures 205 / 365-413 / 470-480 B/clk/SM with
+//     4 / 8 / 16 warps (register bytes; .pack::16b loads deliver the same register bytes), against the ~62 B/clk the
+//     kernels used (profiles/r02_experiments.txt);
+//   * the SS form (activations through shared memory) is bound by the shared-memory pipe: per tile-sample 10 N = 64
+//     UMMAs x 6 KB of operand reads + 5 head UMMAs x 4.25 KB + 48 KB of activation stores = 129 KB = 1008 cycles of
+//     the 128 B/clk pipe;
+//   * the first TS form kept all 16 epilogue warps in lock-step on ONE slot at a time (16 columns per thread), so the
+//     per-slot chain  barrier wake-up -> tcgen05.ld -> wait -> pack -> tcgen05.st -> wait -> arrive  (~300 cycles)
+//     was paid 4 slots x 3 layers = 12 times per round of four samples, one after the other.
+// This version: the 16 epilogue warps form two groups of 8 (TMEM lane quarter x column half: 32 accumulator columns
+// per thread); a group owns two of the four sample slots and walks them alternately, so while one slot's epilogue
+// runs the other slot's UMMAs execute, and the two groups run independently of each other.  Per slot and layer the
+// critical path is  commit -> wake-up -> ld.x32 -> 16 cvt -> st.x16 -> arrive -> issue, four such chains in flight.
+//   * layer 0 leaves the per-sample chain: h0_n = relu(W0f f + zb_n), zb_n = W0z z_n + b0.  G = W0f f is ONE SS-form
+//     UMMA group per tile into its own TMEM region (so the next tile's G is computed while the current tile's
+//     samples run), read once into registers; per sample layer 0 is 16 add.f32x2 + 16 cvt.rn.relu.bf16x2 per thread;
+//   * the constant biases ride in the GEMM: every layer's K is extended by one K = 16 step whose A columns are
+//     constant ones (8 TMEM columns per slot) and whose B tile holds the bias split into bf16 hi + lo;
+//   * TMEM: 4 slots x (X 64 fp32 columns + Y 40 columns = 64 bf16 activations + the ones extension) + G 64 = 480;
+//   * the head's softmax of a slot is done by the column half that matches the slot's parity (one thread per pixel),
+//     the four partial (sum, sum^2) sets of a pixel are combined through shared memory at the end of the tile.
+#include <cudaTypedefs.h>
+
+#include "pmu_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace pmu {
+
+using namespace ptx;
+
+constexpr int F2_F = 64;
+constexpr int F2_SLOTS = 4;
+constexpr int F2_EPI = 512;                       // 16 epilogue warps
+constexpr int F2_THREADS = F2_EPI + 32;           // + issuer warp
+constexpr int F2_NS = 16;                         // samples per group of zb vectors
+constexpr int F2_SLOT_COLS = 104;                 // X 64 + Y 40
+constexpr int F2_G_COL = F2_SLOTS * F2_SLOT_COLS; // 416: G = W0f f of the current / next tile
+constexpr int F2_MAXL = 16;
+constexpr int F2_MAXC = 8;
+constexpr int F2_TILE = 128 * 128;
+constexpr int F2_WT = 64 * 128;
+constexpr int F2_OFF_W0 = 0;
+constexpr int F2_OFF_WM = F2_OFF_W0 + F2_WT;       // 2 mid layers
+constexpr int F2_OFF_WL = F2_OFF_WM + 2 * F2_WT;   // head [16][64]
+constexpr int F2_OFF_BMT = F2_OFF_WL + 2048;       // bias tiles (k0 = hi, k1 = lo)
+constexpr int F2_OFF_BLT = F2_OFF_BMT + 2 * F2_WT;
+constexpr int F2_OFF_F = F2_OFF_BLT + 2048;        // feature tile, double buffered
+constexpr int F2_OFF_ZB = F2_OFF_F + 2 * F2_TILE;  // fp32 zb[F2_NS][64]
+constexpr int F2_SCR_BYTES = 4 * 16 * 128 * 4;     // softmax partials [4 (group, half)][16][128]
+constexpr int F2_OFF_SCR = F2_OFF_ZB + F2_NS * F2_F * 4;       // x 2 (alternating tiles)
+constexpr int F2_OFF_BAR = F2_OFF_SCR + 2 * F2_SCR_BYTES;
+constexpr int F2_NBAR = 2 * F2_SLOTS + 4;          // ready[slot], acc[slot], tma[2], g_full, g_free
+constexpr int F2_OFF_TPTR = F2_OFF_BAR + F2_NBAR * 8;
+constexpr int F2_SMEM = F2_OFF_TPTR + 16;
+static_assert(F2_OFF_F % 1024 == 0 && F2_OFF_BMT % 1024 == 0 && F2_OFF_BLT % 1024 == 0, "operand tiles must be 1024 B aligned");
+static_assert(F2_G_COL + 64 <= 512, "TMEM budget");
+static_assert(F2_SMEM <= 227 * 1024, "shared memory budget");
+
+struct Fcomb2Params {
+  int N, L, C, nmid, B;
+  int64_t HW;
+};
+
+__device__ __forceinline__ void f2_st_bf16(uint8_t* tile, int row, int k, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(tile + (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2)) = __float2bfloat16(v);
+}
+__device__ __forceinline__ uint32_t f2_pack_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// relu(a + b) of two fp32 pairs -> packed bf16x2: one packed add (add.f32x2) + one cvt
+__device__ __forceinline__ uint32_t f2_add_pack_relu(float a0, float a1, float b0, float b1) {
+  uint32_t d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
+      "mov.b64 ra, {%1, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {lo, hi}, rd;\n\t"
+      "cvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}"
+      : "=r"(d) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+  return d;
+}
+__device__ __forceinline__ float4 f2_lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void f2_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void f2_tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void f2_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void f2_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]   (TS form: the A operand is read from tensor memory)
+__device__ __forceinline__ void f2_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one layer on tensor memory: X = Y[128 x 80] * [W | bias]^T   (4 + 1 TS UMMAs; Y columns 32..39 hold the ones)
+__device__ __forceinline__ void f2_issue_layer(uint32_t tX, uint32_t tY, uint32_t w_tile, uint32_t b_tile, uint32_t idesc) {
+  const uint64_t wd = umma_smem_desc_sw128(w_tile);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) f2_umma_ts(tX, tY + 8 * k, wd + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+  f2_umma_ts(tX, tY + 32, umma_smem_desc_sw128(b_tile), idesc, 1u);
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(F2_THREADS, 1)
+fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, const float* __restrict__ mu,
+                 const float* __restrict__ sigma, const float* __restrict__ eps, const float* __restrict__ w0,
+                 const float* __restrict__ b0, const float* __restrict__ wmid, const float* __restrict__ bmid,
+                 const float* __restrict__ wlast, const float* __restrict__ blast, float* __restrict__ slice_sums) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  uint8_t* sgen = smem_raw;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, L = p.L, C = p.C, nmid = p.nmid;
+  const int64_t HW = p.HW;
+  if ((sbase & 1023u) != 0) __trap();
+
+  auto bar_ready = [&](int s) { return sbase + F2_OFF_BAR + s * 8; };
+  auto bar_acc = [&](int s) { return sbase + F2_OFF_BAR + (F2_SLOTS + s) * 8; };
+  auto bar_tma = [&](int i) { return sbase + F2_OFF_BAR + (2 * F2_SLOTS + i) * 8; };
+  const uint32_t bar_g = sbase + F2_OFF_BAR + (2 * F2_SLOTS + 2) * 8;
+  const uint32_t bar_gfree = sbase + F2_OFF_BAR + (2 * F2_SLOTS + 3) * 8;
+  volatile uint32_t* tptr = reinterpret_cast<volatile uint32_t*>(sgen + F2_OFF_TPTR);
+
+  if (tid == 0) {
+    prefetch_tensormap(&tmF);
+    for (int s = 0; s < F2_SLOTS; ++s) { mbar_init(bar_ready(s), 8); mbar_init(bar_acc(s), 1); }   // 8 warps own a slot
+    mbar_init(bar_tma(0), 1); mbar_init(bar_tma(1), 1);
+    mbar_init(bar_g, 1);
+    mbar_init(bar_gfree, F2_EPI / 32);
+    fence_barrier_init();
+  }
+  if (warp == 16) tmem_alloc<512>(sbase + F2_OFF_TPTR);
+  for (int i = tid; i < F2_OFF_F / 16; i += F2_THREADS) reinterpret_cast<uint4*>(sgen)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = tid; i < F2_F * F2_F; i += F2_THREADS) {
+    const int o = i >> 6, k = i & 63;
+    f2_st_bf16(sgen + F2_OFF_W0, o, k, __ldg(w0 + (int64_t)o * (F2_F + L) + k));
+    for (int m = 0; m < nmid; ++m) f2_st_bf16(sgen + F2_OFF_WM + m * F2_WT, o, k, __ldg(wmid + (int64_t)m * F2_F * F2_F + i));
+  }
+  for (int i = tid; i < C * F2_F; i += F2_THREADS) f2_st_bf16(sgen + F2_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
+  for (int i = tid; i < nmid * F2_F; i += F2_THREADS) {
+    const float bv = __ldg(bmid + i);
+    const float bh = __bfloat162float(__float2bfloat16(bv));
+    f2_st_bf16(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 0, bh);
+    f2_st_bf16(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 1, bv - bh);
+  }
+  for (int i = tid; i < C; i += F2_THREADS) {
+    const float bv = __ldg(blast + i);
+    const float bh = __bfloat162float(__float2bfloat16(bv));
+    f2_st_bf16(sgen + F2_OFF_BLT, i, 0, bh);
+    f2_st_bf16(sgen + F2_OFF_BLT, i, 1, bv - bh);
+  }
+  float* zb_s = reinterpret_cast<float*>(sgen + F2_OFF_ZB);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tptr;
+
+  // epilogue thread coordinates: TMEM lane quarter, column half, slot group
+  const int q4 = warp & 3, half = (warp >> 2) & 1, grp = (warp >> 3) & 1;
+  const int row = q4 * 32 + lane;
+  const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+  if (warp < 16 && half == 0) {
+    // the constant K extension of this group's two slots: k = 64, 65 -> 1.0 (bf16 pair), k = 66..79 -> 0
+    const uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) f2_tmem_st8(tmem_base + lane_off + (2 * grp + j) * F2_SLOT_COLS + 64 + 32, ones);
+    f2_tmem_st_wait();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+
+  const int tiles = (int)((HW + 127) / 128);
+  const int64_t total = (int64_t)p.B * tiles;
+  const int cta_lo = (int)(total * blockIdx.x / gridDim.x), cta_hi = (int)(total * (blockIdx.x + 1) / gridDim.x);
+
+  uint32_t phr = 0, pha = 0, phg = 0, phf = 0, pht = 0;     // barrier phase parities (bit = slot / buffer)
+  uint32_t tile_ctr = 0;                                    // scratch buffer selector (epilogue warps)
+
+  for (int seg0 = cta_lo; seg0 < cta_hi;) {
+    const int b = seg0 / tiles;
+    const int seg1 = ((b + 1) * tiles < cta_hi) ? (b + 1) * tiles : cta_hi;
+    const int t0 = seg0 - b * tiles, t1 = seg1 - b * tiles;
+    for (int n0 = 0; n0 < N; n0 += F2_NS) {
+      const int ng = (N - n0 < F2_NS) ? N - n0 : F2_NS;
+      // ---- per-sample layer-0 bias vectors zb_n = W0z z_n + b0 of this slice / sample group (fp32) ----
+      __syncthreads();
+      for (int i = tid; i < ng * F2_F; i += F2_THREADS) {
+        const int n = i >> 6, o = i & 63;
+        float s = __ldg(b0 + o);
+        for (int l = 0; l < L; ++l) {
+          // z = mu + sigma * eps   (Normal.rsample, probabilistic_unet.py:233)
+          const float z = __fadd_rn(__ldg(mu + (int64_t)b * L + l),
+                                    __fmul_rn(__ldg(sigma + (int64_t)b * L + l), __ldg(eps + ((int64_t)b * N + n0 + n) * L + l)));
+          s = fmaf(__ldg(w0 + (int64_t)o * (F2_F + L) + F2_F + l), z, s);
+        }
+        zb_s[i] = s;
+      }
+      __syncthreads();
+      const int rounds = (ng + F2_SLOTS - 1) / F2_SLOTS;
+
+      if (warp == 16) {
+        // ============ issuer (one elected thread: TMA loads of the feature tiles + every UMMA) ============
+        if (elect_one()) {
+          constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
+          constexpr uint32_t idesc16 = umma_idesc_bf16(128, 16);
+          const uint32_t sW0 = sbase + F2_OFF_W0, sWM = sbase + F2_OFF_WM, sWL = sbase + F2_OFF_WL;
+          const uint32_t sBM = sbase + F2_OFF_BMT, sBL = sbase + F2_OFF_BLT;
+          auto load_f = [&](int t, uint32_t buf) {
+            mbar_arrive_expect_tx(bar_tma(buf), F2_TILE);
+            tma_load_2d(sbase + F2_OFF_F + buf * F2_TILE, &tmF, bar_tma(buf), 0, (int)((int64_t)b * HW + (int64_t)t * 128));
+          };
+          auto issue_g = [&](uint32_t buf) {   // G = F W0f^T -> the G columns (SS form)
+            mbar_wait(bar_tma(buf), (pht >> buf) & 1u); pht ^= 1u << buf;
+            tcgen05_fence_after();
+            const uint64_t ad = umma_smem_desc_sw128(sbase + F2_OFF_F + buf * F2_TILE), wd = umma_smem_desc_sw128(sW0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + F2_G_COL, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc64, (uint32_t)(k != 0));
+            umma_commit(bar_g);
+          };
+          load_f(t0, 0);
+          if (t0 + 1 < t1) load_f(t0 + 1, 1);
+          issue_g(0);                                        // (the previous block's G was consumed before the __syncthreads)
+          for (int t = t0; t < t1; ++t) {
+            const uint32_t buf = (uint32_t)(t - t0) & 1u;
+            for (int r = 0; r < rounds; ++r) {
+              for (int layer = 1; layer <= nmid + 1; ++layer) {
+#pragma unroll
+                for (int s = 0; s < F2_SLOTS; ++s) {
+                  if (r * F2_SLOTS + s >= ng) continue;
+                  const uint32_t tX = tmem_base + s * F2_SLOT_COLS, tY = tX + 64;
+                  mbar_wait(bar_ready(s), (phr >> s) & 1u); phr ^= 1u << s;
+                  tcgen05_fence_after();
+                  if (layer <= nmid) f2_issue_layer(tX, tY, sWM + (layer - 1) * F2_WT, sBM + (layer - 1) * F2_WT, idesc64);
+                  else f2_issue_layer(tX, tY, sWL, sBL, idesc16);
+                  umma_commit(bar_acc(s));
+                }
+                if (r == 0 && layer == 1) {
+                  // every epilogue warp holds this tile's G in registers (its first arrivals came after that read):
+                  // compute the next tile's G now and refill the feature buffer this tile used
+                  mbar_wait(bar_gfree, phf); phf ^= 1u;
+                  tcgen05_fence_after();
+                  if (t + 1 < t1) {
+                    issue_g(buf ^ 1u);
+                    if (t + 2 < t1) load_f(t + 2, buf);
+                  }
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      } else {
+        // ============ epilogue warps: (lane quarter q4, column half, slot group grp) ============
+        const uint32_t tbase = tmem_base + lane_off;
+        const uint32_t sZB = sbase + F2_OFF_ZB + half * 32 * 4;
+        for (int t = t0; t < t1; ++t, ++tile_ctr) {
+          const int64_t pix = (int64_t)t * 128 + row;
+          float s1[CMAX], s2[CMAX];
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c) s1[c] = s2[c] = 0.f;
+          uint32_t G[32];
+          mbar_wait(bar_g, phg); phg ^= 1u;
+          tcgen05_fence_after();
+          tmem_ld_32x32(tbase + F2_G_COL + half * 32, G);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_gfree);
+
+          auto softmax_acc = [&](const uint32_t (&hr)[8]) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (c < C) mx = fmaxf(mx, __uint_as_float(hr[c]));
+            float e[CMAX], den = 0.f;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) { e[c] = (c < C) ? __expf(__uint_as_float(hr[c]) - mx) : 0.f; den += e[c]; }
+            const float inv = __fdividef(1.f, den);
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) { const float pr_ = e[c] * inv; s1[c] += pr_; s2[c] = fmaf(pr_, pr_, s2[c]); }
+          };
+
+          bool pend0 = false, pend1 = false;                 // slot j of the group has a head (logits) outstanding
+          for (int r = 0; r <= rounds; ++r) {
+            // ---- slot by slot: consume the previous round's logits, then layer 0 of this round's sample ----
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int sl = 2 * grp + j;
+              const int n = r * F2_SLOTS + sl;
+              const bool pend = j ? pend1 : pend0;
+              const bool live = (r < rounds) && (n < ng);
+              uint32_t hr[8];
+              const bool mine = pend && (half == j);
+              if (pend) {
+                mbar_wait(bar_acc(sl), (pha >> sl) & 1u); pha ^= 1u << sl;     // head UMMAs done: logits in X, Y free
+                tcgen05_fence_after();
+                if (mine) { f2_tmem_ld8(tbase + sl * F2_SLOT_COLS, hr); tmem_ld_wait(); }
+              }
+              if (live) {
+                // h0 = relu(G + zb_n) -> Y (bf16 pairs, 16 columns per thread)
+                const uint32_t zb = sZB + n * F2_F * 4;
+                uint32_t pk[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 z = f2_lds128f(zb + c * 16);
+                  pk[2 * c] = f2_add_pack_relu(__uint_as_float(G[4 * c]), __uint_as_float(G[4 * c + 1]), z.x, z.y);
+                  pk[2 * c + 1] = f2_add_pack_relu(__uint_as_float(G[4 * c + 2]), __uint_as_float(G[4 * c + 3]), z.z, z.w);
+                }
+                f2_tmem_st16(tbase + sl * F2_SLOT_COLS + 64 + half * 16, pk);
+                f2_tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready(sl));
+              }
+              if (mine) softmax_acc(hr);
+              if (j) pend1 = live; else pend0 = live;
+            }
+            if (r == rounds) break;
+            // ---- mid layers: X -> relu -> bf16 -> Y ----
+            for (int layer = 1; layer <= nmid; ++layer) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int sl = 2 * grp + j;
+                if (r * F2_SLOTS + sl >= ng) continue;
+                mbar_wait(bar_acc(sl), (pha >> sl) & 1u); pha ^= 1u << sl;
+                tcgen05_fence_after();
+                uint32_t rr[32], pk[16];
+                tmem_ld_32x32(tbase + sl * F2_SLOT_COLS + half * 32, rr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) pk[c] = f2_pack_relu(__uint_as_float(rr[2 * c]), __uint_as_float(rr[2 * c + 1]));
+                f2_tmem_st16(tbase + sl * F2_SLOT_COLS + 64 + half * 16, pk);
+                f2_tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready(sl));
+              }
+            }
+          }
+          // ---- tile done: combine the four partial sums of a pixel ----
+          float* scr = reinterpret_cast<float*>(sgen + F2_OFF_SCR + (tile_ctr & 1u) * F2_SCR_BYTES);
+          const int part = grp * 2 + half;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c) { scr[(part * 16 + 2 * c) * 128 + row] = s1[c]; scr[(part * 16 + 2 * c + 1) * 128 + row] = s2[c]; }
+          named_bar_sync(1, F2_EPI);
+          if (part == 0 && pix < HW) {
+            float* o1 = slice_sums + ((int64_t)b * 2 + 0) * C * HW + pix;
+            float* o2 = slice_sums + ((int64_t)b * 2 + 1) * C * HW + pix;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+              if (c < C) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) { a1 += scr[(qq * 16 + 2 * c) * 128 + row]; a2 += scr[(qq * 16 + 2 * c + 1) * 128 + row]; }
+                if (n0 == 0) { o1[(int64_t)c * HW] = a1; o2[(int64_t)c * HW] = a2; }
+                else { o1[(int64_t)c * HW] += a1; o2[(int64_t)c * HW] += a2; }
+              }
+          }
+        }
+      }
+    }
+    seg0 = seg1;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc<512>(tmem_base);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 f2_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace pmu
+
+using namespace pmu;
+
+// called by pmu_fcomb_softmax_accum_bf16 (fcomb_tc6.cu) after argument checks
+extern "C" int pmu_fcomb_softmax_accum_bf16_ts2(const void* feat, const float* mu, const float* sigma, const float* eps,
+                                                const float* w0, const float* b0, const float* wmid, const float* bmid,
+                                                const float* wlast, const float* blast, float* slice_sums, int B, int N,
+                                                int L, int C, int nl, int64_t HW, void* stream) {
+  auto fn = f2_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
+  CUtensorMap tmF;
+  cuuint64_t dims[2] = {(cuuint64_t)F2_F, (cuuint64_t)((int64_t)B * HW)};
+  cuuint64_t strides[1] = {(cuuint64_t)F2_F * 2};
+  cuuint32_t box[2] = {(cuuint32_t)F2_F, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&tmF, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(feat), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(features) failed: %d", (int)r); return PMU_ERR_CUDA; }
+  Fcomb2Params p;
+  p.N = N; p.L = L; p.C = C; p.nmid = nl - 2; p.HW = HW; p.B = B;
+  const int64_t tiles = (HW + 127) / 128;
+  const int64_t total = (int64_t)B * tiles;
+  const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
+  auto launch = [&](auto kern) -> int {
+    PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    kern<<<grid, F2_THREADS, F2_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums);
+    PMU_LAUNCH_CHECK();
+    return PMU_OK;
+  };
+  if (C <= 4) return launch(fcomb_ts2_kernel<4>);
+  return launch(fcomb_ts2_kernel<8>);
+}

@@ -260,7 +260,7 @@ def test_pool_head_transpose_bf16(ops):
                                           (4, 20, 3, 3, 20, 24), (5, 3, 3, 3, 20, 24),
                                           (4, 6, 3, 5, 96, 100),     # 190 tile pairs > 148 SMs: CTAs walk several
                                           (3, 18, 4, 7, 72, 72)])    # pairs and cross slice boundaries; 2 sample groups
-@pytest.mark.parametrize("ts_mode", [pytest.param("0", id="ss"), pytest.param("1", id="ts"),
+@pytest.mark.parametrize("ts_mode", [pytest.param("0", id="ss"), pytest.param("1", id="ts"), pytest.param("3", id="ts2"),
                                      pytest.param("2", marks=EXPERIMENTAL, id="tshalf"),
                                      pytest.param("0+f16", marks=EXPERIMENTAL, id="sshalf")])
 def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W, ts_mode, monkeypatch):

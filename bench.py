@@ -45,6 +45,12 @@ def workload(D, N, interp):
             f"[64,128,256,512,1024] C=3 L=6 fcomb=4, mean/var/entropy fusion")
 
 
+def config_dict(D, N, interp):
+    """config — the SAME dict on both arms (what differs between the arms lives in `run`, `cpu_baseline`, `e2e`)."""
+    return {"workload": workload(D, N, interp),
+            "l2": "per-step working set (GBs of activations; the CPU arm: every slice's activations) >> 126 MB L2; no explicit flush"}
+
+
 def load_traffic():
     """DRAM bytes per launch of our kernels from the last committed `ncu --set full` capture
     (profiles/*_traffic.json, written by scripts/summarize_ncu.py)."""
@@ -118,7 +124,8 @@ def cpu_reference_rate(D, N, slices_per_plane, threads=None):
     sd = O.make_state_dict(seed=0)
     vol, _ = O.phantom(D, seed=1234)
     eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
-    idx = [int(round(i)) for i in np.linspace(0, D - 1, slices_per_plane)]
+    # equally spaced slices, centred in their strata (never only index 0, which is background in the phantom)
+    idx = [min(D - 1, int((i + 0.5) * D / slices_per_plane)) for i in range(slices_per_plane)]
     C = 3
     with torch.no_grad():
         x = torch.from_numpy(O.plane_slices(vol, 0, idx[0], 1))
@@ -143,12 +150,36 @@ def cpu_reference_rate(D, N, slices_per_plane, threads=None):
     return (n_done / dt) / (3.0 * D), dt, cores, n_done
 
 
+def cpu_variant_a_rate(D, N, threads=None):
+    """For information (SURVEY.md §8d "variant A"): the literal sample loop of eval.py:148-152 — N FULL predict() calls
+    (U-Net + prior + fcomb) per slice — on the middle slice of each plane; returns (volumes/s extrapolated, seconds)."""
+    import torch
+    from oracle import pmu_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    sd = O.make_state_dict(seed=0)
+    vol, _ = O.phantom(D, seed=1234)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for p in range(3):
+            s = D // 2
+            x = torch.from_numpy(O.plane_slices(vol, p, s, 1))
+            acc = 0
+            for n in range(N):
+                feat = O.unet_features(sd, x)
+                mu, ls = O.gaussian_head(sd, "prior", x)
+                acc = acc + torch.softmax(O.fcomb(sd, feat, mu + torch.exp(ls) * eps[p, s:s + 1, n]), 1)
+        dt = time.perf_counter() - t0
+    return (3 / dt) / (3.0 * D), dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     D, N = args.size, args.samples
-    spp = 1            # one slice per plane per step keeps K+W steps within minutes on few cores
+    spp = args.ref_slices_per_plane     # 8 equally spaced slices per plane per step (SURVEY.md §8d), ~5 s per step on 16 threads
     rates = []
     for i in range(args.warmup + args.steps):
         # all host threads, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
@@ -157,15 +188,19 @@ def run_reference(args):
             rates.append((v, dt))
     tot_t = sum(dt for _, dt in rates)
     value = (len(rates) * 3 * spp / tot_t) / (3.0 * D)
+    va, va_dt = cpu_variant_a_rate(D, N, threads=os.cpu_count())
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(len(rates), 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": workload(D, N, args.interp),
-                       "sampling": f"each step = {3 * spp} slices (one per plane) through the oracle port of the reference "
-                                   f"CPU path (fp32, batch 1 like eval.py:105), extrapolated to {3 * D} slices; on the "
-                                   f"standard plane grids {args.interp} resampling is exact slicing, which the port does"},
+            "config": config_dict(D, N, args.interp),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{3 * spp} of {3 * D} slices per step, forward once + {N} x fcomb + softmax + accumulate"},
+                             "sample": f"each step = {3 * spp} of {3 * D} slices ({spp} equally spaced per plane) through the oracle "
+                                       f"port of the reference CPU path (fp32, batch 1 like eval.py:105): forward once + {N} x fcomb "
+                                       f"+ softmax + accumulate (variant B), extrapolated to {3 * D} slices; on the standard plane "
+                                       f"grids {args.interp} resampling is exact slicing, which the port does",
+                             "variant_a": {"value": va, "unit": UNIT, "seconds": va_dt,
+                                           "what": f"for information: literal eval.py:148-152, {N} full predict() calls per slice, "
+                                                   f"middle slice of each plane, extrapolated"}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -377,36 +412,54 @@ def run_ours(args):
                     "frac": None, "traffic": None, "launches": c["n"], "avg_launch_ms": c["ms"] / c["n"]}
         fc = tot.get("pmu_fcomb_softmax_accum_bf16")
         if fc and fc["ms"] > 0 and roof is not None:
-            # the second kernel of the step: bound by the read-back of its fp32 accumulators from tensor memory
-            # (DESIGN.md §4b), 64 B / clk / SM in the microarchitecture notes, at the SM clock sampled under load
+            # the second kernel of the step, against the tensor pipe (its bound once the activations stay in tensor
+            # memory); tmem_read_gbs next to the MEASURED TMEM read port (scripts/tmem_ld_bench.cu, 16 warps:
+            # ~475 B/clk/SM of register bytes, profiles/r02_experiments.txt) shows that port is not the limit
             mhz = (clocks or {}).get("sm_mhz") or 1965
-            tmem_peak = 148 * 64.0 * mhz * 1e6 / 1e9
-            roof["second_kernel"] = {"kernel": "fcomb_tc6_kernel (tcgen05 N-sample fcomb + softmax + sum / sum^2)",
-                                     "ms_per_step": fc["ms"], "launches": fc["n"],
-                                     "tensor_tflops": fc["flops"] / (fc["ms"] * 1e-3) / 1e12,
-                                     "tensor_frac": fc["flops"] / (fc["ms"] * 1e-3) / 1e12 / peaks["bf16_sustained"],
-                                     "bound": "tmem-read", "achieved": fc["tmem"] / (fc["ms"] * 1e-3) / 1e9, "unit": "GB/s",
-                                     "peak": tmem_peak, "frac": fc["tmem"] / (fc["ms"] * 1e-3) / 1e9 / tmem_peak,
-                                     "peak_source": f"148 SMs x 64 B/clk (B300_MICROARCH.md, TMEM read) x {mhz} MHz"}
+            tf = fc["flops"] / (fc["ms"] * 1e-3) / 1e12
+            roof["second_kernel"] = {"kernel": "fcomb kernel (tcgen05 N-sample fcomb + softmax + sum / sum^2)",
+                                     "ms_per_step": fc["ms"], "launches": fc["n"], "bound": "tensor",
+                                     "achieved": tf, "unit": "TFLOP/s", "peak": peaks["bf16_sustained"],
+                                     "frac": tf / peaks["bf16_sustained"], "tensor_frac": tf / peaks["bf16_sustained"],
+                                     "tmem_read_gbs": fc["tmem"] / (fc["ms"] * 1e-3) / 1e9,
+                                     "tmem_read_port_gbs_measured": 148 * 475.0 * mhz * 1e6 / 1e9,
+                                     "peak_source": peaks["source"] + ", sustained bf16; TMEM port: 148 SMs x 475 B/clk (measured, "
+                                                    f"16 warps) x {mhz} MHz"}
         world_frac = 1.0 / world
         V = float(D) ** 3
         if "pmu_slice_gather" in tot:
             gb = P * V * 8.0 * world_frac / 1e9          # read 4 B + write 4 B per voxel per plane
-            in_step = gb / (tot["pmu_slice_gather"]["ms"] * 1e-3)
-            # The in-step figure brackets every ~10-25 us launch with its own event pair, so it mostly measures
-            # launch gaps.  Kernel throughput: whole-plane gathers of all three planes replayed back to back from
+            # in-step form, measured honestly: the three whole-plane launches of one volume, eagerly launched back to back
+            # behind an L2 flush (a 512 MB fill, so neither the volume nor the outputs are L2-resident), ONE event pair
+            # around the three of them.  (Bracketing each ~25 us launch with its own pair mostly measures launch gaps.)
+            mx = ops.plane_max(vol)
+            offs = [0, D, 2 * D]
+            outs3 = [torch.empty(D, 1, D, D, dtype=torch.float32, device=vol.device) for _ in range(3)]
+            flush = torch.empty(128 << 20, dtype=torch.float32, device=vol.device)
+            mxs = [mx[offs[p]:offs[p] + D].contiguous() for p in range(3)]
+            times = []
+            for _ in range(5):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for p in range(3):
+                    ops.slice_gather(vol, p, 0, D, slice_max_in=mxs[p], out=outs3[p])
+                e1.record(); torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            del flush, outs3
+            times.sort()
+            in_step = P * V * 8.0 / 1e9 / (times[len(times) // 2] * 1e-3)
+            # Kernel throughput without launch gaps: whole-plane gathers of all three planes replayed back to back from
             # a CUDA graph, rotating over 4 volumes + 4 outputs (256 MB + 256 MB >> the 126 MB L2), one event pair
             # around the whole region.
             try:
                 vols = [vol] + [vol.clone() for _ in range(3)]
                 outs = [torch.empty(D, 1, D, D, dtype=torch.float32, device=vol.device) for _ in range(4)]
-                mx = ops.plane_max(vol)
-                offs = [0, D, 2 * D]
 
                 def gather_round():
                     for i in range(4):
                         for p in range(3):
-                            ops.slice_gather(vols[i], p, 0, D, slice_max_in=mx[offs[p]:offs[p] + D].contiguous(), out=outs[(i + p) % 4])
+                            ops.slice_gather(vols[i], p, 0, D, slice_max_in=mxs[p], out=outs[(i + p) % 4])
                 gather_round(); torch.cuda.synchronize()
                 gs = torch.cuda.Stream()
                 graph = torch.cuda.CUDAGraph()
@@ -424,14 +477,15 @@ def run_ours(args):
                     e1.record(gs); torch.cuda.synchronize()
                 gbm = reps * 4 * 3 * V * 8.0 / 1e9
                 ach = gbm / (e0.elapsed_time(e1) * 1e-3)
-                hbm_kernels["slice_gather"] = {"achieved": ach, "unit": "GB/s", "peak": peaks["hbm_gbs"], "algorithmic_gb": gb,
-                                               "how": "CUDA-graph replay of 120 whole-plane launches over 4 volumes (working set 512 MB > L2), "
-                                                      "normalisation fused, one event pair",
-                                               "in_step_event_pairs_gbs": in_step}
                 del vols, outs
             except Exception as ex:  # noqa
-                hbm_kernels["slice_gather"] = {"achieved": in_step, "unit": "GB/s", "peak": peaks["hbm_gbs"], "algorithmic_gb": gb,
-                                               "how": "per-launch event pairs inside the step (graph microbench failed: %s)" % str(ex)[:120]}
+                ach = None
+            hbm_kernels["slice_gather"] = {"achieved": in_step, "unit": "GB/s", "peak": peaks["hbm_gbs"], "algorithmic_gb": gb,
+                                           "how": "the three whole-plane launches of one volume, eager, behind a 512 MB L2 flush, ONE "
+                                                  "event pair around the three (median of 5); normalisation fused",
+                                           "graph_replay_gbs": ach,
+                                           "graph_replay_how": "CUDA-graph replay of 120 whole-plane launches over 4 volumes (working set "
+                                                               "512 MB > L2), one event pair: the kernel without launch gaps"}
         if "pmu_scatter_accum" in tot:
             gb = P * V * 2 * 3 * 4.0 * 3.0 * world_frac / 1e9  # read sums + RMW (read+write) accumulators, 2*C floats/voxel
             hbm_kernels["scatter_accum"] = {"achieved": gb / (tot["pmu_scatter_accum"]["ms"] * 1e-3), "unit": "GB/s",
@@ -473,14 +527,18 @@ def run_ours(args):
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n_done} of {3 * D} slices ({args.cpu_slices_per_plane} equally spaced per plane), "
                                   f"forward once + {N} x fcomb + softmax + accumulate, {dt:.1f} s of CPU time, extrapolated"}
+        va, va_dt = cpu_variant_a_rate(D, N, threads=os.cpu_count())
+        cpu_baseline["variant_a"] = {"value": va, "unit": UNIT, "seconds": va_dt,
+                                     "what": f"for information: literal eval.py:148-152, {N} full predict() calls per slice, "
+                                             f"middle slice of each plane, extrapolated"}
     if rank == 0:
         value = args.steps / (ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": workload(D, N, args.interp),
-                           "slice_batch": args.slice_batch, **({"cuda_graph": True} if args.graph else {}), "parallelism": f"slice-sharded x{world} + 1 " + ("reduce-scatter along x (x-slab outputs per rank)" if slab_res else "reduce"),
-                           "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
+                "config": config_dict(D, N, args.interp),
+                "run": {"slice_batch": args.slice_batch, **({"cuda_graph": True} if args.graph else {}),
+                        "parallelism": f"slice-sharded x{world} + 1 " + ("reduce-scatter along x (x-slab outputs per rank)" if slab_res else "reduce")},
                 "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                         # every rank uploads the volume (--e2e-upload broadcast: rank 0 alone, then NVLink)
                         "h2d_bytes_per_step": int(4 * D ** 3) * (1 if (slab and args.e2e_upload == "broadcast") else world),
@@ -514,6 +572,8 @@ def main():
                     help="slice resampling onto the three standard plane grids (BASELINE configs[2]: trilinear)")
     ap.add_argument("--cpu-slices-per-plane", type=int, default=32,
                     help="cpu_baseline sample: equally spaced slices per plane (32 -> 96 of 768 slices, ~10 s on 16 threads)")
+    ap.add_argument("--ref-slices-per-plane", type=int, default=8,
+                    help="--impl reference: equally spaced slices per plane per step (8 -> 24 slices, ~5 s per step on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: only the warm-up and the timed resident steps")
     ap.add_argument("--resident-output", default="slab", choices=["slab", "rank0"],

@@ -41,7 +41,7 @@ using namespace ptx;
 constexpr int F2_F = 64;
 constexpr int F2_SLOTS = 4;
 constexpr int F2_EPI = 512;                       // 16 epilogue warps
-constexpr int F2_THREADS = F2_EPI + 32;           // + issuer warp
+constexpr int F2_THREADS = F2_EPI + 4 * 32;       // + one issuer warp per sample slot
 constexpr int F2_NS = 16;                         // samples per group of zb vectors
 constexpr int F2_SLOT_COLS = 104;                 // X 64 + Y 40
 constexpr int F2_G_COL = F2_SLOTS * F2_SLOT_COLS; // 416: G = W0f f of the current / next tile
@@ -65,6 +65,18 @@ constexpr int F2_SMEM = F2_OFF_TPTR + 16;
 static_assert(F2_OFF_F % 1024 == 0 && F2_OFF_BMT % 1024 == 0 && F2_OFF_BLT % 1024 == 0, "operand tiles must be 1024 B aligned");
 static_assert(F2_G_COL + 64 <= 512, "TMEM budget");
 static_assert(F2_SMEM <= 227 * 1024, "shared memory budget");
+
+#ifdef F2_TRACE
+// scripts/fcomb_trace.cu: clock stamps of CTA 0's issuer and of one epilogue warp per slot group, kept in shared memory
+// (one CS2R + one STS per stamp) and copied out at the end: word = id << 24 | clock[23:0]
+__device__ uint32_t* f2_trace_buf = nullptr;        // [3 recorders][1024]
+constexpr int F2_TRACE_OFF = F2_SMEM;
+constexpr int F2_SMEM_TOTAL = F2_SMEM + 3 * 1024 * 4;
+#define F2_T(id) do { if (trace_rec >= 0 && trace_idx < 1024) { trace_s[trace_rec * 1024 + trace_idx++] = ((uint32_t)(id) << 24) | ((uint32_t)clock() & 0xFFFFFFu); } } while (0)
+#else
+constexpr int F2_SMEM_TOTAL = F2_SMEM;
+#define F2_T(id) do { } while (0)
+#endif
 
 struct Fcomb2Params {
   int N, L, C, nmid, B;
@@ -129,6 +141,26 @@ __device__ __forceinline__ void f2_issue_layer(uint32_t tX, uint32_t tY, uint32_
   f2_umma_ts(tX, tY + 32, umma_smem_desc_sw128(b_tile), idesc, 1u);
 }
 
+// bounded wait without the clock: a pipeline bug traps after ~2^24 wake-ups instead of hanging the GPU
+__device__ __forceinline__ void f2_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void f2_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
 template <int CMAX>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, const float* __restrict__ mu,
@@ -152,7 +184,7 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
 
   if (tid == 0) {
     prefetch_tensormap(&tmF);
-    for (int s = 0; s < F2_SLOTS; ++s) { mbar_init(bar_ready(s), 8); mbar_init(bar_acc(s), 1); }   // 8 warps own a slot
+    for (int s = 0; s < F2_SLOTS; ++s) { mbar_init(bar_ready(s), 4); mbar_init(bar_acc(s), 1); }   // 4 warps own a slot
     mbar_init(bar_tma(0), 1); mbar_init(bar_tma(1), 1);
     mbar_init(bar_g, 1);
     mbar_init(bar_gfree, F2_EPI / 32);
@@ -186,15 +218,16 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tptr;
 
-  // epilogue thread coordinates: TMEM lane quarter, column half, slot group
-  const int q4 = warp & 3, half = (warp >> 2) & 1, grp = (warp >> 3) & 1;
+  // epilogue thread coordinates: TMEM lane quarter q4, sample slot sl (4 warps own a slot); thread = one pixel row
+  const int q4 = warp & 3, sl = (warp >> 2) & 3;
   const int row = q4 * 32 + lane;
-  const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-  if (warp < 16 && half == 0) {
-    // the constant K extension of this group's two slots: k = 64, 65 -> 1.0 (bf16 pair), k = 66..79 -> 0
+  const uint32_t tX = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sl * F2_SLOT_COLS);   // accumulator of my slot
+  const uint32_t tY = tX + 64;                                                                    // its A operand
+  const uint32_t tG = tmem_base + ((uint32_t)(q4 * 32) << 16) + F2_G_COL;
+  if (warp < 16) {
+    // the constant K extension of the slot's A operand: k = 64, 65 -> 1.0 (bf16 pair), k = 66..79 -> 0
     const uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) f2_tmem_st8(tmem_base + lane_off + (2 * grp + j) * F2_SLOT_COLS + 64 + 32, ones);
+    f2_tmem_st8(tY + 32, ones);
     f2_tmem_st_wait();
   }
   tcgen05_fence_before();
@@ -205,8 +238,13 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
   const int64_t total = (int64_t)p.B * tiles;
   const int cta_lo = (int)(total * blockIdx.x / gridDim.x), cta_hi = (int)(total * (blockIdx.x + 1) / gridDim.x);
 
-  uint32_t phr = 0, pha = 0, phg = 0, phf = 0, pht = 0;     // barrier phase parities (bit = slot / buffer)
+  uint32_t phr = 0, pha = 0, phg = 0, phf = 0, pht = 0;     // barrier phase parities (issuer: bit = slot / buffer)
   uint32_t tile_ctr = 0;                                    // scratch buffer selector (epilogue warps)
+#ifdef F2_TRACE
+  int trace_idx = 0;
+  volatile uint32_t* trace_s = reinterpret_cast<volatile uint32_t*>(sgen + F2_TRACE_OFF);
+  const int trace_rec = (blockIdx.x != 0) ? -1 : (tid == 0 ? 0 : tid == 256 ? 1 : (warp == 16 && elect_one()) ? 2 : -1);
+#endif
 
   for (int seg0 = cta_lo; seg0 < cta_hi;) {
     const int b = seg0 / tiles;
@@ -230,19 +268,24 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
       __syncthreads();
       const int rounds = (ng + F2_SLOTS - 1) / F2_SLOTS;
 
-      if (warp == 16) {
-        // ============ issuer (one elected thread: TMA loads of the feature tiles + every UMMA) ============
+      if (warp >= 16) {
+        // ============ issuers: warp 16 + s owns sample slot s (one elected thread each: a single issuer spends ~110
+        // cycles in every barrier wait with nothing queued behind it, which left the tensor pipe idle half of the time);
+        // warp 16 also loads the feature tiles (TMA) and issues the per-tile G = W0f f ============
         if (elect_one()) {
+          const int s = warp - 16;
           constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
           constexpr uint32_t idesc16 = umma_idesc_bf16(128, 16);
           const uint32_t sW0 = sbase + F2_OFF_W0, sWM = sbase + F2_OFF_WM, sWL = sbase + F2_OFF_WL;
           const uint32_t sBM = sbase + F2_OFF_BMT, sBL = sbase + F2_OFF_BLT;
+          const uint32_t sX = tmem_base + s * F2_SLOT_COLS, sY = sX + 64;
+          const uint32_t b_ready = bar_ready(s), b_acc = bar_acc(s);
           auto load_f = [&](int t, uint32_t buf) {
             mbar_arrive_expect_tx(bar_tma(buf), F2_TILE);
             tma_load_2d(sbase + F2_OFF_F + buf * F2_TILE, &tmF, bar_tma(buf), 0, (int)((int64_t)b * HW + (int64_t)t * 128));
           };
           auto issue_g = [&](uint32_t buf) {   // G = F W0f^T -> the G columns (SS form)
-            mbar_wait(bar_tma(buf), (pht >> buf) & 1u); pht ^= 1u << buf;
+            f2_wait(bar_tma(buf), (pht >> buf) & 1u); pht ^= 1u << buf;
             tcgen05_fence_after();
             const uint64_t ad = umma_smem_desc_sw128(sbase + F2_OFF_F + buf * F2_TILE), wd = umma_smem_desc_sw128(sW0);
 #pragma unroll
@@ -250,27 +293,30 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
               umma_bf16(tmem_base + F2_G_COL, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc64, (uint32_t)(k != 0));
             umma_commit(bar_g);
           };
-          load_f(t0, 0);
-          if (t0 + 1 < t1) load_f(t0 + 1, 1);
-          issue_g(0);                                        // (the previous block's G was consumed before the __syncthreads)
+          if (s == 0) {
+            load_f(t0, 0);
+            if (t0 + 1 < t1) load_f(t0 + 1, 1);
+            issue_g(0);                                      // (the previous block's G was released before the __syncthreads)
+          }
           for (int t = t0; t < t1; ++t) {
             const uint32_t buf = (uint32_t)(t - t0) & 1u;
             for (int r = 0; r < rounds; ++r) {
+              const bool live = r * F2_SLOTS + s < ng;
               for (int layer = 1; layer <= nmid + 1; ++layer) {
-#pragma unroll
-                for (int s = 0; s < F2_SLOTS; ++s) {
-                  if (r * F2_SLOTS + s >= ng) continue;
-                  const uint32_t tX = tmem_base + s * F2_SLOT_COLS, tY = tX + 64;
-                  mbar_wait(bar_ready(s), (phr >> s) & 1u); phr ^= 1u << s;
+                if (live) {
+                  F2_T(100 + s);
+                  f2_wait(b_ready, phr); phr ^= 1u;
                   tcgen05_fence_after();
-                  if (layer <= nmid) f2_issue_layer(tX, tY, sWM + (layer - 1) * F2_WT, sBM + (layer - 1) * F2_WT, idesc64);
-                  else f2_issue_layer(tX, tY, sWL, sBL, idesc16);
-                  umma_commit(bar_acc(s));
+                  F2_T(110 + s);
+                  if (layer <= nmid) f2_issue_layer(sX, sY, sWM + (layer - 1) * F2_WT, sBM + (layer - 1) * F2_WT, idesc64);
+                  else f2_issue_layer(sX, sY, sWL, sBL, idesc16);
+                  umma_commit(b_acc);
+                  F2_T(120 + s);
                 }
-                if (r == 0 && layer == 1) {
-                  // every epilogue warp holds this tile's G in registers (its first arrivals came after that read):
-                  // compute the next tile's G now and refill the feature buffer this tile used
-                  mbar_wait(bar_gfree, phf); phf ^= 1u;
+                if (s == 0 && r == rounds - 1 && layer == 1) {
+                  // once every epilogue warp has read this tile's G for its last sample: compute the next tile's G (it
+                  // overlaps the rest of the last round) and refill the feature buffer the previous G used
+                  f2_wait(bar_gfree, phf); phf ^= 1u;
                   tcgen05_fence_after();
                   if (t + 1 < t1) {
                     issue_g(buf ^ 1u);
@@ -283,22 +329,18 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
         }
         __syncwarp();
       } else {
-        // ============ epilogue warps: (lane quarter q4, column half, slot group grp) ============
-        const uint32_t tbase = tmem_base + lane_off;
-        const uint32_t sZB = sbase + F2_OFF_ZB + half * 32 * 4;
+        // ============ epilogue warps ============
+        const uint32_t sZB = sbase + F2_OFF_ZB;
+        const uint32_t b_acc = bar_acc(sl), b_ready = bar_ready(sl);
+        const int last_live = (sl < ng) ? (ng - 1 - sl) / F2_SLOTS : -1;    // round of my slot's last sample in this group
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
           const int64_t pix = (int64_t)t * 128 + row;
           float s1[CMAX], s2[CMAX];
 #pragma unroll
           for (int c = 0; c < CMAX; ++c) s1[c] = s2[c] = 0.f;
-          uint32_t G[32];
-          mbar_wait(bar_g, phg); phg ^= 1u;
+          f2_wait(bar_g, phg); phg ^= 1u;                    // this tile's G = W0f f is in tensor memory
           tcgen05_fence_after();
-          tmem_ld_32x32(tbase + F2_G_COL + half * 32, G);
-          tmem_ld_wait();
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_gfree);
+          if (last_live < 0) { __syncwarp(); if (lane == 0) mbar_arrive(bar_gfree); }
 
           auto softmax_acc = [&](const uint32_t (&hr)[8]) {
             float mx = -INFINITY;
@@ -312,70 +354,75 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
             for (int c = 0; c < CMAX; ++c) { const float pr_ = e[c] * inv; s1[c] += pr_; s2[c] = fmaf(pr_, pr_, s2[c]); }
           };
 
-          bool pend0 = false, pend1 = false;                 // slot j of the group has a head (logits) outstanding
+          bool pend = false;                                 // my slot has a head (logits) outstanding
           for (int r = 0; r <= rounds; ++r) {
-            // ---- slot by slot: consume the previous round's logits, then layer 0 of this round's sample ----
+            const int n = r * F2_SLOTS + sl;
+            const bool live = (r < rounds) && (n < ng);
+            uint32_t hr[8];
+            if (pend) {
+              F2_T(70);
+              f2_wait(b_acc, pha); pha ^= 1u;                // head UMMAs done: logits in X, Y free
+              tcgen05_fence_after();
+              f2_tmem_ld8(tX, hr);
+              tmem_ld_wait();
+            }
+            if (live) {
+              // layer 0: h0 = relu(G + zb_n) -> Y (bf16 pairs), two halves of 32 columns
+              const uint32_t zb = sZB + n * F2_F * 4;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int sl = 2 * grp + j;
-              const int n = r * F2_SLOTS + sl;
-              const bool pend = j ? pend1 : pend0;
-              const bool live = (r < rounds) && (n < ng);
-              uint32_t hr[8];
-              const bool mine = pend && (half == j);
-              if (pend) {
-                mbar_wait(bar_acc(sl), (pha >> sl) & 1u); pha ^= 1u << sl;     // head UMMAs done: logits in X, Y free
-                tcgen05_fence_after();
-                if (mine) { f2_tmem_ld8(tbase + sl * F2_SLOT_COLS, hr); tmem_ld_wait(); }
-              }
-              if (live) {
-                // h0 = relu(G + zb_n) -> Y (bf16 pairs, 16 columns per thread)
-                const uint32_t zb = sZB + n * F2_F * 4;
-                uint32_t pk[16];
+              for (int h = 0; h < 2; ++h) {
+                uint32_t g[32], pk[16];
+                tmem_ld_32x32(tG + h * 32, g);
+                tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                  const float4 z = f2_lds128f(zb + c * 16);
-                  pk[2 * c] = f2_add_pack_relu(__uint_as_float(G[4 * c]), __uint_as_float(G[4 * c + 1]), z.x, z.y);
-                  pk[2 * c + 1] = f2_add_pack_relu(__uint_as_float(G[4 * c + 2]), __uint_as_float(G[4 * c + 3]), z.z, z.w);
+                  const float4 z = f2_lds128f(zb + h * 128 + c * 16);
+                  pk[2 * c] = f2_add_pack_relu(__uint_as_float(g[4 * c]), __uint_as_float(g[4 * c + 1]), z.x, z.y);
+                  pk[2 * c + 1] = f2_add_pack_relu(__uint_as_float(g[4 * c + 2]), __uint_as_float(g[4 * c + 3]), z.z, z.w);
                 }
-                f2_tmem_st16(tbase + sl * F2_SLOT_COLS + 64 + half * 16, pk);
-                f2_tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_ready(sl));
+                f2_tmem_st16(tY + h * 16, pk);
               }
-              if (mine) softmax_acc(hr);
-              if (j) pend1 = live; else pend0 = live;
+              f2_tmem_st_wait();
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(b_ready);
+                if (r == last_live) mbar_arrive(bar_gfree);  // my last read of this tile's G
+              }
+              F2_T(80);
             }
-            if (r == rounds) break;
+            if (pend) softmax_acc(hr);
+            pend = live;
+            if (!live) break;
             // ---- mid layers: X -> relu -> bf16 -> Y ----
             for (int layer = 1; layer <= nmid; ++layer) {
+              F2_T(10);
+              f2_wait(b_acc, pha); pha ^= 1u;
+              tcgen05_fence_after();
+              F2_T(20);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const int sl = 2 * grp + j;
-                if (r * F2_SLOTS + sl >= ng) continue;
-                mbar_wait(bar_acc(sl), (pha >> sl) & 1u); pha ^= 1u << sl;
-                tcgen05_fence_after();
+              for (int h = 0; h < 2; ++h) {
                 uint32_t rr[32], pk[16];
-                tmem_ld_32x32(tbase + sl * F2_SLOT_COLS + half * 32, rr);
+                tmem_ld_32x32(tX + h * 32, rr);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 16; ++c) pk[c] = f2_pack_relu(__uint_as_float(rr[2 * c]), __uint_as_float(rr[2 * c + 1]));
-                f2_tmem_st16(tbase + sl * F2_SLOT_COLS + 64 + half * 16, pk);
-                f2_tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_ready(sl));
+                f2_tmem_st16(tY + h * 16, pk);
               }
+              F2_T(40);
+              f2_tmem_st_wait();
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(b_ready);
+              F2_T(60);
             }
           }
-          // ---- tile done: combine the four partial sums of a pixel ----
+          // ---- tile done: combine the four slots' partial sums of a pixel ----
           float* scr = reinterpret_cast<float*>(sgen + F2_OFF_SCR + (tile_ctr & 1u) * F2_SCR_BYTES);
-          const int part = grp * 2 + half;
 #pragma unroll
-          for (int c = 0; c < CMAX; ++c) { scr[(part * 16 + 2 * c) * 128 + row] = s1[c]; scr[(part * 16 + 2 * c + 1) * 128 + row] = s2[c]; }
+          for (int c = 0; c < CMAX; ++c) { scr[(sl * 16 + 2 * c) * 128 + row] = s1[c]; scr[(sl * 16 + 2 * c + 1) * 128 + row] = s2[c]; }
           named_bar_sync(1, F2_EPI);
-          if (part == 0 && pix < HW) {
+          if (sl == 0 && pix < HW) {
             float* o1 = slice_sums + ((int64_t)b * 2 + 0) * C * HW + pix;
             float* o2 = slice_sums + ((int64_t)b * 2 + 1) * C * HW + pix;
 #pragma unroll
@@ -396,6 +443,11 @@ fcomb_ts2_kernel(const __grid_constant__ CUtensorMap tmF, const Fcomb2Params p, 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc<512>(tmem_base);
+#ifdef F2_TRACE
+  if (trace_rec >= 0 && f2_trace_buf) {
+    for (int i = 0; i < 1024; ++i) f2_trace_buf[trace_rec * 1024 + i] = (i < trace_idx) ? trace_s[trace_rec * 1024 + i] : 0u;
+  }
+#endif
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 f2_encode_fn() {
@@ -436,8 +488,8 @@ extern "C" int pmu_fcomb_softmax_accum_bf16_ts2(const void* feat, const float* m
   const int64_t total = (int64_t)B * tiles;
   const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
   auto launch = [&](auto kern) -> int {
-    PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    kern<<<grid, F2_THREADS, F2_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums);
+    PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_TOTAL));
+    kern<<<grid, F2_THREADS, F2_SMEM_TOTAL, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums);
     PMU_LAUNCH_CHECK();
     return PMU_OK;
   };

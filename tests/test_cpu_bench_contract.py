@@ -53,7 +53,7 @@ def test_both_arms_describe_the_same_workload():
     w = bench.workload(256, 16, "trilinear")
     assert "256^3" in w and "16 z-samples" in w and "trilinear" in w
     src = open(BENCH).read()
-    assert src.count('"workload": workload(D, N, args.interp)') == 2      # ours + reference
+    assert src.count('"config": config_dict(D, N, args.interp)') == 2     # ours + reference: the same dict
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -43,12 +43,10 @@ struct ConvTcParams {
   int tiles_w, tiles_h, tiles_b;
   int n_tiles;        // Ntot / BN
   int pool_mode;      // -1 none; PMU_POOL_MAX / PMU_POOL_AVG_CEIL: also emit the 2x2-pooled map
-  int debug;          // experiments only (PMU_CONV_DEBUG): bit0 = no global stores, bit1 = no A loads
-  int tma_store;      // full-resolution output leaves through the smem staging tile + TMA tensor stores
-  int pool_split;     // experiment (PMU_POOL_SPLIT=1): host-side selector of the PSPLIT kernel instantiations
+  int tma_store;      // a full-resolution output exists: it leaves through the smem staging tile + TMA tensor stores
 };
 
-// RESW > 0 (experiment, PMU_CONVT_RESW=1): the layer's whole weight matrix — RESW k-blocks of [BN][64] — is loaded
+// RESW > 0 (the Cout = 64 transposed convolution, see convt_pair_epilogue): the layer's whole weight matrix — RESW k-blocks of [BN][64] — is loaded
 // once per CTA and stays resident; only the activation boxes stream through the ring.  For a single-N-tile layer with a
 // short K (the 128 -> 64 transposed convolution: N = 4 * 64 = 256, K = 128) the generic kernel re-fetches 64 KB of
 // weights from L2 for every 128-pixel tile, as much as the tile writes.
@@ -103,7 +101,7 @@ struct EpiCtx {
   float* bias_s;
 };
 
-template <int BN, int NSTG, bool PSPLIT = false>
+template <int BN, int NSTG>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCtx& e, const CUtensorMap* tmY0p,
                                               const CUtensorMap* tmY1p, const CUtensorMap* tmY2p,
                                               const CUtensorMap* tmY3p, const float* __restrict__ bias,
@@ -133,11 +131,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
     named_bar_sync(1, 128);          // bias visible
 
     const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
-    const bool valid = (b < p.B) && (h < p.H) && (w < p.W) && !(p.debug & 1);
-    const bool direct = (y != nullptr) && !p.tma_store;      // fallback: per-thread 16 B global stores
+    const bool valid = (b < p.B) && (h < p.H) && (w < p.W);
     // fused 2x2 pooling (a warp holds 32 / TW complete image rows of the brick, so every pooling
-    // window lives in lanes {l, l^1, l^TW} of one warp — two shuffles, no extra pass over HBM)
-    const bool pool_writer = (p.pool_mode >= 0) && ((lane & (1 | p.TW)) == 0) && valid;
+    // window lives in lanes {l, l^1, l^TW, l^(1|TW)} of one warp — no extra pass over HBM)
     __nv_bfloat16* dstp = nullptr;
     if (p.pool_mode >= 0)
       dstp = y_pool + (((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.Cout + co_base;
@@ -190,23 +186,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128_u32(stg_row + ((((half * 4 + j) ^ (m & 7)) & 7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        } else if (direct && valid) {
-          __nv_bfloat16* dt;
-          if (p.ntaps == 4) {
-            // ConvTranspose2d k2 s2: GEMM column n = (i*2+j)*Cout + co goes to pixel (2h+i, 2w+j)
-            const int n = n0 + c0, ij = n / p.Cout, co = n - ij * p.Cout;
-            dt = y + (((int64_t)b * (2 * p.H) + 2 * h + (ij >> 1)) * (2 * p.W) + 2 * w + (ij & 1)) * p.Cout + co;
-          } else {
-            dt = y + (((int64_t)b * p.H + h) * p.W + w) * p.Cout + co_base + c0;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(dt + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
-        if (PSPLIT && p.pool_mode >= 0) {
-          // Halving exchange over the window lanes {l, l^1, l^TW, l^(1|TW)}.  The butterfly below leaves the whole pooled
-          // row in all four lanes and lets one of them write 64 B: 32 shuffles + 32 max per 32 channels and thread.  Here
-          // a lane keeps half of its channels per step and sends the other half: step 1 (lane ^ 1) 8 registers, step 2
+        if (p.pool_mode >= 0) {
+          // Halving exchange over the window lanes {l, l^1, l^TW, l^(1|TW)}.  (A butterfly that leaves the whole pooled
+          // row in all four lanes and lets one of them write 64 B costs 32 shuffles + 32 max per 32 channels and thread:
+          // 80-95 us per launch on the 64-cout layers, profiles/r02_experiments.txt.)  Here a lane keeps half of its
+          // channels per step and sends the other half: step 1 (lane ^ 1) 8 registers, step 2
           // (lane ^ TW) 4 registers (8 fp32 sums for the average) — 12 (16) shuffles — and every lane ends up with 8
           // channels of the pooled pixel, which it writes itself (16 B each; the four lanes' pieces are contiguous).
           // Same arithmetic as below: max is exact; the average adds (a + b) + (c + d) in fp32 and rounds once.
@@ -249,40 +234,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           }
           if (valid)    // a window never straddles the image edge (even H, W; bricks start at even coordinates)
             *reinterpret_cast<uint4*>(dstp + c0 + (odd ? 16 : 0) + (up ? 8 : 0)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-        } else if (p.pool_mode == PMU_POOL_MAX) {
-          // max of bf16-rounded values == bf16 rounding of the max (monotonic): exact, packed
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-            uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
-            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-            uint32_t au = *reinterpret_cast<uint32_t*>(&a);
-            o = __shfl_xor_sync(0xffffffffu, au, p.TW);
-            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-            pk[j] = *reinterpret_cast<uint32_t*>(&a);
-          }
-        } else if (p.pool_mode == PMU_POOL_AVG_CEIL) {
-          // average of the bf16-stored activations, accumulated in fp32 (what pool2_bf16 computes)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-            float lo = __low2float(a), hi = __high2float(a);
-            lo += __shfl_xor_sync(0xffffffffu, lo, 1);  hi += __shfl_xor_sync(0xffffffffu, hi, 1);
-            lo += __shfl_xor_sync(0xffffffffu, lo, p.TW); hi += __shfl_xor_sync(0xffffffffu, hi, p.TW);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-        }
-        if (!PSPLIT && pool_writer) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(dstp + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
       if (p.tma_store) {
         fence_proxy_async_smem();      // staging writes (generic proxy) -> visible to the TMA engine
         named_bar_sync(3, 128);
-        if (et == 0 && !(p.debug & 1)) {
+        if (et == 0) {
           // one tensor store per 64-channel group: full 128-byte lines, out-of-bounds pixels clipped by TMA
           if (p.ntaps == 4) {
             const int n = n0 + g0, ij = n / p.Cout, co = n - ij * p.Cout;
@@ -300,10 +257,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
   if (p.tma_store && et == 0) tma_store_wait_all();
 }
 
-// Epilogue variant for the one-N-tile transposed convolution (Cout = 64, N = 4 * 64; experiment, PMU_CONVT_PAIR=1).
+// Epilogue of the one-N-tile transposed convolution (Cout = 64, N = 4 * 64).
 // The shared epilogue stores every phase (i, j) through its own strided tensor map: 128 scattered 128-byte pieces per
-// store (pixel stride 256 B) — measured, that layer runs at ~6400 cycles per tile with nothing saturated (L2 28 %,
-// DRAM 44 %, tensor pipe 16 %): it waits for its stores.  Here the two column parities j = 0, 1 of one output-row parity i
+// store (pixel stride 256 B) — measured, that layer ran at ~6400 cycles per tile with nothing saturated (L2 28 %,
+// DRAM 44 %, tensor pipe 16 %): it waited for its stores (0.221 -> 0.148 ms per batch of 64 with this epilogue).  Here the two column parities j = 0, 1 of one output-row parity i
 // are staged INTERLEAVED, staging row = (tb, ty, 2 * tx + j), so that one tensor store per i writes 2 * TW * 128 B = 4 KB
 // contiguous runs of the output row 2 * h + i: half as many stores, each over whole rows.
 template <int NSTG>
@@ -375,7 +332,7 @@ __device__ __forceinline__ void convt_pair_epilogue(const ConvTcParams& p, const
       }
       fence_proxy_async_smem();      // staging writes (generic proxy) -> visible to the TMA engine
       named_bar_sync(3, 128);
-      if (et == 0 && !(p.debug & 1)) {
+      if (et == 0) {
         // box {64 ch, 2 TW output pixels, TH rows of parity i2, TB}: rows 2 h + i2, pixels 2 w0 .. 2 w0 + 2 TW - 1
         tma_store_4d(i2 ? tmP1 : tmP0, stg, 0, 2 * w0, h0, b0);
         tma_store_commit();
@@ -392,7 +349,7 @@ __device__ __forceinline__ void convt_pair_epilogue(const ConvTcParams& p, const
 // current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
 // setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
-template <int BN, int STAGES, int MINB, int NSTG, bool PSPLIT = false, int RESW = 0, bool TPAIR = false>
+template <int BN, int STAGES, int MINB, int NSTG, int RESW = 0, bool TPAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0,
@@ -467,13 +424,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
           const uint32_t sa = smem_base + L::RING_OFF + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
-          if (!RESW && (p.debug & 2)) {
-            mbar_arrive_expect_tx(bar_full + s * 8, L::B_BYTES);
-          } else {
-            mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
-            if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
-            else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
-          }
+          mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+          if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx, h0 + dy, b0);
+          else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx, h0 + dy, b0);
           if (!RESW) tma_load_2d(sb, &tmW, bar_full + s * 8, tap * Cin + c, n0);
         }
       }
@@ -514,7 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // =========================== epilogue (warps 2..5) ===========================
     EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
     if constexpr (TPAIR) convt_pair_epilogue<NSTG>(p, ec, &tmY0, &tmY1, bias, total_tiles, warp, lane);
-    else conv_epilogue<BN, NSTG, PSPLIT>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
+    else conv_epilogue<BN, NSTG>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -532,9 +485,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // A stage = one A box + the three weight taps (dy = 0..2) of that dx: 12 UMMAs per stage.
 // RESB = number of resident 64-channel weight chunks (0 = weights stream with the A boxes).  RESB = 1 (Cin == 64,
 // Cout == 64): all nine weight taps (72 KB) stay resident in smem for the whole kernel and only A streams (18 KB
-// per 384 MMA cycles).  RESB = 2 (Cin == 128, Cout == 64 — the decoder's skip-concat layer at full resolution;
-// experiment, PMU_CONV_RES128=1): 144 KB of weights resident, a 3-stage A ring; the same switch keeps the nine
-// 16 KB taps of the 64 -> 128 layers resident (BN = 128, RESB = 1).
+// per 384 MMA cycles); the 64 -> 128 layers keep their nine 16 KB taps resident the same way (BN = 128, RESB = 1:
+// 0.162 -> 0.148 ms per batch of 64).  (Keeping the 144 KB of the 128 -> 64 layer resident with a 3-stage A ring was
+// measured slower, 0.652 -> 0.809 ms, and is gone: profiles/r02_experiments.txt.)
 // ------------------------------------------------------------------------------------
 template <int BN, int STAGES, int RESB>
 struct ConvRsSmem {
@@ -552,7 +505,7 @@ struct ConvRsSmem {
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int STAGES, int RESB, bool PSPLIT = false>
+template <int BN, int STAGES, int RESB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0, const ConvTcParams p,
@@ -614,13 +567,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_wait(bar_empty + s * 8, ph ^ 1u);
             const uint32_t sa = smem_base + L::RING_OFF + s * L::STAGE_BYTES;
             // rows h0-1 .. h0+16, pixels w0+dx-1 .. +7; out-of-image rows / pixels are zero-filled = conv padding
-            if (p.debug & 2) {           // experiment: no activation loads
-              mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES - L::BOX_BYTES);
-            } else {
-              mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
-              if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx - 1, h0 - 1, b0);
-              else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx - 1, h0 - 1, b0);
-            }
+            mbar_arrive_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+            if (c < p.C0) tma_load_4d(sa, &tmA0, bar_full + s * 8, c, w0 + dx - 1, h0 - 1, b0);
+            else          tma_load_4d(sa, &tmA1, bar_full + s * 8, c - p.C0, w0 + dx - 1, h0 - 1, b0);
             if (!RESB) {
 #pragma unroll
               for (int dy = 0; dy < 3; ++dy)
@@ -651,7 +600,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int dy = 0; dy < 3; ++dy) {
               // tap (dy, dx): image rows dy .. dy+15 of the box = +dy swizzle groups of 8 rows (1024 B each)
               const uint64_t adesc = umma_smem_desc_sw128(sa + dy * 1024);
-              const uint64_t bdesc = umma_smem_desc_sw128(RESB ? smem_base + ((dy * 3 + dx) * RESB + (RESB > 1 ? ch : 0)) * L::W_TAP
+              const uint64_t bdesc = umma_smem_desc_sw128(RESB ? smem_base + (dy * 3 + dx) * L::W_TAP
                                                                : sa + L::BOX_BYTES + dy * L::W_TAP);
 #pragma unroll
               for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
@@ -667,7 +616,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   } else {
     EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
-    conv_epilogue<BN, 1, PSPLIT>(p, ec, &tmY0, &tmY0, &tmY0, &tmY0, bias, y, y_pool, total_tiles, warp, lane);
+    conv_epilogue<BN, 1>(p, ec, &tmY0, &tmY0, &tmY0, &tmY0, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -912,13 +861,13 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN, int STAGES, int MINB, int NSTG = 1, bool PSPLIT = false, int RESW = 0, bool TPAIR = false>
+template <int BN, int STAGES, int MINB, int NSTG = 1, int RESW = 0, bool TPAIR = false>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm, const CUtensorMap* ym,
                           const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
                           cudaStream_t st) {
   using L = ConvTcSmem<BN, STAGES, NSTG, RESW>;
   static_assert(MINB * (L::DYN_BYTES + 1024) <= 228 * 1024 && L::DYN_BYTES <= 227 * 1024, "shared memory budget");
-  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, PSPLIT, RESW, TPAIR>;
+  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, RESW, TPAIR>;
   PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
   grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
   kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, ym[0], ym[1], ym[2], ym[3], p, bias,
@@ -961,20 +910,13 @@ static int make_convt_pair_map(CUtensorMap* m, void* y, int B, int H, int W, int
   return PMU_OK;
 }
 
-// Tile configuration (measured per layer on B200, scripts/time_convs.py, profiles/r01_conv_variants.txt):
-//   Cout % 256 == 0 : BN = 256, one persistent CTA per SM, 4-stage ring (A traffic per flop halves;
-//                     up to ~1.4 PFLOP/s on the 256..1024-channel layers)
-//   otherwise       : BN = 128 / 64 with TWO persistent CTAs per SM (3 / 4 stages each): two
-//                     independent MMA issuers hide each other's barrier round trips.
-// PMU_CONV_VARIANT overrides for experiments: 0 = 1 CTA/SM deep ring, 1 = 2 CTAs/SM, 2 = 0 + BN=256.
-static int conv_variant() {
-  static int v = -2;
-  if (v == -2) {
-    const char* e = getenv("PMU_CONV_VARIANT");
-    v = e ? atoi(e) : -1;
-  }
-  return v;
-}
+// Tile configuration (measured per layer on B200, scripts/time_convs.py, profiles/r01_conv_variants.txt,
+// profiles/r02_experiments.txt):
+//   Cout % 256 == 0, convT : BN = 256, one persistent CTA per SM, 4-stage ring (A traffic per flop halves;
+//                            up to ~1.5 PFLOP/s on the 256..1024-channel layers)
+//   3x3, Cout 64 / 128 on images >= 16 rows : the row-shift kernel (conv_rs_kernel), weights resident at Cin = 64
+//   otherwise              : BN = 128 / 64 with TWO persistent CTAs per SM (3 / 4 stages each): two
+//                            independent MMA issuers hide each other's barrier round trips.
 
 // Cin = 1, Cout = 64, W >= 16, H >= 8: tensor-core first layer; returns PMU_ERR_UNSUPPORTED otherwise (the caller
 // falls back to the CUDA-core stencil of layers_bf16.cu)
@@ -986,7 +928,7 @@ int conv_first_tc_launch(const float* x, const float* w, const float* bias, void
   if (cc_major != 10 || W < 16 || H < 8 || !get_encode_fn()) return PMU_ERR_UNSUPPORTED;
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = 64; p.C1 = 0; p.Cout = 64; p.ntaps = 9; p.relu = relu;
-  p.pool_mode = -1; p.debug = 0; p.tma_store = 1; p.pool_split = 0;
+  p.pool_mode = -1; p.tma_store = 1;
   p.TW = 16; p.TH = 8; p.TB = 1;
   p.tiles_w = cdiv(W, 16); p.tiles_h = cdiv(H, 8); p.tiles_b = B; p.n_tiles = 1;
   const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * B;
@@ -1025,8 +967,6 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout; p.ntaps = ntaps; p.relu = relu;
   p.pool_mode = y_pool ? pool_mode : -1;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMU_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-  { const char* e = getenv("PMU_POOL_SPLIT"); p.pool_split = (e && atoi(e)) ? 1 : 0; }   // read per call: tests flip it
   p.TW = std::min(16, pow2ceil(W));
   p.TH = std::min(TC_BM / p.TW, pow2ceil(H));
   p.TB = TC_BM / (p.TW * p.TH);
@@ -1034,9 +974,8 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   const int Cin = C0 + C1;
   const int Ntot = (ntaps == 4) ? 4 * Cout : Cout;
   const int Ktot = (ntaps == 9) ? 9 * Cin : Cin;
-  const int variant = conv_variant();
   int BN = (Cout % 128 == 0) ? 128 : 64;
-  if ((variant == 2 || variant == -1) && (Cout % 256 == 0 || ntaps == 4)) BN = 256;   // convT: Ntot = 4*Cout
+  if (Cout % 256 == 0 || ntaps == 4) BN = 256;   // convT: Ntot = 4*Cout
   p.n_tiles = Ntot / BN;
   if (y_pool) {
     PMU_CHECK_ARG(pool_mode == PMU_POOL_MAX || pool_mode == PMU_POOL_AVG_CEIL, "pmu_conv_gemm_pool_bf16: unknown pool mode %d", pool_mode);
@@ -1044,10 +983,8 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
                         "pmu_conv_gemm_pool_bf16: fused pooling needs even H, W (got %dx%d)", H, W);
     PMU_CHECK_ARG(aligned16(y_pool), "pmu_conv_gemm_pool_bf16: y_pool must be 16-byte aligned");
   }
-  // small-N 3x3 layers on images >= 16 rows: row-shift kernel (see conv_rs_kernel); PMU_CONV_RS=0 disables
-  static int use_rs = -1;
-  if (use_rs < 0) { const char* e = getenv("PMU_CONV_RS"); use_rs = e ? atoi(e) : 1; }
-  const bool rs = use_rs && variant == -1 && ntaps == 9 && BN <= 128 && H >= 16 && W >= 8 && (!y_pool || (H % 2 == 0 && W % 2 == 0));
+  // small-N 3x3 layers on images >= 16 rows: row-shift kernel (see conv_rs_kernel)
+  const bool rs = ntaps == 9 && BN <= 128 && H >= 16 && W >= 8 && (!y_pool || (H % 2 == 0 && W % 2 == 0));
   if (rs) {
     p.TW = 8; p.TH = 16; p.TB = 1;
     p.tiles_w = cdiv(W, 8); p.tiles_h = cdiv(H, 16); p.tiles_b = B;
@@ -1065,13 +1002,18 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   else a1 = a0;
   rc = make_w_map(&wm, wpack, Ntot, Ktot, BN);
   if (rc) return rc;
-  // output tensor maps for the TMA-store epilogue (PMU_CONV_TMA_STORE=0 falls back to per-thread stores)
-  static int use_tma_store = -1;
-  if (use_tma_store < 0) { const char* e = getenv("PMU_CONV_TMA_STORE"); use_tma_store = e ? atoi(e) : 1; }
+  // output tensor maps for the TMA-store epilogue
   CUtensorMap ym[4];
-  p.tma_store = (y != nullptr && use_tma_store) ? 1 : 0;
+  p.tma_store = (y != nullptr) ? 1 : 0;
+  const bool tpair = BN == 256 && ntaps == 4 && Cout == 64 && Cin <= 128 && y != nullptr;   // paired-phase stores, resident weights
   if (p.tma_store) {
-    if (ntaps == 4) {
+    if (tpair) {
+      for (int i = 0; i < 2; ++i) {
+        rc = make_convt_pair_map(&ym[i], y, B, H, W, Cout, i, p.TW, p.TH, p.TB);
+        if (rc) return rc;
+      }
+      ym[2] = ym[3] = ym[0];
+    } else if (ntaps == 4) {
       for (int ij = 0; ij < 4; ++ij) {
         rc = make_convt_out_map(&ym[ij], y, B, H, W, Cout, ij, p.TW, p.TH, p.TB);
         if (rc) return rc;
@@ -1094,41 +1036,15 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
       PMU_LAUNCH_CHECK();
       return PMU_OK;
     };
-    // PMU_POOL_SPLIT=1 (experiment): pooling epilogue with the halving exchange, on the tile configurations the
-    // pooled layers of the network use
-    const bool psplit = p.pool_split && p.pool_mode >= 0;
-    if (psplit && BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, 1, true>, ConvRsSmem<64, 6, 1>::DYN_BYTES);
-    if (psplit && BN == 128) return launch_rs(conv_rs_kernel<128, 3, 0, true>, ConvRsSmem<128, 3, 0>::DYN_BYTES);
-    if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, 1>, ConvRsSmem<64, 6, 1>::DYN_BYTES);
-    // PMU_CONV_RES128=1 (experiment): weights of the 128 -> 64 layer resident too (144 KB), 3-stage A ring
-    { const char* e = getenv("PMU_CONV_RES128");
-      if (e && atoi(e) && BN == 64 && Cin == 128 && Cout == 64)
-        return launch_rs(conv_rs_kernel<64, 3, 2>, ConvRsSmem<64, 3, 2>::DYN_BYTES);
-      if (e && atoi(e) && BN == 128 && Cin == 64 && Cout == 128 && !psplit)     // 64 -> 128: nine 16 KB taps resident
-        return launch_rs(conv_rs_kernel<128, 3, 1>, ConvRsSmem<128, 3, 1>::DYN_BYTES); }
+    if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, 1>, ConvRsSmem<64, 6, 1>::DYN_BYTES);      // 64 -> 64: weights resident
+    if (BN == 128 && Cin == 64) return launch_rs(conv_rs_kernel<128, 3, 1>, ConvRsSmem<128, 3, 1>::DYN_BYTES);   // 64 -> 128: weights resident
     if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, 0>, ConvRsSmem<64, 4, 0>::DYN_BYTES);
     return launch_rs(conv_rs_kernel<128, 3, 0>, ConvRsSmem<128, 3, 0>::DYN_BYTES);
   }
-  if (variant == 1 || (variant == -1 && BN != 256)) {
-    if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
-    return launch_conv_tc<64, 4, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
-  }
-  { const char* e = getenv("PMU_CONVT_PAIR");      // experiment: resident weights + paired-phase stores (Cout = 64 only)
-    if (e && atoi(e) && BN == 256 && ntaps == 4 && Cout == 64 && Cin <= 128 && y && p.tma_store) {
-      for (int i = 0; i < 2; ++i) {
-        const int rc = make_convt_pair_map(&ym[i], y, B, H, W, Cout, i, p.TW, p.TH, p.TB);
-        if (rc) return rc;
-      }
-      return launch_conv_tc<256, 5, 1, 4, false, 2, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
-    } }
-  { const char* e = getenv("PMU_CONVT_RESW");      // experiment: resident weights for a one-N-tile transposed convolution
-    if (e && atoi(e) && BN == 256 && ntaps == 4 && Ntot == 256 && Cin <= 128)
-      return launch_conv_tc<256, 6, 1, 2, false, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st); }
-  if (BN == 256 && p.pool_split && p.pool_mode >= 0)
-    return launch_conv_tc<256, 4, 1, 2, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+  if (tpair) return launch_conv_tc<256, 5, 1, 4, 2, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   if (BN == 256) return launch_conv_tc<256, 4, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
-  if (BN == 128) return launch_conv_tc<128, 6, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
-  return launch_conv_tc<64, 8, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+  if (BN == 128) return launch_conv_tc<128, 3, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+  return launch_conv_tc<64, 4, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
 }
 
 extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,

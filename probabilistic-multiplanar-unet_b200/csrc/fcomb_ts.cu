@@ -1,30 +1,35 @@
-// K3 + K4 fused, TS-mode variant — the fcomb MLP with its activations RESIDENT IN TENSOR MEMORY.
+// K3 + K4 fused — the fcomb MLP over N latent samples with its hidden activations RESIDENT IN TENSOR
+// MEMORY (TS-form UMMAs: A operand from TMEM, B = weights from shared memory), softmax, per-pixel
+// sum / sum-of-squares.  Per-sample logits never reach HBM.
 //
-// fcomb_tc6.cu is bound by the shared-memory pipe (activation stores + UMMA A-operand fetches, see
-// its header).  Here the hidden activations never touch shared memory: the epilogue reads the fp32
-// accumulator X from TMEM (tcgen05.ld), applies ReLU + bf16 pack and writes the packed row back to
-// TMEM (tcgen05.st) as the A operand Y of the next layer's UMMA ("TS" form: A from TMEM, B = weights
-// from smem).  Only the weight tiles (2 KB per K = 16 step) are fetched from shared memory.
-//   * one 128-pixel tile per CTA at a time, 16 epilogue warps: warp = (TMEM lane quarter, 16-column
-//     quarter), i.e. 4 threads per pixel row, 16 accumulator columns each;
-//   * four samples (slots) in flight; TMEM per slot: X = 64 fp32 columns, Y = 40 columns = 64 bf16
-//     activations (32 columns) + a K extension of 16 whose first two entries are constant ones, so the
-//     bias (bf16 hi + lo in the matching weight columns) rides in the GEMM as a fifth K = 16 step;
-//   * layer 0 as in fcomb_tc6.cu: G = W0f f once per tile (SS UMMA from the TMA-loaded feature tile),
-//     kept in registers (16 per thread); per sample h0 = relu(G + zb_n) goes straight to Y;
-//   * softmax of slot s is done by column quarter s (one thread per pixel), partial sums combined
-//     through shared memory at the end of the tile.
-// Replaces Fcomb.forward / softmax / the sample loop (probabilistic_unet.py:155-181, eval.py:146-157).
+// Replaces Fcomb.forward (probabilistic_unet.py:155-181) called once per sample from
+// ProbabilisticUnet.sample (:225-240), the softmax of eval.py:157 and the sample loop of
+// eval.py:146-154.
 //
-// F16 = true (PMU_FCOMB_TS=2, EXPERIMENT, not the default): the per-sample hidden layers run f16 x f16 -> f16.  A dense
-// UMMA keeps an f16 accumulator in the low half of a 32-bit TMEM column; `tcgen05.ld ... .pack::16b` returns two
-// adjacent columns per register, which is already the packed A-operand layout of the next layer: the epilogue of a
-// hidden layer is ld (8 registers) -> max.f16x2 with 0 -> st.  If the TMEM read port is paced by the bytes delivered
-// to the register file (64 B/clk, see fcomb_tc6.cu) this halves the dominant cost; if it is paced by the columns
-// touched it changes nothing.  Layer 0 (G = W0f f, bf16 features, fp32 accumulate, exact fp32 bias) and the logits
-// (fp32 accumulate) are unchanged; the hidden activations carry 11 significand bits instead of 8.
+// What the round-2 measurements said about the two earlier tcgen05 versions (both ~1130 cycles per 128-pixel
+// tile-sample, tensor pipe ~32 % busy):
+//   * the TMEM read port is NOT the limit: scripts/tmem_ld_bench.cu measures 205 / 365-413 / 470-480 B/clk/SM with
+//     4 / 8 / 16 warps (register bytes; .pack::16b loads deliver the same register bytes), against the ~62 B/clk the
+//     kernels used (profiles/r02_experiments.txt);
+//   * the SS form (activations through shared memory) is bound by the shared-memory pipe: per tile-sample 10 N = 64
+//     UMMAs x 6 KB of operand reads + 5 head UMMAs x 4.25 KB + 48 KB of activation stores = 129 KB = 1008 cycles of
+//     the 128 B/clk pipe;
+//   * the first TS form kept all 16 epilogue warps in lock-step on ONE slot at a time (16 columns per thread), so the
+//     per-slot chain  barrier wake-up -> tcgen05.ld -> wait -> pack -> tcgen05.st -> wait -> arrive  (~300 cycles)
+//     was paid 4 slots x 3 layers = 12 times per round of four samples, one after the other.
+// This version: the 16 epilogue warps form two groups of 8 (TMEM lane quarter x column half: 32 accumulator columns
+// per thread); a group owns two of the four sample slots and walks them alternately, so while one slot's epilogue
+// runs the other slot's UMMAs execute, and the two groups run independently of each other.  Per slot and layer the
+// critical path is  commit -> wake-up -> ld.x32 -> 16 cvt -> st.x16 -> arrive -> issue, four such chains in flight.
+//   * layer 0 leaves the per-sample chain: h0_n = relu(W0f f + zb_n), zb_n = W0z z_n + b0.  G = W0f f is ONE SS-form
+//     UMMA group per tile into its own TMEM region (so the next tile's G is computed while the current tile's
+//     samples run), read once into registers; per sample layer 0 is 16 add.f32x2 + 16 cvt.rn.relu.bf16x2 per thread;
+//   * the constant biases ride in the GEMM: every layer's K is extended by one K = 16 step whose A columns are
+//     constant ones (8 TMEM columns per slot) and whose B tile holds the bias split into bf16 hi + lo;
+//   * TMEM: 4 slots x (X 64 fp32 columns + Y 40 columns = 64 bf16 activations + the ones extension) + G 64 = 480;
+//   * the head's softmax of a slot is done by the column half that matches the slot's parity (one thread per pixel),
+//     the four partial (sum, sum^2) sets of a pixel are combined through shared memory at the end of the tile.
 #include <cudaTypedefs.h>
-#include <cuda_fp16.h>
 
 #include "pmu_common.cuh"
 #include "sm100_ptx.cuh"
@@ -33,80 +38,62 @@ namespace pmu {
 
 using namespace ptx;
 
-constexpr int FT_F = 64;
-constexpr int FT_SLOTS = 4;
-constexpr int FT_EPI = 512;                       // 16 epilogue warps
-constexpr int FT_THREADS = FT_EPI + 32;           // + issuer warp
-constexpr int FT_NS = 16;
-constexpr int FT_SLOT_COLS = 104;                 // X 64 + Y 40
-constexpr int FT_TILE = 128 * 128;
-constexpr int FT_WT = 64 * 128;
-constexpr int FT_OFF_W0 = 0;
-constexpr int FT_OFF_WM = FT_OFF_W0 + FT_WT;       // 2 mid layers
-constexpr int FT_OFF_WL = FT_OFF_WM + 2 * FT_WT;   // head [16][64]
-constexpr int FT_OFF_BMT = FT_OFF_WL + 2048;       // bias tiles (k0 = hi, k1 = lo)
-constexpr int FT_OFF_BLT = FT_OFF_BMT + 2 * FT_WT;
-constexpr int FT_OFF_F = FT_OFF_BLT + 2048;        // feature tile, double buffered
-constexpr int FT_OFF_ZB = FT_OFF_F + 2 * FT_TILE;  // fp32 zb[FT_NS][64]
-constexpr int FT_OFF_SCR = FT_OFF_ZB + FT_NS * FT_F * 4;       // softmax partials [4 quarters][16][128]
-constexpr int FT_OFF_BAR = FT_OFF_SCR + 4 * 16 * 128 * 4;
-constexpr int FT_NBAR = 2 * FT_SLOTS + 4;          // ready[slot], acc[slot], tma[2], g, free
-constexpr int FT_OFF_TPTR = FT_OFF_BAR + FT_NBAR * 8;
-constexpr int FT_SMEM = FT_OFF_TPTR + 16;
-static_assert(FT_OFF_F % 1024 == 0 && FT_OFF_BMT % 1024 == 0 && FT_OFF_BLT % 1024 == 0, "operand tiles must be 1024 B aligned");
-static_assert(FT_SLOTS * FT_SLOT_COLS <= 512, "TMEM budget");
+constexpr int F2_F = 64;
+constexpr int F2_SLOTS = 4;
+constexpr int F2_EPI = 512;                       // 16 epilogue warps
+constexpr int F2_THREADS = F2_EPI + 4 * 32;       // + one issuer warp per sample slot
+constexpr int F2_NS = 16;                         // samples per group of zb vectors
+constexpr int F2_SLOT_COLS = 104;                 // X 64 + Y 40
+constexpr int F2_G_COL = F2_SLOTS * F2_SLOT_COLS; // 416: G = W0f f of the current / next tile
+constexpr int F2_MAXL = 16;
+constexpr int F2_MAXC = 8;
+constexpr int F2_TILE = 128 * 128;
+constexpr int F2_WT = 64 * 128;
+constexpr int F2_OFF_W0 = 0;
+constexpr int F2_MAXMID = 4;                       // hidden layers after layer 0 (no_convs_fcomb <= 6)
+constexpr int F2_OFF_WM = F2_OFF_W0 + F2_WT;       // mid layers
+constexpr int F2_OFF_WL = F2_OFF_WM + F2_MAXMID * F2_WT;   // head [16][64]
+constexpr int F2_OFF_BMT = F2_OFF_WL + 2048;       // bias tiles (k0 = hi, k1 = lo)
+constexpr int F2_OFF_BLT = F2_OFF_BMT + F2_MAXMID * F2_WT;
+constexpr int F2_OFF_F = F2_OFF_BLT + 2048;        // feature tile, double buffered
+constexpr int F2_OFF_ZB = F2_OFF_F + 2 * F2_TILE;  // fp32 zb[F2_NS][64]
+constexpr int F2_SCR_BYTES = 4 * 16 * 128 * 4;     // softmax partials [4 (group, half)][16][128]
+constexpr int F2_OFF_SCR = F2_OFF_ZB + F2_NS * F2_F * 4;       // x 2 (alternating tiles)
+constexpr int F2_OFF_BAR = F2_OFF_SCR + 2 * F2_SCR_BYTES;
+constexpr int F2_NBAR = 2 * F2_SLOTS + 4;          // ready[slot], acc[slot], tma[2], g_full, g_free
+constexpr int F2_OFF_TPTR = F2_OFF_BAR + F2_NBAR * 8;
+constexpr int F2_SMEM = F2_OFF_TPTR + 16;
+static_assert(F2_OFF_F % 1024 == 0 && F2_OFF_BMT % 1024 == 0 && F2_OFF_BLT % 1024 == 0, "operand tiles must be 1024 B aligned");
+static_assert(F2_G_COL + 64 <= 512, "TMEM budget");
+static_assert(F2_SMEM <= 227 * 1024, "shared memory budget");
+
+#ifdef F2_TRACE
+// scripts/fcomb_trace.cu: clock stamps of CTA 0's issuer and of one epilogue warp per slot group, kept in shared memory
+// (one CS2R + one STS per stamp) and copied out at the end: word = id << 24 | clock[23:0]
+__device__ uint32_t* f2_trace_buf = nullptr;        // [3 recorders][1024]
+constexpr int F2_TRACE_OFF = F2_SMEM;
+constexpr int F2_SMEM_TOTAL = F2_SMEM + 3 * 1024 * 4;
+#define F2_T(id) do { if (trace_rec >= 0 && trace_idx < 1024) { trace_s[trace_rec * 1024 + trace_idx++] = ((uint32_t)(id) << 24) | ((uint32_t)clock() & 0xFFFFFFu); } } while (0)
+#else
+constexpr int F2_SMEM_TOTAL = F2_SMEM;
+#define F2_T(id) do { } while (0)
+#endif
 
 struct FcombTsParams {
   int N, L, C, nmid, B;
   int64_t HW;
 };
 
-__device__ __forceinline__ void ft_st_bf16(uint8_t* tile, int row, int k, float v) {
+__device__ __forceinline__ void f2_st_bf16(uint8_t* tile, int row, int k, float v) {
   *reinterpret_cast<__nv_bfloat16*>(tile + (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2)) = __float2bfloat16(v);
 }
-template <bool F16>
-__device__ __forceinline__ void ft_st_w(uint8_t* tile, int row, int k, float v) {   // weight / bias element of a per-sample layer
-  if constexpr (F16)
-    *reinterpret_cast<__half*>(tile + (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2)) = __float2half_rn(v);
-  else
-    ft_st_bf16(tile, row, k, v);
-}
-template <bool F16>
-__device__ __forceinline__ float ft_round_w(float v) {
-  if constexpr (F16) return __half2float(__float2half_rn(v));
-  else return __bfloat162float(__float2bfloat16(v));
-}
-// relu(a + b) of two fp32 pairs -> packed f16x2
-__device__ __forceinline__ uint32_t ft_add_pack_relu_h(float a0, float a1, float b0, float b1) {
-  uint32_t d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
-      "mov.b64 ra, {%1, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {lo, hi}, rd;\n\t"
-      "cvt.rn.relu.f16x2.f32 %0, hi, lo;\n\t}"
-      : "=r"(d) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-  return d;
-}
-__device__ __forceinline__ uint32_t ft_relu_h2(uint32_t v) {
-  uint32_t d;
-  asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(0u));
-  return d;
-}
-// 32 lanes x 16 columns holding one f16 each (low half) -> 8 registers of f16x2 (column 2j low, 2j + 1 high)
-__device__ __forceinline__ void ft_tmem_ld16_pack(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr) : "memory");
-}
-// kind::f16 instruction descriptor, f16 x f16 operands (formats 0), accumulator f16 (D format 0) or fp32 (1)
-__host__ __device__ constexpr uint32_t ft_idesc_f16(int M, int N, bool acc_f32) {
-  return ((acc_f32 ? 1u : 0u) << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ uint32_t ft_pack_relu(float lo, float hi) {
+__device__ __forceinline__ uint32_t f2_pack_relu(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ uint32_t ft_add_pack_relu(float a0, float a1, float b0, float b1) {
+// relu(a + b) of two fp32 pairs -> packed bf16x2: one packed add (add.f32x2) + one cvt
+__device__ __forceinline__ uint32_t f2_add_pack_relu(float a0, float a1, float b0, float b1) {
   uint32_t d;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
       "mov.b64 ra, {%1, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
@@ -115,32 +102,31 @@ __device__ __forceinline__ uint32_t ft_add_pack_relu(float a0, float a1, float b
       : "=r"(d) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
   return d;
 }
-__device__ __forceinline__ float4 ft_lds128f(uint32_t addr) {
+__device__ __forceinline__ float4 f2_lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void ft_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void ft_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+__device__ __forceinline__ void f2_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void ft_tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+__device__ __forceinline__ void f2_tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void ft_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void f2_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void f2_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]   (TS form: the A operand is read from tensor memory)
-__device__ __forceinline__ void ft_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void f2_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -149,19 +135,39 @@ __device__ __forceinline__ void ft_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       : "memory");
 }
 // one layer on tensor memory: X = Y[128 x 80] * [W | bias]^T   (4 + 1 TS UMMAs; Y columns 32..39 hold the ones)
-__device__ __forceinline__ void ft_issue_layer(uint32_t tX, uint32_t tY, uint32_t w_tile, uint32_t b_tile, uint32_t idesc) {
+__device__ __forceinline__ void f2_issue_layer(uint32_t tX, uint32_t tY, uint32_t w_tile, uint32_t b_tile, uint32_t idesc) {
   const uint64_t wd = umma_smem_desc_sw128(w_tile);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) ft_umma_ts(tX, tY + 8 * k, wd + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
-  ft_umma_ts(tX, tY + 32, umma_smem_desc_sw128(b_tile), idesc, 1u);
+  for (int k = 0; k < 4; ++k) f2_umma_ts(tX, tY + 8 * k, wd + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+  f2_umma_ts(tX, tY + 32, umma_smem_desc_sw128(b_tile), idesc, 1u);
 }
 
-template <int CMAX, bool F16>
-__global__ void __launch_bounds__(FT_THREADS, 1)
+// bounded wait without the clock: a pipeline bug traps after ~2^24 wake-ups instead of hanging the GPU
+__device__ __forceinline__ void f2_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void f2_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(F2_THREADS, 1)
 fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, const float* __restrict__ mu,
-                const float* __restrict__ sigma, const float* __restrict__ eps, const float* __restrict__ w0,
-                const float* __restrict__ b0, const float* __restrict__ wmid, const float* __restrict__ bmid,
-                const float* __restrict__ wlast, const float* __restrict__ blast, float* __restrict__ slice_sums) {
+                 const float* __restrict__ sigma, const float* __restrict__ eps, const float* __restrict__ w0,
+                 const float* __restrict__ b0, const float* __restrict__ wmid, const float* __restrict__ bmid,
+                 const float* __restrict__ wlast, const float* __restrict__ blast, float* __restrict__ slice_sums) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   uint8_t* sgen = smem_raw;
@@ -170,60 +176,60 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
   const int64_t HW = p.HW;
   if ((sbase & 1023u) != 0) __trap();
 
-  auto bar_ready = [&](int s) { return sbase + FT_OFF_BAR + s * 8; };
-  auto bar_acc = [&](int s) { return sbase + FT_OFF_BAR + (FT_SLOTS + s) * 8; };
-  auto bar_tma = [&](int i) { return sbase + FT_OFF_BAR + (2 * FT_SLOTS + i) * 8; };
-  const uint32_t bar_g = sbase + FT_OFF_BAR + (2 * FT_SLOTS + 2) * 8;
-  const uint32_t bar_free = sbase + FT_OFF_BAR + (2 * FT_SLOTS + 3) * 8;
-  volatile uint32_t* tptr = reinterpret_cast<volatile uint32_t*>(sgen + FT_OFF_TPTR);
+  auto bar_ready = [&](int s) { return sbase + F2_OFF_BAR + s * 8; };
+  auto bar_acc = [&](int s) { return sbase + F2_OFF_BAR + (F2_SLOTS + s) * 8; };
+  auto bar_tma = [&](int i) { return sbase + F2_OFF_BAR + (2 * F2_SLOTS + i) * 8; };
+  const uint32_t bar_g = sbase + F2_OFF_BAR + (2 * F2_SLOTS + 2) * 8;
+  const uint32_t bar_gfree = sbase + F2_OFF_BAR + (2 * F2_SLOTS + 3) * 8;
+  volatile uint32_t* tptr = reinterpret_cast<volatile uint32_t*>(sgen + F2_OFF_TPTR);
 
   if (tid == 0) {
     prefetch_tensormap(&tmF);
-    for (int s = 0; s < FT_SLOTS; ++s) { mbar_init(bar_ready(s), FT_EPI / 32); mbar_init(bar_acc(s), 1); }   // one arrival per warp
+    for (int s = 0; s < F2_SLOTS; ++s) { mbar_init(bar_ready(s), 4); mbar_init(bar_acc(s), 1); }   // 4 warps own a slot
     mbar_init(bar_tma(0), 1); mbar_init(bar_tma(1), 1);
     mbar_init(bar_g, 1);
-    mbar_init(bar_free, FT_EPI / 32);
+    mbar_init(bar_gfree, F2_EPI / 32);
     fence_barrier_init();
   }
-  if (warp == 16) tmem_alloc<512>(sbase + FT_OFF_TPTR);
-  for (int i = tid; i < FT_OFF_F / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sgen)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 16) tmem_alloc<512>(sbase + F2_OFF_TPTR);
+  for (int i = tid; i < F2_OFF_F / 16; i += F2_THREADS) reinterpret_cast<uint4*>(sgen)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (int i = tid; i < FT_F * FT_F; i += FT_THREADS) {
+  for (int i = tid; i < F2_F * F2_F; i += F2_THREADS) {
     const int o = i >> 6, k = i & 63;
-    ft_st_bf16(sgen + FT_OFF_W0, o, k, __ldg(w0 + (int64_t)o * (FT_F + L) + k));
-    for (int m = 0; m < nmid; ++m) ft_st_w<F16>(sgen + FT_OFF_WM + m * FT_WT, o, k, __ldg(wmid + (int64_t)m * FT_F * FT_F + i));
+    f2_st_bf16(sgen + F2_OFF_W0, o, k, __ldg(w0 + (int64_t)o * (F2_F + L) + k));
+    for (int m = 0; m < nmid; ++m) f2_st_bf16(sgen + F2_OFF_WM + m * F2_WT, o, k, __ldg(wmid + (int64_t)m * F2_F * F2_F + i));
   }
-  for (int i = tid; i < C * FT_F; i += FT_THREADS) ft_st_w<F16>(sgen + FT_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
-  for (int i = tid; i < nmid * FT_F; i += FT_THREADS) {
+  for (int i = tid; i < C * F2_F; i += F2_THREADS) f2_st_bf16(sgen + F2_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
+  for (int i = tid; i < nmid * F2_F; i += F2_THREADS) {
     const float bv = __ldg(bmid + i);
-    const float bh = ft_round_w<F16>(bv);
-    ft_st_w<F16>(sgen + FT_OFF_BMT + (i >> 6) * FT_WT, i & 63, 0, bh);
-    ft_st_w<F16>(sgen + FT_OFF_BMT + (i >> 6) * FT_WT, i & 63, 1, bv - bh);
+    const float bh = __bfloat162float(__float2bfloat16(bv));
+    f2_st_bf16(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 0, bh);
+    f2_st_bf16(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 1, bv - bh);
   }
-  for (int i = tid; i < C; i += FT_THREADS) {
+  for (int i = tid; i < C; i += F2_THREADS) {
     const float bv = __ldg(blast + i);
-    const float bh = ft_round_w<F16>(bv);
-    ft_st_w<F16>(sgen + FT_OFF_BLT, i, 0, bh);
-    ft_st_w<F16>(sgen + FT_OFF_BLT, i, 1, bv - bh);
+    const float bh = __bfloat162float(__float2bfloat16(bv));
+    f2_st_bf16(sgen + F2_OFF_BLT, i, 0, bh);
+    f2_st_bf16(sgen + F2_OFF_BLT, i, 1, bv - bh);
   }
-  float* zb_s = reinterpret_cast<float*>(sgen + FT_OFF_ZB);
-  float* scr = reinterpret_cast<float*>(sgen + FT_OFF_SCR);
+  float* zb_s = reinterpret_cast<float*>(sgen + F2_OFF_ZB);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tptr;
 
-  // epilogue thread coordinates
-  const int q4 = warp & 3, cq = (warp >> 2) & 3;
+  // epilogue thread coordinates: TMEM lane quarter q4, sample slot sl (4 warps own a slot); thread = one pixel row
+  const int q4 = warp & 3, sl = (warp >> 2) & 3;
   const int row = q4 * 32 + lane;
-  const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-  if (warp < 16 && cq == 0) {
-    // the constant K extension of every slot's A operand: k = 64, 65 -> 1.0 (bf16 pair), k = 66..79 -> 0
-    const uint32_t ones[8] = {F16 ? 0x3C003C00u : 0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // (1.0, 1.0) as f16 / bf16 pairs
-#pragma unroll
-    for (int s = 0; s < FT_SLOTS; ++s) ft_tmem_st8(tmem_base + lane_off + s * FT_SLOT_COLS + 64 + 32, ones);
-    ft_tmem_st_wait();
+  const uint32_t tX = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sl * F2_SLOT_COLS);   // accumulator of my slot
+  const uint32_t tY = tX + 64;                                                                    // its A operand
+  const uint32_t tG = tmem_base + ((uint32_t)(q4 * 32) << 16) + F2_G_COL;
+  if (warp < 16) {
+    // the constant K extension of the slot's A operand: k = 64, 65 -> 1.0 (bf16 pair), k = 66..79 -> 0
+    const uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    f2_tmem_st8(tY + 32, ones);
+    f2_tmem_st_wait();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -233,180 +239,191 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
   const int64_t total = (int64_t)p.B * tiles;
   const int cta_lo = (int)(total * blockIdx.x / gridDim.x), cta_hi = (int)(total * (blockIdx.x + 1) / gridDim.x);
 
-  uint32_t phr = 0, pha = 0, phg = 0, phf = 0, pht = 0;     // pht: bit i = parity of tma barrier i
-  bool first_tile = true;
-  uint32_t fbuf = 0;                                        // which F buffer the next tile uses (issuer + everyone in step)
+  uint32_t phr = 0, pha = 0, phg = 0, phf = 0, pht = 0;     // barrier phase parities (issuer: bit = slot / buffer)
+  uint32_t tile_ctr = 0;                                    // scratch buffer selector (epilogue warps)
+#ifdef F2_TRACE
+  int trace_idx = 0;
+  volatile uint32_t* trace_s = reinterpret_cast<volatile uint32_t*>(sgen + F2_TRACE_OFF);
+  const int trace_rec = (blockIdx.x != 0) ? -1 : (tid == 0 ? 0 : tid == 256 ? 1 : (warp == 16 && elect_one()) ? 2 : -1);
+#endif
 
   for (int seg0 = cta_lo; seg0 < cta_hi;) {
     const int b = seg0 / tiles;
     const int seg1 = ((b + 1) * tiles < cta_hi) ? (b + 1) * tiles : cta_hi;
     const int t0 = seg0 - b * tiles, t1 = seg1 - b * tiles;
-    for (int n0 = 0; n0 < N; n0 += FT_NS) {
-      const int ng = (N - n0 < FT_NS) ? N - n0 : FT_NS;
+    for (int n0 = 0; n0 < N; n0 += F2_NS) {
+      const int ng = (N - n0 < F2_NS) ? N - n0 : F2_NS;
+      // ---- per-sample layer-0 bias vectors zb_n = W0z z_n + b0 of this slice / sample group (fp32) ----
       __syncthreads();
-      for (int i = tid; i < ng * FT_F; i += FT_THREADS) {
+      for (int i = tid; i < ng * F2_F; i += F2_THREADS) {
         const int n = i >> 6, o = i & 63;
         float s = __ldg(b0 + o);
         for (int l = 0; l < L; ++l) {
+          // z = mu + sigma * eps   (Normal.rsample, probabilistic_unet.py:233)
           const float z = __fadd_rn(__ldg(mu + (int64_t)b * L + l),
                                     __fmul_rn(__ldg(sigma + (int64_t)b * L + l), __ldg(eps + ((int64_t)b * N + n0 + n) * L + l)));
-          s = fmaf(__ldg(w0 + (int64_t)o * (FT_F + L) + FT_F + l), z, s);
+          s = fmaf(__ldg(w0 + (int64_t)o * (F2_F + L) + F2_F + l), z, s);
         }
         zb_s[i] = s;
       }
       __syncthreads();
-      const int rounds = (ng + FT_SLOTS - 1) / FT_SLOTS;
+      const int rounds = (ng + F2_SLOTS - 1) / F2_SLOTS;
 
-      if (warp == 16) {
-        // ============ issuer ============
-        // elect.sync (not `lane == 0`): with a provably single active thread the compiler keeps the UMMA descriptors in
-        // uniform registers; `lane == 0` costs a 12-instruction waterfall (ELECT / R2UR.BROADCAST / BRA.U.ANY) per UMMA.
-        // elect.sync over the full warp always picks the same lane, so the per-thread barrier phases persist.
+      if (warp >= 16) {
+        // ============ issuers: warp 16 + s owns sample slot s (one elected thread each: a single issuer spends ~110
+        // cycles in every barrier wait with nothing queued behind it, which left the tensor pipe idle half of the time);
+        // warp 16 also loads the feature tiles (TMA) and issues the per-tile G = W0f f ============
         if (elect_one()) {
-          constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);                                   // layer 0: bf16 features
-          constexpr uint32_t idesc_mid = F16 ? ft_idesc_f16(128, 64, false) : umma_idesc_bf16(128, 64);
-          constexpr uint32_t idesc16 = F16 ? ft_idesc_f16(128, 16, true) : umma_idesc_bf16(128, 16);
-          const uint32_t sW0 = sbase + FT_OFF_W0, sWM = sbase + FT_OFF_WM, sWL = sbase + FT_OFF_WL;
-          const uint32_t sBM = sbase + FT_OFF_BMT, sBL = sbase + FT_OFF_BLT;
-          bool f_in_flight = false;
-          for (int t = t0; t < t1; ++t) {
-            const uint32_t sF = sbase + FT_OFF_F + fbuf * FT_TILE;
-            if (!f_in_flight) {
-              mbar_arrive_expect_tx(bar_tma(fbuf), FT_TILE);
-              tma_load_2d(sF, &tmF, bar_tma(fbuf), 0, (int)((int64_t)b * HW + (int64_t)t * 128));
-            }
-            f_in_flight = false;
-            if (t + 1 < t1) {           // prefetch the next tile's features into the other buffer
-              mbar_arrive_expect_tx(bar_tma(fbuf ^ 1u), FT_TILE);
-              tma_load_2d(sbase + FT_OFF_F + (fbuf ^ 1u) * FT_TILE, &tmF, bar_tma(fbuf ^ 1u), 0,
-                          (int)((int64_t)b * HW + (int64_t)(t + 1) * 128));
-              f_in_flight = true;
-            }
-            if (!first_tile) { mbar_wait(bar_free, phf); phf ^= 1u; }     // slot 0's X is free again
-            first_tile = false;
-            mbar_wait(bar_tma(fbuf), (pht >> fbuf) & 1u); pht ^= 1u << fbuf;
+          const int s = warp - 16;
+          constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
+          constexpr uint32_t idesc16 = umma_idesc_bf16(128, 16);
+          const uint32_t sW0 = sbase + F2_OFF_W0, sWM = sbase + F2_OFF_WM, sWL = sbase + F2_OFF_WL;
+          const uint32_t sBM = sbase + F2_OFF_BMT, sBL = sbase + F2_OFF_BLT;
+          const uint32_t sX = tmem_base + s * F2_SLOT_COLS, sY = sX + 64;
+          const uint32_t b_ready = bar_ready(s), b_acc = bar_acc(s);
+          auto load_f = [&](int t, uint32_t buf) {
+            mbar_arrive_expect_tx(bar_tma(buf), F2_TILE);
+            tma_load_2d(sbase + F2_OFF_F + buf * F2_TILE, &tmF, bar_tma(buf), 0, (int)((int64_t)b * HW + (int64_t)t * 128));
+          };
+          auto issue_g = [&](uint32_t buf) {   // G = F W0f^T -> the G columns (SS form)
+            f2_wait(bar_tma(buf), (pht >> buf) & 1u); pht ^= 1u << buf;
             tcgen05_fence_after();
-            {   // G = F W0f^T -> slot 0's X (SS form)
-              const uint64_t ad = umma_smem_desc_sw128(sF), wd = umma_smem_desc_sw128(sW0);
+            const uint64_t ad = umma_smem_desc_sw128(sbase + F2_OFF_F + buf * F2_TILE), wd = umma_smem_desc_sw128(sW0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 0, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc64, (uint32_t)(k != 0));
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + F2_G_COL, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc64, (uint32_t)(k != 0));
             umma_commit(bar_g);
-            fbuf ^= 1u;
+          };
+          if (s == 0) {
+            load_f(t0, 0);
+            if (t0 + 1 < t1) load_f(t0 + 1, 1);
+            issue_g(0);                                      // (the previous block's G was released before the __syncthreads)
+          }
+          for (int t = t0; t < t1; ++t) {
+            const uint32_t buf = (uint32_t)(t - t0) & 1u;
             for (int r = 0; r < rounds; ++r) {
+              const bool live = r * F2_SLOTS + s < ng;
               for (int layer = 1; layer <= nmid + 1; ++layer) {
-#pragma unroll
-                for (int s = 0; s < FT_SLOTS; ++s) {
-                  if (r * FT_SLOTS + s >= ng) continue;
-                  const uint32_t tX = tmem_base + s * FT_SLOT_COLS, tY = tX + 64;
-                  mbar_wait(bar_ready(s), (phr >> s) & 1u); phr ^= 1u << s;
+                if (live) {
+                  F2_T(100 + s);
+                  f2_wait(b_ready, phr); phr ^= 1u;
                   tcgen05_fence_after();
-                  if (layer <= nmid) ft_issue_layer(tX, tY, sWM + (layer - 1) * FT_WT, sBM + (layer - 1) * FT_WT, idesc_mid);
-                  else ft_issue_layer(tX, tY, sWL, sBL, idesc16);
-                  umma_commit(bar_acc(s));
+                  F2_T(110 + s);
+                  if (layer <= nmid) f2_issue_layer(sX, sY, sWM + (layer - 1) * F2_WT, sBM + (layer - 1) * F2_WT, idesc64);
+                  else f2_issue_layer(sX, sY, sWL, sBL, idesc16);
+                  umma_commit(b_acc);
+                  F2_T(120 + s);
+                }
+                if (s == 0 && r == rounds - 1 && layer == 1) {
+                  // once every epilogue warp has read this tile's G for its last sample: compute the next tile's G (it
+                  // overlaps the rest of the last round) and refill the feature buffer the previous G used
+                  f2_wait(bar_gfree, phf); phf ^= 1u;
+                  tcgen05_fence_after();
+                  if (t + 1 < t1) {
+                    issue_g(buf ^ 1u);
+                    if (t + 2 < t1) load_f(t + 2, buf);
+                  }
                 }
               }
             }
           }
         }
         __syncwarp();
-        // keep fbuf in step for the (unused) other lanes: only lane 0's copy matters
       } else {
-        // ============ epilogue warps: (lane quarter q4, column quarter cq) ============
-        const uint32_t tbase = tmem_base + lane_off;
-        const uint32_t sZB = sbase + FT_OFF_ZB + cq * 16 * 4;
-        for (int t = t0; t < t1; ++t) {
+        // ============ epilogue warps ============
+        const uint32_t sZB = sbase + F2_OFF_ZB;
+        const uint32_t b_acc = bar_acc(sl), b_ready = bar_ready(sl);
+        const int last_live = (sl < ng) ? (ng - 1 - sl) / F2_SLOTS : -1;    // round of my slot's last sample in this group
+        for (int t = t0; t < t1; ++t, ++tile_ctr) {
           const int64_t pix = (int64_t)t * 128 + row;
           float s1[CMAX], s2[CMAX];
 #pragma unroll
           for (int c = 0; c < CMAX; ++c) s1[c] = s2[c] = 0.f;
-          uint32_t G[16];
-          mbar_wait(bar_g, phg); phg ^= 1u;
+          f2_wait(bar_g, phg); phg ^= 1u;                    // this tile's G = W0f f is in tensor memory
           tcgen05_fence_after();
-          ft_tmem_ld16(tbase + cq * 16, G);
-          tmem_ld_wait();
-          for (int r = 0; r < rounds; ++r) {
-            // ---- layer 0: h0 = relu(G + zb_n) -> Y (bf16 pairs, 8 columns per thread) ----
+          if (last_live < 0) { __syncwarp(); if (lane == 0) mbar_arrive(bar_gfree); }
+
+          auto softmax_acc = [&](const uint32_t (&hr)[8]) {
+            float mx = -INFINITY;
 #pragma unroll
-            for (int s = 0; s < FT_SLOTS; ++s) {
-              const int n = r * FT_SLOTS + s;
-              if (n >= ng) continue;
-              const uint32_t zb = sZB + n * FT_F * 4;
-              uint32_t pk[8];
+            for (int c = 0; c < CMAX; ++c) if (c < C) mx = fmaxf(mx, __uint_as_float(hr[c]));
+            float e[CMAX], den = 0.f;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 z = ft_lds128f(zb + j * 16);
-                if constexpr (F16) {
-                  pk[2 * j] = ft_add_pack_relu_h(__uint_as_float(G[4 * j]), __uint_as_float(G[4 * j + 1]), z.x, z.y);
-                  pk[2 * j + 1] = ft_add_pack_relu_h(__uint_as_float(G[4 * j + 2]), __uint_as_float(G[4 * j + 3]), z.z, z.w);
-                } else {
-                  pk[2 * j] = ft_add_pack_relu(__uint_as_float(G[4 * j]), __uint_as_float(G[4 * j + 1]), z.x, z.y);
-                  pk[2 * j + 1] = ft_add_pack_relu(__uint_as_float(G[4 * j + 2]), __uint_as_float(G[4 * j + 3]), z.z, z.w);
+            for (int c = 0; c < CMAX; ++c) { e[c] = (c < C) ? __expf(__uint_as_float(hr[c]) - mx) : 0.f; den += e[c]; }
+            const float inv = __fdividef(1.f, den);
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) { const float pr_ = e[c] * inv; s1[c] += pr_; s2[c] = fmaf(pr_, pr_, s2[c]); }
+          };
+
+          bool pend = false;                                 // my slot has a head (logits) outstanding
+          for (int r = 0; r <= rounds; ++r) {
+            const int n = r * F2_SLOTS + sl;
+            const bool live = (r < rounds) && (n < ng);
+            uint32_t hr[8];
+            if (pend) {
+              F2_T(70);
+              f2_wait(b_acc, pha); pha ^= 1u;                // head UMMAs done: logits in X, Y free
+              tcgen05_fence_after();
+              f2_tmem_ld8(tX, hr);
+              tmem_ld_wait();
+            }
+            if (live) {
+              // layer 0: h0 = relu(G + zb_n) -> Y (bf16 pairs), two halves of 32 columns
+              const uint32_t zb = sZB + n * F2_F * 4;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t g[32], pk[16];
+                tmem_ld_32x32(tG + h * 32, g);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 z = f2_lds128f(zb + h * 128 + c * 16);
+                  pk[2 * c] = f2_add_pack_relu(__uint_as_float(g[4 * c]), __uint_as_float(g[4 * c + 1]), z.x, z.y);
+                  pk[2 * c + 1] = f2_add_pack_relu(__uint_as_float(g[4 * c + 2]), __uint_as_float(g[4 * c + 3]), z.z, z.w);
                 }
+                f2_tmem_st16(tY + h * 16, pk);
               }
-              ft_tmem_st8(tbase + s * FT_SLOT_COLS + 64 + cq * 8, pk);
-              ft_tmem_st_wait();
+              f2_tmem_st_wait();
               tcgen05_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar_ready(s));      // one arrival per warp (barrier count = 16)
+              if (lane == 0) {
+                mbar_arrive(b_ready);
+                if (r == last_live) mbar_arrive(bar_gfree);  // my last read of this tile's G
+              }
+              F2_T(80);
             }
+            if (pend) softmax_acc(hr);
+            pend = live;
+            if (!live) break;
             // ---- mid layers: X -> relu -> bf16 -> Y ----
             for (int layer = 1; layer <= nmid; ++layer) {
-#pragma unroll
-              for (int s = 0; s < FT_SLOTS; ++s) {
-                if (r * FT_SLOTS + s >= ng) continue;
-                mbar_wait(bar_acc(s), (pha >> s) & 1u); pha ^= 1u << s;
-                tcgen05_fence_after();
-                uint32_t pk[8];
-                if constexpr (F16) {
-                  ft_tmem_ld16_pack(tbase + s * FT_SLOT_COLS + cq * 16, pk);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) pk[j] = ft_relu_h2(pk[j]);
-                } else {
-                  uint32_t rr[16];
-                  ft_tmem_ld16(tbase + s * FT_SLOT_COLS + cq * 16, rr);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) pk[j] = ft_pack_relu(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
-                }
-                ft_tmem_st8(tbase + s * FT_SLOT_COLS + 64 + cq * 8, pk);
-                ft_tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_ready(s));
-              }
-            }
-            // ---- head: softmax of slot s by column quarter s ----
-#pragma unroll
-            for (int s = 0; s < FT_SLOTS; ++s) {
-              if (r * FT_SLOTS + s >= ng) continue;
-              mbar_wait(bar_acc(s), (pha >> s) & 1u); pha ^= 1u << s;
+              F2_T(10);
+              f2_wait(b_acc, pha); pha ^= 1u;
               tcgen05_fence_after();
-              if (cq == s) {
-                uint32_t hr[8];
-                ft_tmem_ld8(tbase + s * FT_SLOT_COLS, hr);
+              F2_T(20);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t rr[32], pk[16];
+                tmem_ld_32x32(tX + h * 32, rr);
                 tmem_ld_wait();
-                float mx = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c) if (c < C) mx = fmaxf(mx, __uint_as_float(hr[c]));
-                float e[CMAX], den = 0.f;
-#pragma unroll
-                for (int c = 0; c < CMAX; ++c) { e[c] = (c < C) ? __expf(__uint_as_float(hr[c]) - mx) : 0.f; den += e[c]; }
-                const float inv = __fdividef(1.f, den);
-#pragma unroll
-                for (int c = 0; c < CMAX; ++c) { const float pr_ = e[c] * inv; s1[c] += pr_; s2[c] = fmaf(pr_, pr_, s2[c]); }
+                for (int c = 0; c < 16; ++c) pk[c] = f2_pack_relu(__uint_as_float(rr[2 * c]), __uint_as_float(rr[2 * c + 1]));
+                f2_tmem_st16(tY + h * 16, pk);
               }
+              F2_T(40);
+              f2_tmem_st_wait();
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(b_ready);
+              F2_T(60);
             }
           }
-          // ---- tile done ----
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_free);
+          // ---- tile done: combine the four slots' partial sums of a pixel ----
+          float* scr = reinterpret_cast<float*>(sgen + F2_OFF_SCR + (tile_ctr & 1u) * F2_SCR_BYTES);
 #pragma unroll
-          for (int c = 0; c < CMAX; ++c) { scr[(cq * 16 + 2 * c) * 128 + row] = s1[c]; scr[(cq * 16 + 2 * c + 1) * 128 + row] = s2[c]; }
-          named_bar_sync(1, FT_EPI);
-          if (cq == 0 && pix < HW) {
+          for (int c = 0; c < CMAX; ++c) { scr[(sl * 16 + 2 * c) * 128 + row] = s1[c]; scr[(sl * 16 + 2 * c + 1) * 128 + row] = s2[c]; }
+          named_bar_sync(1, F2_EPI);
+          if (sl == 0 && pix < HW) {
             float* o1 = slice_sums + ((int64_t)b * 2 + 0) * C * HW + pix;
             float* o2 = slice_sums + ((int64_t)b * 2 + 1) * C * HW + pix;
 #pragma unroll
@@ -419,7 +436,6 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
                 else { o1[(int64_t)c * HW] += a1; o2[(int64_t)c * HW] += a2; }
               }
           }
-          named_bar_sync(1, FT_EPI);
         }
       }
     }
@@ -428,9 +444,14 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc<512>(tmem_base);
+#ifdef F2_TRACE
+  if (trace_rec >= 0 && f2_trace_buf) {
+    for (int i = 0; i < 1024; ++i) f2_trace_buf[trace_rec * 1024 + i] = (i < trace_idx) ? trace_s[trace_rec * 1024 + i] : 0u;
+  }
+#endif
 }
 
-static PFN_cuTensorMapEncodeTiled_v12000 ft_encode_fn() {
+static PFN_cuTensorMapEncodeTiled_v12000 f2_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;
@@ -446,17 +467,29 @@ static PFN_cuTensorMapEncodeTiled_v12000 ft_encode_fn() {
 
 using namespace pmu;
 
-// called by pmu_fcomb_softmax_accum_bf16 (fcomb_tc6.cu) after argument checks
-extern "C" int pmu_fcomb_softmax_accum_bf16_ts(const void* feat, const float* mu, const float* sigma, const float* eps,
-                                               const float* w0, const float* b0, const float* wmid, const float* bmid,
-                                               const float* wlast, const float* blast, float* slice_sums, int B, int N,
-                                               int L, int C, int nl, int64_t HW, void* stream) {
-  auto fn = ft_encode_fn();
+extern "C" int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, const float* sigma,
+                                            const float* eps, const float* w0, const float* b0,
+                                            const float* wmid, const float* bmid, const float* wlast,
+                                            const float* blast, float* slice_sums, int B, int N, int L,
+                                            int C, int nl, int64_t HW, void* stream) {
+  PMU_CHECK_ARG(feat && mu && sigma && eps && w0 && b0 && wlast && blast && slice_sums,
+                "pmu_fcomb_softmax_accum_bf16: null pointer");
+  PMU_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && HW > 0, "pmu_fcomb_softmax_accum_bf16: bad shape");
+  PMU_CHECK_ARG(nl >= 2 && (nl == 2 || (wmid && bmid)), "pmu_fcomb_softmax_accum_bf16: no_convs_fcomb >= 2; mid weights needed for > 2");
+  PMU_CHECK_SUPPORTED(L >= 1 && L <= F2_MAXL && C >= 1 && C <= F2_MAXC, "pmu_fcomb_softmax_accum_bf16: needs L <= 16, C <= 8 (got L=%d C=%d)", L, C);
+  PMU_CHECK_SUPPORTED(nl - 2 <= F2_MAXMID, "pmu_fcomb_softmax_accum_bf16: no_convs_fcomb <= %d on the tensor-core path (got %d); use pmu_fcomb_f32", F2_MAXMID + 2, nl);
+  PMU_CHECK_ARG(aligned16(feat), "pmu_fcomb_softmax_accum_bf16: feat must be 16-byte aligned");
+  PMU_CHECK_SUPPORTED((int64_t)B * HW < (1ll << 31), "pmu_fcomb_softmax_accum_bf16: B * HW must be below 2^31 (split the batch)");
+  int cc_major = 0, dev = 0;
+  PMU_CUDA(cudaGetDevice(&dev));
+  PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  PMU_CHECK_SUPPORTED(cc_major == 10, "pmu_fcomb_softmax_accum_bf16: needs an sm_100 device; found cc %d.x", cc_major);
+  auto fn = f2_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
   CUtensorMap tmF;
-  cuuint64_t dims[2] = {(cuuint64_t)FT_F, (cuuint64_t)((int64_t)B * HW)};
-  cuuint64_t strides[1] = {(cuuint64_t)FT_F * 2};
-  cuuint32_t box[2] = {(cuuint32_t)FT_F, 128};
+  cuuint64_t dims[2] = {(cuuint64_t)F2_F, (cuuint64_t)((int64_t)B * HW)};
+  cuuint64_t strides[1] = {(cuuint64_t)F2_F * 2};
+  cuuint32_t box[2] = {(cuuint32_t)F2_F, 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(&tmF, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(feat), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -467,15 +500,12 @@ extern "C" int pmu_fcomb_softmax_accum_bf16_ts(const void* feat, const float* mu
   const int64_t tiles = (HW + 127) / 128;
   const int64_t total = (int64_t)B * tiles;
   const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
-  // PMU_FCOMB_TS=2 (the dispatcher in fcomb_tc6.cu only comes here for a non-zero value): f16 hidden layers (experiment)
-  const char* ts_env = getenv("PMU_FCOMB_TS");
-  const bool f16 = ts_env && atoi(ts_env) == 2;
   auto launch = [&](auto kern) -> int {
-    PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-    kern<<<grid, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums);
+    PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_TOTAL));
+    kern<<<grid, F2_THREADS, F2_SMEM_TOTAL, (cudaStream_t)stream>>>(tmF, p, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, slice_sums);
     PMU_LAUNCH_CHECK();
     return PMU_OK;
   };
-  if (C <= 4) return f16 ? launch(fcomb_ts_kernel<4, true>) : launch(fcomb_ts_kernel<4, false>);
-  return f16 ? launch(fcomb_ts_kernel<8, true>) : launch(fcomb_ts_kernel<8, false>);
+  if (C <= 4) return launch(fcomb_ts_kernel<4>);
+  return launch(fcomb_ts_kernel<8>);
 }

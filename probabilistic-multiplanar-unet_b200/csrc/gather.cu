@@ -490,11 +490,8 @@ extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int pla
     for (int i = 0; i < 12; ++i) A.a[i] = affine_host[i];
     // Fast path: on a standard plane grid (o = 0, n/u/v = the view's unit vectors) every tap weight is exactly
     // 0 or 1, so nearest and trilinear reproduce plain slicing bit for bit (oracle test_oracle_slicing_identities,
-    // GPU test_gather_affine_bit_exact) — hand the launch to the HBM-rate copy kernels.  PMU_GATHER_NO_FASTPATH=1
-    // forces the general kernel (bench.py uses it to report the resampling kernel's own roofline).
-    static int no_fast = -1;
-    if (no_fast < 0) { const char* e = getenv("PMU_GATHER_NO_FASTPATH"); no_fast = (e && atoi(e)) ? 1 : 0; }
-    if (!no_fast) {
+    // GPU test_gather_affine_bit_exact) — hand the launch to the HBM-rate copy kernels.
+    {
       static const float std_aff[3][12] = {{0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1},
                                            {0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 1},
                                            {0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0}};

@@ -259,9 +259,7 @@ extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const fl
   PMU_CHECK_SUPPORTED(Cout % 8 == 0 && Cout <= 128, "pmu_conv3x3_first_bf16: Cout must be a multiple of 8, <= 128 (got %d)", Cout);
   PMU_CHECK_ARG(aligned16(y), "pmu_conv3x3_first_bf16: y must be 16-byte aligned");
   // tensor-core path (conv_tc.cu): im2col rows in shared memory, two K = 16 UMMAs per 128 pixels, TMA-store epilogue
-  static int use_tc = -1;
-  if (use_tc < 0) { const char* e = getenv("PMU_FIRST_TC"); use_tc = e ? atoi(e) : 1; }
-  if (use_tc && Cin == 1 && Cout == 64) {
+  if (Cin == 1 && Cout == 64) {
     const int rc = conv_first_tc_launch(x0, w, bias, y, B, H, W, relu, (cudaStream_t)stream);
     if (rc != PMU_ERR_UNSUPPORTED) return rc;
   }

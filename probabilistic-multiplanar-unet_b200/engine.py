@@ -204,9 +204,10 @@ class PackedNet:
 
     def fcomb_sums(self, feat: torch.Tensor, mu, sigma, eps, out=None) -> torch.Tensor:
         """Fused N-sample fcomb + softmax + (sum, sum^2): slice_sums [B,2,C,H,W]."""
-        if self.precision == "bf16" and self.fcomb["F"] == 64:
+        if self.precision == "bf16" and self.fcomb["F"] == 64 and self.fcomb["nl"] <= 6:
             return ops.fcomb_softmax_accum_bf16(feat, mu, sigma, eps, self.fcomb, out=out)
+        # fp32 mode, or a head the tensor-core kernel does not cover (F != 64, no_convs_fcomb > 6): CUDA-core kernel
         f = self.features_nchw_f32(feat)
         z = (mu[:, None, :] + sigma[:, None, :] * eps).contiguous()
-        _, sums = ops.fcomb_f32(f, z, self.fcomb, want_logits=False, want_sums=True)
+        _, sums = ops.fcomb_f32(f, z, self.fcomb, want_logits=False, want_sums=True, sums_out=out)
         return sums

@@ -181,15 +181,19 @@ def gauss_head_f32(enc, w, b, L):
     return mu, ls
 
 
-def fcomb_f32(feat, z, fw, want_logits=True, want_sums=False):
-    """feat [B,F,H,W] fp32, z [B,N,L] -> logits [B,N,C,H,W] and/or slice_sums [B,2,C,H,W]."""
-    _f32(feat, "feat"); _f32(z, "z")
+def fcomb_f32(feat, z, fw, want_logits=True, want_sums=False, sums_out=None):
+    """feat [B,F,H,W] fp32, z [B,N,L] -> logits [B,N,C,H,W] and/or slice_sums [B,2,C,H,W] (into sums_out when given)."""
+    _f32(feat, "feat"); _f32(z, "z"); _f32(sums_out, "sums_out")
     B, F_, H, W = feat.shape
     N, L = z.shape[1], z.shape[2]
     C, nl = fw["wlast"].shape[0], fw["nl"]
     logits = torch.empty(B, N, C, H, W, dtype=torch.float32, device=feat.device) if want_logits else None
-    sums = torch.empty(B, 2, C, H, W, dtype=torch.float32, device=feat.device) if want_sums else None
-    lib, st = _prep(feat, z, logits, sums)
+    sums = None
+    if want_sums:
+        if sums_out is not None and tuple(sums_out.shape) != (B, 2, C, H, W):
+            raise RuntimeError(f"fcomb_f32: sums_out must be {(B, 2, C, H, W)}, got {tuple(sums_out.shape)}")
+        sums = sums_out if sums_out is not None else torch.empty(B, 2, C, H, W, dtype=torch.float32, device=feat.device)
+    lib, st = _prep(feat, z, logits, sums, fw["w0"], fw["b0"], fw["wmid"], fw["bmid"], fw["wlast"], fw["blast"])
     _launch(lib, "pmu_fcomb_f32", (_p(feat), _p(z), _p(fw["w0"]), _p(fw["b0"]), _p(fw["wmid"]), _p(fw["bmid"]),
                                  _p(fw["wlast"]), _p(fw["blast"]), _p(logits), _p(sums), B, N, F_, L, C, nl, H * W, st,))
     return logits, sums

@@ -1,4 +1,4 @@
-// Timeline of fcomb_ts2_kernel: clock64 stamps of CTA 0's issuer thread and of one epilogue warp per slot group
+// Timeline of fcomb_ts_kernel: clock64 stamps of CTA 0's issuer thread and of one epilogue warp per slot group
 // (compiled with F2_TRACE).  Prints, per recorder, the event id and the cycles since the previous event.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I probabilistic-multiplanar-unet_b200/csrc \
 //        -o /tmp/fcomb_trace scripts/fcomb_trace.cu && /tmp/fcomb_trace
@@ -6,7 +6,7 @@
 // the group); 70+j start of the head/L0 step, 80+j L0 arrived, 90+j softmax done; issuer 100+s wait ready / 110+s woke / 120+s issued.
 #define F2_TRACE 1
 #include "../probabilistic-multiplanar-unet_b200/csrc/api.cu"
-#include "../probabilistic-multiplanar-unet_b200/csrc/fcomb_ts2.cu"
+#include "../probabilistic-multiplanar-unet_b200/csrc/fcomb_ts.cu"
 #include <vector>
 #include <cstdlib>
 
@@ -26,7 +26,7 @@ int main(int argc, char** argv) {
     uint32_t* t = (it == 2) ? trace : nullptr;
     cudaMemcpyToSymbol(pmu::f2_trace_buf, &t, sizeof(t));
     cudaEventRecord(e0);
-    int rc = pmu_fcomb_softmax_accum_bf16_ts2(feat, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, sums, B, N, L, C, nl, HW, 0);
+    int rc = pmu_fcomb_softmax_accum_bf16(feat, mu, sigma, eps, w0, b0, wmid, bmid, wlast, blast, sums, B, N, L, C, nl, HW, 0);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e != cudaSuccess) { printf("rc %d %s %s\n", rc, pmu_last_error(), cudaGetErrorString(e)); return 1; }

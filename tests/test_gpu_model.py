@@ -69,7 +69,6 @@ def test_small_model_vs_reference_golden(pmu, golden_dir):
         np.testing.assert_allclose(unet(x).cpu().numpy(), g["eval/unet_out"], **tol)
 
 
-@pytest.mark.skipif(os.environ.get("PMU_TEST_EXPERIMENTAL") != "1", reason="written without GPU time (set PMU_TEST_EXPERIMENTAL=1)")
 def test_small_model_mc_kl_and_posterior_mean(pmu, golden_dir):
     """The less-travelled arguments of the drop-in API against the REAL reference (golden_small_extra.npz): the
     Monte-Carlo KL, the ELBO built on it, and the posterior-mean reconstruction — which the reference itself cannot
@@ -296,7 +295,6 @@ def test_eval_entry_point(pmu, tmp_path):
     torch.testing.assert_close(out["mean"], avg, atol=1e-6, rtol=1e-5)
 
 
-@pytest.mark.skipif(os.environ.get("PMU_TEST_EXPERIMENTAL") != "1", reason="experimental path (set PMU_TEST_EXPERIMENTAL=1)")
 def test_accumulate_graphed_matches_eager(pmu, trainer_sd):
     """accumulate_graphed(): the slice pass of a volume replayed as one CUDA graph gives the bits of the eager pass, for
     a second volume written into the same buffer too (the graph is captured once per buffer triple)."""

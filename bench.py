@@ -567,7 +567,8 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--samples", type=int, default=16)
     ap.add_argument("--slice-batch", type=int, default=64)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "fp32"],
+                    help="f16: tensor-core mode, IEEE-half operands + fp32 accumulation (the inference format); bf16: the same kernels on bfloat16")
     ap.add_argument("--interp", default="trilinear", choices=["exact", "nearest", "trilinear"],
                     help="slice resampling onto the three standard plane grids (BASELINE configs[2]: trilinear)")
     ap.add_argument("--cpu-slices-per-plane", type=int, default=32,

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """eval.py — multi-planar evaluation entry point (drop-in for the reference's eval.py CLI).
 
-    python eval.py -f CHECKPOINT -d DIR -m probunet [--samples 16] [--precision bf16] [--out OUTDIR]
+    python eval.py -f CHECKPOINT -d DIR -m probunet [--samples 16] [--precision f16] [--out OUTDIR]
 
 Same flags as the reference (eval.py:25-36): -f/--load a state_dict checkpoint, -d/--dir a folder
 with images/ and labels/ (eval.py:96-98), -m/--model.  For every scan: predict labels along the
@@ -33,7 +33,7 @@ def get_args():
     parser.add_argument("-d", "--dir", dest="dir", type=str, default=None, help="image and label superdirs.")
     parser.add_argument("-m", "--model", dest="net", type=str, default="probunet", help="what model to use: unet or probunet")
     parser.add_argument("--samples", type=int, default=16, help="latent samples per slice")
-    parser.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--precision", default="f16", choices=["f16", "bf16", "fp32"])
     parser.add_argument("--slice-batch", type=int, default=64)
     parser.add_argument("--seed", type=int, default=4321)
     parser.add_argument("--out", type=str, default="predictions", help="where the label / uncertainty volumes go")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """predict.py — the reference's predict() hook (predict.py:15-19) and a one-volume CLI.
 
-    python predict.py -f CHECKPOINT -i VOLUME.nii[.gz] [-o OUTDIR] [--samples 16] [--precision bf16]
+    python predict.py -f CHECKPOINT -i VOLUME.nii[.gz] [-o OUTDIR] [--samples 16] [--precision f16]
 """
 import argparse
 import os
@@ -29,7 +29,7 @@ def main():
     ap.add_argument("-i", "--input", type=str, required=True)
     ap.add_argument("-o", "--out", type=str, default="predictions")
     ap.add_argument("--samples", type=int, default=16)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "fp32"])
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("predict.py needs a CUDA device (there is no CPU fallback)")

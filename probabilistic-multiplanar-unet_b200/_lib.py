@@ -34,14 +34,14 @@ _SIG = {
     "pmu_gauss_head_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_fcomb_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_int64, _P]),
-    "pmu_conv3x3_first_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "pmu_conv_gemm_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "pmu_conv_gemm_pool_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "pmu_pool2_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    "pmu_gauss_head_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    "pmu_nhwc_bf16_to_nchw_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "pmu_conv3x3_first_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_conv_gemm_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_conv_gemm_pool_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_pool2_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_gauss_head_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_nhwc_bf16_to_nchw_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_fcomb_softmax_accum_bf16": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
-                                             c_int, c_int64, _P]),
+                                             c_int, c_int64, c_int, _P]),
     "pmu_softmax_accum": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P]),
     "pmu_scatter_accum": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int32), c_int, _P, _P, _P]),
     "pmu_fuse_finalize": (c_int, [_P, _P, c_float, POINTER(c_int32), c_int, _P, _P, _P, _P, _P]),

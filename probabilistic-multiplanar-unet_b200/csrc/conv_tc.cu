@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "pmu_common.cuh"
+#include "h16.cuh"
 #include "sm100_ptx.cuh"
 
 namespace pmu {
@@ -44,6 +45,7 @@ struct ConvTcParams {
   int n_tiles;        // Ntot / BN
   int pool_mode;      // -1 none; PMU_POOL_MAX / PMU_POOL_AVG_CEIL: also emit the 2x2-pooled map
   int tma_store;      // a full-resolution output exists: it leaves through the smem staging tile + TMA tensor stores
+  int f16;            // the 16-bit operands and outputs are IEEE f16 (inference) instead of bf16 (training), see h16.cuh
 };
 
 // RESW > 0 (the Cout = 64 transposed convolution, see convt_pair_epilogue): the layer's whole weight matrix — RESW k-blocks of [BN][64] — is loaded
@@ -72,23 +74,22 @@ struct ConvTcSmem {
 // 2x2 pooling.  The tile brick is p.TW x p.TH pixels (16 x 8 or 8 x 16): a warp always holds
 // complete pooling windows in lanes {l, l^1, l^TW}.
 // ------------------------------------------------------------------------------------
-// (a0 + b0, a1 + b1) -> [relu] -> packed bf16x2 (low half = first element): add.f32x2 + cvt.rn[.relu].bf16x2.f32
-template <bool RELU>
-__device__ __forceinline__ uint32_t add_pack_bf16x2(float a0, float a1, float b0, float b1) {
-  uint32_t d;
-  if (RELU)
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
-        "mov.b64 ra, {%1, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {lo, hi}, rd;\n\t"
-        "cvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}"
-        : "=r"(d) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-  else
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
-        "mov.b64 ra, {%1, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {lo, hi}, rd;\n\t"
-        "cvt.rn.bf16x2.f32 %0, hi, lo;\n\t}"
-        : "=r"(d) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-  return d;
+// bias + [ReLU] + 16-bit pack of 32 accumulator columns: one packed fp32 add (add.f32x2) + one cvt per output pair, the
+// ReLU rides in the cvt.  (The scalar form — 2 FADD, 2 FMNMX, 1 F2FP and 2 LDS per pair — made this epilogue, not the
+// MMA, the critical path of the 64/128-cout layers: ~3000 cycles per tile against 1152 of UMMA at 64 -> 64.)
+__device__ __forceinline__ float4 lds128_f4(uint32_t addr);
+template <bool RELU, bool F16>
+__device__ __forceinline__ void bias_pack32(const uint32_t (&r)[32], uint32_t bs_addr, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b4 = lds128_f4(bs_addr + j * 16);
+    pk[2 * j] = add_pack16<RELU, F16>(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b4.x, b4.y);
+    pk[2 * j + 1] = add_pack16<RELU, F16>(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b4.z, b4.w);
+  }
+}
+__device__ __forceinline__ void bias_pack32(const uint32_t (&r)[32], uint32_t bs_addr, uint32_t (&pk)[16], int relu, int f16) {
+  if (f16) { if (relu) bias_pack32<true, true>(r, bs_addr, pk); else bias_pack32<false, true>(r, bs_addr, pk); }
+  else { if (relu) bias_pack32<true, false>(r, bs_addr, pk); else bias_pack32<false, false>(r, bs_addr, pk); }
 }
 __device__ __forceinline__ float4 lds128_f4(uint32_t addr) {
   float4 v;
@@ -161,26 +162,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           tcgen05_fence_before();
           mbar_arrive(bar_tempty + as * 8);
         }
-        // bias + (ReLU) + bf16 pack: one packed fp32 add (add.f32x2) + one cvt per output pair; the ReLU rides in
-        // the cvt.  (The scalar form — 2 FADD, 2 FMNMX, 1 F2FP and 2 LDS per pair — made this epilogue, not the MMA,
-        // the critical path of the 64/128-cout layers: ~3000 cycles per tile against 1152 of UMMA at 64 -> 64.)
         uint32_t pk[16];
-        const uint32_t bs_addr = smem_u32(bs) + (uint32_t)c0 * 4;
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = lds128_f4(bs_addr + j * 16);
-            pk[2 * j] = add_pack_bf16x2<true>(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b4.x, b4.y);
-            pk[2 * j + 1] = add_pack_bf16x2<true>(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b4.z, b4.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = lds128_f4(bs_addr + j * 16);
-            pk[2 * j] = add_pack_bf16x2<false>(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b4.x, b4.y);
-            pk[2 * j + 1] = add_pack_bf16x2<false>(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b4.z, b4.w);
-          }
-        }
+        bias_pack32(r, smem_u32(bs) + (uint32_t)c0 * 4, pk, p.relu, p.f16);
         if (p.tma_store) {
           // staging row m, 16-byte chunk (half*4 + j), 128-byte swizzle (chunk ^ (row & 7))
 #pragma unroll
@@ -194,7 +177,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           // channels per step and sends the other half: step 1 (lane ^ 1) 8 registers, step 2
           // (lane ^ TW) 4 registers (8 fp32 sums for the average) — 12 (16) shuffles — and every lane ends up with 8
           // channels of the pooled pixel, which it writes itself (16 B each; the four lanes' pieces are contiguous).
-          // Same arithmetic as below: max is exact; the average adds (a + b) + (c + d) in fp32 and rounds once.
+          // max is exact; the average adds (a + b) + (c + d) in fp32 and rounds once.
           const bool odd = (lane & 1) != 0, up = (lane & p.TW) != 0;
           uint32_t o4[4];
           if (p.pool_mode == PMU_POOL_MAX) {
@@ -203,15 +186,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
             for (int j = 0; j < 8; ++j) {
               const uint32_t send = odd ? pk[j] : pk[j + 8], keep = odd ? pk[j + 8] : pk[j];
               const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-              __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv));
-              k8[j] = *reinterpret_cast<uint32_t*>(&a);
+              k8[j] = p.f16 ? max16x2<true>(keep, recv) : max16x2<false>(keep, recv);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t send = up ? k8[j] : k8[j + 4], keep = up ? k8[j + 4] : k8[j];
               const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, p.TW);
-              __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv));
-              o4[j] = *reinterpret_cast<uint32_t*>(&a);
+              o4[j] = p.f16 ? max16x2<true>(keep, recv) : max16x2<false>(keep, recv);
             }
           } else {
             float lo8[8], hi8[8];
@@ -219,17 +200,16 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
             for (int j = 0; j < 8; ++j) {
               const uint32_t send = odd ? pk[j] : pk[j + 8], keep = odd ? pk[j + 8] : pk[j];
               const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-              const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&keep), c = *reinterpret_cast<const __nv_bfloat162*>(&recv);
-              lo8[j] = __low2float(a) + __low2float(c);
-              hi8[j] = __high2float(a) + __high2float(c);
+              const float2 a = p.f16 ? unpack16<true>(keep) : unpack16<false>(keep), c = p.f16 ? unpack16<true>(recv) : unpack16<false>(recv);
+              lo8[j] = a.x + c.x;
+              hi8[j] = a.y + c.y;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float slo = up ? lo8[j] : lo8[j + 4], shi = up ? hi8[j] : hi8[j + 4];
               const float klo = up ? lo8[j + 4] : lo8[j], khi = up ? hi8[j + 4] : hi8[j];
               const float lo = klo + __shfl_xor_sync(0xffffffffu, slo, p.TW), hi = khi + __shfl_xor_sync(0xffffffffu, shi, p.TW);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo * 0.25f, hi * 0.25f);
-              o4[j] = *reinterpret_cast<uint32_t*>(&h2);
+              o4[j] = p.f16 ? pack16_rn<true>(lo * 0.25f, hi * 0.25f) : pack16_rn<false>(lo * 0.25f, hi * 0.25f);
             }
           }
           if (valid)    // a window never straddles the image edge (even H, W; bricks start at even coordinates)
@@ -309,22 +289,7 @@ __device__ __forceinline__ void convt_pair_epilogue(const ConvTcParams& p, const
             mbar_arrive(bar_tempty + as * 8);
           }
           uint32_t pk[16];
-          const uint32_t bs_addr = smem_u32(bs) + (uint32_t)c0 * 4;
-          if (p.relu) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 b4 = lds128_f4(bs_addr + k * 16);
-              pk[2 * k] = add_pack_bf16x2<true>(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), b4.x, b4.y);
-              pk[2 * k + 1] = add_pack_bf16x2<true>(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]), b4.z, b4.w);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 b4 = lds128_f4(bs_addr + k * 16);
-              pk[2 * k] = add_pack_bf16x2<false>(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), b4.x, b4.y);
-              pk[2 * k + 1] = add_pack_bf16x2<false>(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]), b4.z, b4.w);
-            }
-          }
+          bias_pack32(r, smem_u32(bs) + (uint32_t)c0 * 4, pk, p.relu, p.f16);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             sts128_u32(stg_row + ((((half * 4 + k) ^ (row & 7)) & 7) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
@@ -435,7 +400,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // =========================== MMA issuer ===========================
     // one elected thread runs the whole issue loop: nothing but barrier polls between MMAs
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      const uint32_t idesc = p.f16 ? umma_idesc_f16(TC_BM, BN) : umma_idesc_bf16(TC_BM, BN);
       if (RESW) { mbar_wait(bar_wfull, 0); tcgen05_fence_after(); }
       uint32_t kc = 0, iter = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -582,7 +547,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      const uint32_t idesc = p.f16 ? umma_idesc_f16(TC_BM, BN) : umma_idesc_bf16(TC_BM, BN);
       if (RESB) { mbar_wait(bar_wfull, 0); tcgen05_fence_after(); }
       uint32_t kc = 0, iter = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -674,7 +639,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmY, const ConvTcParams
   for (int i = threadIdx.x; i < 64 * 18; i += CF_THREADS) {
     const int co = i / 18, k = i % 18;
     const uint32_t off = (uint32_t)(co * 128 + ((((k >> 3) ^ (co & 7)) & 7) << 4) + (k & 7) * 2);
-    *reinterpret_cast<__nv_bfloat16*>(smem_raw + L::W_OFF + off) = __float2bfloat16(__ldg(w + co * 9 + (k % 9)));
+    const float wv = __ldg(w + co * 9 + (k % 9));
+    *reinterpret_cast<uint16_t*>(smem_raw + L::W_OFF + off) = p.f16 ? cvt16<true>(wv) : cvt16<false>(wv);
   }
   for (int i = threadIdx.x; i < 64; i += CF_THREADS) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
   fence_proxy_async_smem();
@@ -686,7 +652,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmY, const ConvTcParams
   if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, 64);
+      const uint32_t idesc = p.f16 ? umma_idesc_f16(TC_BM, 64) : umma_idesc_bf16(TC_BM, 64);
       const uint64_t bdesc = umma_smem_desc_sw128(smem_base + L::W_OFF);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -730,17 +696,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmY, const ConvTcParams
         tmem_ld_wait();
         if (half == 1) { tcgen05_fence_before(); mbar_arrive(bar_tempty + e * 8); }
         uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = lds128_f4(bs_addr + (half * 32 + 4 * j) * 4);
-          if (p.relu) {
-            pk[2 * j] = add_pack_bf16x2<true>(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b4.x, b4.y);
-            pk[2 * j + 1] = add_pack_bf16x2<true>(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b4.z, b4.w);
-          } else {
-            pk[2 * j] = add_pack_bf16x2<false>(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), b4.x, b4.y);
-            pk[2 * j + 1] = add_pack_bf16x2<false>(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), b4.z, b4.w);
-          }
-        }
+        bias_pack32(r, bs_addr + (uint32_t)(half * 32) * 4, pk, p.relu, p.f16);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           sts128_u32(stg_row + ((((half * 4 + j) ^ (m & 7)) & 7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -783,26 +739,22 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmY, const ConvTcParams
       if (m + 128 < PH * PW) patch[m + 128] = nxt[1];
       load_patch(tile + gridDim.x, nxt);                 // in flight during the build below
       named_bar_sync(5, 128);
-      // k = 0..8: bf16(x_tap); k = 9..17: bf16(x_tap - hi)
-      __nv_bfloat16 kv[24];
+      // k = 0..8: hi = the 16-bit rounding of x_tap; k = 9..17: the rounding of (x_tap - hi)
+      uint16_t kv[24];
 #pragma unroll
       for (int t9 = 0; t9 < 9; ++t9) {
         const float v = patch[(ty + t9 / 3) * PW + tx + t9 % 3];
-        const __nv_bfloat16 hi = __float2bfloat16(v);
-        kv[t9] = hi;
-        kv[9 + t9] = __float2bfloat16(v - __bfloat162float(hi));
+        if (p.f16) { kv[t9] = cvt16<true>(v); kv[9 + t9] = cvt16<true>(v - cvt16_to_f32<true>(kv[t9])); }
+        else { kv[t9] = cvt16<false>(v); kv[9 + t9] = cvt16<false>(v - cvt16_to_f32<false>(kv[t9])); }
       }
 #pragma unroll
-      for (int j = 18; j < 24; ++j) kv[j] = __float2bfloat16(0.f);
+      for (int j = 18; j < 24; ++j) kv[j] = 0;
       const uint32_t arow = smem_base + s * L::A_BYTES + m * 128;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 h2 = __halves2bfloat162(kv[c * 8 + 2 * j], kv[c * 8 + 2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-        }
+        for (int j = 0; j < 4; ++j) pk[j] = (uint32_t)kv[c * 8 + 2 * j] | ((uint32_t)kv[c * 8 + 2 * j + 1] << 16);
         sts128_u32(arow + (((c ^ (m & 7)) & 7) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async_smem();
@@ -921,14 +873,14 @@ static int make_convt_pair_map(CUtensorMap* m, void* y, int B, int H, int W, int
 // Cin = 1, Cout = 64, W >= 16, H >= 8: tensor-core first layer; returns PMU_ERR_UNSUPPORTED otherwise (the caller
 // falls back to the CUDA-core stencil of layers_bf16.cu)
 int conv_first_tc_launch(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int relu,
-                         cudaStream_t st) {
+                         int f16, cudaStream_t st) {
   int cc_major = 0, dev = 0;
   PMU_CUDA(cudaGetDevice(&dev));
   PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
   if (cc_major != 10 || W < 16 || H < 8 || !get_encode_fn()) return PMU_ERR_UNSUPPORTED;
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = 64; p.C1 = 0; p.Cout = 64; p.ntaps = 9; p.relu = relu;
-  p.pool_mode = -1; p.tma_store = 1;
+  p.pool_mode = -1; p.tma_store = 1; p.f16 = f16 ? 1 : 0;
   p.TW = 16; p.TH = 8; p.TB = 1;
   p.tiles_w = cdiv(W, 16); p.tiles_h = cdiv(H, 8); p.tiles_b = B; p.n_tiles = 1;
   const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * B;
@@ -949,7 +901,7 @@ using namespace pmu;
 
 static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                           const float* bias, void* y, void* y_pool, int pool_mode, int B, int H, int W, int Cout,
-                          int ntaps, int relu, void* stream) {
+                          int ntaps, int relu, int f16, void* stream) {
   PMU_CHECK_ARG(x0 && wpack && (y || y_pool), "pmu_conv_gemm_bf16: null pointer");
   PMU_CHECK_ARG(ntaps == 9 || ntaps == 4 || ntaps == 1, "pmu_conv_gemm_bf16: ntaps must be 9, 4 or 1 (got %d)", ntaps);
   PMU_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && C1 >= 0, "pmu_conv_gemm_bf16: bad shape");
@@ -967,6 +919,7 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout; p.ntaps = ntaps; p.relu = relu;
   p.pool_mode = y_pool ? pool_mode : -1;
+  p.f16 = f16 ? 1 : 0;
   p.TW = std::min(16, pow2ceil(W));
   p.TH = std::min(TC_BM / p.TW, pow2ceil(H));
   p.TB = TC_BM / (p.TW * p.TH);
@@ -1049,13 +1002,13 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
 
 extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                                   const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
-                                  int relu, void* stream) {
-  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, nullptr, -1, B, H, W, Cout, ntaps, relu, stream);
+                                  int relu, int f16, void* stream) {
+  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, nullptr, -1, B, H, W, Cout, ntaps, relu, f16, stream);
 }
 
 extern "C" int pmu_conv_gemm_pool_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                                        const float* bias, void* y, void* y_pool, int pool_mode, int B, int H,
-                                       int W, int Cout, int relu, void* stream) {
+                                       int W, int Cout, int relu, int f16, void* stream) {
   PMU_CHECK_ARG(y_pool != nullptr, "pmu_conv_gemm_pool_bf16: y_pool is null");
-  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, y_pool, pool_mode, B, H, W, Cout, 9, relu, stream);
+  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, y_pool, pool_mode, B, H, W, Cout, 9, relu, f16, stream);
 }

@@ -30,8 +30,10 @@
 //   * the head's softmax of a slot is done by the column half that matches the slot's parity (one thread per pixel),
 //     the four partial (sum, sum^2) sets of a pixel are combined through shared memory at the end of the tile.
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include "pmu_common.cuh"
+#include "h16.cuh"
 #include "sm100_ptx.cuh"
 
 namespace pmu {
@@ -84,23 +86,10 @@ struct FcombTsParams {
   int64_t HW;
 };
 
-__device__ __forceinline__ void f2_st_bf16(uint8_t* tile, int row, int k, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(tile + (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2)) = __float2bfloat16(v);
-}
-__device__ __forceinline__ uint32_t f2_pack_relu(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-// relu(a + b) of two fp32 pairs -> packed bf16x2: one packed add (add.f32x2) + one cvt
-__device__ __forceinline__ uint32_t f2_add_pack_relu(float a0, float a1, float b0, float b1) {
-  uint32_t d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t.reg .f32 lo, hi;\n\t"
-      "mov.b64 ra, {%1, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {lo, hi}, rd;\n\t"
-      "cvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}"
-      : "=r"(d) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-  return d;
+// weight / bias tiles in the activations' 16-bit format (h16.cuh)
+template <bool F16>
+__device__ __forceinline__ void f2_st_w(uint8_t* tile, int row, int k, float v) {
+  *reinterpret_cast<uint16_t*>(tile + (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2)) = cvt16<F16>(v);
 }
 __device__ __forceinline__ float4 f2_lds128f(uint32_t addr) {
   float4 v;
@@ -162,7 +151,7 @@ __device__ __forceinline__ void f2_tmem_st32(uint32_t taddr, const uint32_t (&r)
       : "memory");
 }
 
-template <int CMAX>
+template <int CMAX, bool F16>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, const float* __restrict__ mu,
                  const float* __restrict__ sigma, const float* __restrict__ eps, const float* __restrict__ w0,
@@ -196,21 +185,21 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
   __syncthreads();
   for (int i = tid; i < F2_F * F2_F; i += F2_THREADS) {
     const int o = i >> 6, k = i & 63;
-    f2_st_bf16(sgen + F2_OFF_W0, o, k, __ldg(w0 + (int64_t)o * (F2_F + L) + k));
-    for (int m = 0; m < nmid; ++m) f2_st_bf16(sgen + F2_OFF_WM + m * F2_WT, o, k, __ldg(wmid + (int64_t)m * F2_F * F2_F + i));
+    f2_st_w<F16>(sgen + F2_OFF_W0, o, k, __ldg(w0 + (int64_t)o * (F2_F + L) + k));
+    for (int m = 0; m < nmid; ++m) f2_st_w<F16>(sgen + F2_OFF_WM + m * F2_WT, o, k, __ldg(wmid + (int64_t)m * F2_F * F2_F + i));
   }
-  for (int i = tid; i < C * F2_F; i += F2_THREADS) f2_st_bf16(sgen + F2_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
+  for (int i = tid; i < C * F2_F; i += F2_THREADS) f2_st_w<F16>(sgen + F2_OFF_WL, i >> 6, i & 63, __ldg(wlast + i));
   for (int i = tid; i < nmid * F2_F; i += F2_THREADS) {
     const float bv = __ldg(bmid + i);
-    const float bh = __bfloat162float(__float2bfloat16(bv));
-    f2_st_bf16(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 0, bh);
-    f2_st_bf16(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 1, bv - bh);
+    const float bh = cvt16_to_f32<F16>(cvt16<F16>(bv));
+    f2_st_w<F16>(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 0, bh);
+    f2_st_w<F16>(sgen + F2_OFF_BMT + (i >> 6) * F2_WT, i & 63, 1, bv - bh);
   }
   for (int i = tid; i < C; i += F2_THREADS) {
     const float bv = __ldg(blast + i);
-    const float bh = __bfloat162float(__float2bfloat16(bv));
-    f2_st_bf16(sgen + F2_OFF_BLT, i, 0, bh);
-    f2_st_bf16(sgen + F2_OFF_BLT, i, 1, bv - bh);
+    const float bh = cvt16_to_f32<F16>(cvt16<F16>(bv));
+    f2_st_w<F16>(sgen + F2_OFF_BLT, i, 0, bh);
+    f2_st_w<F16>(sgen + F2_OFF_BLT, i, 1, bv - bh);
   }
   float* zb_s = reinterpret_cast<float*>(sgen + F2_OFF_ZB);
   fence_proxy_async_smem();
@@ -227,7 +216,7 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
   const uint32_t tG = tmem_base + ((uint32_t)(q4 * 32) << 16) + F2_G_COL;
   if (warp < 16) {
     // the constant K extension of the slot's A operand: k = 64, 65 -> 1.0 (bf16 pair), k = 66..79 -> 0
-    const uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const uint32_t ones[8] = {F16 ? 0x3C003C00u : 0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // (1.0, 1.0)
     f2_tmem_st8(tY + 32, ones);
     f2_tmem_st_wait();
   }
@@ -275,8 +264,8 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
         // warp 16 also loads the feature tiles (TMA) and issues the per-tile G = W0f f ============
         if (elect_one()) {
           const int s = warp - 16;
-          constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
-          constexpr uint32_t idesc16 = umma_idesc_bf16(128, 16);
+          constexpr uint32_t idesc64 = F16 ? umma_idesc_f16(128, 64) : umma_idesc_bf16(128, 64);
+          constexpr uint32_t idesc16 = F16 ? umma_idesc_f16(128, 16) : umma_idesc_bf16(128, 16);
           const uint32_t sW0 = sbase + F2_OFF_W0, sWM = sbase + F2_OFF_WM, sWL = sbase + F2_OFF_WL;
           const uint32_t sBM = sbase + F2_OFF_BMT, sBL = sbase + F2_OFF_BLT;
           const uint32_t sX = tmem_base + s * F2_SLOT_COLS, sY = sX + 64;
@@ -378,8 +367,8 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                   const float4 z = f2_lds128f(zb + h * 128 + c * 16);
-                  pk[2 * c] = f2_add_pack_relu(__uint_as_float(g[4 * c]), __uint_as_float(g[4 * c + 1]), z.x, z.y);
-                  pk[2 * c + 1] = f2_add_pack_relu(__uint_as_float(g[4 * c + 2]), __uint_as_float(g[4 * c + 3]), z.z, z.w);
+                  pk[2 * c] = add_pack16<true, F16>(__uint_as_float(g[4 * c]), __uint_as_float(g[4 * c + 1]), z.x, z.y);
+                  pk[2 * c + 1] = add_pack16<true, F16>(__uint_as_float(g[4 * c + 2]), __uint_as_float(g[4 * c + 3]), z.z, z.w);
                 }
                 f2_tmem_st16(tY + h * 16, pk);
               }
@@ -407,7 +396,7 @@ fcomb_ts_kernel(const __grid_constant__ CUtensorMap tmF, const FcombTsParams p, 
                 tmem_ld_32x32(tX + h * 32, rr);
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 16; ++c) pk[c] = f2_pack_relu(__uint_as_float(rr[2 * c]), __uint_as_float(rr[2 * c + 1]));
+                for (int c = 0; c < 16; ++c) pk[c] = pack16_relu<F16>(__uint_as_float(rr[2 * c]), __uint_as_float(rr[2 * c + 1]));
                 f2_tmem_st16(tY + h * 16, pk);
               }
               F2_T(40);
@@ -471,7 +460,7 @@ extern "C" int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, c
                                             const float* eps, const float* w0, const float* b0,
                                             const float* wmid, const float* bmid, const float* wlast,
                                             const float* blast, float* slice_sums, int B, int N, int L,
-                                            int C, int nl, int64_t HW, void* stream) {
+                                            int C, int nl, int64_t HW, int f16, void* stream) {
   PMU_CHECK_ARG(feat && mu && sigma && eps && w0 && b0 && wlast && blast && slice_sums,
                 "pmu_fcomb_softmax_accum_bf16: null pointer");
   PMU_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && HW > 0, "pmu_fcomb_softmax_accum_bf16: bad shape");
@@ -506,6 +495,6 @@ extern "C" int pmu_fcomb_softmax_accum_bf16(const void* feat, const float* mu, c
     PMU_LAUNCH_CHECK();
     return PMU_OK;
   };
-  if (C <= 4) return launch(fcomb_ts_kernel<4>);
-  return launch(fcomb_ts_kernel<8>);
+  if (C <= 4) return f16 ? launch(fcomb_ts_kernel<4, true>) : launch(fcomb_ts_kernel<4, false>);
+  return f16 ? launch(fcomb_ts_kernel<8, true>) : launch(fcomb_ts_kernel<8, false>);
 }

@@ -3,6 +3,7 @@
 //   2x2 pooling (MaxPool2d(2), unet_parts.py:33; AvgPool2d(2,2,ceil_mode), probabilistic_unet.py:36)
 //   NHWC bf16 -> NCHW fp32 (hands unet_features back in the reference's layout)
 #include "pmu_common.cuh"
+#include "h16.cuh"
 
 namespace pmu {
 
@@ -13,6 +14,7 @@ namespace pmu {
 // ---------------------------------------------------------------------------------
 constexpr int FL_MAX_W = 128 * 2 * 9;  // Cout <= 128, Cin <= 2
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
 conv3x3_first_bf16_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                           const float* __restrict__ w, const float* __restrict__ bias,
@@ -61,8 +63,7 @@ conv3x3_first_bf16_kernel(const float* __restrict__ x0, const float* __restrict_
     for (int j = 0; j < 4; ++j) {
       float a = acc[2 * j], c = acc[2 * j + 1];
       if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
-      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      pk[j] = pack16_rn<F16>(a, c);
     }
     *reinterpret_cast<uint4*>(y + pix * Cout + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
@@ -74,6 +75,7 @@ conv3x3_first_bf16_kernel(const float* __restrict__ x0, const float* __restrict_
 // load latency.  Inputs come in as one float4 + two halo scalars per row; 32-bit index math only.
 // Per 4 pixels: 9 global loads, 288 FMA, 4 x 16-byte stores (a warp writes four full 128-byte
 // lines per store instruction).
+template <bool F16>
 __global__ void __launch_bounds__(256, 3)
 conv3x3_first_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
@@ -128,8 +130,7 @@ conv3x3_first_c1_kernel(const float* __restrict__ x, const float* __restrict__ w
       for (int j = 0; j < 4; ++j) {
         float a = acc[p][2 * j], c = acc[p][2 * j + 1];
         if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
-        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        pk[j] = pack16_rn<F16>(a, c);
       }
       *reinterpret_cast<uint4*>(dst + (size_t)p * Cout) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
@@ -139,6 +140,7 @@ conv3x3_first_c1_kernel(const float* __restrict__ x, const float* __restrict__ w
 // ---------------------------------------------------------------------------------
 // 2x2 stride-2 pooling, NHWC bf16; thread = (output pixel, 8 channels = 16 B)
 // ---------------------------------------------------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(256)
 pool2_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                   int C, int Ho, int Wo, int mode) {
@@ -164,8 +166,8 @@ pool2_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
           const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&u[j]);
-            const float lo = __low2float(h2), hi = __high2float(h2);
+            const float2 f2 = unpack16<F16>(u[j]);
+            const float lo = f2.x, hi = f2.y;
             m[2 * j] = fmaxf(m[2 * j], lo); m[2 * j + 1] = fmaxf(m[2 * j + 1], hi);
             s[2 * j] += lo; s[2 * j + 1] += hi;
           }
@@ -178,8 +180,7 @@ pool2_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
     for (int j = 0; j < 4; ++j) {
       const float a = (mode == PMU_POOL_MAX) ? m[2 * j] : s[2 * j] * inv;
       const float c = (mode == PMU_POOL_MAX) ? m[2 * j + 1] : s[2 * j + 1] * inv;
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
-      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      pk[j] = pack16_rn<F16>(a, c);
     }
     *reinterpret_cast<uint4*>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
@@ -188,6 +189,7 @@ pool2_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
 // ---------------------------------------------------------------------------------
 // [B][HW][C] bf16 -> [B][C][HW] fp32 through a 64 px x 64 ch shared tile
 // ---------------------------------------------------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t HW, int C) {
   __shared__ float tile[64][65];
@@ -202,8 +204,8 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, 
     const int pp = idx >> 5, c2 = (idx & 31) * 2;
     float lo = 0.f, hi = 0.f;
     if (p0 + pp < HW && c0 + c2 < C) {
-      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(x + ((int64_t)b * HW + p0 + pp) * C + c0 + c2);
-      lo = __low2float(h2); hi = __high2float(h2);
+      const float2 f2 = unpack16<F16>(*reinterpret_cast<const uint32_t*>(x + ((int64_t)b * HW + p0 + pp) * C + c0 + c2));
+      lo = f2.x; hi = f2.y;
     }
     tile[pp][c2] = lo; tile[pp][c2 + 1] = hi;
   }
@@ -248,19 +250,19 @@ nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, 
 
 namespace pmu {
 int conv_first_tc_launch(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int relu,
-                         cudaStream_t st);   // conv_tc.cu
+                         int f16, cudaStream_t st);   // conv_tc.cu
 }
 using namespace pmu;
 
 extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const float* w, const float* bias,
-                                      void* y, int B, int H, int W, int Cin, int Cout, int relu, void* stream) {
+                                      void* y, int B, int H, int W, int Cin, int Cout, int relu, int f16, void* stream) {
   PMU_CHECK_ARG(x0 && w && y && B > 0 && H > 0 && W > 0, "pmu_conv3x3_first_bf16: bad arguments");
   PMU_CHECK_SUPPORTED(Cin >= 1 && Cin <= 2 && (Cin == 1 || x1), "pmu_conv3x3_first_bf16: Cin must be 1, or 2 with x1 (got %d)", Cin);
   PMU_CHECK_SUPPORTED(Cout % 8 == 0 && Cout <= 128, "pmu_conv3x3_first_bf16: Cout must be a multiple of 8, <= 128 (got %d)", Cout);
   PMU_CHECK_ARG(aligned16(y), "pmu_conv3x3_first_bf16: y must be 16-byte aligned");
   // tensor-core path (conv_tc.cu): im2col rows in shared memory, two K = 16 UMMAs per 128 pixels, TMA-store epilogue
   if (Cin == 1 && Cout == 64) {
-    const int rc = conv_first_tc_launch(x0, w, bias, y, B, H, W, relu, (cudaStream_t)stream);
+    const int rc = conv_first_tc_launch(x0, w, bias, y, B, H, W, relu, f16, (cudaStream_t)stream);
     if (rc != PMU_ERR_UNSUPPORTED) return rc;
   }
   const int groups = Cout / 8;
@@ -268,20 +270,20 @@ extern "C" int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const fl
     const int64_t quads = (int64_t)B * H * (W / 4);
     const int qpb = 256 / groups;
     const int blocks = (int)std::min<int64_t>(cdiv64(quads, qpb), (int64_t)sm_count() * 16);
-    conv3x3_first_c1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, w, bias, reinterpret_cast<__nv_bfloat16*>(y),
-                                                                     B, H, W, Cout, relu);
+    if (f16) conv3x3_first_c1_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, w, bias, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, Cout, relu);
+    else conv3x3_first_c1_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, w, bias, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, Cout, relu);
     PMU_LAUNCH_CHECK();
     return PMU_OK;
   }
   const int64_t total = (int64_t)B * H * W * (Cout / 8);
   const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 32);
-  conv3x3_first_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, x1, w, bias, reinterpret_cast<__nv_bfloat16*>(y),
-                                                                     B, H, W, Cin, Cout, relu);
+  if (f16) conv3x3_first_bf16_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, x1, w, bias, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, Cin, Cout, relu);
+  else conv3x3_first_bf16_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, x1, w, bias, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, Cin, Cout, relu);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }
 
-extern "C" int pmu_pool2_bf16(const void* x, void* y, int B, int H, int W, int C, int mode, void* stream) {
+extern "C" int pmu_pool2_bf16(const void* x, void* y, int B, int H, int W, int C, int mode, int f16, void* stream) {
   PMU_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0, "pmu_pool2_bf16: bad arguments");
   PMU_CHECK_ARG(mode == PMU_POOL_MAX || mode == PMU_POOL_AVG_CEIL, "pmu_pool2_bf16: unknown mode %d", mode);
   PMU_CHECK_SUPPORTED(C % 8 == 0, "pmu_pool2_bf16: C must be a multiple of 8 (got %d)", C);
@@ -291,18 +293,19 @@ extern "C" int pmu_pool2_bf16(const void* x, void* y, int B, int H, int W, int C
   PMU_CHECK_ARG(Ho > 0 && Wo > 0, "pmu_pool2_bf16: input too small");
   const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
   const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 32);
-  pool2_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                             reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C, Ho, Wo, mode);
+  if (f16) pool2_bf16_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C, Ho, Wo, mode);
+  else pool2_bf16_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C, Ho, Wo, mode);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }
 
-extern "C" int pmu_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, void* stream) {
+extern "C" int pmu_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, int f16, void* stream) {
   PMU_CHECK_ARG(x && y && B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0, "pmu_nhwc_bf16_to_nchw_f32: bad arguments");
   PMU_CHECK_SUPPORTED(C % 2 == 0, "pmu_nhwc_bf16_to_nchw_f32: C must be even");
   const int64_t HW = (int64_t)H * W;
   dim3 grid((unsigned)cdiv64(HW, 64), cdiv(C, 64), B);
-  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, HW, C);
+  if (f16) nhwc_to_nchw_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, HW, C);
+  else nhwc_to_nchw_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, HW, C);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

@@ -8,6 +8,8 @@
 //   Gaussian head (mean over H, W + 1x1 conv)                           probabilistic_unet.py:97-108
 //   Fcomb over N samples (+ fused softmax / sum / sum-of-squares)       probabilistic_unet.py:155-181
 #include "pmu_common.cuh"
+#include "h16.cuh"
+#include <type_traits>
 
 namespace pmu {
 
@@ -222,6 +224,7 @@ pool2_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t BC,
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 
 // NHWC = false: enc[B][C][hw];  NHWC = true: enc[B][hw][C]
 template <typename T, bool NHWC>
@@ -252,9 +255,12 @@ gauss_head_kernel(const T* __restrict__ enc, const float* __restrict__ w, const 
 #pragma unroll 4
     for (int i = pg; i < hw; i += pgs) {
       const uint4 v = __ldg(p + (int64_t)i * groups);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { acc[2 * j] += __low2float(h[j]); acc[2 * j + 1] += __high2float(h[j]); }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f2 = unpack16<sizeof(T) == 2 && !std::is_same<T, __nv_bfloat16>::value>(u[j]);
+        acc[2 * j] += f2.x; acc[2 * j + 1] += f2.y;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) part[pg * C + cg * 8 + j] = acc[j];
@@ -498,7 +504,7 @@ extern "C" int pmu_gauss_head_f32(const float* enc, const float* w, const float*
 }
 
 extern "C" int pmu_gauss_head_bf16(const void* enc, const float* w, const float* b, float* mu,
-                                   float* log_sigma, int B, int C, int h, int w_, int L, void* stream) {
+                                   float* log_sigma, int B, int C, int h, int w_, int L, int f16, void* stream) {
   PMU_CHECK_ARG(enc && w && b && mu && log_sigma, "pmu_gauss_head_bf16: null pointer");
   PMU_CHECK_ARG(B > 0 && C > 0 && h > 0 && w_ > 0 && L > 0 && C <= 12288, "pmu_gauss_head_bf16: bad shape");
   // vector path: threads = (C/8 channel groups) x (pixel groups), as many pixel groups as fit 1024 threads
@@ -514,10 +520,15 @@ extern "C" int pmu_gauss_head_bf16(const void* enc, const float* w, const float*
     }
     if (threads % groups == 0) smem = (size_t)(1 + threads / groups) * C * sizeof(float);   // the kernel takes the vector path
   }
-  auto kern = gauss_head_kernel<__nv_bfloat16, true>;
-  if (smem > 48 * 1024) PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<B, threads, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(enc), w, b, mu, log_sigma, C,
-                                                  h * w_, L);
+  if (f16) {
+    auto kern = gauss_head_kernel<__half, true>;
+    if (smem > 48 * 1024) PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, threads, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(enc), w, b, mu, log_sigma, C, h * w_, L);
+  } else {
+    auto kern = gauss_head_kernel<__nv_bfloat16, true>;
+    if (smem > 48 * 1024) PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, threads, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(enc), w, b, mu, log_sigma, C, h * w_, L);
+  }
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

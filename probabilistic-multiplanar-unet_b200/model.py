@@ -100,8 +100,15 @@ def _no_autograd(module: nn.Module, what: str):
 class _PackedMixin:
     _pack_prefix = ""
 
-    def _state_version(self) -> int:
-        return sum(t._version for t in list(self.parameters()) + list(self.buffers()))
+    def _state_version(self):
+        # (storage, version) per tensor: parameter replacement and load_state_dict(assign=True) change the storage,
+        # in-place updates the version.  Writes through `.data` bump neither: call invalidate_pack() after them.
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def invalidate_pack(self):
+        """Drop the packed (BatchNorm-folded, 16-bit) weights; the next inference call re-packs from the parameters."""
+        object.__setattr__(self, "_pack_key", None)
+        return self
 
     def packed(self) -> PackedNet:
         dev = next(self.parameters()).device
@@ -115,8 +122,9 @@ class _PackedMixin:
         return self._pack
 
     def set_precision(self, precision: str):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "f16", "bf16"):
+            raise ValueError("precision must be 'fp32', 'f16' (tensor-core inference format; training runs its GEMMs "
+                             "in bf16) or 'bf16'")
         self.precision = precision
         return self
 
@@ -287,8 +295,8 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             if not (self.training and training):
                 raise NotImplementedError("gradients are built for net.train() + forward(training=True) (what train.py "
                                           "does); wrap inference in torch.no_grad()")
-            if self.precision == "bf16" and (any(f % 64 for f in self.num_filters) or patch.shape[2] % 16 or patch.shape[3] % 16):
-                raise NotImplementedError("bf16 training needs channel counts that are multiples of 64 and H, W divisible "
+            if self.precision != "fp32" and (any(f % 64 for f in self.num_filters) or patch.shape[2] % 16 or patch.shape[3] % 16):
+                raise NotImplementedError("tensor-core training needs channel counts that are multiples of 64 and H, W divisible "
                                           "by 16 (tcgen05 / TMA tiles); use precision='fp32' for this model")
             if segm is None:
                 raise ValueError("forward(training=True) needs segm for the posterior")

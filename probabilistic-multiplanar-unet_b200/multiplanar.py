@@ -96,7 +96,7 @@ def reduce_scatter_accumulators(acc: torch.Tensor, rank: int, world: int, group=
 class MultiPlanarPredictor:
     """3-plane, N-sample probabilistic prediction of a volume on the current CUDA device."""
 
-    def __init__(self, state_dict, device="cuda", precision: str = "bf16", n_samples: int = 16,
+    def __init__(self, state_dict, device="cuda", precision: str = "f16", n_samples: int = 16,
                  planes: Sequence[int] = (0, 1, 2), slice_batch: int = 32, interp: str = "exact",
                  affines: Optional[Dict[int, Sequence[float]]] = None, out_hw: Optional[Tuple[int, int]] = None,
                  rank: int = 0, world_size: int = 1, process_group=None, output: str = "rank0",

@@ -80,6 +80,21 @@ def _bf16(t, name):
         raise RuntimeError(f"{name} must be bfloat16, got {t.dtype}")
 
 
+def _h16(*named) -> int:
+    """The 16-bit tensors of a tensor-core op — (tensor, name) pairs, None tensors skipped — must share ONE format:
+    bfloat16 (training path) or float16 (inference path).  Returns the `f16` flag of the C-ABI."""
+    dt = None
+    for t, name in named:
+        if t is None:
+            continue
+        if t.dtype not in (torch.bfloat16, torch.float16):
+            raise RuntimeError(f"{name} must be bfloat16 or float16, got {t.dtype}")
+        if dt is not None and t.dtype != dt:
+            raise RuntimeError(f"{name} is {t.dtype} but the other 16-bit operands are {dt}: one format per call")
+        dt = t.dtype
+    return int(dt == torch.float16)
+
+
 # ----------------------------------------------------------------------------- K1
 def plane_max(vol: torch.Tensor) -> torch.Tensor:
     """Per-slice maxima of all three planes, one pass: [d0 + d1 + d2] fp32."""
@@ -200,24 +215,27 @@ def fcomb_f32(feat, z, fw, want_logits=True, want_sums=False, sums_out=None):
 
 
 # ----------------------------------------------------------------------------- bf16 layers
-def conv3x3_first_bf16(x0, w, bias, relu=True, x1=None):
+def conv3x3_first_bf16(x0, w, bias, relu=True, x1=None, out_dtype=torch.bfloat16):
+    """fp32 NCHW input -> 16-bit NHWC output in `out_dtype` (bfloat16 or float16)."""
     _f32(x0, "x0"); _f32(x1, "x1")
     B, _, H, W = x0.shape
     Cin = 1 if x1 is None else 2
     Cout = w.shape[0]
-    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x0.device)
+    out = torch.empty(B, H, W, Cout, dtype=out_dtype, device=x0.device)
+    f16 = _h16((out, "out_dtype"))
     lib, st = _prep(x0, x1, w, bias, out)
-    _launch(lib, "pmu_conv3x3_first_bf16", (_p(x0), _p(x1), _p(w), _p(bias), _p(out), B, H, W, Cin, Cout, int(relu), st,))
+    _launch(lib, "pmu_conv3x3_first_bf16", (_p(x0), _p(x1), _p(w), _p(bias), _p(out), B, H, W, Cin, Cout, int(relu), f16, st,))
     return out
 
 
 def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None):
-    """tcgen05 implicit-GEMM conv: x NHWC bf16 -> y NHWC bf16 (2H x 2W for ntaps=4)."""
-    _bf16(x0, "x0"); _bf16(x1, "x1"); _bf16(wpack, "wpack"); _f32(bias, "bias")
+    """tcgen05 implicit-GEMM conv: x NHWC 16-bit -> y NHWC in the same format (2H x 2W for ntaps=4)."""
+    _f32(bias, "bias")
+    wf = _h16((x0, "x0"), (x1, "x1"), (wpack, "wpack"))
     B, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
     oh, ow = (2 * H, 2 * W) if ntaps == 4 else (H, W)
-    out = torch.empty(B, oh, ow, Cout, dtype=torch.bfloat16, device=x0.device)
+    out = torch.empty(B, oh, ow, Cout, dtype=x0.dtype, device=x0.device)
     lib, st = _prep(x0, x1, wpack, bias, out)
     global _META
     ktot = (9 if ntaps == 9 else 1) * (C0 + C1)
@@ -225,24 +243,25 @@ def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None):
     _META = {"flops": 2.0 * B * H * W * ntot * ktot,
              "bytes": 2.0 * (B * H * W * (C0 + C1) + out.numel() + ntot * ktot)}
     _launch(lib, "pmu_conv_gemm_bf16", (_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), B, H, W, Cout, ntaps,
-                                      int(relu), st,))
+                                      int(relu), wf, st,))
     return out
 
 
 def conv_gemm_pool_bf16(x0, wpack, bias, Cout, relu, pool_mode, x1=None, want_full=True):
     """conv3x3 + fused 2x2 pooling epilogue: returns (y [B,H,W,Cout] or None, y_pool [B,H/2,W/2,Cout])."""
-    _bf16(x0, "x0"); _bf16(x1, "x1"); _bf16(wpack, "wpack"); _f32(bias, "bias")
+    _f32(bias, "bias")
+    wf = _h16((x0, "x0"), (x1, "x1"), (wpack, "wpack"))
     B, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
-    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x0.device) if want_full else None
-    outp = torch.empty(B, H // 2, W // 2, Cout, dtype=torch.bfloat16, device=x0.device)
+    out = torch.empty(B, H, W, Cout, dtype=x0.dtype, device=x0.device) if want_full else None
+    outp = torch.empty(B, H // 2, W // 2, Cout, dtype=x0.dtype, device=x0.device)
     lib, st = _prep(x0, x1, wpack, bias, out, outp)
     global _META
     ktot = 9 * (C0 + C1)
     _META = {"flops": 2.0 * B * H * W * Cout * ktot,
              "bytes": 2.0 * (B * H * W * (C0 + C1) + (out.numel() if want_full else 0) + outp.numel() + Cout * ktot)}
     _launch(lib, "pmu_conv_gemm_pool_bf16", (_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), _p(outp), int(pool_mode),
-                                             B, H, W, Cout, int(relu), st,))
+                                             B, H, W, Cout, int(relu), wf, st,))
     return out, outp
 
 
@@ -251,37 +270,37 @@ def fused_pool_ok(H, W):
 
 
 def pool2_bf16(x, mode):
-    _bf16(x, "x")
+    f16 = _h16((x, "x"))
     B, H, W, C = x.shape
     Ho, Wo = (H // 2, W // 2) if mode == POOL_MAX else ((H + 1) // 2, (W + 1) // 2)
-    out = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
     lib, st = _prep(x, out)
-    _launch(lib, "pmu_pool2_bf16", (_p(x), _p(out), B, H, W, C, mode, st,))
+    _launch(lib, "pmu_pool2_bf16", (_p(x), _p(out), B, H, W, C, mode, f16, st,))
     return out
 
 
 def gauss_head_bf16(enc, w, b, L):
-    _bf16(enc, "enc")
+    f16 = _h16((enc, "enc"))
     B, h, w_, C = enc.shape
     mu = torch.empty(B, L, dtype=torch.float32, device=enc.device)
     ls = torch.empty_like(mu)
     lib, st = _prep(enc, w, b, mu, ls)
-    _launch(lib, "pmu_gauss_head_bf16", (_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, st,))
+    _launch(lib, "pmu_gauss_head_bf16", (_p(enc), _p(w), _p(b), _p(mu), _p(ls), B, C, h, w_, L, f16, st,))
     return mu, ls
 
 
 def nhwc_bf16_to_nchw_f32(x):
-    _bf16(x, "x")
+    f16 = _h16((x, "x"))
     B, H, W, C = x.shape
     out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
     lib, st = _prep(x, out)
-    _launch(lib, "pmu_nhwc_bf16_to_nchw_f32", (_p(x), _p(out), B, H, W, C, st,))
+    _launch(lib, "pmu_nhwc_bf16_to_nchw_f32", (_p(x), _p(out), B, H, W, C, f16, st,))
     return out
 
 
 def fcomb_softmax_accum_bf16(feat, mu, sigma, eps, fw, out=None):
-    """feat NHWC bf16 [B,H,W,64]; mu/sigma [B,L]; eps [B,N,L] -> slice_sums [B,2,C,H,W] fp32."""
-    _bf16(feat, "feat"); _f32(mu, "mu"); _f32(sigma, "sigma"); _f32(eps, "eps")
+    """feat NHWC 16-bit [B,H,W,64]; mu/sigma [B,L]; eps [B,N,L] -> slice_sums [B,2,C,H,W] fp32."""
+    f16 = _h16((feat, "feat")); _f32(mu, "mu"); _f32(sigma, "sigma"); _f32(eps, "eps")
     B, H, W, F_ = feat.shape
     if F_ != 64:
         raise RuntimeError(f"fcomb_softmax_accum_bf16 needs 64 feature channels, got {F_}")
@@ -300,7 +319,7 @@ def fcomb_softmax_accum_bf16(feat, mu, sigma, eps, fw, out=None):
              "tmem_read_bytes": 4.0 * B * H * W * (64 + N * (nmid * 64 + 8))}
     _launch(lib, "pmu_fcomb_softmax_accum_bf16", (_p(feat), _p(mu), _p(sigma), _p(eps), _p(fw["w0"]), _p(fw["b0"]),
                                                 _p(fw["wmid"]), _p(fw["bmid"]), _p(fw["wlast"]), _p(fw["blast"]),
-                                                _p(out), B, N, L, C, nl, H * W, st,))
+                                                _p(out), B, N, L, C, nl, H * W, f16, st,))
     return out
 
 

@@ -322,7 +322,7 @@ class TrainStep:
     def __init__(self, net, patch: torch.Tensor, segm: torch.Tensor):
         self.net = net
         self.patch, self.segm = patch, segm
-        self.bf16 = net.precision == "bf16"
+        self.bf16 = net.precision in ("bf16", "f16")      # the training GEMMs always take bf16 operands
         self._mode(True)
         try:
             self._forward(net, patch, segm)

@@ -9,8 +9,8 @@ from pmu_b200.engine import PackedNet
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 sd = trainer_state_dict(0)
-fw = PackedNet({k: v for k, v in sd.items() if k.startswith("fcomb")}, "cuda", "bf16").fcomb
-feat = torch.relu(torch.randn(B, 256, 256, 64, device="cuda")).to(torch.bfloat16)
+fw = PackedNet({k: v for k, v in sd.items() if k.startswith("fcomb")}, "cuda", "f16").fcomb
+feat = torch.relu(torch.randn(B, 256, 256, 64, device="cuda")).to(torch.float16)
 mu = torch.randn(B, 6, device="cuda"); sigma = torch.rand(B, 6, device="cuda") + 0.2
 eps = torch.randn(B, N, 6, device="cuda")
 for _ in range(2): ops.fcomb_softmax_accum_bf16(feat, mu, sigma, eps, fw)

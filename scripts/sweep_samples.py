@@ -49,7 +49,7 @@ def main():
         torch.cuda.synchronize()
 
     for N in [int(x) for x in args.samples.split(",")]:
-        pred = pmu_b200.MultiPlanarPredictor(sd, dev, precision="bf16", n_samples=N, slice_batch=args.slice_batch,
+        pred = pmu_b200.MultiPlanarPredictor(sd, dev, precision="f16", n_samples=N, slice_batch=args.slice_batch,
                                              interp="trilinear", rank=rank, world_size=world,
                                              output="slab" if world > 1 else "rank0")
         eps = torch.randn(P, D, N, 6, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)

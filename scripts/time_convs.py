@@ -35,11 +35,11 @@ MULT = {0: 2, 1: 2, 2: 2, 3: 2, 4: 2, 5: 2, 6: 2, 7: 2, 8: 2}
 tot_ms, tot_fl = 0.0, 0.0
 print(f"variant={os.environ.get('PMU_CONV_VARIANT', '0')} B={B}")
 for i, (name, C0, C1, Cout, H, ntaps, pool) in enumerate(LAYERS):
-    x0 = torch.randn(B, H, H, C0, device="cuda").to(torch.bfloat16)
-    x1 = torch.randn(B, H, H, C1, device="cuda").to(torch.bfloat16) if C1 else None
+    x0 = torch.randn(B, H, H, C0, device="cuda").to(torch.float16)
+    x1 = torch.randn(B, H, H, C1, device="cuda").to(torch.float16) if C1 else None
     K = (9 if ntaps == 9 else 1) * (C0 + C1)
     N = (4 if ntaps == 4 else 1) * Cout
-    wp = (torch.randn(N, K, device="cuda") * 0.01).to(torch.bfloat16)
+    wp = (torch.randn(N, K, device="cuda") * 0.01).to(torch.float16)
     bias = torch.zeros(Cout, device="cuda")
     def run():
         if pool is not None:

@@ -8,9 +8,9 @@ LAYERS = [("64->64 @256 +pool", 64, 0, 64, 256, 0), ("64->64 @256", 64, 0, 64, 2
           ("64->128 @128", 64, 0, 128, 128, None), ("128->128 @128", 128, 0, 128, 128, None), ("128+128->128 @128", 128, 128, 128, 128, None)]
 print("debug =", os.environ.get("PMU_CONV_DEBUG", "0"), " rs =", os.environ.get("PMU_CONV_RS", "1"))
 for name, C0, C1, Cout, H, pool in LAYERS:
-    x0 = torch.randn(B, H, H, C0, device="cuda").to(torch.bfloat16)
-    x1 = torch.randn(B, H, H, C1, device="cuda").to(torch.bfloat16) if C1 else None
-    wp = (torch.randn(Cout, 9 * (C0 + C1), device="cuda") * 0.01).to(torch.bfloat16)
+    x0 = torch.randn(B, H, H, C0, device="cuda").to(torch.float16)
+    x1 = torch.randn(B, H, H, C1, device="cuda").to(torch.float16) if C1 else None
+    wp = (torch.randn(Cout, 9 * (C0 + C1), device="cuda") * 0.01).to(torch.float16)
     bias = torch.zeros(Cout, device="cuda")
     def run():
         if pool is not None: ops.conv_gemm_pool_bf16(x0, wp, bias, Cout, True, pool)

@@ -24,6 +24,10 @@ def _g(seed):
     return torch.Generator().manual_seed(seed)
 
 
+# the two 16-bit storage formats of the tensor-core family: bfloat16 (training path) and IEEE half (inference path)
+H16 = pytest.mark.parametrize("h16", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+
+
 # --------------------------------------------------------------------------- fp32
 @pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 1, 0, 4, 9, 13), (1, 5, 3, 7, 32, 48), (3, 16, 16, 33, 8, 8),
                                               (2, 64, 0, 64, 16, 40), (1, 2, 0, 64, 5, 3)])
@@ -87,8 +91,8 @@ def test_fcomb_f32(ops, F_, L, C, nl, N):
 
 
 # --------------------------------------------------------------------------- bf16 / tcgen05
-def _bf(t):
-    return t.to(torch.bfloat16).float()
+def _q(t, h16):
+    return t.to(h16).float()
 
 
 def _nhwc(t):
@@ -97,7 +101,8 @@ def _nhwc(t):
 
 @pytest.mark.parametrize("Cin,B,H,W", [(1, 3, 16, 24), (2, 3, 16, 24), (1, 2, 40, 56), (1, 5, 8, 16), (1, 1, 64, 64),
                                         (1, 2, 6, 12)])       # last: below the tensor-core tile -> CUDA-core stencil
-def test_first_conv_bf16(ops, Cin, B, H, W):
+@H16
+def test_first_conv_bf16(ops, Cin, B, H, W, h16):
     """Cin = 1 with W >= 16, H >= 8 runs the tcgen05 first layer (im2col rows in smem, input split into bf16 hi + lo);
     everything else the CUDA-core stencil."""
     g = _g(5)
@@ -106,7 +111,8 @@ def test_first_conv_bf16(ops, Cin, B, H, W):
     b = torch.randn(64, generator=g) * 0.1
     ref = F.relu(F.conv2d(x, w, b, padding=1))
     got = ops.conv3x3_first_bf16(x[:, :1].contiguous().cuda(), w.cuda(), b.cuda(), True,
-                                 x[:, 1:2].contiguous().cuda() if Cin == 2 else None)
+                                 x[:, 1:2].contiguous().cuda() if Cin == 2 else None, out_dtype=h16)
+    assert got.dtype == h16
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1e-2)
 
 
@@ -123,18 +129,21 @@ CONV_TC_CASES = [
 
 
 @pytest.mark.parametrize("B,C0,C1,Cout,H,W", CONV_TC_CASES)
-def test_conv_gemm_bf16_3x3(ops, B, C0, C1, Cout, H, W):
+@H16
+def test_conv_gemm_bf16_3x3(ops, B, C0, C1, Cout, H, W, h16):
+    """bf16 activations x packed weights in bf16 (training path) or IEEE f16 (inference path, w_f16 = 1): torch on the
+    same rounded operands."""
     g = _g(6)
-    x0 = _bf(torch.randn(B, C0, H, W, generator=g))
-    x1 = _bf(torch.randn(B, C1, H, W, generator=g)) if C1 else None
+    x0 = _q(torch.randn(B, C0, H, W, generator=g), h16)
+    x1 = _q(torch.randn(B, C1, H, W, generator=g), h16) if C1 else None
     Cin = C0 + C1
-    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(h16).float()
     b = torch.randn(Cout, generator=g) * 0.1
     xin = torch.cat([x0, x1], 1) if C1 else x0
     ref = F.relu(F.conv2d(xin, w, b, padding=1))
-    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(torch.bfloat16).contiguous().cuda()
-    got = ops.conv_gemm_bf16(_nhwc(x0).to(torch.bfloat16).cuda(), wpack, b.cuda(), Cout, 9, True,
-                             _nhwc(x1).to(torch.bfloat16).cuda() if C1 else None)
+    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(h16).contiguous().cuda()
+    got = ops.conv_gemm_bf16(_nhwc(x0).to(h16).cuda(), wpack, b.cuda(), Cout, 9, True,
+                             _nhwc(x1).to(h16).cuda() if C1 else None)
     err = (got.float().cpu() - _nhwc(ref)).abs().max().item()
     assert err < 3e-2, f"max abs err {err}"
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
@@ -142,61 +151,65 @@ def test_conv_gemm_bf16_3x3(ops, B, C0, C1, Cout, H, W):
 
 @pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 64, 64, 64, 24, 40), (3, 128, 0, 64, 64, 72), (1, 64, 64, 64, 256, 256),
                                               (2, 64, 0, 128, 32, 40), (1, 64, 0, 128, 128, 128), (2, 64, 0, 64, 48, 40)])
-def test_conv_rs_row_shift_shapes(ops, B, C0, C1, Cout, H, W):
+@H16
+def test_conv_rs_row_shift_shapes(ops, B, C0, C1, Cout, H, W, h16):
     """The row-shift kernel at the shapes the network gives it (64 -> 64 and 64 -> 128 with resident weights, 128 -> 64
     streaming, full resolution, partial tiles) against torch on the same bf16 operands."""
     g = _g(16)
     Cin = C0 + C1
-    x0 = _bf(torch.randn(B, C0, H, W, generator=g))
-    x1 = _bf(torch.randn(B, C1, H, W, generator=g)) if C1 else None
-    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5)
+    x0 = _q(torch.randn(B, C0, H, W, generator=g), h16)
+    x1 = _q(torch.randn(B, C1, H, W, generator=g), h16) if C1 else None
+    w = _q(torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5, h16)
     b = torch.randn(Cout, generator=g) * 0.1
     ref = F.relu(F.conv2d(torch.cat([x0, x1], 1) if C1 else x0, w, b, padding=1))
-    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(torch.bfloat16).contiguous().cuda()
-    got = ops.conv_gemm_bf16(_nhwc(x0).to(torch.bfloat16).cuda(), wpack, b.cuda(), Cout, 9, True,
-                             _nhwc(x1).to(torch.bfloat16).cuda() if C1 else None)
+    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(h16).contiguous().cuda()
+    got = ops.conv_gemm_bf16(_nhwc(x0).to(h16).cuda(), wpack, b.cuda(), Cout, 9, True,
+                             _nhwc(x1).to(h16).cuda() if C1 else None)
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
 
 
 @pytest.mark.parametrize("B,Cin,H,W", [(2, 128, 8, 8), (3, 128, 128, 128), (5, 64, 24, 40), (9, 128, 4, 4), (2, 128, 20, 12)])
-def test_convt_paired_phase_store(ops, B, Cin, H, W):
+@H16
+def test_convt_paired_phase_store(ops, B, Cin, H, W, h16):
     """The one-N-tile transposed convolution (Cout = 64, N = 256): resident weights + paired-phase epilogue (both column
     parities of an output row staged interleaved, one tensor store per row parity) against torch; the cases cover
     partial tiles, bricks that span several images (4 x 4) and non-power-of-two extents."""
     g = _g(17)
     Cout = 64
-    x = _bf(torch.randn(B, Cin, H, W, generator=g))
-    w = _bf(torch.randn(Cin, Cout, 2, 2, generator=g) * (1.0 / Cin) ** 0.5)
+    x = _q(torch.randn(B, Cin, H, W, generator=g), h16)
+    w = _q(torch.randn(Cin, Cout, 2, 2, generator=g) * (1.0 / Cin) ** 0.5, h16)
     b = torch.randn(Cout, generator=g) * 0.1
     ref = F.conv_transpose2d(x, w, b, stride=2)
-    wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(torch.bfloat16).contiguous().cuda()
-    got = ops.conv_gemm_bf16(_nhwc(x).to(torch.bfloat16).cuda(), wpack, b.cuda(), Cout, 4, False)
+    wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(h16).contiguous().cuda()
+    got = ops.conv_gemm_bf16(_nhwc(x).to(h16).cuda(), wpack, b.cuda(), Cout, 4, False)
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
 
 
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 128, 64, 8, 8), (1, 1024, 512, 4, 4), (3, 256, 128, 16, 12)])
-def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W):
+@H16
+def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W, h16):
     g = _g(7)
-    x = _bf(torch.randn(B, Cin, H, W, generator=g))
-    w = _bf(torch.randn(Cin, Cout, 2, 2, generator=g) * (1.0 / Cin) ** 0.5)
+    x = _q(torch.randn(B, Cin, H, W, generator=g), h16)
+    w = _q(torch.randn(Cin, Cout, 2, 2, generator=g) * (1.0 / Cin) ** 0.5, h16)
     b = torch.randn(Cout, generator=g) * 0.1
     ref = F.conv_transpose2d(x, w, b, stride=2)
-    wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(torch.bfloat16).contiguous().cuda()
-    got = ops.conv_gemm_bf16(_nhwc(x).to(torch.bfloat16).cuda(), wpack, b.cuda(), Cout, 4, False)
+    wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(h16).contiguous().cuda()
+    got = ops.conv_gemm_bf16(_nhwc(x).to(h16).cuda(), wpack, b.cuda(), Cout, 4, False)
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
 
 
 @pytest.mark.parametrize("B,C0,Cout,H,W,mode", [(2, 64, 64, 32, 48, 0), (1, 128, 128, 16, 16, 1), (3, 64, 128, 8, 16, 0),
                                                   (2, 64, 64, 24, 40, 1),
                                                   (2, 128, 256, 16, 32, 0), (2, 128, 256, 16, 32, 1)])   # BN = 256 tiles
-def test_conv_gemm_pool_bf16(ops, B, C0, Cout, H, W, mode):
+@H16
+def test_conv_gemm_pool_bf16(ops, B, C0, Cout, H, W, mode, h16):
     """Fused pooling epilogue (halving exchange over the window lanes): y identical to the unfused conv,
     y_pool == pool(y) — bit for bit for the max, and equal to the separate pooling kernel for the average."""
     g = _g(12)
-    x = _nhwc(_bf(torch.randn(B, C0, H, W, generator=g))).to(torch.bfloat16).cuda()
-    w = _bf(torch.randn(Cout, C0, 3, 3, generator=g) * (2.0 / (9 * C0)) ** 0.5)
+    x = _nhwc(_q(torch.randn(B, C0, H, W, generator=g), h16)).to(h16).cuda()
+    w = _q(torch.randn(Cout, C0, 3, 3, generator=g) * (2.0 / (9 * C0)) ** 0.5, h16)
     b = (torch.randn(Cout, generator=g) * 0.1).cuda()
-    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C0).to(torch.bfloat16).contiguous().cuda()
+    wpack = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C0).to(h16).contiguous().cuda()
     y_ref = ops.conv_gemm_bf16(x, wpack, b, Cout, 9, True)
     y, yp = ops.conv_gemm_pool_bf16(x, wpack, b, Cout, True, mode)
     assert torch.equal(y, y_ref)
@@ -210,31 +223,33 @@ def test_conv_gemm_pool_bf16(ops, B, C0, Cout, H, W, mode):
         torch.testing.assert_close(yp.float(), ops.pool2_bf16(y, 1).float(), atol=1e-2, rtol=8e-3)
 
 
-def test_conv_gemm_bf16_1x1(ops):
+@H16
+def test_conv_gemm_bf16_1x1(ops, h16):
     g = _g(8)
-    x = _bf(torch.randn(2, 128, 8, 16, generator=g))
-    w = _bf(torch.randn(64, 128, generator=g) * 0.1)
+    x = _q(torch.randn(2, 128, 8, 16, generator=g), h16)
+    w = _q(torch.randn(64, 128, generator=g) * 0.1, h16)
     b = torch.randn(64, generator=g) * 0.1
     ref = F.conv2d(x, w[:, :, None, None], b)
-    got = ops.conv_gemm_bf16(_nhwc(x).to(torch.bfloat16).cuda(), w.to(torch.bfloat16).cuda(), b.cuda(), 64, 1, False)
+    got = ops.conv_gemm_bf16(_nhwc(x).to(h16).cuda(), w.to(h16).cuda(), b.cuda(), 64, 1, False)
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
 
 
-def test_pool_head_transpose_bf16(ops):
+@H16
+def test_pool_head_transpose_bf16(ops, h16):
     g = _g(9)
     for (H, W) in [(8, 8), (7, 9)]:
-        x = _bf(torch.randn(2, 64, H, W, generator=g))
-        xb = _nhwc(x).to(torch.bfloat16).cuda()
+        x = _q(torch.randn(2, 64, H, W, generator=g), h16)
+        xb = _nhwc(x).to(h16).cuda()
         if H % 2 == 0:
             assert torch.equal(ops.pool2_bf16(xb, 0).float().cpu(), _nhwc(F.max_pool2d(x, 2)))
         torch.testing.assert_close(ops.pool2_bf16(xb, 1).float().cpu(),
                                    _nhwc(F.avg_pool2d(x, 2, 2, 0, ceil_mode=True)), atol=1e-2, rtol=1e-2)
         assert torch.equal(ops.nhwc_bf16_to_nchw_f32(xb).cpu(), x)
-    enc = _bf(torch.randn(3, 128, 4, 4, generator=g))
+    enc = _q(torch.randn(3, 128, 4, 4, generator=g), h16)
     hw_ = torch.randn(12, 128, generator=g)
     hb = torch.randn(12, generator=g)
     ml = enc.mean((2, 3)) @ hw_.t() + hb
-    mu, ls = ops.gauss_head_bf16(_nhwc(enc).to(torch.bfloat16).cuda(), hw_.cuda(), hb.cuda(), 6)
+    mu, ls = ops.gauss_head_bf16(_nhwc(enc).to(h16).cuda(), hw_.cuda(), hb.cuda(), 6)
     torch.testing.assert_close(torch.cat([mu, ls], 1).cpu(), ml, atol=1e-4, rtol=1e-4)
 
 
@@ -242,19 +257,20 @@ def test_pool_head_transpose_bf16(ops):
                                           (4, 20, 3, 3, 20, 24), (5, 3, 3, 3, 20, 24), (6, 7, 3, 2, 20, 24),
                                           (4, 6, 3, 5, 96, 100),     # 190 tile pairs > 148 SMs: CTAs walk several
                                           (3, 18, 4, 7, 72, 72)])    # pairs and cross slice boundaries; 2 sample groups
-def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W):
+@H16
+def test_fcomb_softmax_accum_bf16(ops, nl, N, C, B, H, W, h16):
     """Fused tensor-core fcomb (activations resident in tensor memory, fcomb_ts.cu) vs the fp32 oracle: probabilities
     within the bf16 budget 2e-2.  HW = 480 is ragged against the 128-pixel tile; N = 5, 18, 20 leave sample slots empty in
     the last round; N > 16 runs two sample groups."""
     sd = O.make_state_dict((64, 128), num_classes=C, latent_dim=6, no_convs_fcomb=nl, seed=10)
     g = _g(11)
-    feat = _bf(torch.relu(torch.randn(B, 64, H, W, generator=g)))
+    feat = _q(torch.relu(torch.randn(B, 64, H, W, generator=g)), h16)
     mu = torch.randn(B, 6, generator=g)
     sigma = torch.rand(B, 6, generator=g) + 0.2
     eps = torch.randn(B, N, 6, generator=g)
     from pmu_b200.engine import PackedNet
     fw = PackedNet({k: v for k, v in sd.items() if k.startswith("fcomb")}, "cuda").fcomb
-    got = ops.fcomb_softmax_accum_bf16(_nhwc(feat).to(torch.bfloat16).cuda(), mu.cuda(), sigma.cuda(), eps.cuda(), fw).cpu()
+    got = ops.fcomb_softmax_accum_bf16(_nhwc(feat).to(h16).cuda(), mu.cuda(), sigma.cuda(), eps.cuda(), fw).cpu()
     p = torch.stack([torch.softmax(O.fcomb(sd, feat, mu + sigma * eps[:, n]), 1) for n in range(N)], 1)
     ref = torch.stack([p.sum(1), (p * p).sum(1)], 1)
     err = (got - ref).abs().max().item() / N

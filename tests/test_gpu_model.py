@@ -17,7 +17,7 @@ from oracle import pmu_oracle as O
 pytestmark = pytest.mark.gpu
 
 FP32_PROB_TOL = 1e-4
-BF16_PROB_TOL = 2e-2
+BF16_PROB_TOL = 2e-2          # north-star bound of the 16-bit tensor-core mode (f16 operands; also what bf16 is held to on fused outputs)
 
 
 @pytest.fixture(scope="module")
@@ -137,10 +137,11 @@ def test_trainer_model_vs_golden_trainer(pmu, golden_dir, trainer_sd):
         p = torch.softmax(net.sample(z=zz), 1).cpu()
         assert (p - ref_p).abs().max() < FP32_PROB_TOL
         np.testing.assert_allclose(net.kl_divergence().cpu().numpy(), g["kl"], rtol=1e-3, atol=1e-4)
-        net.set_precision("bf16")
-        net.forward(x, segm, training=True)
-        p16 = torch.softmax(net.sample(z=zz), 1).cpu()
-        assert (p16 - ref_p).abs().max() < BF16_PROB_TOL
+        for prec in ("f16", "bf16"):
+            net.set_precision(prec)
+            net.forward(x, segm, training=True)
+            p16 = torch.softmax(net.sample(z=zz), 1).cpu()
+            assert (p16 - ref_p).abs().max() < BF16_PROB_TOL, prec
         np.testing.assert_allclose(net.prior_latent_space.base_dist.loc.cpu().numpy(), g["mu_p"], rtol=5e-2, atol=3e-2)
 
 
@@ -152,7 +153,7 @@ def _dice_labels(a, b, C):
     return d
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
 def test_multiplanar_vs_oracle(pmu, trainer_sd, precision):
     """Config-2-shaped case shrunk to what the CPU oracle finishes in seconds: 32^3, 3 planes,
     4 samples, injected eps, trainer model."""
@@ -183,7 +184,7 @@ def test_multiplanar_properties_and_sharding(pmu, trainer_sd):
     D, N = 64, 2
     vol, _ = O.phantom(D, seed=7)
     eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(1)).cuda()
-    one = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=32)
+    one = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=32)
     out = one.predict(vol, eps=eps, keep_sums=True)
     mean, var, ent = out["mean"], out["var"], out["entropy"]
     torch.testing.assert_close(mean.sum(1), torch.ones_like(mean[:, 0]), atol=1e-4, rtol=1e-4)
@@ -192,7 +193,7 @@ def test_multiplanar_properties_and_sharding(pmu, trainer_sd):
     v = torch.from_numpy(vol).cuda()
     acc = []
     for r in range(2):
-        pr = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=32, rank=r, world_size=2)
+        pr = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=32, rank=r, world_size=2)
         a = torch.zeros(2, D, 3, D, D, device="cuda")
         n_done = pr.accumulate(v, eps, a)
         assert n_done == 96
@@ -228,7 +229,7 @@ def test_fitted_model_dice(pmu, golden_dir):
     eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
     ref = O.multiplanar_predict(vol, sd, eps, N, batch=32)
     lab_ref = torch.argmax(ref["mean"], 1)
-    for precision, tol in (("fp32", FP32_PROB_TOL), ("bf16", BF16_PROB_TOL)):
+    for precision, tol in (("fp32", FP32_PROB_TOL), ("f16", BF16_PROB_TOL), ("bf16", BF16_PROB_TOL)):
         pred = pmu.MultiPlanarPredictor(sd, "cuda", precision=precision, n_samples=N, slice_batch=32)
         out = pred.predict(vol, eps=eps, want_labels=True)
         err = (out["mean"].cpu() - ref["mean"]).abs().max().item()
@@ -281,7 +282,7 @@ def test_eval_entry_point(pmu, tmp_path):
         nifti_io.save(str(d / "images" / f"scan{i}.nii"), vol)
         nifti_io.save(str(d / "labels" / f"scan{i}.nii"), lab)
     r = subprocess.run([sys.executable, os.path.join(root, "eval.py"), "-d", str(d), "-m", "probunet", "--samples", "2",
-                        "--precision", "bf16", "--slice-batch", "16", "--out", str(tmp_path / "out")],
+                        "--precision", "f16", "--slice-batch", "16", "--out", str(tmp_path / "out")],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "avg volume: mean=" in r.stdout and "view 3 dice" in r.stdout
@@ -299,7 +300,7 @@ def test_accumulate_graphed_matches_eager(pmu, trainer_sd):
     """accumulate_graphed(): the slice pass of a volume replayed as one CUDA graph gives the bits of the eager pass, for
     a second volume written into the same buffer too (the graph is captured once per buffer triple)."""
     D, N = 32, 2
-    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=16)
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=16)
     eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(5)).cuda()
     vol = torch.empty(D, D, D, device="cuda")
     acc = torch.empty(2, D, 3, D, D, device="cuda")
@@ -319,7 +320,7 @@ def test_pipelined_submit_matches_predict(pmu, trainer_sd):
     """submit()/wait(): a stream of different volumes through two buffer slots and three CUDA streams gives, for every
     volume, the bits of the one-at-a-time predict(host_out=...) call (same kernels, only the scheduling differs)."""
     D, N = 32, 2
-    one = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=16)
+    one = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=16)
     eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(5)).cuda()
     vols = [torch.from_numpy(O.phantom(D, seed=20 + i)[0]).pin_memory() for i in range(5)]
 
@@ -349,10 +350,9 @@ def test_pipelined_submit_matches_predict(pmu, trainer_sd):
         one.submit(torch.zeros(D, D, D - 1).pin_memory(), eps, got[0])     # needs padding -> predict()
 
 
-# a single view's N-sample mean carries the bf16 noise of ONE network pass (the fused mean averages three): with the
-# random-init trainer model (logits +-5, sigma up to 6) the worst of ~10^5 pixels of a full-size slice sits at 2.0-2.3e-2
-# (tests/tools/diag_bf16_error.py: all of it is the 1.1 % rms error of the bf16 U-Net features; p99.9 = 1e-2)
-BF16_VIEW_TOL = 3e-2
+# Per-view probabilities (the reference's volume1/2/3, eval.py:176-190) are held to the SAME 2e-2 as the fused outputs.
+# That is why the tensor-core inference format is IEEE f16: with bf16 operands the worst of ~10^5 pixels of one view's
+# N-sample mean sat at 2.0-2.3e-2 (22 layers of 8-bit significands, tests/tools/emulate_bf16_net.py); with f16 ~3e-3.
 
 
 def _spot_check_planes(out, ref, spots, N, tol):
@@ -367,6 +367,7 @@ def _spot_check_planes(out, ref, spots, N, tol):
             e = (got - want[i]).abs()
             worst = max(worst, float(e.max()))
             errs.append(e.flatten())
+    print(f"per-view worst pixel {worst:.4f} (tol {tol})")
     assert worst < tol, f"per-view probabilities off by {worst}"
     return worst, torch.cat(errs)
 
@@ -389,7 +390,7 @@ def _check_lattice(out, golden_dir, name, tol, ent_tol):
     return e_mean, e_var, e_ent
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
 def test_config2_full_size(pmu, trainer_sd, golden_dir, precision):
     """BASELINE config 2 at its full size (128^3, 3 planes x 8 samples, mean / variance fusion): the fused outputs on a
     16^3 voxel lattice against the oracle's whole-volume run, whole slices of every view against the oracle (two per
@@ -404,7 +405,7 @@ def test_config2_full_size(pmu, trainer_sd, golden_dir, precision):
     out = pred.predict(vol, eps=eps, per_plane=True, keep_sums=True)
     fp32 = precision == "fp32"
     _check_lattice(out, golden_dir, "golden_cfg2_lattice.npz", FP32_PROB_TOL if fp32 else BF16_PROB_TOL, 1e-3 if fp32 else 6e-2)
-    _, errs = _spot_check_planes(out, ref, spots, N, FP32_PROB_TOL if fp32 else BF16_VIEW_TOL)
+    _, errs = _spot_check_planes(out, ref, spots, N, FP32_PROB_TOL if fp32 else BF16_PROB_TOL)
     if not fp32:
         assert float(errs.quantile(0.999)) < BF16_PROB_TOL and float(errs.mean()) < 4e-3
     mean, var, ent = out["mean"], out["var"], out["entropy"]
@@ -426,11 +427,11 @@ def test_config3_full_size(pmu, trainer_sd, golden_dir):
     spots = {0: 100, 1: 3, 2: 255}
     ref = O.multiplanar_predict(vol, trainer_sd, eps, N, batch=1, slice_ranges={p: (s, s + 1) for p, s in spots.items()},
                                 return_per_slice=True)
-    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=64, interp="trilinear")
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=64, interp="trilinear")
     epsd = eps.cuda()
     out = pred.predict(vol, eps=epsd, per_plane=True, keep_sums=True)
     _check_lattice(out, golden_dir, "golden_cfg3_lattice.npz", BF16_PROB_TOL, 6e-2)
-    _, errs = _spot_check_planes(out, ref, spots, N, BF16_VIEW_TOL)
+    _, errs = _spot_check_planes(out, ref, spots, N, BF16_PROB_TOL)
     assert float(errs.quantile(0.999)) < BF16_PROB_TOL and float(errs.mean()) < 4e-3
     mean = out["mean"]
     torch.testing.assert_close(mean.sum(1), torch.ones_like(mean[:, 0]), atol=1e-4, rtol=0)
@@ -442,7 +443,7 @@ def test_config3_full_size(pmu, trainer_sd, golden_dir):
     tot = torch.zeros(2, D, 3, D, D, device="cuda")
     done = 0
     for r in range(4):
-        pr = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="bf16", n_samples=N, slice_batch=64, interp="trilinear",
+        pr = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=64, interp="trilinear",
                                       rank=r, world_size=4)
         done += pr.accumulate(v, epsd, tot)
     assert done == 3 * D

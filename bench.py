@@ -558,6 +558,143 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------
+def run_config4(args):
+    """BASELINE config 4: data-parallel training step, 8 slices of 256 x 256 per GPU (global batch 64 on 8 GPUs), GEMMs on
+    tcgen05 in bf16, gradients SUM-all-reduced over NCCL in buckets (pmu_b200.dp_train_step).  One JSON line: slices/s,
+    ms/step (CUDA events, max over ranks), per-kernel time shares of one instrumented step, replica consistency."""
+    import torch
+    import torch.distributed as dist
+    import pmu_b200
+    from pmu_b200 import ops
+    from pmu_b200.synthetic import phantom_volume, phantom_labels
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.train_batch
+    torch.manual_seed(0)
+    trainer = pmu_b200.ProbUNetTrainer(dev, n_channels=1, n_classes=3, latent_dim=6, beta=10, precision=args.train_precision)
+    net = trainer.net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
+    D = 256
+    vol, lab = phantom_volume(D, seed=3), phantom_labels(D)
+    s0 = 40 + rank * B                                   # every rank its own shard of x-slices (mixed content)
+    mx = vol[s0:s0 + B].amax(dim=(1, 2), keepdim=True)
+    imgs = (vol[s0:s0 + B] / mx)[:, None].contiguous().to(dev)
+    masks = lab[s0:s0 + B, None].contiguous().to(dev)
+
+    def step():
+        return pmu_b200.dp_train_step(trainer, imgs, masks, opt)
+
+    for _ in range(max(args.warmup, 6)):                 # the caching allocator still grows during the first five steps
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ops.LAUNCHES
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = ops.LAUNCHES - l0
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    gl = loss.clone()
+    chk = torch.stack([p.detach().double().sum() for p in net.parameters()]).sum()
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(gl)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ops.PROFILE = []
+    step(); torch.cuda.synchronize()
+    tot = {}
+    for name, meta, a, b in ops.PROFILE:
+        tot[name] = tot.get(name, 0.0) + a.elapsed_time(b)
+    ops.PROFILE = None
+    ssum = sum(tot.values())
+    if rank == 0:
+        fwd = 96.18 + 2 * 33.90 + 2 * 1.69            # GFLOP per 256^2 slice: U-Net + prior + posterior + two fcomb passes
+        flop = B * world * (fwd + 2 * (fwd - 1.69)) * 1e9
+        print(json.dumps({"metric": "slices/sec (data-parallel training step, 256x256 slices)", "value": B * world / float(ms) * 1e3,
+                          "unit": "slices/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 6),
+                          "ms_per_step": float(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": args.train_precision, "data": "synthetic",
+                          "config": {"workload": f"BASELINE config 4: DP training step, {B} slices of 256x256 per GPU (global batch "
+                                                 f"{B * world}), trainer model, SGD + clip, gradient all-reduce over NCCL"},
+                          "useful_tflops": flop / float(ms) / 1e9, "global_loss": float(gl), "replicas_identical": bool(lo == hi),
+                          "gpu_launches": launches,
+                          "kernel_time_shares": {k: round(v / ssum, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:14]},
+                          "kernel_ms_instrumented_step": round(ssum, 2)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_config5(args):
+    """BASELINE config 5: sample-count sweep N = 1 ... 128 on a synthetic 512^3 volume with voxel entropy maps, slab-sharded
+    over the ranks (reduce-scatter along x, every rank finalises its x-slab).  One JSON line per N."""
+    import torch
+    import torch.distributed as dist
+    import pmu_b200
+    from pmu_b200.synthetic import phantom_volume, trainer_state_dict
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    D, P = args.sweep_size, 3
+    sd = trainer_state_dict(seed=0)
+    vol = phantom_volume(D, seed=1234).to(dev)
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for N in [int(x) for x in args.sweep_samples.split(",")]:
+        pred = pmu_b200.MultiPlanarPredictor(sd, dev, precision=args.precision, n_samples=N, slice_batch=16, interp=args.interp,
+                                             rank=rank, world_size=world, output="slab" if world > 1 else "rank0")
+        eps = torch.randn(P, D, N, 6, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)
+        out = pred.predict(vol, eps=eps)                         # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.sweep_steps):
+            out = pred.predict(vol, eps=eps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / args.sweep_steps], device=dev)
+        ent = out["entropy"]
+        stats = torch.stack([ent.sum(), ent.max(), out["var"].max(), torch.tensor(float(ent.numel()), device=dev)])
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            mx = stats[1:3].clone()
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            stats[1:3] = mx
+        if rank == 0:
+            tflop = 3 * D * (130.61 + 1.099 * N) * (D / 256.0) ** 2 / 1e3
+            assert int(stats[3]) == D ** 3, "entropy slabs do not tile the volume"
+            tf = tflop / float(ms) * 1e3
+            print(json.dumps({"metric": f"volumes/sec ({D}^3, 3 planes x N samples, entropy map)", "n_samples": N, "n_gpus": world,
+                              "value": 1e3 / float(ms), "unit": "volumes/s", "ms_per_step": float(ms),
+                              "config": {"workload": f"BASELINE config 5: {D}^3 x 3 planes x {N} samples, entropy map, "
+                                                     f"{'x-slab outputs (reduce-scatter)' if world > 1 else 'single output'}"},
+                              "dtype": args.precision, "algorithmic_tflop": round(tflop, 1), "tflops": round(tf, 1),
+                              "frac_of_sustained_peak_per_gpu": round(tf / world / peaks["bf16_sustained"], 4),
+                              "entropy_mean": round(float(stats[0]) / D ** 3, 5), "entropy_max": round(float(stats[1]), 5),
+                              "var_max": round(float(stats[2]), 5)}), flush=True)
+        del pred, eps, out
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -588,9 +725,21 @@ def main():
     ap.add_argument("--e2e-phases", action="store_true",
                     help="diagnostic: also time the e2e leg's host->device copy, device->host copy and resident slab step "
                          "on their own (all ranks at once), reported under e2e.phases_ms")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="3 (default): the headline metric (BASELINE configs[2]); 4: data-parallel training step (slices/s); "
+                         "5: sample-count sweep on 512^3 (one JSON line per N)")
+    ap.add_argument("--train-batch", type=int, default=8, help="--config 4: slices per GPU")
+    ap.add_argument("--train-precision", default="bf16", choices=["bf16", "fp32"], help="--config 4")
+    ap.add_argument("--sweep-size", type=int, default=512, help="--config 5: volume edge")
+    ap.add_argument("--sweep-samples", default="1,2,4,8,16,32,64,128", help="--config 5")
+    ap.add_argument("--sweep-steps", type=int, default=2, help="--config 5: timed predictions per N")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 4:
+        run_config4(args)
+    elif args.config == 5:
+        run_config5(args)
     else:
         run_ours(args)
 

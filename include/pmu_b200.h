@@ -149,10 +149,13 @@ int pmu_conv3x3_first_bf16(const float* x0, const float* x1, const float* w, con
  *             (row = (i*2+j)*Cout + co); y bf16 [B,2H,2W,Cout]; relu must be 0.
  *  ntaps = 1: conv1x1, wpack [Cout][C0].
  *  C0, C1 multiples of 64; Cout multiple of 64; bias fp32 [Cout].
- *  f16: format of x0, x1, wpack and y (see the group comment). */
+ *  f16: format of x0, x1, wpack and y (see the group comment).
+ *  out_h, out_w (ntaps = 4 only, else 0): extents of the output TENSOR when it is larger than 2H x 2W — Up.forward pads
+ *  the upsampled map to the skip connection's size (F.pad, unet_parts.py:58-62; an odd extent's pad row / column goes
+ *  to the high side): y is then [B,out_h,out_w,Cout], the result lands at its origin and the caller zero-fills the rest. */
 int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                        const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
-                       int relu, int f16, void* stream);
+                       int relu, int f16, int out_h, int out_w, void* stream);
 
 /* conv3x3 (as above, ntaps = 9) that ALSO writes the 2x2-pooled map y_pool bf16 [B,H/2,W/2,Cout]
  * from its epilogue (pool_mode PMU_POOL_MAX: unet_parts.py:33 after DoubleConv;
@@ -197,6 +200,18 @@ int pmu_softmax_accum(const float* logits, float* slice_sums, int B, int N, int 
  * plane 0 -> (s,r,c), plane 1 -> (r,s,c), plane 2 -> (r,c,s)  (eval.py:176,182,188). */
 int pmu_scatter_accum(const float* slice_sums, int plane, int s0, int ns, const int32_t dims[3],
                       int C, float* S1, float* S2, void* stream);
+/* [build-defined; closes the use_standard_axis=False TODO of utils/mri_dataset.py:60-71 for
+ * the fusion side] Scatter for a NON-identity slice grid: every pixel (s, r, c) of slice_sums [ns,2,C,H,W] is added to
+ * the voxel nearest to q = fma(c, v, fma(r, u, fma(s, n, o))) (affine = 12 HOST floats [o, n, u, v], the grid
+ * pmu_slice_gather sampled), pixels outside the volume are dropped, cnt [x][y][z] += weight (the number of latent
+ * samples behind the sums, so that mean = S1 / cnt).  fp32 atomics: several pixels can share a voxel. */
+int pmu_scatter_accum_affine(const float* slice_sums, const float* affine, int s0, int ns, int H, int W,
+                             const int32_t dims[3], int C, float weight, float* S1, float* S2, float* cnt,
+                             void* stream);
+/* pmu_fuse_finalize with a per-voxel count (the companion of pmu_scatter_accum_affine): mean = S1 / cnt,
+ * var = max(S2 / cnt - mean^2, 0), entropy, argmax labels; voxels with cnt = 0 read 0 (eval.py:193 generalised). */
+int pmu_fuse_finalize_counted(const float* S1, const float* S2, const float* cnt, const int32_t dims[3], int C,
+                              float* mean, float* var, float* entropy, uint8_t* labels, void* stream);
 /* mean = S1/count, var = max(S2/count - mean^2, 0) ([x][C][y][z]); entropy [x][y][z]
  * = sum_k -mean_k ln mean_k; labels (nullable, uint8 [x][y][z]) = argmax_k mean
  * (eval.py:52).  Any of mean/var/entropy may be NULL. */
@@ -204,8 +219,9 @@ int pmu_fuse_finalize(const float* S1, const float* S2, float count, const int32
                       float* mean, float* var, float* entropy, uint8_t* labels, void* stream);
 
 /* ---- K5: reductions for the training step / evaluation ------------------- */
-/* sum over b,pixels of CE(logits[B,C,HW], target[B,HW] float labels) -> out[1]
- * (probabilistic_unet.py:288,303-304).  out is overwritten. */
+/* sum over b,pixels of CE(logits[B,C,HW], target[B,HW] float labels) -> out[0]
+ * (probabilistic_unet.py:288,303-304).  out has TWO floats and is overwritten: out[1] > 0 reports that some label
+ * was outside [0, C) — nn.CrossEntropyLoss raises "Target k is out of bounds" there, and so must the caller. */
 int pmu_ce_sum(const float* logits, const float* target, int B, int C, int64_t HW, float* out,
                void* stream);
 /* analytic KL(q||p) of diagonal Gaussians -> out[B] (probabilistic_unet.py:272). */

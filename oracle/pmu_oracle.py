@@ -32,6 +32,7 @@ averaging of probabilities, per-voxel variance and entropy, nearest / trilinear 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -140,66 +141,74 @@ def identity_affine(view: int) -> np.ndarray:
     return np.concatenate([o, n, u, v]).astype(np.float32)
 
 
-def _grid_coords(affine: np.ndarray, s0: int, ns: int, H: int, W: int):
-    """fp32, fixed op order: ((o + s*n) + r*u) + c*v  — each op rounded to fp32
-    (the CUDA kernel uses __fmul_rn/__fadd_rn in the same order)."""
-    a = affine.astype(np.float32).reshape(4, 3)
-    s = np.arange(s0, s0 + ns, dtype=np.float32)[:, None, None]
-    r = np.arange(H, dtype=np.float32)[None, :, None]
-    c = np.arange(W, dtype=np.float32)[None, None, :]
-    q = []
-    for ax in range(3):
-        t = (a[0, ax] + s * a[1, ax]).astype(np.float32)
-        t = (t + (r * a[2, ax]).astype(np.float32)).astype(np.float32)
-        t = (t + (c * a[3, ax]).astype(np.float32)).astype(np.float32)
-        q.append(np.broadcast_to(t, (ns, H, W)))
-    return q
+def _c_oracle():
+    """The C part of the oracle (oracle/resample_fma.c: the resampling spec needs correctly rounded fused multiply-adds,
+    which numpy cannot express), compiled with gcc into oracle/_build/ on first use and loaded with ctypes."""
+    global _C_LIB
+    if _C_LIB is not None:
+        return _C_LIB
+    import ctypes
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "resample_fma.c")
+    out_dir = os.path.join(here, "_build")
+    lib = os.path.join(out_dir, "libpmu_oracle.so")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        os.makedirs(out_dir, exist_ok=True)
+        tmp = lib + f".{os.getpid()}.tmp"
+        # -ffp-contract=off: the ONLY fused operations are the explicit fmaf() calls of the spec
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", src, "-o", tmp, "-lm"], check=True)
+        os.replace(tmp, lib)
+    L = ctypes.CDLL(lib)
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.pmu_oracle_resample.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, fp]
+    L.pmu_oracle_resample.restype = None
+    L.pmu_oracle_scatter_nearest.argtypes = [fp, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, fp]
+    L.pmu_oracle_scatter_nearest.restype = None
+    _C_LIB = L
+    return L
+
+
+_C_LIB = None
+
+
+def _fptr(a: np.ndarray):
+    import ctypes
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
 
 def resample_slices(vol: np.ndarray, affine: np.ndarray, s0: int, ns: int, H: int, W: int,
                     mode: str = "nearest") -> np.ndarray:
     """[ns,H,W] fp32 raw (un-normalised) resampled slices, zeros outside the volume.
 
-    nearest : index = floor(q + 0.5) per axis.
-    trilinear: 8 taps, lerp along z, then y, then x, each ``a + t*(b-a)`` with
-    separately rounded fp32 mul/add (align_corners=True convention, voxel
-    centres at integer coordinates).  On the identity grid both modes reproduce
-    plain slicing bit-exactly.
-    """
-    vol = np.ascontiguousarray(vol, dtype=np.float32)
-    D0, D1, D2 = vol.shape
-    qx, qy, qz = _grid_coords(affine, s0, ns, H, W)
-
-    def fetch(ix, iy, iz):
-        ok = (ix >= 0) & (ix < D0) & (iy >= 0) & (iy < D1) & (iz >= 0) & (iz < D2)
-        v = vol[np.clip(ix, 0, D0 - 1), np.clip(iy, 0, D1 - 1), np.clip(iz, 0, D2 - 1)]
-        return np.where(ok, v, np.float32(0)).astype(np.float32)
-
-    if mode == "nearest":
-        half = np.float32(0.5)
-        ix = np.floor((qx + half).astype(np.float32)).astype(np.int64)
-        iy = np.floor((qy + half).astype(np.float32)).astype(np.int64)
-        iz = np.floor((qz + half).astype(np.float32)).astype(np.int64)
-        return fetch(ix, iy, iz)
-    if mode != "trilinear":
+    Spec (oracle/resample_fma.c, every operation a correctly rounded fp32 operation):
+      q[ax] = fma(c, v[ax], fma(r, u[ax], fma(s, n[ax], o[ax])))
+      nearest  : index = floor(q + 0.5) per axis.
+      trilinear: 8 taps, lerp along z, then y, then x, lerp(a, b, t) = fma(t, b - a, a) (align_corners=True convention,
+                 voxel centres at integer coordinates).
+    On the identity grid both modes reproduce plain slicing bit-exactly."""
+    if mode not in ("nearest", "trilinear"):
         raise ValueError(mode)
-    fx, fy, fz = np.floor(qx), np.floor(qy), np.floor(qz)
-    tx = (qx - fx).astype(np.float32)
-    ty = (qy - fy).astype(np.float32)
-    tz = (qz - fz).astype(np.float32)
-    x0, y0, z0 = fx.astype(np.int64), fy.astype(np.int64), fz.astype(np.int64)
+    vol = np.ascontiguousarray(vol, dtype=np.float32)
+    aff = np.ascontiguousarray(np.asarray(affine, dtype=np.float32).reshape(12))
+    out = np.empty((ns, H, W), dtype=np.float32)
+    _c_oracle().pmu_oracle_resample(_fptr(vol), vol.shape[0], vol.shape[1], vol.shape[2], _fptr(aff), int(s0), int(ns), int(H),
+                                    int(W), int(mode == "trilinear"), _fptr(out))
+    return out
 
-    def lerp(a, b, t):
-        d = (b - a).astype(np.float32)
-        return (a + (t * d).astype(np.float32)).astype(np.float32)
 
-    c00 = lerp(fetch(x0, y0, z0), fetch(x0, y0, z0 + 1), tz)
-    c01 = lerp(fetch(x0, y0 + 1, z0), fetch(x0, y0 + 1, z0 + 1), tz)
-    c10 = lerp(fetch(x0 + 1, y0, z0), fetch(x0 + 1, y0, z0 + 1), tz)
-    c11 = lerp(fetch(x0 + 1, y0 + 1, z0), fetch(x0 + 1, y0 + 1, z0 + 1), tz)
-    c0 = lerp(c00, c01, ty)
-    c1 = lerp(c10, c11, ty)
-    return lerp(c0, c1, tx)
+def scatter_nearest(vals: np.ndarray, affine: np.ndarray, s0: int, dims: Sequence[int], acc: np.ndarray, cnt: np.ndarray) -> None:
+    """[build-defined] App. A step 6 for a non-identity grid: vals [ns,K,H,W] are added to acc [d0,K,d1,d2] at the voxel
+    NEAREST to every output pixel (floor(q + 0.5)), cnt [d0,d1,d2] counts the contributions; pixels outside the volume
+    are dropped.  In place."""
+    vals = np.ascontiguousarray(vals, dtype=np.float32)
+    aff = np.ascontiguousarray(np.asarray(affine, dtype=np.float32).reshape(12))
+    assert acc.dtype == np.float32 and cnt.dtype == np.float32 and acc.flags.c_contiguous and cnt.flags.c_contiguous
+    ns, K, H, W = vals.shape
+    _c_oracle().pmu_oracle_scatter_nearest(_fptr(vals), K, _fptr(aff), int(s0), ns, H, W, int(dims[0]), int(dims[1]), int(dims[2]),
+                                           _fptr(acc), _fptr(cnt))
 
 
 def normalise_slices(raw: np.ndarray) -> np.ndarray:

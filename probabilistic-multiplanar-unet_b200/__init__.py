@@ -11,6 +11,6 @@ from .mri_dataset import MRI_Dataset, view_affine  # noqa: F401
 from .multiplanar import (MultiPlanarPredictor, padded_dims, reduce_accumulators, reduce_scatter_accumulators,  # noqa: F401
                           shard_slices)
 from .trainer import ProbUNetTrainer  # noqa: F401
-from .train_dp import allreduce_gradients, dp_train_step  # noqa: F401
+from .train_dp import allreduce_gradients, dp_train_step, sync_batchnorm_buffers  # noqa: F401
 
 __version__ = "0.1.0"

@@ -35,7 +35,7 @@ _SIG = {
     "pmu_fcomb_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_int64, _P]),
     "pmu_conv3x3_first_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "pmu_conv_gemm_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_conv_gemm_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_conv_gemm_pool_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_pool2_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_gauss_head_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -44,6 +44,8 @@ _SIG = {
                                              c_int, c_int64, c_int, _P]),
     "pmu_softmax_accum": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P]),
     "pmu_scatter_accum": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int32), c_int, _P, _P, _P]),
+    "pmu_scatter_accum_affine": (c_int, [_P, POINTER(c_float), c_int, c_int, c_int, c_int, POINTER(c_int32), c_int, c_float, _P, _P, _P, _P]),
+    "pmu_fuse_finalize_counted": (c_int, [_P, _P, _P, POINTER(c_int32), c_int, _P, _P, _P, _P, _P]),
     "pmu_fuse_finalize": (c_int, [_P, _P, c_float, POINTER(c_int32), c_int, _P, _P, _P, _P, _P]),
     "pmu_ce_sum": (c_int, [_P, _P, c_int, c_int, c_int64, _P, _P]),
     "pmu_kl_diag_gauss": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),

@@ -156,6 +156,64 @@ scatter_plane2_kernel(const float* __restrict__ sums, int s0, int ns, int C, int
 }
 
 // ---------------------------------------------------------------------------------
+// [build-defined] scatter for a NON-identity slice grid: every output pixel adds its sums to
+// the voxel NEAREST to its coordinate q = fma(c, v, fma(r, u, fma(s, n, o))) (the resampling gather's coordinate, same
+// op order as oracle/resample_fma.c), pixels outside the volume are dropped, and a per-voxel weight counts the
+// contributions.  Pixels of different slices can land on one voxel: fp32 atomics (red.global.add).
+// ---------------------------------------------------------------------------------
+struct ScAffine { float a[12]; };
+__global__ void __launch_bounds__(256)
+scatter_affine_kernel(const float* __restrict__ sums, ScAffine A, int s0, int ns, int H, int W, int d0, int d1, int d2,
+                      int C, float weight, float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ cnt) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)ns * hw;
+  const int64_t yz = (int64_t)d1 * d2;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int b = (int)(i / hw);
+    const int64_t p = i % hw;
+    const float sf = (float)(s0 + b), rf = (float)(int)(p / W), cf = (float)(int)(p % W);
+    int v3[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      const float q = __fmaf_rn(cf, A.a[9 + ax], __fmaf_rn(rf, A.a[6 + ax], __fmaf_rn(sf, A.a[3 + ax], A.a[ax])));
+      v3[ax] = __float2int_rd(__fadd_rn(q, 0.5f));
+    }
+    if (v3[0] < 0 || v3[0] >= d0 || v3[1] < 0 || v3[1] >= d1 || v3[2] < 0 || v3[2] >= d2) continue;
+    const int64_t vox = (int64_t)v3[1] * d2 + v3[2];
+    const float* src = sums + (int64_t)b * 2 * C * hw + p;
+    for (int k = 0; k < C; ++k) {
+      atomicAdd(S1 + ((int64_t)v3[0] * C + k) * yz + vox, __ldg(src + (int64_t)k * hw));
+      atomicAdd(S2 + ((int64_t)v3[0] * C + k) * yz + vox, __ldg(src + (int64_t)(C + k) * hw));
+    }
+    atomicAdd(cnt + (int64_t)v3[0] * yz + vox, weight);
+  }
+}
+
+// finalise with a per-voxel count: mean = S1 / cnt, var = max(S2 / cnt - mean^2, 0); voxels nothing landed on read 0
+__global__ void __launch_bounds__(256)
+finalize_counted_kernel(const float* __restrict__ S1, const float* __restrict__ S2, const float* __restrict__ cnt, int64_t X,
+                        int C, int64_t YZ, float* __restrict__ mean, float* __restrict__ var, float* __restrict__ entropy,
+                        uint8_t* __restrict__ labels) {
+  const int64_t total = X * YZ;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t x = i / YZ, q = i % YZ;
+    const float n = __ldg(cnt + i);
+    const float inv = (n > 0.f) ? 1.f / n : 0.f;
+    float ent = 0.f, best = -INFINITY;
+    int lab = 0;
+    for (int k = 0; k < C; ++k) {
+      const int64_t off = (x * C + k) * YZ + q;
+      const float m = __ldg(S1 + off) * inv;
+      if (mean) mean[off] = m;
+      if (var) var[off] = fmaxf(__ldg(S2 + off) * inv - m * m, 0.f);
+      ent -= (m > 0.f) ? m * logf(m) : 0.f;
+      if (m > best) { best = m; lab = k; }
+    }
+    if (entropy) entropy[i] = ent;
+    if (labels) labels[i] = (uint8_t)lab;
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // finalise: mean / variance / entropy / argmax labels.  Thread = V consecutive (y,z).
 // ---------------------------------------------------------------------------------
 template <bool VEC>
@@ -235,10 +293,14 @@ ce_sum_kernel(const float* __restrict__ logits, const float* __restrict__ target
               int64_t total, float* __restrict__ out) {
   __shared__ float red[8];
   float acc = 0.f;
+  int bad = 0;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int64_t b = i / HW, p = i % HW;
     const float* lp = logits + b * C * HW + p;
-    const int t = (int)__ldg(target + i);  // .long() truncation of the float label
+    const float tf = __ldg(target + i);
+    const int t = (int)tf;                 // .long() truncation of the float label
+    // nn.CrossEntropyLoss raises on a target outside [0, C) ("Target k is out of bounds"): counted here, raised by the caller
+    if (!(tf > -1.f && tf < (float)C)) ++bad;
     float mx = -INFINITY;
     for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(lp + (int64_t)c * HW));
     float den = 0.f, lt = 0.f;
@@ -251,6 +313,7 @@ ce_sum_kernel(const float* __restrict__ logits, const float* __restrict__ target
   }
   const float s = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(out, s);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicAdd(out + 1, 1.f);     // out[1] > 0: some label was out of range
 }
 
 // analytic KL(q||p), diagonal Gaussians (probabilistic_unet.py:272)
@@ -384,11 +447,41 @@ extern "C" int pmu_fuse_finalize(const float* S1, const float* S2, float count, 
   return PMU_OK;
 }
 
+extern "C" int pmu_scatter_accum_affine(const float* slice_sums, const float* affine_host, int s0, int ns, int H, int W,
+                                        const int32_t dims[3], int C, float weight, float* S1, float* S2, float* cnt,
+                                        void* stream) {
+  PMU_CHECK_ARG(ns >= 0, "pmu_scatter_accum_affine: negative slice count");
+  if (ns == 0) return PMU_OK;
+  PMU_CHECK_ARG(slice_sums && affine_host && dims && S1 && S2 && cnt, "pmu_scatter_accum_affine: null pointer");
+  PMU_CHECK_ARG(H > 0 && W > 0 && C > 0 && dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && weight > 0.f, "pmu_scatter_accum_affine: bad shape");
+  ScAffine A;
+  for (int i = 0; i < 12; ++i) A.a[i] = affine_host[i];
+  const int64_t total = (int64_t)ns * H * W;
+  const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 16);
+  scatter_affine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(slice_sums, A, s0, ns, H, W, dims[0], dims[1], dims[2], C, weight,
+                                                                 S1, S2, cnt);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_fuse_finalize_counted(const float* S1, const float* S2, const float* cnt, const int32_t dims[3], int C,
+                                         float* mean, float* var, float* entropy, uint8_t* labels, void* stream) {
+  PMU_CHECK_ARG(S1 && cnt && dims, "pmu_fuse_finalize_counted: bad arguments");
+  PMU_CHECK_ARG(!var || S2, "pmu_fuse_finalize_counted: variance needs S2");
+  PMU_CHECK_SUPPORTED(C > 0 && C <= 255, "pmu_fuse_finalize_counted: C must be in 1..255");
+  const int64_t X = dims[0], YZ = (int64_t)dims[1] * dims[2];
+  PMU_CHECK_ARG(X > 0 && YZ > 0, "pmu_fuse_finalize_counted: bad dims");
+  const int blocks = (int)std::min<int64_t>(cdiv64(X * YZ, 256), (int64_t)sm_count() * 16);
+  finalize_counted_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(S1, S2, cnt, X, C, YZ, mean, var, entropy, labels);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
 extern "C" int pmu_ce_sum(const float* logits, const float* target, int B, int C, int64_t HW, float* out,
                           void* stream) {
   PMU_CHECK_ARG(logits && target && out && B > 0 && C > 0 && HW > 0, "pmu_ce_sum: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  PMU_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  PMU_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(float), st));
   const int64_t total = (int64_t)B * HW;
   const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)sm_count() * 8);
   ce_sum_kernel<<<blocks, 256, 0, st>>>(logits, target, C, HW, total, out);

@@ -831,13 +831,16 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 
 // output of ConvTranspose2d k2 s2, phase (i,j): the pixels (2h+i, 2w+j) of y[B][2H][2W][Cout] seen as a
 // strided [B][H][W][Cout] tensor, so the same {64 ch, TW, TH, TB} brick store applies
-static int make_convt_out_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int ij, int TW, int TH, int TB) {
+// (Ho, Wo) = extents of the output TENSOR: 2H x 2W, or the skip tensor's size when Up.forward pads the upsampled map
+// (F.pad, unet_parts.py:58-62: the pad of an odd extent goes to the high side, so the data sits at the origin)
+static int make_convt_out_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int ij, int TW, int TH, int TB,
+                              int Ho, int Wo) {
   auto fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
   const int i = ij >> 1, j = ij & 1;
-  char* base = reinterpret_cast<char*>(y) + ((int64_t)i * 2 * W + j) * Cout * 2;
+  char* base = reinterpret_cast<char*>(y) + ((int64_t)i * Wo + j) * Cout * 2;
   cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)2 * Cout * 2, (cuuint64_t)2 * (2 * W) * Cout * 2, (cuuint64_t)(2 * H) * (2 * W) * Cout * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * Cout * 2, (cuuint64_t)2 * Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
   cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -848,12 +851,13 @@ static int make_convt_out_map(CUtensorMap* m, void* y, int B, int H, int W, int 
 
 // rows of parity i of the ConvTranspose2d output y[B][2H][2W][Cout] as a [B][H][2W][Cout] tensor (row stride = two
 // output rows): one box {64 ch, 2 TW, TH, TB} covers both column parities of a tile (convt_pair_epilogue)
-static int make_convt_pair_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int i, int TW, int TH, int TB) {
+static int make_convt_pair_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int i, int TW, int TH, int TB,
+                               int Ho, int Wo) {
   auto fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
-  char* base = reinterpret_cast<char*>(y) + (int64_t)i * 2 * W * Cout * 2;
+  char* base = reinterpret_cast<char*>(y) + (int64_t)i * Wo * Cout * 2;
   cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)(2 * W), (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)2 * (2 * W) * Cout * 2, (cuuint64_t)(2 * H) * (2 * W) * Cout * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)2 * Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
   cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(2 * TW), (cuuint32_t)TH, (cuuint32_t)TB};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -901,8 +905,11 @@ using namespace pmu;
 
 static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                           const float* bias, void* y, void* y_pool, int pool_mode, int B, int H, int W, int Cout,
-                          int ntaps, int relu, int f16, void* stream) {
+                          int ntaps, int relu, int f16, int out_h, int out_w, void* stream) {
   PMU_CHECK_ARG(x0 && wpack && (y || y_pool), "pmu_conv_gemm_bf16: null pointer");
+  const int Ho = out_h > 0 ? out_h : 2 * H, Wo = out_w > 0 ? out_w : 2 * W;     // convT output tensor extents
+  PMU_CHECK_ARG(ntaps == 4 ? (Ho >= 2 * H && Wo >= 2 * W) : (out_h <= 0 && out_w <= 0),
+                "pmu_conv_gemm_bf16: out_h / out_w are the (padded) output extents of the transposed convolution, >= 2H x 2W");
   PMU_CHECK_ARG(ntaps == 9 || ntaps == 4 || ntaps == 1, "pmu_conv_gemm_bf16: ntaps must be 9, 4 or 1 (got %d)", ntaps);
   PMU_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && C1 >= 0, "pmu_conv_gemm_bf16: bad shape");
   PMU_CHECK_ARG(C1 == 0 || x1, "pmu_conv_gemm_bf16: C1 > 0 needs x1");
@@ -962,13 +969,13 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   if (p.tma_store) {
     if (tpair) {
       for (int i = 0; i < 2; ++i) {
-        rc = make_convt_pair_map(&ym[i], y, B, H, W, Cout, i, p.TW, p.TH, p.TB);
+        rc = make_convt_pair_map(&ym[i], y, B, H, W, Cout, i, p.TW, p.TH, p.TB, Ho, Wo);
         if (rc) return rc;
       }
       ym[2] = ym[3] = ym[0];
     } else if (ntaps == 4) {
       for (int ij = 0; ij < 4; ++ij) {
-        rc = make_convt_out_map(&ym[ij], y, B, H, W, Cout, ij, p.TW, p.TH, p.TB);
+        rc = make_convt_out_map(&ym[ij], y, B, H, W, Cout, ij, p.TW, p.TH, p.TB, Ho, Wo);
         if (rc) return rc;
       }
     } else {
@@ -1002,13 +1009,13 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
 
 extern "C" int pmu_conv_gemm_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                                   const float* bias, void* y, int B, int H, int W, int Cout, int ntaps,
-                                  int relu, int f16, void* stream) {
-  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, nullptr, -1, B, H, W, Cout, ntaps, relu, f16, stream);
+                                  int relu, int f16, int out_h, int out_w, void* stream) {
+  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, nullptr, -1, B, H, W, Cout, ntaps, relu, f16, out_h, out_w, stream);
 }
 
 extern "C" int pmu_conv_gemm_pool_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                                        const float* bias, void* y, void* y_pool, int pool_mode, int B, int H,
                                        int W, int Cout, int relu, int f16, void* stream) {
   PMU_CHECK_ARG(y_pool != nullptr, "pmu_conv_gemm_pool_bf16: y_pool is null");
-  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, y_pool, pool_mode, B, H, W, Cout, 9, relu, f16, stream);
+  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, y_pool, pool_mode, B, H, W, Cout, 9, relu, f16, 0, 0, stream);
 }

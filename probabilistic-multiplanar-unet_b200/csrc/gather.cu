@@ -247,9 +247,11 @@ gather_plane2_kernel(const float* __restrict__ vol, int d1, int d2, int s0, int 
 }
 
 // ---------------------------------------------------------------------------------
-// affine-grid gather: nearest / trilinear, zeros outside.  fp32 arithmetic with
-// explicitly rounded mul/add (no FMA contraction) in the oracle's op order so the
-// result is bit-identical to oracle.resample_slices.
+// affine-grid gather: nearest / trilinear, zeros outside.  fp32 arithmetic in EXACTLY the op order of the oracle
+// (oracle/resample_fma.c): q = fma(c, v, fma(r, u, fma(s, n, o))), lerp(a, b, t) = fma(t, b - a, a) — explicit
+// __fmaf_rn / __fsub_rn / __fadd_rn, so nothing is left to the compiler's contraction and the result is bit-identical
+// to oracle.resample_slices.  (Round 1 specified separately rounded multiplies and adds: 75 instructions per output
+// pixel, which bounded the brick kernel at 0.23-0.26 of HBM; the fused spec needs half as many.)
 // ---------------------------------------------------------------------------------
 struct Affine12 { float a[12]; };
 
@@ -259,7 +261,7 @@ __device__ __forceinline__ float fetch_vox(const float* __restrict__ vol, int d0
   return __ldg(vol + ((int64_t)ix * d1 + iy) * d2 + iz);
 }
 __device__ __forceinline__ float lerp_rn(float a, float b, float t) {
-  return __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+  return __fmaf_rn(t, __fsub_rn(b, a), a);
 }
 
 template <bool TRILINEAR>
@@ -277,11 +279,8 @@ gather_affine_kernel(const float* __restrict__ vol, int d0, int d1, int d2, Affi
     const float rf = (float)(int)(i / W), cf = (float)(int)(i % W);
     float q[3];
 #pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-      float t = __fadd_rn(A.a[ax], __fmul_rn(sf, A.a[3 + ax]));
-      t = __fadd_rn(t, __fmul_rn(rf, A.a[6 + ax]));
-      q[ax] = __fadd_rn(t, __fmul_rn(cf, A.a[9 + ax]));
-    }
+    for (int ax = 0; ax < 3; ++ax)
+      q[ax] = __fmaf_rn(cf, A.a[9 + ax], __fmaf_rn(rf, A.a[6 + ax], __fmaf_rn(sf, A.a[3 + ax], A.a[ax])));
     float v;
     if (!TRILINEAR) {
       const int ix = (int)floorf(__fadd_rn(q[0], 0.5f));
@@ -322,11 +321,8 @@ struct BrickCfg { int ts, tr, tc; int lg_tc, lg_tr; int bx, by, bz; int tiles_r,
 
 __device__ __forceinline__ void affine_q(const Affine12& A, float sf, float rf, float cf, float (&q)[3]) {
 #pragma unroll
-  for (int ax = 0; ax < 3; ++ax) {
-    float t = __fadd_rn(A.a[ax], __fmul_rn(sf, A.a[3 + ax]));
-    t = __fadd_rn(t, __fmul_rn(rf, A.a[6 + ax]));
-    q[ax] = __fadd_rn(t, __fmul_rn(cf, A.a[9 + ax]));
-  }
+  for (int ax = 0; ax < 3; ++ax)
+    q[ax] = __fmaf_rn(cf, A.a[9 + ax], __fmaf_rn(rf, A.a[6 + ax], __fmaf_rn(sf, A.a[3 + ax], A.a[ax])));
 }
 
 template <bool TRILINEAR>
@@ -371,7 +367,12 @@ gather_affine_brick_kernel(const __grid_constant__ CUtensorMap tmV, Affine12 A, 
   auto tap = [&](int ix, int iy, int iz) -> float {
     return brick[(ix - ox) * sx + (iy - oy) * sy + (iz - oz)];
   };
-#pragma unroll 1
+  // 4 output pixels per thread, pixel = t + 256 k: the 32 lanes of a warp are 32 CONSECUTIVE output columns (tc >= 32:
+  // one row of one slice), so on a grid whose columns walk z their taps fall into 32 consecutive shared-memory banks and
+  // their stores into one 128-byte line.  (A thread owning 4 consecutive columns strides the lanes by 16 B: 4-way bank
+  // conflicts on all 8 taps put the shared-memory pipe at 83 % and the kernel at 0.26 of HBM, profiles/r02_gather_oblique.txt.)
+  const int K0 = -(ox * sx + oy * sy + oz);
+#pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int idx = t + 256 * k;                  // 0 .. ts*tr*tc - 1 (== 1023)
     const int cl = idx & (g.tc - 1), rl = (idx >> g.lg_tc) & (g.tr - 1), sl = idx >> (g.lg_tc + g.lg_tr);   // powers of two
@@ -381,11 +382,13 @@ gather_affine_brick_kernel(const __grid_constant__ CUtensorMap tmV, Affine12 A, 
     affine_q(A, (float)(s0 + b), (float)r, (float)c, q);
     float v;
     if (!TRILINEAR) {
-      v = tap((int)floorf(__fadd_rn(q[0], 0.5f)), (int)floorf(__fadd_rn(q[1], 0.5f)), (int)floorf(__fadd_rn(q[2], 0.5f)));
+      const int ix = __float2int_rd(__fadd_rn(q[0], 0.5f)), iy = __float2int_rd(__fadd_rn(q[1], 0.5f)), iz = __float2int_rd(__fadd_rn(q[2], 0.5f));
+      v = brick[ix * sx + iy * sy + iz + K0];
     } else {
-      const float fx = floorf(q[0]), fy = floorf(q[1]), fz = floorf(q[2]);
-      const float tx = __fsub_rn(q[0], fx), ty = __fsub_rn(q[1], fy), tz = __fsub_rn(q[2], fz);
-      const float* bp = brick + ((int)fx - ox) * sx + ((int)fy - oy) * sy + ((int)fz - oz);   // one base, 8 offsets
+      // floor as one conversion each way (cvt.rmi.s32.f32, cvt.rn.f32.s32): the integer floor is exact for |q| < 2^24
+      const int x0 = __float2int_rd(q[0]), y0 = __float2int_rd(q[1]), z0 = __float2int_rd(q[2]);
+      const float tx = __fsub_rn(q[0], (float)x0), ty = __fsub_rn(q[1], (float)y0), tz = __fsub_rn(q[2], (float)z0);
+      const float* bp = brick + (x0 * sx + y0 * sy + z0 + K0);   // one base, 8 offsets
       const float c00 = lerp_rn(bp[0], bp[1], tz);
       const float c01 = lerp_rn(bp[sy], bp[sy + 1], tz);
       const float c10 = lerp_rn(bp[sx], bp[sx + 1], tz);
@@ -506,11 +509,25 @@ extern "C" int pmu_slice_gather(const float* vol, const int32_t dims[3], int pla
     }
     // ---- TMA-staged brick path ----
     if (d2 % 4 == 0 && aligned16(vol)) {
-      BrickCfg g;
-      const float nz = fabsf(A.a[3 + 2]), uz = fabsf(A.a[6 + 2]), vz = fabsf(A.a[9 + 2]);
-      // 1024 outputs per block (4 per thread) amortise the brick load latency
-      if (nz > vz && nz > uz) { g.ts = 32; g.tr = 4; g.tc = 8; g.lg_tr = 2; g.lg_tc = 3; }     // slices walk z
-      else                    { g.ts = 1; g.tr = 32; g.tc = 32; g.lg_tr = 5; g.lg_tc = 5; }    // columns / rows walk z
+      // Tile = ts x tr x tc output pixels (slices x rows x columns, powers of two, 1024 per block, tc >= 32: a warp is 32
+      // consecutive output columns).  The brick the tile's taps touch is (tile extent along each volume axis + 3)
+      // voxels: a flat 1 x 32 x 32 tile of an oblique grid reads 3 x-planes to produce one — 4x read amplification,
+      // which is what held this kernel at 0.23 of HBM.  Pick the tile shape with the smallest brick.
+      BrickCfg g = {};
+      double best = 1e30;
+      for (int lts = 0; lts <= 5; ++lts)
+        for (int ltr = 0; lts + ltr <= 8; ++ltr) {
+          const int ltc = 10 - lts - ltr;
+          if (ltc < 5 || ltc > 8) continue;      // a warp = 32 consecutive output columns
+          const int ts = 1 << lts, tr = 1 << ltr, tc = 1 << ltc;
+          int e3[3];
+          for (int ax = 0; ax < 3; ++ax)
+            e3[ax] = (int)floorf((ts - 1) * fabsf(A.a[3 + ax]) + (tr - 1) * fabsf(A.a[6 + ax]) + (tc - 1) * fabsf(A.a[9 + ax])) + 3;
+          const double vol_b = (double)e3[0] * e3[1] * (((e3[2] + 3) & ~3) + 4);
+          // prefer tiles that are long along the output columns (16-byte stores) when the bricks are equal
+          const double cost = vol_b - 1e-3 * tc;
+          if (cost < best) { best = cost; g.ts = ts; g.tr = tr; g.tc = tc; g.lg_tr = ltr; g.lg_tc = ltc; }
+        }
       int ext[3];
       for (int ax = 0; ax < 3; ++ax) {
         const float e = (g.ts - 1) * fabsf(A.a[3 + ax]) + (g.tr - 1) * fabsf(A.a[6 + ax]) + (g.tc - 1) * fabsf(A.a[9 + ax]);

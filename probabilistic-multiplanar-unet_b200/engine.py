@@ -143,10 +143,6 @@ class PackedNet:
     def unet_features(self, x: torch.Tensor) -> torch.Tensor:
         """x fp32 [B,1,H,W] -> last decoder map: fp32 NCHW [B,F,H,W] or bf16 NHWC [B,H,W,F]."""
         fp32 = self.precision == "fp32"
-        if not fp32:
-            H, W = x.shape[2], x.shape[3]
-            if H % (1 << (self.levels - 1)) or W % (1 << (self.levels - 1)):
-                raise RuntimeError(f"the tensor-core modes need H, W divisible by {1 << (self.levels - 1)} (got {H}x{W}); use fp32")
         a, b = self.inc
         blocks = [self.inc] + list(self.down)
         xs, h = [], x
@@ -167,7 +163,10 @@ class PackedNet:
             if fp32:
                 u = ops.convt2x2_f32(h, up["w"], up["b"], out_hw=(skip.shape[2], skip.shape[3]))
             else:
-                u = ops.conv_gemm_bf16(h, up["wpack"], up["b"], up["cout"], 4, False)
+                # any H x W: MaxPool2d floors odd extents, so the upsampled map can be one row / column short of the skip
+                # connection; F.pad (unet_parts.py:58-62) fills the high side with zeros — the transposed convolution
+                # writes straight into a zeroed tensor of the skip's size
+                u = ops.conv_gemm_bf16(h, up["wpack"], up["b"], up["cout"], 4, False, out_hw=(skip.shape[1], skip.shape[2]))
             a, b = up["conv"]
             h = self._conv(b, self._conv(a, skip, x1=u))   # cat([skip, up]) as a two-source K loop
         return h

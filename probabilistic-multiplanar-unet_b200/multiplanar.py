@@ -147,7 +147,7 @@ class MultiPlanarPredictor:
         return vol.contiguous()
 
     def accumulate(self, vol: torch.Tensor, eps: torch.Tensor, acc: torch.Tensor, only_plane: Optional[int] = None,
-                   plane0_last: bool = False, on_slab=None) -> int:
+                   plane0_last: bool = False, on_slab=None, cnt: Optional[torch.Tensor] = None) -> int:
         """Run this rank's slices and add their sums into acc [2,X,C,Y,Z]; returns #slices done.
         only_plane restricts the pass to one view (per-view volumes of eval.py:176-190).
         plane0_last processes the x-slicing view after the others, so that after every plane-0 batch the voxels
@@ -185,7 +185,11 @@ class MultiPlanarPredictor:
                 mu, ls = net.gaussian("prior", x)
                 sigma = torch.exp(ls)          # Normal(scale=exp(log_sigma)), probabilistic_unet.py:113
                 sums = net.fcomb_sums(feat, mu, sigma, eps[pi, s0:s0 + ns].contiguous())
-                ops.scatter_accum_(sums, p, s0, dims, acc[0], acc[1])
+                if exact:
+                    ops.scatter_accum_(sums, p, s0, dims, acc[0], acc[1])
+                else:
+                    # non-identity grid (App. A step 6): nearest-voxel scatter with a per-voxel count of the samples
+                    ops.scatter_accum_affine_(sums, self.affines[p], s0, dims, acc[0], acc[1], cnt, float(N))
                 done += ns
                 if on_slab is not None and p == 0:
                     on_slab(s0, s0 + ns)
@@ -336,6 +340,36 @@ class MultiPlanarPredictor:
         pipe["pending"][k] = s["out"]
         return k
 
+    @torch.no_grad()
+    def _predict_oblique(self, vol, eps, seed, want_labels, keep_sums):
+        """predict() on NON-identity slice grids (arbitrary view vectors — the reference's use_standard_axis=False TODO,
+        utils/mri_dataset.py:60-71): slices are resampled (nearest / trilinear) on the
+        affine grids, every pixel's sums go to its nearest voxel and a per-voxel count replaces the constant P * N of
+        the standard views: mean = S1 / cnt, var = S2 / cnt - mean^2.  Voxels no slice pixel lands on read 0
+        ("count" in the result is the per-voxel tensor).  Multi-GPU: the counts are reduced with the accumulators."""
+        vol = self._to_device_volume(vol)
+        dims = tuple(vol.shape)
+        P, N, L = len(self.planes), self.n_samples, self.L
+        if eps is None:
+            g = torch.Generator(device=self.device).manual_seed(seed)
+            eps = torch.randn(P, max(dims), N, L, generator=g, device=self.device)
+        else:
+            eps = eps.to(self.device, torch.float32, non_blocking=True)
+        acc = torch.zeros(2, dims[0], self.C, dims[1], dims[2], dtype=torch.float32, device=self.device)
+        cnt = torch.zeros(dims, dtype=torch.float32, device=self.device)
+        self.accumulate(vol, eps, acc, cnt=cnt)
+        reduce_accumulators(acc, self.world, self.group, dst=0)
+        reduce_accumulators(cnt, self.world, self.group, dst=0)
+        out: Dict[str, torch.Tensor] = {"count": cnt}
+        if self.rank == 0:
+            mean, var, ent, lab = ops.fuse_finalize_counted(acc[0], acc[1], cnt, want_labels=want_labels)
+            out.update(mean=mean, var=var, entropy=ent)
+            if want_labels:
+                out["labels"] = lab
+        if keep_sums:
+            out["S1"], out["S2"] = acc[0], acc[1]
+        return out
+
     def wait(self, ticket: Optional[int] = None) -> None:
         """Block the host until `ticket`'s results (default: everything submitted) are complete in host memory."""
         pipe = getattr(self, "_pipe", None)
@@ -359,9 +393,7 @@ class MultiPlanarPredictor:
         side stream while the next slice batch computes (the 470 MB device->host copy of a 256^3 result leaves
         the critical path), and the call returns with the copies complete on the current stream."""
         if self.interp != "exact" and not self.identity_grid:
-            raise NotImplementedError("voxel fusion (scatter back onto the voxel lattice) is defined for the standard "
-                                      "axis-aligned grids; arbitrary resampling grids are available through "
-                                      "ops.slice_gather (SURVEY.md App. A step 6)")
+            return self._predict_oblique(vol, eps, seed, want_labels, keep_sums)
         vol = self._to_device_volume(vol)
         dims = tuple(vol.shape)
         P, N, L = len(self.planes), self.n_samples, self.L

@@ -228,14 +228,21 @@ def conv3x3_first_bf16(x0, w, bias, relu=True, x1=None, out_dtype=torch.bfloat16
     return out
 
 
-def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None):
-    """tcgen05 implicit-GEMM conv: x NHWC 16-bit -> y NHWC in the same format (2H x 2W for ntaps=4)."""
+def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None, out_hw=None):
+    """tcgen05 implicit-GEMM conv: x NHWC 16-bit -> y NHWC in the same format (2H x 2W for ntaps=4; out_hw = the skip
+    connection's size when Up.forward pads the upsampled map, unet_parts.py:58-62: zero rows / columns at the high side)."""
     _f32(bias, "bias")
     wf = _h16((x0, "x0"), (x1, "x1"), (wpack, "wpack"))
     B, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
     oh, ow = (2 * H, 2 * W) if ntaps == 4 else (H, W)
-    out = torch.empty(B, oh, ow, Cout, dtype=x0.dtype, device=x0.device)
+    padded = ntaps == 4 and out_hw is not None and tuple(out_hw) != (oh, ow)
+    if padded:
+        if out_hw[0] < oh or out_hw[1] < ow:
+            raise RuntimeError(f"conv_gemm_bf16: out_hw {tuple(out_hw)} smaller than the upsampled map {(oh, ow)}")
+        out = torch.zeros(B, out_hw[0], out_hw[1], Cout, dtype=x0.dtype, device=x0.device)
+    else:
+        out = torch.empty(B, oh, ow, Cout, dtype=x0.dtype, device=x0.device)
     lib, st = _prep(x0, x1, wpack, bias, out)
     global _META
     ktot = (9 if ntaps == 9 else 1) * (C0 + C1)
@@ -243,7 +250,7 @@ def conv_gemm_bf16(x0, wpack, bias, Cout, ntaps, relu, x1=None):
     _META = {"flops": 2.0 * B * H * W * ntot * ktot,
              "bytes": 2.0 * (B * H * W * (C0 + C1) + out.numel() + ntot * ktot)}
     _launch(lib, "pmu_conv_gemm_bf16", (_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), B, H, W, Cout, ntaps,
-                                      int(relu), wf, st,))
+                                      int(relu), wf, int(out.shape[1]) if padded else 0, int(out.shape[2]) if padded else 0, st,))
     return out
 
 
@@ -340,6 +347,30 @@ def scatter_accum_(slice_sums, plane, s0, dims, S1, S2):
     _launch(lib, "pmu_scatter_accum", (_p(slice_sums), int(plane), int(s0), int(ns), _dims(dims), int(C), _p(S1), _p(S2), st,))
 
 
+def scatter_accum_affine_(slice_sums, affine, s0, dims, S1, S2, cnt, weight):
+    """Non-identity slice grid (App. A step 6): nearest-voxel scatter of slice_sums [ns,2,C,H,W] with a per-voxel count
+    (cnt [x,y,z] += weight)."""
+    _f32(slice_sums, "slice_sums"); _f32(S1, "S1"); _f32(S2, "S2"); _f32(cnt, "cnt")
+    ns, _, C, H, W = slice_sums.shape
+    lib, st = _prep(slice_sums, S1, S2, cnt)
+    aff = (c_float * 12)(*[float(a) for a in affine])
+    _launch(lib, "pmu_scatter_accum_affine", (_p(slice_sums), aff, int(s0), int(ns), int(H), int(W), _dims(dims), int(C),
+                                             float(weight), _p(S1), _p(S2), _p(cnt), st,))
+
+
+def fuse_finalize_counted(S1, S2, cnt, want_var=True, want_entropy=True, want_labels=False):
+    """mean / var / entropy / labels with a per-voxel count (voxels nothing landed on read 0)."""
+    _f32(S1, "S1"); _f32(S2, "S2"); _f32(cnt, "cnt")
+    X, C, Y, Z = S1.shape
+    mean = torch.empty_like(S1)
+    var = torch.empty_like(S1) if want_var else None
+    ent = torch.empty(X, Y, Z, dtype=torch.float32, device=S1.device) if want_entropy else None
+    lab = torch.empty(X, Y, Z, dtype=torch.uint8, device=S1.device) if want_labels else None
+    lib, st = _prep(S1, S2, cnt, mean, var, ent, lab)
+    _launch(lib, "pmu_fuse_finalize_counted", (_p(S1), _p(S2), _p(cnt), _dims((X, Y, Z)), C, _p(mean), _p(var), _p(ent), _p(lab), st,))
+    return mean, var, ent, lab
+
+
 def fuse_finalize(S1, S2, count, want_var=True, want_entropy=True, want_labels=False, out=None):
     """out = (mean, var, entropy, labels) writes into caller tensors (x-slabs of the full outputs)."""
     _f32(S1, "S1"); _f32(S2, "S2")
@@ -363,9 +394,13 @@ def ce_sum(logits, target):
     _f32(logits, "logits"); _f32(target, "target")
     B, C = logits.shape[:2]
     HW = logits.numel() // (B * C)
-    out = torch.empty(1, dtype=torch.float32, device=logits.device)
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
     lib, st = _prep(logits, target, out)
     _launch(lib, "pmu_ce_sum", (_p(logits), _p(target), B, C, HW, _p(out), st,))
+    # nn.CrossEntropyLoss raises on a target outside [0, C) (probabilistic_unet.py:288,303): so do we — one 4-byte
+    # read-back per loss evaluation instead of training on garbage labels (255, a 4-class map on a 3-class net, ...)
+    if float(out[1]) > 0:
+        raise IndexError(f"Target out of bounds: labels must lie in [0, {C}) (mask values outside the class range)")
     return out[0]
 
 

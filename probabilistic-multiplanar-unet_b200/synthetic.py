@@ -26,6 +26,19 @@ def phantom_volume(D: int, seed: int = 1234) -> torch.Tensor:
     return (0.6 * ph + 0.4 * torch.rand(D, D, D, generator=g)).float().contiguous()
 
 
+def phantom_labels(D: int) -> torch.Tensor:
+    """Label volume of the same phantom: 0 background, 1 outer shell, 2 inner ellipsoid; fp32 [D,D,D] (the reference's
+    mask_type is float32, probunet_trainer.py:14)."""
+    ax = torch.linspace(-1, 1, D)
+    X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
+    outer = ((X - 0.05) / 0.80) ** 2 + ((Y + 0.10) / 0.65) ** 2 + (Z / 0.70) ** 2 <= 1.0
+    inner = ((X - 0.15) / 0.40) ** 2 + ((Y + 0.05) / 0.30) ** 2 + ((Z - 0.10) / 0.35) ** 2 <= 1.0
+    lab = torch.zeros(D, D, D)
+    lab[outer] = 1.0
+    lab[inner] = 2.0
+    return lab.contiguous()
+
+
 def trainer_state_dict(seed: int = 0, num_filters: Sequence[int] = TRAINER_FILTERS, num_classes: int = 3,
                        latent_dim: int = 6, no_convs_fcomb: int = 4):
     """Random-init weights of the trainer model (the reference's initialisers) with randomised

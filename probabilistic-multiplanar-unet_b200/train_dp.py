@@ -47,10 +47,15 @@ def dp_train_step(trainer, imgs, masks, optimizer, acc_steps: int = 1, clip_valu
     """train.py:85-110 for one shard: predict -> loss / acc_steps -> backward -> (all-reduce, clip, SGD step).
     Returns the local loss (sum over ranks of the local losses == the global loss)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    # scoped to this step: the no-grad elbo() used for validation keeps the single-process weighting (beta * mean KL),
+    # so logged training and validation losses stay comparable
     trainer.net.kl_world_size = world
-    trainer.predict(imgs, masks)
-    loss = trainer.loss(imgs, masks, None) / acc_steps
-    loss.backward()
+    try:
+        trainer.predict(imgs, masks)
+        loss = trainer.loss(imgs, masks, None) / acc_steps
+        loss.backward()
+    finally:
+        trainer.net.kl_world_size = 1
     if step_now:
         allreduce_gradients(trainer.net.parameters(), group)
         if clip_value is not None:
@@ -58,3 +63,24 @@ def dp_train_step(trainer, imgs, masks, optimizer, acc_steps: int = 1, clip_valu
         optimizer.step()
         optimizer.zero_grad()
     return loss.detach()
+
+
+def sync_batchnorm_buffers(net: torch.nn.Module, group=None) -> int:
+    """Average BatchNorm running_mean / running_var over the ranks (num_batches_tracked: max) — call before a checkpoint
+    or an evaluation: every rank has trained on its own shard, so the running statistics differ between ranks although
+    the parameters are bit-identical, and the folded eval-mode inference path is built from exactly these buffers (what
+    DDP's broadcast_buffers does for its rank-0 copy).  Returns the number of buffers reduced."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    n = 0
+    for name, buf in net.named_buffers():
+        if name.endswith("num_batches_tracked"):
+            dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=group)
+        elif buf.is_floating_point():
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            buf.div_(world)
+        else:
+            continue
+        n += 1
+    return n

@@ -34,6 +34,9 @@ class ProbUNetTrainer(Trainer):
             self.net.load_state_dict(torch.load(load_model, map_location=device), strict=False)
         self.net = self.net.to(device)
         self.net.set_precision(precision)
+        # probunet_trainer.py:25 — an attribute the reference's ProbUNetTrainer never calls (its loss is -elbo); kept so
+        # code that touches trainer.criterion keeps working.  It is a plain torch module, not part of any pmu_b200 path.
+        self.criterion = torch.nn.BCELoss() if self.net.n_classes == 1 else torch.nn.CrossEntropyLoss()
 
     def predict(self, imgs, true_masks, z=None):
         """probunet_trainer.py:27-32 (train == grad enabled decides posterior + rsample)."""

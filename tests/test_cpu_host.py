@@ -97,12 +97,14 @@ def test_oracle_trilinear_matches_grid_sample():
     vol, _ = O.phantom(0, dims=(9, 10, 11))
     aff = np.array([0.3, -0.2, 0.4, 0.9, 0.1, 0.0, -0.1, 0.95, 0.05, 0.02, 0.0, 1.05], np.float32)
     out = O.resample_slices(vol, aff, 0, 8, 10, 11, "trilinear")
-    qx, qy, qz = O._grid_coords(aff, 0, 8, 10, 11)
+    a = aff.astype(np.float64).reshape(4, 3)
+    sg, rg, cg = np.meshgrid(np.arange(8.0), np.arange(10.0), np.arange(11.0), indexing="ij")
+    qx, qy, qz = [a[0, ax] + sg * a[1, ax] + rg * a[2, ax] + cg * a[3, ax] for ax in range(3)]   # the affine grid, exactly
     D0, D1, D2 = vol.shape
     grid = torch.from_numpy(np.stack([2 * qz / (D2 - 1) - 1, 2 * qy / (D1 - 1) - 1, 2 * qx / (D0 - 1) - 1], -1))[None].float()
     ref = torch.nn.functional.grid_sample(torch.from_numpy(vol)[None, None], grid, mode="bilinear",
                                           padding_mode="zeros", align_corners=True)[0, 0].numpy()
-    np.testing.assert_allclose(out, ref, atol=2e-6)
+    np.testing.assert_allclose(out, ref, atol=1e-5)
 
 
 def test_oracle_fusion_reduces_to_reference_average():

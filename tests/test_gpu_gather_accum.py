@@ -135,6 +135,48 @@ def test_scatter_accum_and_finalize(ops, dims):
     assert torch.equal(lab.cpu().long(), torch.argmax(m, 1))
 
 
+def test_scatter_affine_and_counted_finalize(ops):
+    """Non-identity slice grids: the nearest-voxel scatter with a per-voxel count against the
+    oracle (oracle/resample_fma.c; same fused coordinate chain), the identity grid reducing to the plane scatter, and the
+    counted finalise (voxels nothing landed on read 0)."""
+    g = torch.Generator().manual_seed(31)
+    dims = (12, 14, 16)
+    C, N = 3, 4
+    aff = np.array([1.3, -0.7, 0.4, 0.9, 0.1, 0.05, -0.1, 0.95, 0.05, 0.02, -0.06, 1.02], np.float32)
+    ns, H, W = 11, 13, 15
+    p = torch.softmax(torch.randn(ns, N, C, H, W, generator=g), 2)
+    sums = torch.stack([p.sum(1), (p * p).sum(1)], 1).contiguous()          # [ns, 2, C, H, W]
+    acc = np.zeros((2, dims[0], C, dims[1], dims[2]), np.float32)
+    cnt = np.zeros(dims, np.float32)
+    cnt2 = np.zeros(dims, np.float32)
+    O.scatter_nearest(sums[:, 0].numpy(), aff, 2, dims, acc[0], cnt)
+    O.scatter_nearest(sums[:, 1].numpy(), aff, 2, dims, acc[1], cnt2)
+    S = torch.zeros(2, dims[0], C, dims[1], dims[2], device="cuda")
+    K = torch.zeros(dims, device="cuda")
+    ops.scatter_accum_affine_(sums.cuda(), aff, 2, dims, S[0], S[1], K, float(N))
+    np.testing.assert_allclose(K.cpu().numpy(), cnt * N, atol=0)
+    np.testing.assert_allclose(S.cpu().numpy(), acc, rtol=1e-5, atol=1e-5)
+    assert 0 < int((cnt > 0).sum()) < cnt.size and float(cnt.max()) >= 2        # holes AND shared voxels are exercised
+    mean, var, ent, lab = ops.fuse_finalize_counted(S[0], S[1], K, want_labels=True)
+    hit = torch.from_numpy(cnt > 0)
+    want_mean = torch.from_numpy(acc[0]) / torch.from_numpy(np.maximum(cnt * N, 1.0))[:, None]
+    torch.testing.assert_close(mean.cpu(), want_mean * hit[:, None], atol=1e-5, rtol=1e-5)
+    want_var = (torch.from_numpy(acc[1]) / torch.from_numpy(np.maximum(cnt * N, 1.0))[:, None] - want_mean ** 2).clamp_min(0)
+    torch.testing.assert_close(var.cpu(), want_var * hit[:, None], atol=1e-5, rtol=1e-4)
+    assert float(ent.cpu()[~hit].abs().max()) == 0.0 and float(mean.cpu().sum(1)[hit].sub(1).abs().max()) < 1e-5
+    assert torch.equal(lab.cpu()[hit].long(), want_mean.argmax(1)[hit])
+    # the identity grid: every pixel is its own voxel, count 1 -> the plane scatter
+    for plane in range(3):
+        hw = [dims[a] for a in range(3) if a != plane]
+        q = torch.rand(dims[plane], 2, C, hw[0], hw[1], generator=g)
+        S = torch.zeros(2, dims[0], C, dims[1], dims[2], device="cuda")
+        S_ref = torch.zeros_like(S)
+        K = torch.zeros(dims, device="cuda")
+        ops.scatter_accum_affine_(q.cuda(), O.identity_affine(plane), 0, dims, S[0], S[1], K, 1.0)
+        ops.scatter_accum_(q.cuda(), plane, 0, dims, S_ref[0], S_ref[1])
+        assert torch.equal(S, S_ref) and float(K.min()) == 1.0 and float(K.max()) == 1.0
+
+
 def test_reductions(ops):
     g = torch.Generator().manual_seed(6)
     logits = torch.randn(4, 3, 31, 17, generator=g) * 2
@@ -142,6 +184,15 @@ def test_reductions(ops):
     ref = O.ce_sum(logits, tgt)
     got = ops.ce_sum(logits.cuda(), tgt.cuda())
     np.testing.assert_allclose(float(got), float(ref), rtol=1e-5)
+    # a label outside [0, C) raises like nn.CrossEntropyLoss does (255 = "ignore" in other label maps, 3 = a 4-class map)
+    import pytest
+    for bad_label in (255.0, 3.0, -1.0):
+        bad = tgt.clone()
+        bad[2, 0, 5, 7] = bad_label
+        with pytest.raises(IndexError):
+            ops.ce_sum(logits.cuda(), bad.cuda())
+        with pytest.raises(Exception):
+            torch.nn.functional.cross_entropy(logits, bad[:, 0].long())       # what the reference's criterion does
     mq, lq, mp_, lp = [torch.randn(5, 6, generator=g) * 0.5 for _ in range(4)]
     np.testing.assert_allclose(ops.kl_diag_gauss(mq.cuda(), lq.cuda(), mp_.cuda(), lp.cuda()).cpu().numpy(),
                                O.kl_diag_gauss(mq, lq, mp_, lp).numpy(), rtol=1e-5, atol=1e-6)

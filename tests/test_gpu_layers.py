@@ -198,6 +198,24 @@ def test_conv_gemm_bf16_convt(ops, B, Cin, Cout, H, W, h16):
     torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W,oh,ow", [(2, 128, 64, 5, 7, 11, 15), (3, 256, 128, 2, 2, 5, 4), (1, 128, 64, 15, 15, 31, 31)])
+@H16
+def test_convt_into_padded_skip_size(ops, B, Cin, Cout, H, W, oh, ow, h16):
+    """ConvTranspose2d k2 s2 written straight into a tensor of the skip connection's size: F.pad of Up.forward
+    (unet_parts.py:58-62) puts the pad row / column of an odd extent at the high side, zeros."""
+    g = _g(27)
+    x = _q(torch.randn(B, Cin, H, W, generator=g), h16)
+    w = _q(torch.randn(Cin, Cout, 2, 2, generator=g) * (1.0 / Cin) ** 0.5, h16)
+    b = torch.randn(Cout, generator=g) * 0.1
+    up = F.conv_transpose2d(x, w, b, stride=2)
+    dy, dx = oh - up.shape[2], ow - up.shape[3]
+    ref = F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    wpack = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(h16).contiguous().cuda()
+    got = ops.conv_gemm_bf16(_nhwc(x).to(h16).cuda(), wpack, b.cuda(), Cout, 4, False, out_hw=(oh, ow))
+    assert tuple(got.shape) == (B, oh, ow, Cout)
+    torch.testing.assert_close(got.float().cpu(), _nhwc(ref), atol=2e-2, rtol=1.6e-2)
+
+
 @pytest.mark.parametrize("B,C0,Cout,H,W,mode", [(2, 64, 64, 32, 48, 0), (1, 128, 128, 16, 16, 1), (3, 64, 128, 8, 16, 0),
                                                   (2, 64, 64, 24, 40, 1),
                                                   (2, 128, 256, 16, 32, 0), (2, 128, 256, 16, 32, 1)])   # BN = 256 tiles

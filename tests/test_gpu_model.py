@@ -145,6 +145,42 @@ def test_trainer_model_vs_golden_trainer(pmu, golden_dir, trainer_sd):
         np.testing.assert_allclose(net.prior_latent_space.base_dist.loc.cpu().numpy(), g["mu_p"], rtol=5e-2, atol=3e-2)
 
 
+def test_config1_forward_elbo_dice(pmu, golden_dir, trainer_sd):
+    """BASELINE config 1 through the drop-in API against the REAL reference (golden_cfg1.npz, made by
+    tests/golden/make_golden_cfg1.py): x = randn(4,1,128,128) seed 7, mask seed 8, eps_q seed 9; kl, reconstruction_loss,
+    elbo (rel 1e-4 in fp32 mode), probabilities (1e-4 / 2e-2) and dice_coeff of the argmax labels."""
+    z = np.load(os.path.join(golden_dir, "golden_cfg1.npz"))
+    g = {k: z[k] for k in z.files}
+    x = torch.randn(4, 1, 128, 128, generator=torch.Generator().manual_seed(7)).cuda()
+    mask = torch.randint(0, 3, (4, 1, 128, 128), generator=torch.Generator().manual_seed(8)).float().cuda()
+    eps_q = _t(g["eps_q"]).cuda()
+    net = pmu.ProbabilisticUnet(1, 3, [64, 128, 256, 512, 1024], 6, 4, 10)
+    net.load_state_dict(trainer_sd, strict=True)
+    net = net.cuda().eval()
+    ref_p = torch.from_numpy(g["eval/prob_f16"].astype(np.float32))
+    with torch.no_grad():
+        for prec, ptol, rtol in (("fp32", FP32_PROB_TOL + 5e-4, 1e-4), ("f16", BF16_PROB_TOL, 2e-3)):
+            net.set_precision(prec)
+            net.forward(x, mask, training=True)
+            e = net.elbo(mask, eps=eps_q)
+            np.testing.assert_allclose(float(net.kl), float(g["eval/kl"]), rtol=rtol * 10 if prec != "fp32" else rtol)
+            np.testing.assert_allclose(float(net.reconstruction_loss), float(g["eval/reconstruction_loss"]), rtol=rtol)
+            np.testing.assert_allclose(float(e), float(g["eval/elbo"]), rtol=rtol)
+            prob = torch.softmax(net.reconstruction, 1)
+            assert float((prob.cpu() - ref_p).abs().max()) < ptol, prec
+            lab = torch.argmax(net.reconstruction, 1)
+            dice = [float(pmu.dice_coeff((lab == k).float(), (mask[:, 0] == k).float())) for k in (1, 2)]
+            np.testing.assert_allclose(dice, g["eval/dice"], rtol=1e-4 if prec == "fp32" else 2e-2, atol=1e-5)
+    # train-mode BatchNorm (what train.py runs): the training path with the same injected noise
+    net.train()
+    net.set_precision("fp32")
+    net.forward(x, mask, training=True)
+    e = net.elbo(mask, eps=eps_q)
+    np.testing.assert_allclose(float(net.kl), float(g["train/kl"]), rtol=2e-4)
+    np.testing.assert_allclose(float(net.reconstruction_loss), float(g["train/reconstruction_loss"]), rtol=2e-4)
+    np.testing.assert_allclose(float(e), float(g["train/elbo"]), rtol=2e-4)
+
+
 def _dice_labels(a, b, C):
     d = []
     for k in range(1, C):
@@ -296,6 +332,50 @@ def test_eval_entry_point(pmu, tmp_path):
     torch.testing.assert_close(out["mean"], avg, atol=1e-6, rtol=1e-5)
 
 
+def test_predict_entry_point(pmu, golden_dir, tmp_path):
+    """predict.py: the reference's predict(net, imgs, masks, train, prob) hook (predict.py:15-19:
+    forward + one prior sample) against the oracle with the sample's z replayed, and the one-volume CLI end to end
+    (checkpoint + NIfTI in, label / entropy / variance NIfTI out, equal to MultiPlanarPredictor on the same inputs)."""
+    import importlib.util
+    import subprocess
+    import sys
+    from pmu_b200 import nifti_io
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("pmu_predict_entry", os.path.join(root, "predict.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(golden_dir, "golden_small.npz"))
+    sd = {k[3:]: _t(z[k]) for k in z.files if k.startswith("sd/")}
+    net = pmu.ProbabilisticUnet(1, 3, [4, 8, 16, 32, 64], 6, 4, 10)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x, segm = _t(z["x"]).cuda(), _t(z["segm"]).cuda()
+    logits = mod.predict(net, x, segm, train=False, prob=True)            # the reference's stub forgets this return
+    assert logits.shape == (2, 3, 32, 48) and net.z_prior_sample.shape == (2, 6)
+    with torch.no_grad():
+        feat = O.unet_features(sd, x.cpu())
+        want = O.fcomb(sd, feat, net.z_prior_sample.cpu())
+    torch.testing.assert_close(logits.cpu(), want, atol=2e-4, rtol=1e-3)
+    with pytest.raises(NotImplementedError):
+        mod.predict(net, x, segm, train=False, prob=False)                  # the plain-UNet branch is off the B200 path
+    # ---- CLI: a trainer-architecture checkpoint + one non-cubic NIfTI volume ----
+    tsd = O.make_state_dict(seed=0)
+    ckpt = tmp_path / "ckpt.pth"
+    torch.save(tsd, str(ckpt))
+    vol, _ = O.phantom(16, seed=12, dims=(16, 16, 12))
+    nifti_io.save(str(tmp_path / "scan.nii"), vol)
+    r = subprocess.run([sys.executable, os.path.join(root, "predict.py"), "-f", str(ckpt), "-i", str(tmp_path / "scan.nii"),
+                        "-o", str(tmp_path / "out"), "--samples", "2", "--precision", "fp32"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lab = nifti_io.load(str(tmp_path / "out" / "scan_labels.nii"))
+    ent = nifti_io.load(str(tmp_path / "out" / "scan_entropy.nii"))
+    assert lab.shape == (16, 16, 16) and ent.shape == (16, 16, 16)       # pad_dimensions: arg-min axis padded to the max
+    out = pmu.MultiPlanarPredictor(tsd, "cuda", precision="fp32", n_samples=2).predict(vol, want_labels=True)   # same default seed
+    np.testing.assert_array_equal(lab.astype(np.uint8), out["labels"].cpu().numpy())
+    np.testing.assert_allclose(ent, out["entropy"].cpu().numpy(), atol=1e-6)
+
+
 def test_accumulate_graphed_matches_eager(pmu, trainer_sd):
     """accumulate_graphed(): the slice pass of a volume replayed as one CUDA graph gives the bits of the eager pass, for
     a second volume written into the same buffer too (the graph is captured once per buffer triple)."""
@@ -390,6 +470,115 @@ def _check_lattice(out, golden_dir, name, tol, ent_tol):
     return e_mean, e_var, e_ent
 
 
+def _check_dense_lattice(out, golden_dir, name, tol):
+    """FUSED mean / entropy / argmax labels on 1,048,576 voxels of the full-size volume (every 2nd voxel in x and y, every
+    4th in z) against the oracle's whole-volume run (tests/golden/make_golden_fullsize.py; probabilities stored as
+    uint8, half a step = 2e-3, which the bound below includes)."""
+    g = np.load(os.path.join(golden_dir, name))
+    D = int(g["D"])
+    ix = torch.arange(int(g["x0"]), D, int(g["xs"]), device="cuda")
+    iz = torch.arange(int(g["z0"]), D, int(g["zs"]), device="cuda")
+    m = out["mean"][ix][:, :, ix][:, :, :, iz]
+    want = torch.from_numpy(g["mean01_u8"]).cuda().float() / 255.0
+    assert m.shape[0] * m.shape[2] * m.shape[3] >= 1 << 20
+    e_mean = float((m[:, :2] - want).abs().max())
+    ent = out["entropy"][ix][:, ix][:, :, iz] / float(np.log(3.0))
+    e_ent = float((ent - torch.from_numpy(g["entropy_u8"]).cuda().float() / 255.0).abs().max())
+    lab, lab_ref = m.argmax(1), torch.from_numpy(g["labels"]).cuda().long()
+    sure = torch.from_numpy(g["margin_u8"]).cuda().float() / 255.0 > 2 * tol     # the oracle's own top-2 margin exceeds the budget
+    dices = _dice_labels(lab[sure], lab_ref[sure], 3)
+    dices_all = _dice_labels(lab, lab_ref, 3)
+    print(f"dense lattice ({lab.numel()} voxels): mean err {e_mean:.4f}, entropy/ln3 err {e_ent:.4f}, Dice (confident {float(sure.float().mean()):.3f} "
+          f"of voxels) {dices}, Dice (all) {dices_all}")
+    assert e_mean < tol and e_ent < 6e-2, (e_mean, e_ent)
+    assert bool((lab[sure] == lab_ref[sure]).all()) and min(dices) >= 0.999, dices
+    assert min(dices_all) >= 0.99, dices_all
+    return e_mean
+
+
+def test_ragged_volumes_on_the_tensor_core_path(pmu, trainer_sd):
+    """Any H x W in the tensor-core mode (the reference pads: F.pad in Up.forward, unet_parts.py:58-62; MaxPool2d floors;
+    AvgPool2d ceil_mode, probabilistic_unet.py:36): a 24 x 40 x 40 scan (padded to 40^3 by pad_dimensions: 40 -> 20 -> 10
+    -> 5 -> 2, every decoder level pads) against the oracle's whole-volume run, and a 250^3 volume (250 -> 125 -> 62 -> 31
+    -> 15) on one whole slice per view."""
+    N = 2
+    vol, _ = O.phantom(40, seed=9, dims=(24, 40, 40))
+    eps = torch.randn(3, 40, N, 6, generator=torch.Generator().manual_seed(17))
+    ref = O.multiplanar_predict(vol, trainer_sd, eps, N, batch=8)
+    for precision, tol in (("fp32", FP32_PROB_TOL), ("f16", BF16_PROB_TOL)):
+        out = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision=precision, n_samples=N, slice_batch=16).predict(vol, eps=eps)
+        assert tuple(out["mean"].shape) == (40, 3, 40, 40)
+        err = float((out["mean"].cpu() - ref["mean"]).abs().max())
+        assert err < tol, (precision, err)
+    D = 250
+    vol, _ = O.phantom(D, seed=1234)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    spots = {0: 100, 1: 249, 2: 7}
+    ref = O.multiplanar_predict(vol, trainer_sd, eps, N, batch=1, slice_ranges={p: (s, s + 1) for p, s in spots.items()},
+                                return_per_slice=True)
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=32)
+    out = pred.predict(vol, eps=eps.cuda(), per_plane=True)
+    _spot_check_planes(out, ref, spots, N, BF16_PROB_TOL)
+    torch.testing.assert_close(out["mean"].sum(1), torch.ones_like(out["mean"][:, 0]), atol=1e-4, rtol=0)
+
+
+def test_oblique_views_fuse_onto_the_lattice(pmu, trainer_sd):
+    """Non-standard view vectors end to end (the reference's use_standard_axis=False TODO, utils/mri_dataset.py:60-71;
+    SURVEY.md App. A steps 2 and 6): trilinear resampling on three oblique grids, the network per slice, nearest-voxel
+    scatter with a per-voxel count, counted fusion — against the same pipeline built from the oracle's pieces."""
+    from pmu_b200 import view_affine
+    D, N = 24, 2
+    vol, _ = O.phantom(D, seed=5)
+    views = [(1.0, 0.2, 0.1), (0.1, 1.0, -0.3), (0.25, -0.15, 1.0)]
+    grids = [view_affine(v, vol.shape) for v in views]
+    assert all(g[1] == (D, D) and g[2] == D for g in grids)
+    affs = {p: grids[p][0] for p in range(3)}
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(23))
+    # ---- oracle pipeline ----
+    S = np.zeros((2, D, 3, D, D), np.float32)
+    cnt = np.zeros((D, D, D), np.float32)
+    scratch = np.zeros((D, D, D), np.float32)
+    for p in range(3):
+        raw = O.resample_slices(vol, np.asarray(affs[p], np.float32), 0, D, D, D, "trilinear")
+        x = torch.from_numpy(O.normalise_slices(raw))[:, None]
+        with torch.no_grad():
+            feat = O.unet_features(trainer_sd, x)
+            mu, ls = O.gaussian_head(trainer_sd, "prior", x)
+            pr = torch.stack([torch.softmax(O.fcomb(trainer_sd, feat, mu + torch.exp(ls) * eps[p, :, n]), 1) for n in range(N)], 1)
+        O.scatter_nearest(pr.sum(1).numpy(), affs[p], 0, (D, D, D), S[0], cnt)
+        O.scatter_nearest((pr * pr).sum(1).numpy(), affs[p], 0, (D, D, D), S[1], scratch)
+    hit = torch.from_numpy(cnt > 0)
+    want = torch.from_numpy(S[0]) / torch.from_numpy(np.maximum(cnt * N, 1.0))[:, None]
+    assert float(hit.float().mean()) > 0.5
+    for precision, tol in (("fp32", FP32_PROB_TOL), ("f16", BF16_PROB_TOL)):
+        pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision=precision, n_samples=N, slice_batch=8, interp="trilinear",
+                                        affines=affs, out_hw=(D, D))
+        out = pred.predict(vol, eps=eps)
+        np.testing.assert_array_equal(out["count"].cpu().numpy(), cnt * N)
+        err = float((out["mean"].cpu() - want)[hit[:, None].expand_as(want)].abs().max())
+        assert err < tol, (precision, err)
+        assert float(out["mean"].cpu()[~hit[:, None].expand_as(want)].abs().max()) == 0.0
+        torch.testing.assert_close(out["mean"].cpu().sum(1)[hit], torch.ones(int(hit.sum())), atol=1e-4, rtol=0)
+
+
+def test_config5_512_spot_check(pmu, trainer_sd):
+    """BASELINE config 5 at its real size and low N (512^3, 2 samples, entropy map): one whole 512 x 512 slice per view
+    against the oracle (the same per-view check the 128^3 / 256^3 configurations get) + the size-independent properties."""
+    D, N = 512, 2
+    vol, _ = O.phantom(D, seed=1234)
+    eps = torch.randn(3, D, N, 6, generator=torch.Generator().manual_seed(4321))
+    spots = {0: 200, 1: 5, 2: 511}
+    ref = O.multiplanar_predict(vol, trainer_sd, eps, N, batch=1, slice_ranges={p: (s, s + 1) for p, s in spots.items()},
+                                return_per_slice=True)
+    pred = pmu.MultiPlanarPredictor(trainer_sd, "cuda", precision="f16", n_samples=N, slice_batch=16, interp="trilinear")
+    out = pred.predict(vol, eps=eps.cuda(), per_plane=True)
+    _spot_check_planes(out, ref, spots, N, BF16_PROB_TOL)
+    mean, ent = out["mean"], out["entropy"]
+    torch.testing.assert_close(mean.sum(1), torch.ones_like(mean[:, 0]), atol=1e-4, rtol=0)
+    assert float(out["var"].min()) >= 0.0 and float(ent.min()) >= 0.0 and float(ent.max()) <= np.log(3) + 1e-5
+    torch.testing.assert_close(mean, (out["plane_means"][0] + out["plane_means"][1] + out["plane_means"][2]) / 3, atol=1e-6, rtol=0)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "f16"])
 def test_config2_full_size(pmu, trainer_sd, golden_dir, precision):
     """BASELINE config 2 at its full size (128^3, 3 planes x 8 samples, mean / variance fusion): the fused outputs on a
@@ -431,6 +620,7 @@ def test_config3_full_size(pmu, trainer_sd, golden_dir):
     epsd = eps.cuda()
     out = pred.predict(vol, eps=epsd, per_plane=True, keep_sums=True)
     _check_lattice(out, golden_dir, "golden_cfg3_lattice.npz", BF16_PROB_TOL, 6e-2)
+    _check_dense_lattice(out, golden_dir, "golden_cfg3_dense.npz", BF16_PROB_TOL)
     _, errs = _spot_check_planes(out, ref, spots, N, BF16_PROB_TOL)
     assert float(errs.quantile(0.999)) < BF16_PROB_TOL and float(errs.mean()) < 4e-3
     mean = out["mean"]

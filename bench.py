@@ -251,8 +251,12 @@ def run_ours(args):
     # --resident-output rank0 sum-reduces everything to rank 0 instead (what rounds 1a-1d measured).
     slab_res = world > 1 and D % world == 0 and args.resident_output == "slab"
 
+    # N > 1: the slice pass of a rank is replayed as ONE CUDA graph (one launch per volume instead of ~270 per rank; 8 GPUs:
+    # 14.68 -> 14.53 ms resident, 16.3 -> 15.5 ms e2e); one GPU keeps eager launches (no gain measured: 120.4 vs 119.7 ms)
+    use_graph = args.graph or (world > 1 and not args.no_graph)
+
     def step_resident():
-        if args.graph:
+        if use_graph:
             pred.accumulate_graphed(vol, eps, acc)          # zero + slice pass, one CUDA-graph launch
         else:
             acc.zero_()
@@ -271,7 +275,7 @@ def run_ours(args):
     slab = world > 1 and D % world == 0
     pred_e2e = pred if not slab else pmu_b200.MultiPlanarPredictor(
         sd, dev, precision=args.precision, n_samples=N, slice_batch=args.slice_batch, interp=args.interp, rank=rank,
-        world_size=world, output="slab", upload=args.e2e_upload, graph=args.graph)
+        world_size=world, output="slab", upload=args.e2e_upload, graph=True if args.graph else (False if args.no_graph else None))
 
     def pinned_outputs():
         if not (rank == 0 or slab):
@@ -537,7 +541,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": config_dict(D, N, args.interp),
-                "run": {"slice_batch": args.slice_batch, **({"cuda_graph": True} if args.graph else {}),
+                "run": {"slice_batch": args.slice_batch, **({"cuda_graph": True} if use_graph else {}),
                         "parallelism": f"slice-sharded x{world} + 1 " + ("reduce-scatter along x (x-slab outputs per rank)" if slab_res else "reduce")},
                 "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                         # every rank uploads the volume (--e2e-upload broadcast: rank 0 alone, then NVLink)
@@ -718,7 +722,8 @@ def main():
                     help="N > 1, resident step: reduce-scatter the accumulators along x and let every rank finalise its x-slab "
                          "(default), or sum-reduce them to rank 0")
     ap.add_argument("--graph", action="store_true",
-                    help="experiment: replay the slice pass of a volume as one CUDA graph (resident step; e2e leg for N > 1)")
+                    help="replay the slice pass of a volume as one CUDA graph in the RESIDENT step too (the e2e leg for N > 1 does by default)")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1 e2e leg: eager launches instead of the CUDA-graph replay (the default there)")
     ap.add_argument("--e2e-upload", default="each", choices=["each", "broadcast"],
                     help="N > 1 e2e leg: every rank uploads the volume over its own PCIe link (default), or rank 0 uploads "
                          "once and broadcasts over NVLink (experiment)")

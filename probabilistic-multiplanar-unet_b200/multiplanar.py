@@ -100,7 +100,7 @@ class MultiPlanarPredictor:
                  planes: Sequence[int] = (0, 1, 2), slice_batch: int = 32, interp: str = "exact",
                  affines: Optional[Dict[int, Sequence[float]]] = None, out_hw: Optional[Tuple[int, int]] = None,
                  rank: int = 0, world_size: int = 1, process_group=None, output: str = "rank0",
-                 upload: str = "each", graph: bool = False):
+                 upload: str = "each", graph: Optional[bool] = None):
         if hasattr(state_dict, "state_dict"):
             state_dict = state_dict.state_dict()
         self.device = torch.device(device)
@@ -123,9 +123,11 @@ class MultiPlanarPredictor:
             raise ValueError("upload must be 'each' (every rank copies the volume from its own host buffer) or 'broadcast' "
                              "(submit(): rank 0 copies it once, the other ranks receive it over NVLink)")
         self.upload = upload
-        # graph=True (experiment): submit() on several GPUs replays the whole slice pass of a volume as ONE CUDA graph
-        # (accumulate_graphed) instead of ~45 launches per slice batch — the host thread of every rank goes idle
-        self.graph = bool(graph)
+        # graph: submit() on several GPUs replays the whole slice pass of a volume as ONE CUDA graph (accumulate_graphed)
+        # instead of ~45 launches per slice batch — the host thread of every rank goes idle.  Default (None): on when
+        # world_size > 1, where it is the faster e2e path (8 GPUs, 256^3 x 16 samples: 16.3 -> 15.5 ms per volume,
+        # profiles/r02a_n8_bench*.json.log); one GPU keeps the streaming path (results leave x-slab by x-slab).
+        self.graph = (int(world_size) > 1) if graph is None else bool(graph)
         self.C = self.net.fcomb["C"]
         self.L = self.net.fcomb["L"]
 

@@ -309,6 +309,31 @@ int pmu_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int 
  * With it the data / weight gradients of nn.ConvTranspose2d(k=2, s=2) (unet_parts.py:52) are 1x1 GEMMs:
  * pmu_conv_gemm_bf16(ntaps = 1, K = 4*Cout) and pmu_conv_wgrad_bf16(ntaps = 1, N = 4*Cout). */
 int pmu_s2d_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* ---- training step, tensor-core mode: elementwise / reduction side on bf16 NHWC [npix = B*H*W][C] (C % 8 == 0, C/8 | 256),
+ * the layout the tcgen05 GEMMs read and write — no cast between two GEMMs of the step. --------------------------------- */
+/* nn.BatchNorm2d in train() mode + ReLU (unet_parts.py:16-20, probabilistic_unet.py:39-45; train.py:94): batch statistics
+ * of y (one pass, fp64 accumulation), running statistics updated like torch, a = [relu](gamma * (y - mean) / sqrt(var + eps)
+ * + beta) as bf16.  ws: 2*C doubles; scale_shift: 2*C floats of scratch (the folded per-channel scale / shift). */
+int pmu_bn_train_fwd_nhwc_bf16(const void* y, const float* gamma, const float* beta, float eps, int relu,
+                               float momentum, float* run_mean, float* run_var, float* mean, float* var,
+                               void* a, double* ws, float* scale_shift, int64_t npix, int C, void* stream);
+/* its backward (loss.backward(), train.py:95): dy (bf16), dgamma, dbeta from da (bf16) and the recorded y / mean / var;
+ * the ReLU mask is recomputed from y.  ws: 2*C doubles. */
+int pmu_bn_train_bwd_nhwc_bf16(const void* da, const void* y, const float* mean, const float* var, const float* gamma,
+                               const float* beta, float eps, int relu, void* dy, float* dgamma, float* dbeta,
+                               double* ws, int64_t npix, int C, void* stream);
+/* out[C] = sum over pixels of x[npix][C] (bias gradient of nn.ConvTranspose2d, unet_parts.py:52).  ws: C doubles. */
+int pmu_channel_sums_nhwc_bf16(const void* x, float* out, double* ws, int64_t npix, int C, void* stream);
+/* backward of nn.MaxPool2d(2) (unet_parts.py:33; x = the pooling input, gradient to the first maximum in row-major order
+ * like torch) / nn.AvgPool2d(2, 2, ceil_mode=True) (probabilistic_unet.py:36; x may be NULL): dy [B,Ho,Wo,C] -> dx [B,H,W,C]. */
+int pmu_pool2_bwd_nhwc_bf16(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int mode, void* stream);
+/* dst += src (bf16, n % 8 == 0): the gradient of a skip connection meets the gradient from the level below (torch.cat,
+ * unet_parts.py:65). */
+int pmu_add_bf16(void* dst, const void* src, int64_t n, void* stream);
+/* backward of the AxisAlignedConvGaussian head (probabilistic_unet.py:97-108) on a bf16 NHWC encoder map [B,h,w,C]:
+ * denc (bf16), dw [2L,C] +=, db [2L] +=  (zero-fill dw, db). */
+int pmu_gauss_head_bwd_nhwc_bf16(const void* enc, const float* w, const float* dmu, const float* dls, void* denc,
+                                 float* dw, float* db, int B, int C, int h, int w_, int L, void* stream);
 /* tcgen05 weight gradient of conv3x3 pad 1 (ntaps = 9) / conv1x1 (ntaps = 1):
  * dw fp32 [Cout][ntaps][C0+C1] += sum_{b,h,w} dy[b,h,w,co] * cat(x0,x1)[b,h+ky-1,w+kx-1,ci]   (tap = ky*3+kx)
  * x0 bf16 [B,H,W,C0], x1 (nullable) bf16 [B,H,W,C1], dy bf16 [B,H,W,Cout]; channels multiples of 64.

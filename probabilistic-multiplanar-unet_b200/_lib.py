@@ -44,6 +44,12 @@ _SIG = {
                                              c_int, c_int64, c_int, _P]),
     "pmu_softmax_accum": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P]),
     "pmu_scatter_accum": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int32), c_int, _P, _P, _P]),
+    "pmu_bn_train_fwd_nhwc_bf16": (c_int, [_P, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "pmu_bn_train_bwd_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "pmu_channel_sums_nhwc_bf16": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
+    "pmu_pool2_bwd_nhwc_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_add_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "pmu_gauss_head_bwd_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_scatter_accum_affine": (c_int, [_P, POINTER(c_float), c_int, c_int, c_int, c_int, POINTER(c_int32), c_int, c_float, _P, _P, _P, _P]),
     "pmu_fuse_finalize_counted": (c_int, [_P, _P, _P, POINTER(c_int32), c_int, _P, _P, _P, _P, _P]),
     "pmu_fuse_finalize": (c_int, [_P, _P, c_float, POINTER(c_int32), c_int, _P, _P, _P, _P, _P]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpmu_b200.so")
-SOURCES = ["api.cu", "gather.cu", "layers_f32.cu", "layers_bf16.cu", "conv_tc.cu", "fcomb_ts.cu", "accum.cu", "train_f32.cu", "wgrad_tc.cu"]
+SOURCES = ["api.cu", "gather.cu", "layers_f32.cu", "layers_bf16.cu", "conv_tc.cu", "fcomb_ts.cu", "accum.cu", "train_f32.cu", "train_bf16.cu", "wgrad_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

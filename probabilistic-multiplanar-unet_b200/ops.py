@@ -625,3 +625,74 @@ def conv_wgrad_bf16(x0, dy, dw, x1=None, ntaps=9):
     global _META
     _META = {"flops": 2.0 * B * H * W * Cout * ntaps * (C0 + C1)}
     _launch(lib, "pmu_conv_wgrad_bf16", (_p(x0), C0, _p(x1), C1, _p(dy), _p(dw), B, H, W, Cout, int(ntaps), st,))
+
+
+# ----------------------------------------------------------------------------- training step on bf16 NHWC activations
+def bn_train_fwd_nhwc_bf16(y, gamma, beta, eps, relu, momentum=0.1, run_mean=None, run_var=None):
+    """Train-mode BatchNorm2d (+ReLU) on y bf16 [B,H,W,C]: returns (a bf16, mean, var); running stats updated in place."""
+    _bf16(y, "y")
+    C = y.shape[-1]
+    npix = y.numel() // C
+    mean = torch.empty(C, dtype=torch.float32, device=y.device)
+    var = torch.empty_like(mean)
+    a = torch.empty_like(y)
+    ws = _ws(C, y.device)
+    ss = torch.empty(2 * C, dtype=torch.float32, device=y.device)
+    lib, st = _prep(y, gamma, beta, run_mean, run_var, mean, var, a, ws, ss)
+    _launch(lib, "pmu_bn_train_fwd_nhwc_bf16", (_p(y), _p(gamma), _p(beta), float(eps), int(relu), float(momentum), _p(run_mean),
+                                              _p(run_var), _p(mean), _p(var), _p(a), _p(ws), _p(ss), npix, C, st,))
+    return a, mean, var
+
+
+def bn_train_bwd_nhwc_bf16(da, y, mean, var, gamma, beta, eps, relu):
+    """-> (dy bf16, dgamma, dbeta)."""
+    _bf16(da, "da"); _bf16(y, "y")
+    C = y.shape[-1]
+    npix = y.numel() // C
+    dy = torch.empty_like(y)
+    dg = torch.empty(C, dtype=torch.float32, device=y.device)
+    db = torch.empty_like(dg)
+    ws = _ws(C, y.device)
+    lib, st = _prep(da, y, mean, var, gamma, beta, dy, dg, db, ws)
+    _launch(lib, "pmu_bn_train_bwd_nhwc_bf16", (_p(da), _p(y), _p(mean), _p(var), _p(gamma), _p(beta), float(eps), int(relu),
+                                              _p(dy), _p(dg), _p(db), _p(ws), npix, C, st,))
+    return dy, dg, db
+
+
+def channel_sums_nhwc_bf16(x):
+    _bf16(x, "x")
+    C = x.shape[-1]
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = torch.empty(C, dtype=torch.float64, device=x.device)
+    lib, st = _prep(x, out, ws)
+    _launch(lib, "pmu_channel_sums_nhwc_bf16", (_p(x), _p(out), _p(ws), x.numel() // C, C, st,))
+    return out
+
+
+def pool2_bwd_nhwc_bf16(x, dy, mode, in_hw=None):
+    """x: the pooling input [B,H,W,C] (None for the average, then in_hw = (H, W)); dy [B,Ho,Wo,C] -> dx [B,H,W,C]."""
+    _bf16(x, "x"); _bf16(dy, "dy")
+    B, Ho, Wo, C = dy.shape
+    H, W = (x.shape[1], x.shape[2]) if x is not None else in_hw
+    dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dy.device)
+    lib, st = _prep(x, dy, dx)
+    _launch(lib, "pmu_pool2_bwd_nhwc_bf16", (_p(x), _p(dy), _p(dx), B, H, W, C, mode, st,))
+    return dx
+
+
+def add_bf16_(dst, src):
+    _bf16(dst, "dst"); _bf16(src, "src")
+    assert dst.shape == src.shape
+    lib, st = _prep(dst, src)
+    _launch(lib, "pmu_add_bf16", (_p(dst), _p(src), dst.numel(), st,))
+    return dst
+
+
+def gauss_head_bwd_nhwc_bf16(enc, w, dmu, dls, dw, db):
+    _bf16(enc, "enc")
+    B, h, w_, C = enc.shape
+    denc = torch.empty_like(enc)
+    lib, st = _prep(enc, w, dmu, dls, denc, dw, db)
+    _launch(lib, "pmu_gauss_head_bwd_nhwc_bf16", (_p(enc), _p(w), _p(dmu), _p(dls), _p(denc), _p(dw), _p(db), B, C, h, w_,
+                                                dmu.shape[1], st,))
+    return denc

@@ -1,5 +1,7 @@
 """Training step of ProbabilisticUnet through the CUDA kernels: fp32 NCHW parity mode and the bf16
-tensor-core mode (precision="bf16": every convolution GEMM — forward, dgrad, wgrad — on tcgen05).
+tensor-core mode (precision="bf16" / "f16": every convolution GEMM — forward, dgrad, wgrad — on tcgen05, activations
+and their gradients bf16 NHWC END TO END: BatchNorm / pooling / skip adds / the Gaussian head run on that layout
+(csrc/train_bf16.cu), so no layout or precision cast sits between two GEMMs of the step).
 
 What the reference's training loop asks of autograd (train.py:85-110 via
 ProbUNetTrainer.predict / loss, trainer/probunet_trainer.py:27-39):
@@ -48,49 +50,26 @@ class _Tape:
 
 
 # ------------------------------------------------------------------ conv3x3 + BN(train) + ReLU
-# bf16 tensor-core mode: BatchNorm / ReLU / pooling stay fp32 NCHW (batch statistics in fp32); the three
-# GEMMs of every convolution — forward, data gradient, weight gradient — run on tcgen05 with bf16 NHWC
-# operands (conv_tc.cu forward kernel twice, wgrad_tc.cu), bracketed by layout casts.
-_BF16 = {"on": False, "cache": {}}
-# Self-check hook (tests / debugging): when CHECK_LOG is a list, every tcgen05 dgrad / wgrad of the step is
-# recomputed by the fp32 CUDA-core kernel on the SAME operands and (kind, Cin, Cout, H, relative L2 deviation)
-# is appended — the deviation is then pure bf16 operand rounding (~3e-3).
+# Self-check hook (tests / debugging): when CHECK_LOG is a list, every tcgen05 forward / dgrad / wgrad of a tensor-core step
+# is recomputed by the fp32 CUDA-core kernel on the SAME (bf16-rounded) operands and (kind, Cin, Cout, H, relative L2
+# deviation) is appended — the deviation is then accumulation order + the bf16 rounding of the GEMM's output (~3e-3).
 CHECK_LOG = None
-
-
-def _to_bf16_nhwc(t):
-    """bf16 NHWC copy of an fp32 NCHW activation, cached per step (skips / pooled maps feed several GEMMs)."""
-    c = _BF16["cache"]
-    k = id(t)
-    if k not in c:
-        c[k] = (t, ops.nchw_f32_to_nhwc_bf16(t))      # keep t alive so id() stays unique
-    return c[k][1]
-
-
-def _tc_ok(conv):
-    return _BF16["on"] and conv.weight.shape[0] % 64 == 0 and conv.weight.shape[1] % 64 == 0
+_BF16 = {"on": False}
 
 
 def _cbr_fwd(conv: nn.Conv2d, bn: nn.BatchNorm2d, x0, x1=None):
-    tc = _tc_ok(conv) and x0.shape[1] % 64 == 0 and (x1 is None or x1.shape[1] % 64 == 0)
-    if tc:
-        w = _d(conv.weight)
-        wpack = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()     # [Cout][tap][Cin]
-        yb = ops.conv_gemm_bf16(_to_bf16_nhwc(x0), wpack, _d(conv.bias), w.shape[0], 9, False,
-                                x1=None if x1 is None else _to_bf16_nhwc(x1))
-        y = ops.nhwc_bf16_to_nchw_f32(yb)
-        if CHECK_LOG is not None:
-            ref = ops.conv3x3_f32(x0, w, _d(conv.bias), relu=False, x1=x1)
-            CHECK_LOG.append(("fwd", w.shape[1], w.shape[0], y.shape[2], float((y - ref).norm() / ref.norm())))
-    else:
-        y = ops.conv3x3_f32(x0, _d(conv.weight), _d(conv.bias), relu=False, x1=x1)
+    if _BF16["on"]:
+        return _tc_cbr_fwd(conv, bn, x0, x1)
+    y = ops.conv3x3_f32(x0, _d(conv.weight), _d(conv.bias), relu=False, x1=x1)
     a, mean, var = ops.bn_train_fwd_f32(y, _d(bn.weight), _d(bn.bias), bn.eps, True,
                                         0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var)
     bn.num_batches_tracked += 1
-    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var, "tc": tc}
+    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var}
 
 
 def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
+    if _BF16["on"]:
+        return _tc_cbr_bwd(rec, da, tape, need_dx)
     conv, bn = rec["conv"], rec["bn"]
     dy, dg, db, dcb = ops.bn_train_bwd_f32(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True,
                                            want_dbias=True)
@@ -98,34 +77,7 @@ def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
     tape.put(bn.bias, db)
     tape.put(conv.bias, dcb)
     w = _d(conv.weight)
-    Cout, Cin = w.shape[0], w.shape[1]
     C0 = rec["x0"].shape[1]
-    if rec["tc"]:
-        dyb = ops.nchw_f32_to_nhwc_bf16(dy)
-        x0b = _to_bf16_nhwc(rec["x0"])
-        x1b = None if rec["x1"] is None else _to_bf16_nhwc(rec["x1"])
-        dwp = torch.zeros(Cout, 9, Cin, dtype=torch.float32, device=dy.device)
-        ops.conv_wgrad_bf16(x0b, dyb, dwp, x1b, 9)
-        tape.put(conv.weight, dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous())
-        if CHECK_LOG is not None:
-            ref = torch.zeros_like(w)
-            ops.conv3x3_wgrad_f32(rec["x0"], dy, ref, rec["x1"])
-            got = dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
-            CHECK_LOG.append(("wgrad", Cin, Cout, dy.shape[2], float((got - ref).norm() / ref.norm())))
-        if not need_dx:
-            return None, None
-        # data gradient: the forward tcgen05 kernel with W transposed (ci <-> co) and flipped, [ci][tap][co]
-        wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).to(torch.bfloat16)
-        dx0 = ops.nhwc_bf16_to_nchw_f32(ops.conv_gemm_bf16(dyb, wt[:C0].contiguous(), None, C0, 9, False))
-        if CHECK_LOG is not None:
-            ref = ops.conv3x3_f32(dy, w.flip(2, 3).transpose(0, 1)[:C0].contiguous(), None, relu=False)
-            CHECK_LOG.append(("dgrad", Cin, Cout, dy.shape[2], float((dx0 - ref).norm() / ref.norm())))
-        dx1 = None
-        if rec["x1"] is not None:
-            dx1b = ops.conv_gemm_bf16(dyb, wt[C0:].contiguous(), None, Cin - C0, 9, False)
-            dx1 = ops.nhwc_bf16_to_nchw_f32(dx1b)
-            _BF16["cache"][id(dx1)] = (dx1, dx1b)               # the transposed-convolution backward reads the bf16 form
-        return dx0, dx1
     dw = torch.zeros_like(w)
     ops.conv3x3_wgrad_f32(rec["x0"], dy, dw, rec["x1"])
     tape.put(conv.weight, dw)
@@ -135,6 +87,70 @@ def _cbr_bwd(rec, da, tape: _Tape, need_dx=True):
     wt = w.flip(2, 3).transpose(0, 1)
     dx0 = ops.conv3x3_f32(dy, wt[:C0].contiguous(), None, relu=False)
     dx1 = ops.conv3x3_f32(dy, wt[C0:].contiguous(), None, relu=False) if rec["x1"] is not None else None
+    return dx0, dx1
+
+
+# ------------------------------------------------------------------ the same layer in the tensor-core mode
+# Activations and gradients are bf16 NHWC [B,H,W,C].  The three first layers (Cin = 1: U-Net, prior; Cin = 2: posterior) take the
+# fp32 NCHW image (+ mask) and have no data gradient; their weight gradient (576 / 1152 values) uses the fp32 small-Cin
+# kernel on a cast of dy — the only casts left in the step besides the fcomb head's input / output.
+def _f32(t_bf16_nhwc):
+    return ops.nhwc_bf16_to_nchw_f32(t_bf16_nhwc)
+
+
+def _tc_cbr_fwd(conv, bn, x0, x1=None):
+    w = _d(conv.weight)
+    Cout, Cin = w.shape[0], w.shape[1]
+    first = Cin <= 2
+    if first:
+        if Cout % 8 or Cout > 128:
+            raise NotImplementedError("tensor-core training needs a first layer with Cout % 8 == 0, <= 128")
+        y = ops.conv3x3_first_bf16(x0, w, _d(conv.bias), relu=False, x1=x1, out_dtype=torch.bfloat16)
+    else:
+        wpack = w.permute(0, 2, 3, 1).reshape(Cout, -1).to(torch.bfloat16).contiguous()        # [Cout][tap][Cin]
+        y = ops.conv_gemm_bf16(x0, wpack, _d(conv.bias), Cout, 9, False, x1=x1)
+        if CHECK_LOG is not None:
+            ref = ops.conv3x3_f32(_f32(x0), w.to(torch.bfloat16).float(), _d(conv.bias), relu=False, x1=None if x1 is None else _f32(x1))
+            CHECK_LOG.append(("fwd", Cin, Cout, y.shape[1], float((_f32(y) - ref).norm() / ref.norm())))
+    a, mean, var = ops.bn_train_fwd_nhwc_bf16(y, _d(bn.weight), _d(bn.bias), bn.eps, True,
+                                              0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var)
+    bn.num_batches_tracked += 1
+    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var, "first": first}
+
+
+def _tc_cbr_bwd(rec, da, tape: _Tape, need_dx=True):
+    conv, bn = rec["conv"], rec["bn"]
+    dy, dg, db = ops.bn_train_bwd_nhwc_bf16(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True)
+    tape.put(bn.weight, dg)
+    tape.put(bn.bias, db)
+    # a bias in front of a train-mode BatchNorm has an exactly zero gradient (BatchNorm subtracts the batch mean); autograd's
+    # value is the rounding residue of sum(dy), which the fp32 path reproduces and a bf16 dy would only replace by other noise
+    tape.put(conv.bias, torch.zeros_like(_d(conv.bias)))
+    w = _d(conv.weight)
+    Cout, Cin = w.shape[0], w.shape[1]
+    if rec["first"]:
+        dw = torch.zeros_like(w)
+        ops.conv3x3_wgrad_f32(rec["x0"], _f32(dy), dw, rec["x1"])
+        tape.put(conv.weight, dw)
+        return None, None
+    C0 = rec["x0"].shape[3]
+    dwp = torch.zeros(Cout, 9, Cin, dtype=torch.float32, device=dy.device)
+    ops.conv_wgrad_bf16(rec["x0"], dy, dwp, rec["x1"], 9)
+    tape.put(conv.weight, dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous())
+    if CHECK_LOG is not None:
+        ref = torch.zeros_like(w)
+        ops.conv3x3_wgrad_f32(_f32(rec["x0"]), _f32(dy), ref, None if rec["x1"] is None else _f32(rec["x1"]))
+        got = dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+        CHECK_LOG.append(("wgrad", Cin, Cout, dy.shape[1], float((got - ref).norm() / ref.norm())))
+    if not need_dx:
+        return None, None
+    # data gradient: the forward tcgen05 kernel with W transposed (ci <-> co) and flipped, [ci][tap][co]
+    wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).to(torch.bfloat16)
+    dx0 = ops.conv_gemm_bf16(dy, wt[:C0].contiguous(), None, C0, 9, False)
+    if CHECK_LOG is not None:
+        ref = ops.conv3x3_f32(_f32(dy), w.to(torch.bfloat16).float().flip(2, 3).transpose(0, 1)[:C0].contiguous(), None, relu=False)
+        CHECK_LOG.append(("dgrad", Cin, Cout, dy.shape[1], float((_f32(dx0) - ref).norm() / ref.norm())))
+    dx1 = ops.conv_gemm_bf16(dy, wt[C0:].contiguous(), None, Cin - C0, 9, False) if rec["x1"] is not None else None
     return dx0, dx1
 
 
@@ -151,11 +167,23 @@ def _dconv_bwd(recs, d, tape, need_dx=True):
 
 
 # ------------------------------------------------------------------ U-Net (unet_model.py:31-54)
+def _tc() -> bool:
+    return _BF16["on"]
+
+
+def _pool_fwd(h, mode):
+    return ops.pool2_bf16(h, mode) if _tc() else ops.pool2_f32(h, mode)
+
+
+def _hw(t):
+    return (t.shape[1], t.shape[2]) if _tc() else (t.shape[2], t.shape[3])
+
+
 def _unet_fwd(unet, x):
     h, r = _dconv_fwd(unet.inc, x)
     skips, recs = [h], [r]
     for down in unet.down_blocks:
-        p = ops.pool2_f32(h, ops.POOL_MAX)
+        p = _pool_fwd(h, ops.POOL_MAX)
         h, r = _dconv_fwd(down.maxpool_conv[1], p)
         skips.append(h)
         recs.append(r)
@@ -163,19 +191,19 @@ def _unet_fwd(unet, x):
     n = len(unet.down_blocks)
     for i, up in enumerate(unet.up_blocks):
         skip = skips[n - 1 - i]
-        if skip.shape[2] != 2 * h.shape[2] or skip.shape[3] != 2 * h.shape[3]:
+        if _hw(skip) != (2 * _hw(h)[0], 2 * _hw(h)[1]):
             raise NotImplementedError("training needs H, W divisible by 2^levels (the F.pad branch of Up.forward, "
                                       "unet_parts.py:58-62, is only built for inference)")
         wt = _d(up.up.weight)                                   # [Cin, Cout, 2, 2]
-        if _BF16["on"] and wt.shape[0] % 64 == 0 and wt.shape[1] % 64 == 0:
+        if _tc():
+            if wt.shape[0] % 64 or wt.shape[1] % 64:
+                raise NotImplementedError("tensor-core training needs transposed-convolution channels that are multiples of 64")
             # transposed convolution on tcgen05: one K tap, N = 4 * Cout (the four output phases share one A load)
             wpack = wt.permute(2, 3, 1, 0).reshape(4 * wt.shape[1], wt.shape[0]).to(torch.bfloat16).contiguous()
-            ub = ops.conv_gemm_bf16(_to_bf16_nhwc(h), wpack, _d(up.up.bias), wt.shape[1], 4, False)
-            u = ops.nhwc_bf16_to_nchw_f32(ub)
-            _BF16["cache"][id(u)] = (u, ub)                    # the decoder convolution reads the bf16 NHWC form
+            u = ops.conv_gemm_bf16(h, wpack, _d(up.up.bias), wt.shape[1], 4, False)
             if CHECK_LOG is not None:
-                ref = ops.convt2x2_f32(h, wt, _d(up.up.bias))
-                CHECK_LOG.append(("convt", wt.shape[0], wt.shape[1], u.shape[2], float((u - ref).norm() / ref.norm())))
+                ref = ops.convt2x2_f32(_f32(h), wt.to(torch.bfloat16).float(), _d(up.up.bias))
+                CHECK_LOG.append(("convt", wt.shape[0], wt.shape[1], u.shape[1], float((_f32(u) - ref).norm() / ref.norm())))
         else:
             u = ops.convt2x2_f32(h, wt, _d(up.up.bias))
         h_in = h
@@ -188,6 +216,7 @@ def _unet_bwd(unet, st, dfeat, tape):
     n = len(unet.down_blocks)
     dskip: List[Optional[torch.Tensor]] = [None] * (n + 1)
     d = dfeat
+    add_ = ops.add_bf16_ if _tc() else ops.add_f32_
     for i in reversed(range(len(st["ups"]))):
         u = st["ups"][i]
         ds, du = _dconv_bwd(u["recs"], d, tape)
@@ -195,24 +224,24 @@ def _unet_bwd(unet, st, dfeat, tape):
         up = u["up"].up
         wt = _d(up.weight)                                      # [Cin, Cout, 2, 2]
         Cin, Co = wt.shape[0], wt.shape[1]
-        tape.put(up.bias, ops.channel_sums_f32(du))
-        if _BF16["on"] and Cin % 64 == 0 and Co % 64 == 0:
+        if _tc():
+            tape.put(up.bias, ops.channel_sums_nhwc_bf16(du))
             # transposed-convolution backward on tcgen05: space-to-depth of du turns both gradients into 1x1 GEMMs
-            D = ops.s2d_nhwc_bf16(_to_bf16_nhwc(du))            # [B, H, W, (i, j, co)]
-            xb = _to_bf16_nhwc(u["h_in"])
+            D = ops.s2d_nhwc_bf16(du)                           # [B, H, W, (i, j, co)]
             dwp = torch.zeros(4 * Co, 1, Cin, dtype=torch.float32, device=du.device)
-            ops.conv_wgrad_bf16(xb, D, dwp, None, 1)            # dwp[(i,j,co)][ci] = sum_pix D * x
+            ops.conv_wgrad_bf16(u["h_in"], D, dwp, None, 1)     # dwp[(i,j,co)][ci] = sum_pix D * x
             dw = dwp.reshape(2, 2, Co, Cin).permute(3, 2, 0, 1).contiguous()
             tape.put(up.weight, dw)
             wd = wt.permute(0, 2, 3, 1).reshape(Cin, 4 * Co).to(torch.bfloat16).contiguous()       # [ci][(i,j,co)]
-            d = ops.nhwc_bf16_to_nchw_f32(ops.conv_gemm_bf16(D, wd, None, Cin, 1, False))
+            d = ops.conv_gemm_bf16(D, wd, None, Cin, 1, False)
             if CHECK_LOG is not None:
                 ref = torch.zeros_like(wt)
-                ops.convt2x2_wgrad_f32(u["h_in"], du, ref)
-                CHECK_LOG.append(("convt_wgrad", Cin, Co, du.shape[2], float((dw - ref).norm() / ref.norm())))
-                ref = ops.convt2x2_dgrad_f32(du, wt)
-                CHECK_LOG.append(("convt_dgrad", Cin, Co, du.shape[2], float((d - ref).norm() / ref.norm())))
+                ops.convt2x2_wgrad_f32(_f32(u["h_in"]), _f32(du), ref)
+                CHECK_LOG.append(("convt_wgrad", Cin, Co, du.shape[1], float((dw - ref).norm() / ref.norm())))
+                ref = ops.convt2x2_dgrad_f32(_f32(du), wt.to(torch.bfloat16).float())
+                CHECK_LOG.append(("convt_dgrad", Cin, Co, du.shape[1], float((_f32(d) - ref).norm() / ref.norm())))
         else:
+            tape.put(up.bias, ops.channel_sums_f32(du))
             dw = torch.zeros_like(wt)
             ops.convt2x2_wgrad_f32(u["h_in"], du, dw)
             tape.put(up.weight, dw)
@@ -220,11 +249,11 @@ def _unet_bwd(unet, st, dfeat, tape):
     # d = gradient w.r.t. the deepest encoder map
     for lvl in range(n, 0, -1):
         if dskip[lvl] is not None:
-            ops.add_f32_(d, dskip[lvl])
+            add_(d, dskip[lvl])
         d, _ = _dconv_bwd(st["recs"][lvl], d, tape)
-        d = ops.pool2_bwd_f32(st["skips"][lvl - 1], d, ops.POOL_MAX)
+        d = ops.pool2_bwd_nhwc_bf16(st["skips"][lvl - 1], d, ops.POOL_MAX) if _tc() else ops.pool2_bwd_f32(st["skips"][lvl - 1], d, ops.POOL_MAX)
     if dskip[0] is not None:
-        ops.add_f32_(d, dskip[0])
+        add_(d, dskip[0])
     _dconv_bwd(st["recs"][0], d, tape, need_dx=False)
 
 
@@ -236,28 +265,32 @@ def _gauss_fwd(net, x, segm=None):
     for i in range(nblk):
         if i > 0:
             pool_in.append(h)
-            h = ops.pool2_f32(h, ops.POOL_AVG_CEIL)
+            h = _pool_fwd(h, ops.POOL_AVG_CEIL)
         a, r1 = _cbr_fwd(layers[7 * i], layers[7 * i + 1], h, segm if i == 0 else None)
         h, r2 = _cbr_fwd(layers[7 * i + 3], layers[7 * i + 4], a)
         recs.append((r1, r2))
     cl = net.conv_layer
     L = cl.weight.shape[0] // 2
-    mu, ls = ops.gauss_head_f32(h, _d(cl.weight).reshape(2 * L, -1), _d(cl.bias), L)
+    head = ops.gauss_head_bf16 if _tc() else ops.gauss_head_f32
+    mu, ls = head(h, _d(cl.weight).reshape(2 * L, -1), _d(cl.bias), L)
     return mu, ls, {"enc": h, "recs": recs, "pool_in": pool_in}
 
 
 def _gauss_bwd(net, st, dmu, dls, tape):
     cl = net.conv_layer
     L = cl.weight.shape[0] // 2
-    dw = torch.zeros(2 * L, st["enc"].shape[1], dtype=torch.float32, device=dmu.device)
+    C = st["enc"].shape[3] if _tc() else st["enc"].shape[1]
+    dw = torch.zeros(2 * L, C, dtype=torch.float32, device=dmu.device)
     db = torch.zeros(2 * L, dtype=torch.float32, device=dmu.device)
-    d = ops.gauss_head_bwd_f32(st["enc"], _d(cl.weight).reshape(2 * L, -1), dmu.contiguous(), dls.contiguous(), dw, db)
+    head_bwd = ops.gauss_head_bwd_nhwc_bf16 if _tc() else ops.gauss_head_bwd_f32
+    d = head_bwd(st["enc"], _d(cl.weight).reshape(2 * L, -1), dmu.contiguous(), dls.contiguous(), dw, db)
     tape.put(cl.weight, dw)
     tape.put(cl.bias, db)
     for i in reversed(range(len(st["recs"]))):
         d, _ = _dconv_bwd(st["recs"][i], d, tape, need_dx=i > 0)
         if i > 0:
-            d = ops.pool2_bwd_f32(st["pool_in"][i - 1], d, ops.POOL_AVG_CEIL)
+            pin = st["pool_in"][i - 1]
+            d = ops.pool2_bwd_nhwc_bf16(None, d, ops.POOL_AVG_CEIL, in_hw=_hw(pin)) if _tc() else ops.pool2_bwd_f32(pin, d, ops.POOL_AVG_CEIL)
 
 
 # ------------------------------------------------------------------ fcomb (probabilistic_unet.py:155-181)
@@ -331,13 +364,14 @@ class TrainStep:
 
     def _mode(self, on: bool):
         _BF16["on"] = on and self.bf16
-        if not on:
-            _BF16["cache"] = {}
 
     def _forward(self, net, patch, segm):
         self.mu_q, self.ls_q, self.post = _gauss_fwd(net.posterior, patch, segm)
         self.mu_p, self.ls_p, self.prior = _gauss_fwd(net.prior, patch)
         self.feat, self.unet = _unet_fwd(net.unet, patch)
+        if self.bf16:
+            # the fcomb head (1x1 layers, 64 channels, per-slice latent bias) keeps its fp32 NCHW kernels: one cast in, one out
+            self.feat = ops.nhwc_bf16_to_nchw_f32(self.feat)
         self.fc = None
 
     def _beta(self) -> float:
@@ -383,7 +417,7 @@ class TrainStep:
             dls_q = dls_q + dz * self.eps_q * torch.exp(self.ls_q)
         _gauss_bwd(net.posterior, self.post, dmu_q, dls_q, tape)
         _gauss_bwd(net.prior, self.prior, dmu_p, dls_p, tape)
-        _unet_bwd(net.unet, self.unet, dfeat, tape)
+        _unet_bwd(net.unet, self.unet, ops.nchw_f32_to_nhwc_bf16(dfeat) if self.bf16 else dfeat, tape)
         return tape.g
 
 

@@ -316,10 +316,72 @@ def test_space_to_depth_and_convt_backward_as_gemms(ops):
     _close(dwp.reshape(2, 2, Co, Cin).permute(3, 2, 0, 1), w.grad, 2e-4, "convT wgrad as a 1x1 wgrad")
 
 
+@pytest.mark.parametrize("B,C,H,W,relu", [(2, 64, 16, 16, True), (3, 128, 9, 13, True), (2, 8, 40, 24, False), (1, 1024, 4, 4, True),
+                                          (4, 256, 32, 32, True)])
+def test_bn_train_nhwc_bf16(ops, B, C, H, W, relu):
+    """Train-mode BatchNorm (+ReLU) forward / backward on bf16 NHWC against torch autograd on the SAME bf16-rounded
+    inputs: the statistics are fp64-accumulated, so what differs is the bf16 rounding of the outputs."""
+    g = _g(41)
+    y = _bf(torch.randn(B, C, H, W, generator=g) * 2 + 0.5).requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.3).requires_grad_(True)
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    a_ref = F.batch_norm(y, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+    if relu:
+        a_ref = F.relu(a_ref)
+    da = _bf(torch.randn(B, C, H, W, generator=g))
+    a_ref.backward(da)
+    rm_c, rv_c = rm.cuda(), rv.cuda()
+    yb = _nhwc(y.detach()).to(torch.bfloat16).cuda()
+    a, mean, var = ops.bn_train_fwd_nhwc_bf16(yb, gamma.detach().cuda(), beta.detach().cuda(), 1e-5, relu, 0.1, rm_c, rv_c)
+    assert a.dtype == torch.bfloat16 and tuple(a.shape) == (B, H, W, C)
+    _close(a.float().permute(0, 3, 1, 2), a_ref, 6e-3, "bn forward (bf16 output)")
+    _close(rm_c, rm_ref, 1e-5, "running_mean")
+    _close(rv_c, rv_ref, 1e-5, "running_var")
+    dy, dg, db = ops.bn_train_bwd_nhwc_bf16(_nhwc(da).to(torch.bfloat16).cuda(), yb, mean, var, gamma.detach().cuda(),
+                                            beta.detach().cuda(), 1e-5, relu)
+    _close(dy.float().permute(0, 3, 1, 2), y.grad, 6e-3, "bn dy (bf16 output)")
+    _close(dg, gamma.grad, 2e-4, "bn dgamma")
+    _close(db, beta.grad, 2e-4, "bn dbeta")
+
+
+def test_pool_add_sums_head_bwd_nhwc_bf16(ops):
+    """The other elementwise / reduction kernels of the tensor-core training step on bf16 NHWC, against torch autograd."""
+    g = _g(42)
+    for mode, (H, W) in ((0, (8, 12)), (1, (8, 12)), (1, (7, 9))):
+        x = _bf(torch.randn(2, 16, H, W, generator=g)).requires_grad_(True)
+        yp = F.max_pool2d(x, 2) if mode == 0 else F.avg_pool2d(x, 2, 2, 0, ceil_mode=True, count_include_pad=False)
+        dy = _bf(torch.randn(yp.shape, generator=g))
+        yp.backward(dy)
+        dx = ops.pool2_bwd_nhwc_bf16(_nhwc(x.detach()).to(torch.bfloat16).cuda() if mode == 0 else None,
+                                     _nhwc(dy).to(torch.bfloat16).cuda(), mode, in_hw=(H, W))
+        _close(dx.float().permute(0, 3, 1, 2), x.grad, 5e-3, f"pool backward mode {mode} {H}x{W}")
+    a, b = _bf(torch.randn(3, 8, 8, 64, generator=g)), _bf(torch.randn(3, 8, 8, 64, generator=g))
+    got = ops.add_bf16_(a.to(torch.bfloat16).cuda(), b.to(torch.bfloat16).cuda())
+    assert torch.equal(got.cpu(), (a + b).to(torch.bfloat16))
+    x = _bf(torch.randn(2, 20, 12, 128, generator=g))
+    torch.testing.assert_close(ops.channel_sums_nhwc_bf16(x.to(torch.bfloat16).cuda()).cpu(), x.sum((0, 1, 2)), atol=1e-3, rtol=1e-5)
+    # Gaussian head: mean over H, W then a 1x1 conv to 2L
+    B, C, h, w_, L = 3, 128, 4, 4, 6
+    enc = _bf(torch.randn(B, C, h, w_, generator=g)).requires_grad_(True)
+    wgt = (torch.randn(2 * L, C, generator=g) * 0.1).requires_grad_(True)
+    bias = torch.zeros(2 * L, requires_grad=True)
+    out = enc.mean((2, 3)) @ wgt.t() + bias
+    d = torch.randn(B, 2 * L, generator=g)
+    out.backward(d)
+    dw = torch.zeros(2 * L, C, device="cuda"); db = torch.zeros(2 * L, device="cuda")
+    denc = ops.gauss_head_bwd_nhwc_bf16(_nhwc(enc.detach()).to(torch.bfloat16).cuda(), wgt.detach().cuda(), d[:, :L].contiguous().cuda(),
+                                        d[:, L:].contiguous().cuda(), dw, db)
+    _close(denc.float().permute(0, 3, 1, 2), enc.grad, 5e-3, "head denc")
+    _close(dw, wgt.grad, 1e-4, "head dw")
+    _close(db, bias.grad, 1e-5, "head db")
+
+
 def test_bf16_training_step(ops):
-    """Trainer architecture [64..1024] in the bf16 tensor-core training mode (tcgen05 forward / dgrad / wgrad,
-    fp32 BatchNorm).  Every tensor-core GEMM of a real step is recomputed by the fp32 kernels on the SAME
-    operands (train_engine.CHECK_LOG): the deviation must be bf16 operand rounding only.  End to end, losses
+    """Trainer architecture [64..1024] in the bf16 tensor-core training mode (tcgen05 forward / dgrad / wgrad, activations
+    and gradients bf16 NHWC end to end).  Every tensor-core GEMM of a real step is recomputed by the fp32 kernels on the
+    SAME bf16 operands (train_engine.CHECK_LOG): the deviation must be the bf16 rounding of the GEMM's output only.  End to end, losses
     agree with the fp32 path; parameter gradients are NOT compared end to end — on this randomly initialised
     net a 4e-3 activation perturbation moves BatchNorm-projected gradient sums by tens of percent (the fp32
     path needs 1e-3 against the reference for the same reason), so a bound there would test conditioning,

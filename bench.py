@@ -590,7 +590,7 @@ def run_config4(args):
     masks = lab[s0:s0 + B, None].contiguous().to(dev)
 
     def step():
-        return pmu_b200.dp_train_step(trainer, imgs, masks, opt)
+        return pmu_b200.dp_train_step(trainer, imgs, masks, opt, graph=not args.no_graph)
 
     for _ in range(max(args.warmup, 6)):                 # the caching allocator still grows during the first five steps
         step()
@@ -614,10 +614,11 @@ def run_config4(args):
         dist.all_reduce(gl)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     ops.PROFILE = []
-    step(); torch.cuda.synchronize()
+    pmu_b200.dp_train_step(trainer, imgs, masks, opt, graph=False); torch.cuda.synchronize()     # eager: per-call events
     tot = {}
     for name, meta, a, b in ops.PROFILE:
         tot[name] = tot.get(name, 0.0) + a.elapsed_time(b)
+    launches = max(launches, len(ops.PROFILE) * args.steps)      # a graph replay launches the same kernels: count them, not the replays
     ops.PROFILE = None
     ssum = sum(tot.values())
     if rank == 0:
@@ -629,7 +630,7 @@ def run_config4(args):
                           "dtype": args.train_precision, "data": "synthetic",
                           "config": {"workload": f"BASELINE config 4: DP training step, {B} slices of 256x256 per GPU (global batch "
                                                  f"{B * world}), trainer model, SGD + clip, gradient all-reduce over NCCL"},
-                          "useful_tflops": flop / float(ms) / 1e9, "global_loss": float(gl), "replicas_identical": bool(lo == hi),
+                          "cuda_graph": not args.no_graph, "useful_tflops": flop / float(ms) / 1e9, "global_loss": float(gl), "replicas_identical": bool(lo == hi),
                           "gpu_launches": launches,
                           "kernel_time_shares": {k: round(v / ssum, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:14]},
                           "kernel_ms_instrumented_step": round(ssum, 2)}))

@@ -389,6 +389,10 @@ def fuse_finalize(S1, S2, count, want_var=True, want_entropy=True, want_labels=F
 
 
 # ----------------------------------------------------------------------------- K5
+CE_CHECK_LABELS = True      # False while a CUDA graph is being captured (the read-back below is a host synchronisation)
+CE_LAST_FLAG = None         # the device-side out-of-range flag of the last call made with the check off
+
+
 def ce_sum(logits, target):
     """sum over batch and pixels of CE(logits [B,C,H,W], target float labels [B,1,H,W] or [B,H,W])."""
     _f32(logits, "logits"); _f32(target, "target")
@@ -399,6 +403,10 @@ def ce_sum(logits, target):
     _launch(lib, "pmu_ce_sum", (_p(logits), _p(target), B, C, HW, _p(out), st,))
     # nn.CrossEntropyLoss raises on a target outside [0, C) (probabilistic_unet.py:288,303): so do we — one 4-byte
     # read-back per loss evaluation instead of training on garbage labels (255, a 4-class map on a 3-class net, ...)
+    global CE_LAST_FLAG
+    if not CE_CHECK_LABELS:
+        CE_LAST_FLAG = out[1]
+        return out[0]
     if float(out[1]) > 0:
         raise IndexError(f"Target out of bounds: labels must lie in [0, {C}) (mask values outside the class range)")
     return out[0]

@@ -43,10 +43,36 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket
 
 
 def dp_train_step(trainer, imgs, masks, optimizer, acc_steps: int = 1, clip_value: Optional[float] = 0.1,
-                  group=None, step_now: bool = True):
+                  group=None, step_now: bool = True, graph: bool = False):
     """train.py:85-110 for one shard: predict -> loss / acc_steps -> backward -> (all-reduce, clip, SGD step).
-    Returns the local loss (sum over ranks of the local losses == the global loss)."""
+    Returns the local loss (sum over ranks of the local losses == the global loss).
+    graph=True: forward + elbo + backward replayed as ONE CUDA graph (train_engine.GraphedTrainStep, captured on the first
+    call for these input shapes; the eager step is bound by the host's ~3000 launches).  The look-at sample of
+    trainer.predict() (its return value never enters the loss, probunet_trainer.py:27-39) is skipped."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if graph:
+        from . import train_engine
+        key = (tuple(imgs.shape), tuple(masks.shape), world, acc_steps)
+        gs = getattr(trainer, "_graph_step", None)
+        if gs is None or gs[0] != key:
+            trainer.net.kl_world_size = world
+            try:
+                gs = (key, train_engine.GraphedTrainStep(trainer.net, imgs, masks, loss_scale=1.0 / acc_steps))
+            finally:
+                trainer.net.kl_world_size = 1
+            trainer._graph_step = gs
+        trainer.net.kl_world_size = world
+        try:
+            loss = gs[1].step(imgs, masks, accumulate=acc_steps > 1)
+        finally:
+            trainer.net.kl_world_size = 1
+        if step_now:
+            allreduce_gradients(trainer.net.parameters(), group)
+            if clip_value is not None:
+                torch.nn.utils.clip_grad_value_(trainer.net.parameters(), clip_value)
+            optimizer.step()
+            optimizer.zero_grad()
+        return loss.detach()
     # scoped to this step: the no-grad elbo() used for validation keeps the single-process weighting (beta * mean KL),
     # so logged training and validation losses stay comparable
     trainer.net.kl_world_size = world

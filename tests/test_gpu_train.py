@@ -434,3 +434,42 @@ def test_bf16_training_step(ops):
     # (lr 1e-2 with momentum 0.9 on four slices is a noisy regime — single iterations spike by 5-10x and the fp32-atomic
     #  weight-gradient sums make the trajectory run-dependent — so the trend is read from the median of the last six)
     assert np.median(losses[-6:]) < 0.9 * np.mean(losses[:2]), losses
+
+
+def test_graphed_training_step_matches_eager(ops):
+    """GraphedTrainStep (forward + elbo + backward as ONE CUDA graph) against the eager step on the same inputs and the same
+    injected posterior noise, in both modes: same kernels, so the same loss and the same gradients up to the run-to-run
+    noise of the atomics-based weight-gradient sums; a second replay on new inputs follows them; out-of-range labels raise."""
+    import pmu_b200
+    from pmu_b200 import train_engine
+    sd = O.make_state_dict(seed=0)
+    g = _g(50)
+    xs = [torch.rand(2, 1, 32, 32, generator=g).cuda() for _ in range(2)]
+    ms = [torch.randint(0, 3, (2, 1, 32, 32), generator=g).float().cuda() for _ in range(2)]
+    eps = [torch.randn(2, 6, generator=g).cuda() for _ in range(2)]
+    for prec in ("fp32", "bf16"):
+        def fresh():
+            net = pmu_b200.ProbabilisticUnet(1, 3, [64, 128, 256, 512, 1024], 6, 4, 10)
+            net.load_state_dict(sd, strict=True)
+            return net.cuda().train().set_precision(prec)
+        ref_net, net = fresh(), fresh()
+        gs = train_engine.GraphedTrainStep(net, xs[0], ms[0], eps=eps[0])
+        net.load_state_dict(sd, strict=True)              # the warm-up / capture runs moved the BatchNorm running statistics
+        for i in range(2):
+            ref_net.zero_grad()
+            ref_net.forward(xs[i], ms[i], training=True)
+            loss_ref = -ref_net.elbo(ms[i], eps=eps[i])
+            loss_ref.backward()
+            net.zero_grad()
+            loss = gs.step(xs[i], ms[i], eps=eps[i])
+            np.testing.assert_allclose(float(loss), float(loss_ref.detach()), rtol=1e-5 if prec == "fp32" else 1e-3)
+            for (n_, p), q in zip(net.named_parameters(), ref_net.parameters()):
+                if q.grad is None:
+                    assert p.grad is None, n_
+                    continue
+                scale = max(float(q.grad.abs().max()), 1e-6)
+                assert float((p.grad - q.grad).abs().max()) <= (1e-4 if prec == "fp32" else 2e-2) * scale, (prec, i, n_)
+        bad = ms[0].clone()
+        bad[0, 0, 3, 3] = 7.0
+        with pytest.raises(IndexError):
+            gs.step(xs[0], bad, eps=eps[0])

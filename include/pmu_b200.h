@@ -49,6 +49,10 @@ extern "C" {
 #define PMU_POOL_MAX 0         /* nn.MaxPool2d(2)                 unet_parts.py:33 */
 #define PMU_POOL_AVG_CEIL 1    /* nn.AvgPool2d(2,2,0,ceil_mode)   probabilistic_unet.py:36 */
 
+/* rows of the fp32 workspace of the two-level per-channel reductions on bf16 NHWC tensors (training step): each block of
+ * the first pass writes one row of per-channel partials, the finalize pass adds the rows in fp64 (deterministic, no atomics) */
+#define PMU_RED_MAX_BLOCKS 592
+
 /* ---- housekeeping ------------------------------------------------------- */
 const char* pmu_last_error(void);
 int pmu_version(void);
@@ -312,18 +316,22 @@ int pmu_s2d_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* 
 /* ---- training step, tensor-core mode: elementwise / reduction side on bf16 NHWC [npix = B*H*W][C] (C % 8 == 0, C/8 | 256),
  * the layout the tcgen05 GEMMs read and write — no cast between two GEMMs of the step. --------------------------------- */
 /* nn.BatchNorm2d in train() mode + ReLU (unet_parts.py:16-20, probabilistic_unet.py:39-45; train.py:94): batch statistics
- * of y (one pass, fp64 accumulation), running statistics updated like torch, a = [relu](gamma * (y - mean) / sqrt(var + eps)
- * + beta) as bf16.  ws: 2*C doubles; scale_shift: 2*C floats of scratch (the folded per-channel scale / shift). */
+ * of y (one pass: per-block fp32 partials, added in fp64), running statistics updated like torch,
+ * a = [relu](gamma * (y - mean) / sqrt(var + eps) + beta) as bf16.  ws: PMU_RED_MAX_BLOCKS * 2 * C floats of scratch;
+ * scale_shift: 2*C floats of scratch (the folded per-channel scale / shift). */
 int pmu_bn_train_fwd_nhwc_bf16(const void* y, const float* gamma, const float* beta, float eps, int relu,
                                float momentum, float* run_mean, float* run_var, float* mean, float* var,
-                               void* a, double* ws, float* scale_shift, int64_t npix, int C, void* stream);
+                               void* a, float* ws, float* scale_shift, int64_t npix, int C, void* stream);
 /* its backward (loss.backward(), train.py:95): dy (bf16), dgamma, dbeta from da (bf16) and the recorded y / mean / var;
- * the ReLU mask is recomputed from y.  ws: 2*C doubles. */
+ * the ReLU mask is recomputed from y.  ws: PMU_RED_MAX_BLOCKS * 2 * C floats; coef: 4*C floats of scratch (the elementwise
+ * pass is dy = coef0 * dz + coef2 * y + coef3 with the mask y * coef0 + coef1 > 0). */
 int pmu_bn_train_bwd_nhwc_bf16(const void* da, const void* y, const float* mean, const float* var, const float* gamma,
                                const float* beta, float eps, int relu, void* dy, float* dgamma, float* dbeta,
-                               double* ws, int64_t npix, int C, void* stream);
-/* out[C] = sum over pixels of x[npix][C] (bias gradient of nn.ConvTranspose2d, unet_parts.py:52).  ws: C doubles. */
-int pmu_channel_sums_nhwc_bf16(const void* x, float* out, double* ws, int64_t npix, int C, void* stream);
+                               float* ws, float* coef, int64_t npix, int C, void* stream);
+/* out[s][C] = sum over the pixels of segment s of x[nseg][npix][C]: the bias gradient of nn.ConvTranspose2d
+ * (unet_parts.py:52) and of the Fcomb 1x1 layers (probabilistic_unet.py:137-146) with nseg = 1; the per-slice sums behind
+ * the latent part of Fcomb's first layer (probabilistic_unet.py:167-176) with nseg = B.  ws: PMU_RED_MAX_BLOCKS * C floats. */
+int pmu_channel_sums_nhwc_bf16(const void* x, float* out, float* ws, int nseg, int64_t npix, int C, void* stream);
 /* backward of nn.MaxPool2d(2) (unet_parts.py:33; x = the pooling input, gradient to the first maximum in row-major order
  * like torch) / nn.AvgPool2d(2, 2, ceil_mode=True) (probabilistic_unet.py:36; x may be NULL): dy [B,Ho,Wo,C] -> dx [B,H,W,C]. */
 int pmu_pool2_bwd_nhwc_bf16(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int mode, void* stream);
@@ -334,6 +342,36 @@ int pmu_add_bf16(void* dst, const void* src, int64_t n, void* stream);
  * denc (bf16), dw [2L,C] +=, db [2L] +=  (zero-fill dw, db). */
 int pmu_gauss_head_bwd_nhwc_bf16(const void* enc, const float* w, const float* dmu, const float* dls, void* denc,
                                  float* dw, float* db, int B, int C, int h, int w_, int L, void* stream);
+/* ---- training step, tensor-core mode: weight layouts and the Fcomb head on bf16 NHWC ---------------------------------- */
+/* nn.Conv2d weights (unet_parts.py:15,18; probabilistic_unet.py:38,43), fp32 OIHW [Cout][Cin][3][3] -> the two bf16
+ * operand layouts of the tcgen05 GEMMs in one pass: wf [Cout][9][Cin] (forward, tap = ky*3+kx; nullable) and
+ * wd [Cin][9][Cout] with the taps flipped (data gradient of loss.backward(), train.py:95; nullable).  Channels % 32 == 0. */
+int pmu_pack_conv3x3_weights_bf16(const float* w, void* wf, void* wd, int Cout, int Cin, void* stream);
+/* the weight gradient pmu_conv_wgrad_bf16 produced, fp32 [Cout][9][Cin] -> the parameter's OIHW [Cout][Cin][3][3]
+ * (what autograd hands to nn.Conv2d.weight.grad, train.py:95).  Cin % 64 == 0. */
+int pmu_unpack_conv3x3_wgrad_f32(const float* dwp, float* dw, int Cout, int Cin, void* stream);
+/* 1x1 convolution with a per-image bias on tcgen05: y[b,h,w,co] = [relu](sum_ci wpack[co][ci] x[b,h,w,ci] + bias[b][co]).
+ * Fcomb's first layer (probabilistic_unet.py:167-176: the latent vector is tiled over the image and concatenated to the
+ * features; its part of the 1x1 convolution is a per-slice bias W0z * z_b + b0).  Images of >= 128 pixels, channels % 64. */
+int pmu_conv1x1_slicebias_bf16(const void* x, int Cin, const void* wpack, const float* bias, void* y, int B, int H,
+                               int W, int Cout, int relu, int f16, void* stream);
+/* Fcomb's last layer (probabilistic_unet.py:146,181: nn.Conv2d(F, n_classes, 1), no activation) from the bf16 NHWC hidden
+ * map h [B*HW][F] to fp32 NCHW logits [B][C][HW] for the cross entropy (probabilistic_unet.py:294-299).  C <= 8. */
+int pmu_fcomb_last_fwd_bf16(const void* h, const float* w, const float* bias, float* logits, int B, int64_t HW, int F,
+                            int C, void* stream);
+/* its backward in loss.backward() (train.py:95): dh (bf16 NHWC) = (h > 0) * W^T dlogits — the ReLU in front folded in —
+ * and dw [C][F] = sum_p dlogits[k] h[c] (written, not accumulated).  ws: PMU_RED_MAX_BLOCKS * C * F floats.  C <= 4. */
+int pmu_fcomb_last_bwd_bf16(const void* h, const float* dlogits, const float* w, void* dh, float* dw, float* ws, int B,
+                            int64_t HW, int F, int C, void* stream);
+/* d = (h > 0) ? d : 0 in place (bf16, n % 8 == 0): backward of the nn.ReLU between Fcomb's 1x1 layers
+ * (probabilistic_unet.py:141-144). */
+int pmu_relu_mask_bf16(void* d, const void* h, int64_t n, void* stream);
+/* weight gradient of the first convolution of the U-Net / prior (Cin = 1: x1 NULL) / posterior (Cin = 2: image x0 and
+ * mask x1, the torch.cat of probabilistic_unet.py:88-92 never materialised) in the tensor-core training step:
+ * dw fp32 OIHW [Cout][Cin][3][3] (written) from the fp32 NCHW inputs and the bf16 NHWC gradient dy [B,H,W,Cout]
+ * (unet_parts.py:15 / probabilistic_unet.py:38 in loss.backward(), train.py:95).  ws: PMU_RED_MAX_BLOCKS * 9 * Cout floats. */
+int pmu_conv3x3_wgrad_smallcin_bf16(const float* x0, const float* x1, const void* dy, float* dw, float* ws, int B, int H,
+                                    int W, int Cout, void* stream);
 /* tcgen05 weight gradient of conv3x3 pad 1 (ntaps = 9) / conv1x1 (ntaps = 1):
  * dw fp32 [Cout][ntaps][C0+C1] += sum_{b,h,w} dy[b,h,w,co] * cat(x0,x1)[b,h+ky-1,w+kx-1,ci]   (tap = ky*3+kx)
  * x0 bf16 [B,H,W,C0], x1 (nullable) bf16 [B,H,W,C1], dy bf16 [B,H,W,Cout]; channels multiples of 64.

@@ -45,8 +45,8 @@ _SIG = {
     "pmu_softmax_accum": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P]),
     "pmu_scatter_accum": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int32), c_int, _P, _P, _P]),
     "pmu_bn_train_fwd_nhwc_bf16": (c_int, [_P, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
-    "pmu_bn_train_bwd_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, c_int64, c_int, _P]),
-    "pmu_channel_sums_nhwc_bf16": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
+    "pmu_bn_train_bwd_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "pmu_channel_sums_nhwc_bf16": (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P]),
     "pmu_pool2_bwd_nhwc_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_add_bf16": (c_int, [_P, _P, c_int64, _P]),
     "pmu_gauss_head_bwd_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -77,6 +77,13 @@ _SIG = {
     "pmu_nchw_f32_to_nhwc_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pmu_s2d_nhwc_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pmu_conv_wgrad_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_pack_conv3x3_weights_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "pmu_unpack_conv3x3_wgrad_f32": (c_int, [_P, _P, c_int, c_int, _P]),
+    "pmu_conv1x1_slicebias_bf16": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_fcomb_last_fwd_bf16": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P]),
+    "pmu_fcomb_last_bwd_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P]),
+    "pmu_conv3x3_wgrad_smallcin_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "pmu_relu_mask_bf16": (c_int, [_P, _P, c_int64, _P]),
     "pmu_conv1x1_bb_f32": (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
 }
 

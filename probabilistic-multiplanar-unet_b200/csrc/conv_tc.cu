@@ -46,6 +46,8 @@ struct ConvTcParams {
   int pool_mode;      // -1 none; PMU_POOL_MAX / PMU_POOL_AVG_CEIL: also emit the 2x2-pooled map
   int tma_store;      // a full-resolution output exists: it leaves through the smem staging tile + TMA tensor stores
   int f16;            // the 16-bit operands and outputs are IEEE f16 (inference) instead of bf16 (training), see h16.cuh
+  int bias_bstride = 0;  // > 0: the bias is per image, bias[b * bias_bstride + co] (Fcomb's first layer after the split of
+                         // its latent part, probabilistic_unet.py:167-176); needs TB == 1 (a tile lies in one image)
 };
 
 // RESW > 0 (the Cout = 64 transposed convolution, see convt_pair_epilogue): the layer's whole weight matrix — RESW k-blocks of [BN][64] — is loaded
@@ -128,7 +130,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
     float* bs = bias_s;
     named_bar_sync(4, 128);          // every warp is done reading the previous tile's bias
     for (int i = et; i < BN; i += 128)
-      bs[i] = bias ? __ldg(bias + ((p.ntaps == 4) ? (n0 + i) % p.Cout : n0 + i)) : 0.f;
+      bs[i] = bias ? __ldg(bias + (int64_t)b0 * p.bias_bstride + ((p.ntaps == 4) ? (n0 + i) % p.Cout : n0 + i)) : 0.f;
     named_bar_sync(1, 128);          // bias visible
 
     const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
@@ -905,7 +907,7 @@ using namespace pmu;
 
 static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                           const float* bias, void* y, void* y_pool, int pool_mode, int B, int H, int W, int Cout,
-                          int ntaps, int relu, int f16, int out_h, int out_w, void* stream) {
+                          int ntaps, int relu, int f16, int out_h, int out_w, void* stream, int bias_bstride = 0) {
   PMU_CHECK_ARG(x0 && wpack && (y || y_pool), "pmu_conv_gemm_bf16: null pointer");
   const int Ho = out_h > 0 ? out_h : 2 * H, Wo = out_w > 0 ? out_w : 2 * W;     // convT output tensor extents
   PMU_CHECK_ARG(ntaps == 4 ? (Ho >= 2 * H && Wo >= 2 * W) : (out_h <= 0 && out_w <= 0),
@@ -936,6 +938,11 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   const int Ktot = (ntaps == 9) ? 9 * Cin : Cin;
   int BN = (Cout % 128 == 0) ? 128 : 64;
   if (Cout % 256 == 0 || ntaps == 4) BN = 256;   // convT: Ntot = 4*Cout
+  // few-tile launches (the deep layers of a batch-8 training step: 16 pixel tiles x 4 N tiles on 148 SMs, every CTA a
+  // serial chain of 576 UMMAs): halve the tile so that twice as many SMs share the same chain
+  const bool halved = BN == 256 && ntaps != 4 &&
+                      (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * (Ntot / 256) * 2 <= (int64_t)sm_count();
+  if (halved) BN = 128;
   p.n_tiles = Ntot / BN;
   if (y_pool) {
     PMU_CHECK_ARG(pool_mode == PMU_POOL_MAX || pool_mode == PMU_POOL_AVG_CEIL, "pmu_conv_gemm_pool_bf16: unknown pool mode %d", pool_mode);
@@ -944,7 +951,7 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
     PMU_CHECK_ARG(aligned16(y_pool), "pmu_conv_gemm_pool_bf16: y_pool must be 16-byte aligned");
   }
   // small-N 3x3 layers on images >= 16 rows: row-shift kernel (see conv_rs_kernel)
-  const bool rs = ntaps == 9 && BN <= 128 && H >= 16 && W >= 8 && (!y_pool || (H % 2 == 0 && W % 2 == 0));
+  const bool rs = ntaps == 9 && BN <= 128 && !halved && H >= 16 && W >= 8 && (!y_pool || (H % 2 == 0 && W % 2 == 0));
   if (rs) {
     p.TW = 8; p.TH = 16; p.TB = 1;
     p.tiles_w = cdiv(W, 8); p.tiles_h = cdiv(H, 16); p.tiles_b = B;
@@ -953,6 +960,9 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   }
   const int64_t grid = (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   PMU_CHECK_ARG(grid > 0 && grid < (1ll << 31), "pmu_conv_gemm_bf16: grid too large");
+  p.bias_bstride = bias_bstride;
+  PMU_CHECK_SUPPORTED(bias_bstride == 0 || (p.TB == 1 && ntaps == 1 && bias),
+                      "pmu_conv1x1_slicebias_bf16: a per-image bias needs images of at least 128 pixels (got %dx%d)", H, W);
 
   CUtensorMap a0, a1, wm;
   const int a_th = rs ? p.TH + 2 : p.TH;      // row-shift kernel: the A box carries the two halo rows
@@ -1018,4 +1028,10 @@ extern "C" int pmu_conv_gemm_pool_bf16(const void* x0, int C0, const void* x1, i
                                        int W, int Cout, int relu, int f16, void* stream) {
   PMU_CHECK_ARG(y_pool != nullptr, "pmu_conv_gemm_pool_bf16: y_pool is null");
   return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, y_pool, pool_mode, B, H, W, Cout, 9, relu, f16, 0, 0, stream);
+}
+
+extern "C" int pmu_conv1x1_slicebias_bf16(const void* x, int Cin, const void* wpack, const float* bias, void* y, int B, int H,
+                                          int W, int Cout, int relu, int f16, void* stream) {
+  PMU_CHECK_ARG(bias != nullptr, "pmu_conv1x1_slicebias_bf16: bias is null");
+  return conv_gemm_impl(x, Cin, nullptr, 0, wpack, bias, y, nullptr, -1, B, H, W, Cout, 1, relu, f16, 0, 0, stream, Cout);
 }

@@ -285,6 +285,19 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             self._warned_train = True
 
     # -- reference API --------------------------------------------------------------
+    @property
+    def unet_features(self):
+        """probabilistic_unet.py:223: the U-Net feature map, fp32 NCHW.  The tensor-core training step keeps it bf16 NHWC
+        for its Fcomb GEMMs; the reference's view of it is made when somebody reads the attribute."""
+        v = self.__dict__.get("_unet_features")
+        if callable(v):
+            v = self.__dict__["_unet_features"] = v()
+        return v
+
+    @unet_features.setter
+    def unet_features(self, v):
+        self.__dict__["_unet_features"] = v
+
     def forward(self, patch, segm, training=True):
         """probabilistic_unet.py:215-223: sets posterior_latent_space (if training),
         prior_latent_space, unet_features; returns None."""
@@ -307,7 +320,7 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             self._post, self._prior = (st.mu_q, st.ls_q), (st.mu_p, st.ls_p)
             self.posterior_latent_space = self._dist(st.mu_q, st.ls_q)
             self.prior_latent_space = self._dist(st.mu_p, st.ls_p)
-            self.unet_features = st.feat
+            self.unet_features = st.features_nchw_f32 if st.tc_fcomb else st.feat     # cast on first read (property below)
             return
         self._enter("ProbabilisticUnet.forward")
         pk = self.packed()
@@ -340,8 +353,7 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
             # training step: the sample is only looked at (trainer.predict's return value never enters the loss,
             # probunet_trainer.py:27-39) — computed from the live weights, detached
             # (layer by layer through the register-tiled 1x1 kernels: 4x faster than the thread-per-pixel fused kernel)
-            logits, _ = train_engine._fcomb_fwd(self.fcomb, self.unet_features, z.detach().float().contiguous())
-            return logits
+            return train_engine.fcomb_forward(step, z.detach().float().contiguous())
         return self.packed().fcomb_logits(self.unet_features, z.float())
 
     def sample_at(self, z):

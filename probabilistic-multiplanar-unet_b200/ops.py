@@ -446,6 +446,14 @@ def _ws(C, dev):
     return torch.empty(2 * C, dtype=torch.float64, device=dev)
 
 
+RED_MAX_BLOCKS = 592      # PMU_RED_MAX_BLOCKS of include/pmu_b200.h
+
+
+def _red_ws(row_floats, dev):
+    """Workspace of a two-level per-channel reduction: one fp32 row of partials per block of the first pass."""
+    return torch.empty(RED_MAX_BLOCKS * row_floats, dtype=torch.float32, device=dev)
+
+
 def bn_train_fwd_f32(y, gamma, beta, eps, relu, momentum=0.1, run_mean=None, run_var=None):
     """Train-mode BatchNorm2d (+ReLU): returns (a, mean, var); running stats updated in place."""
     _f32(y, "y")
@@ -644,7 +652,7 @@ def bn_train_fwd_nhwc_bf16(y, gamma, beta, eps, relu, momentum=0.1, run_mean=Non
     mean = torch.empty(C, dtype=torch.float32, device=y.device)
     var = torch.empty_like(mean)
     a = torch.empty_like(y)
-    ws = _ws(C, y.device)
+    ws = _red_ws(2 * C, y.device)
     ss = torch.empty(2 * C, dtype=torch.float32, device=y.device)
     lib, st = _prep(y, gamma, beta, run_mean, run_var, mean, var, a, ws, ss)
     _launch(lib, "pmu_bn_train_fwd_nhwc_bf16", (_p(y), _p(gamma), _p(beta), float(eps), int(relu), float(momentum), _p(run_mean),
@@ -660,20 +668,23 @@ def bn_train_bwd_nhwc_bf16(da, y, mean, var, gamma, beta, eps, relu):
     dy = torch.empty_like(y)
     dg = torch.empty(C, dtype=torch.float32, device=y.device)
     db = torch.empty_like(dg)
-    ws = _ws(C, y.device)
-    lib, st = _prep(da, y, mean, var, gamma, beta, dy, dg, db, ws)
+    ws = _red_ws(2 * C, y.device)
+    coef = torch.empty(4 * C, dtype=torch.float32, device=y.device)
+    lib, st = _prep(da, y, mean, var, gamma, beta, dy, dg, db, ws, coef)
     _launch(lib, "pmu_bn_train_bwd_nhwc_bf16", (_p(da), _p(y), _p(mean), _p(var), _p(gamma), _p(beta), float(eps), int(relu),
-                                              _p(dy), _p(dg), _p(db), _p(ws), npix, C, st,))
+                                              _p(dy), _p(dg), _p(db), _p(ws), _p(coef), npix, C, st,))
     return dy, dg, db
 
 
-def channel_sums_nhwc_bf16(x):
+def channel_sums_nhwc_bf16(x, per_image=False):
+    """Sum over the pixels of a bf16 NHWC tensor: [C], or [B, C] (one row per image) with per_image."""
     _bf16(x, "x")
     C = x.shape[-1]
-    out = torch.empty(C, dtype=torch.float32, device=x.device)
-    ws = torch.empty(C, dtype=torch.float64, device=x.device)
+    nseg = x.shape[0] if per_image else 1
+    out = torch.empty((nseg, C) if per_image else (C,), dtype=torch.float32, device=x.device)
+    ws = _red_ws(C, x.device)
     lib, st = _prep(x, out, ws)
-    _launch(lib, "pmu_channel_sums_nhwc_bf16", (_p(x), _p(out), _p(ws), x.numel() // C, C, st,))
+    _launch(lib, "pmu_channel_sums_nhwc_bf16", (_p(x), _p(out), _p(ws), nseg, x.numel() // (C * nseg), C, st,))
     return out
 
 
@@ -704,3 +715,84 @@ def gauss_head_bwd_nhwc_bf16(enc, w, dmu, dls, dw, db):
     _launch(lib, "pmu_gauss_head_bwd_nhwc_bf16", (_p(enc), _p(w), _p(dmu), _p(dls), _p(denc), _p(dw), _p(db), B, C, h, w_,
                                                 dmu.shape[1], st,))
     return denc
+
+
+def pack_conv3x3_weights_bf16(w, want_fwd=True, want_dgrad=True):
+    """fp32 OIHW conv weights -> (wf bf16 [Cout, 9*Cin] forward operand, wd bf16 [Cin, 9*Cout] data-gradient operand with
+    the taps flipped), one kernel."""
+    _f32(w, "w")
+    Cout, Cin = w.shape[0], w.shape[1]
+    wf = torch.empty(Cout, 9 * Cin, dtype=torch.bfloat16, device=w.device) if want_fwd else None
+    wd = torch.empty(Cin, 9 * Cout, dtype=torch.bfloat16, device=w.device) if want_dgrad else None
+    lib, st = _prep(w, wf, wd)
+    _launch(lib, "pmu_pack_conv3x3_weights_bf16", (_p(w), _p(wf), _p(wd), Cout, Cin, st,))
+    return wf, wd
+
+
+def unpack_conv3x3_wgrad_f32(dwp, out=None):
+    """fp32 [Cout, 9, Cin] (pmu_conv_wgrad_bf16) -> OIHW [Cout, Cin, 3, 3]."""
+    _f32(dwp, "dwp")
+    Cout, _, Cin = dwp.shape
+    dw = torch.empty(Cout, Cin, 3, 3, dtype=torch.float32, device=dwp.device) if out is None else out
+    lib, st = _prep(dwp, dw)
+    _launch(lib, "pmu_unpack_conv3x3_wgrad_f32", (_p(dwp), _p(dw), Cout, Cin, st,))
+    return dw
+
+
+def conv1x1_slicebias_bf16(x, wpack, bias, relu):
+    """tcgen05 1x1 convolution with a per-image bias [B, Cout]: x 16-bit NHWC -> y NHWC in the same format."""
+    _f32(bias, "bias")
+    wf = _h16((x, "x"), (wpack, "wpack"))
+    B, H, W, Cin = x.shape
+    Cout = wpack.shape[0]
+    assert tuple(bias.shape) == (B, Cout), bias.shape
+    y = torch.empty(B, H, W, Cout, dtype=x.dtype, device=x.device)
+    lib, st = _prep(x, wpack, bias, y)
+    global _META
+    _META = {"flops": 2.0 * B * H * W * Cout * Cin}
+    _launch(lib, "pmu_conv1x1_slicebias_bf16", (_p(x), Cin, _p(wpack), _p(bias), _p(y), B, H, W, Cout, int(relu), wf, st,))
+    return y
+
+
+def fcomb_last_fwd_bf16(h, w, bias):
+    """h bf16 [B,H,W,F], w fp32 [C,F], bias [C] -> logits fp32 [B,C,H,W]."""
+    _bf16(h, "h"); _f32(w, "w")
+    B, H, W, F = h.shape
+    C = w.shape[0]
+    logits = torch.empty(B, C, H, W, dtype=torch.float32, device=h.device)
+    lib, st = _prep(h, w, bias, logits)
+    _launch(lib, "pmu_fcomb_last_fwd_bf16", (_p(h), _p(w), _p(bias), _p(logits), B, H * W, F, C, st,))
+    return logits
+
+
+def fcomb_last_bwd_bf16(h, dlogits, w):
+    """-> (dh bf16 [B,H,W,F] with the ReLU mask of h applied, dw fp32 [C,F])."""
+    _bf16(h, "h"); _f32(dlogits, "dlogits"); _f32(w, "w")
+    B, H, W, F = h.shape
+    C = w.shape[0]
+    dh = torch.empty_like(h)
+    dw = torch.empty(C, F, dtype=torch.float32, device=h.device)
+    ws = _red_ws(C * F, h.device)
+    lib, st = _prep(h, dlogits, w, dh, dw, ws)
+    _launch(lib, "pmu_fcomb_last_bwd_bf16", (_p(h), _p(dlogits), _p(w), _p(dh), _p(dw), _p(ws), B, H * W, F, C, st,))
+    return dh, dw
+
+
+def relu_mask_bf16_(d, h):
+    _bf16(d, "d"); _bf16(h, "h")
+    assert d.shape == h.shape
+    lib, st = _prep(d, h)
+    _launch(lib, "pmu_relu_mask_bf16", (_p(d), _p(h), d.numel(), st,))
+    return d
+
+
+def conv3x3_wgrad_smallcin_bf16(x0, dy, x1=None):
+    """First-layer weight gradient: x0 (and x1) fp32 [B,1,H,W], dy bf16 [B,H,W,Cout] -> dw fp32 [Cout, 1 or 2, 3, 3]."""
+    _f32(x0, "x0"); _f32(x1, "x1"); _bf16(dy, "dy")
+    B, H, W, Cout = dy.shape
+    assert x0.shape[1] == 1 and (x1 is None or x1.shape[1] == 1)
+    dw = torch.empty(Cout, 1 if x1 is None else 2, 3, 3, dtype=torch.float32, device=dy.device)
+    ws = _red_ws(9 * Cout, dy.device)
+    lib, st = _prep(x0, x1, dy, dw, ws)
+    _launch(lib, "pmu_conv3x3_wgrad_smallcin_bf16", (_p(x0), _p(x1), _p(dy), _p(dw), _p(ws), B, H, W, Cout, st,))
+    return dw

@@ -54,7 +54,33 @@ class _Tape:
 # is recomputed by the fp32 CUDA-core kernel on the SAME (bf16-rounded) operands and (kind, Cin, Cout, H, relative L2
 # deviation) is appended — the deviation is then accumulation order + the bf16 rounding of the GEMM's output (~3e-3).
 CHECK_LOG = None
-_BF16 = {"on": False}
+_BF16 = {"on": False, "arena": None}
+_PENDING_NBT: List[torch.Tensor] = []     # BatchNorm num_batches_tracked counters of this forward: ONE foreach add at its end
+
+
+class _Arena:
+    """Zero-filled fp32 scratch of one backward: every weight-gradient accumulator of the step (the tcgen05 wgrad kernel
+    adds its split-K partials with atomics) and the zero bias gradients are views of ONE buffer cleared by ONE fill,
+    instead of ~90 torch.zeros calls."""
+
+    def __init__(self, n: int, device):
+        self.buf = torch.zeros(n, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.off + n > self.buf.numel():
+            return torch.zeros(*shape, dtype=torch.float32, device=self.buf.device)
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 3) // 4 * 4                  # views stay 16-byte aligned
+        return v
+
+
+def _zeros(*shape, device=None):
+    a = _BF16["arena"]
+    return a.take(*shape) if a is not None else torch.zeros(*shape, dtype=torch.float32, device=device)
 
 
 def _cbr_fwd(conv: nn.Conv2d, bn: nn.BatchNorm2d, x0, x1=None):
@@ -63,7 +89,7 @@ def _cbr_fwd(conv: nn.Conv2d, bn: nn.BatchNorm2d, x0, x1=None):
     y = ops.conv3x3_f32(x0, _d(conv.weight), _d(conv.bias), relu=False, x1=x1)
     a, mean, var = ops.bn_train_fwd_f32(y, _d(bn.weight), _d(bn.bias), bn.eps, True,
                                         0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var)
-    bn.num_batches_tracked += 1
+    _PENDING_NBT.append(bn.num_batches_tracked)
     return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var}
 
 
@@ -102,20 +128,23 @@ def _tc_cbr_fwd(conv, bn, x0, x1=None):
     w = _d(conv.weight)
     Cout, Cin = w.shape[0], w.shape[1]
     first = Cin <= 2
+    wd = None
     if first:
         if Cout % 8 or Cout > 128:
             raise NotImplementedError("tensor-core training needs a first layer with Cout % 8 == 0, <= 128")
         y = ops.conv3x3_first_bf16(x0, w, _d(conv.bias), relu=False, x1=x1, out_dtype=torch.bfloat16)
     else:
-        wpack = w.permute(0, 2, 3, 1).reshape(Cout, -1).to(torch.bfloat16).contiguous()        # [Cout][tap][Cin]
-        y = ops.conv_gemm_bf16(x0, wpack, _d(conv.bias), Cout, 9, False, x1=x1)
+        # both operand layouts of this layer from one read of the fp32 weights: wf [Cout][tap][Cin] for this GEMM,
+        # wd [Cin][flipped tap][Cout] for the data gradient in the backward
+        wf, wd = ops.pack_conv3x3_weights_bf16(w)
+        y = ops.conv_gemm_bf16(x0, wf, _d(conv.bias), Cout, 9, False, x1=x1)
         if CHECK_LOG is not None:
             ref = ops.conv3x3_f32(_f32(x0), w.to(torch.bfloat16).float(), _d(conv.bias), relu=False, x1=None if x1 is None else _f32(x1))
             CHECK_LOG.append(("fwd", Cin, Cout, y.shape[1], float((_f32(y) - ref).norm() / ref.norm())))
     a, mean, var = ops.bn_train_fwd_nhwc_bf16(y, _d(bn.weight), _d(bn.bias), bn.eps, True,
                                               0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var)
-    bn.num_batches_tracked += 1
-    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var, "first": first}
+    _PENDING_NBT.append(bn.num_batches_tracked)
+    return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var, "first": first, "wd": wd}
 
 
 def _tc_cbr_bwd(rec, da, tape: _Tape, need_dx=True):
@@ -125,18 +154,16 @@ def _tc_cbr_bwd(rec, da, tape: _Tape, need_dx=True):
     tape.put(bn.bias, db)
     # a bias in front of a train-mode BatchNorm has an exactly zero gradient (BatchNorm subtracts the batch mean); autograd's
     # value is the rounding residue of sum(dy), which the fp32 path reproduces and a bf16 dy would only replace by other noise
-    tape.put(conv.bias, torch.zeros_like(_d(conv.bias)))
+    tape.put(conv.bias, _zeros(conv.bias.numel(), device=dy.device))
     w = _d(conv.weight)
     Cout, Cin = w.shape[0], w.shape[1]
     if rec["first"]:
-        dw = torch.zeros_like(w)
-        ops.conv3x3_wgrad_f32(rec["x0"], _f32(dy), dw, rec["x1"])
-        tape.put(conv.weight, dw)
+        tape.put(conv.weight, ops.conv3x3_wgrad_smallcin_bf16(rec["x0"], dy, rec["x1"]))
         return None, None
     C0 = rec["x0"].shape[3]
-    dwp = torch.zeros(Cout, 9, Cin, dtype=torch.float32, device=dy.device)
+    dwp = _zeros(Cout, 9, Cin, device=dy.device)
     ops.conv_wgrad_bf16(rec["x0"], dy, dwp, rec["x1"], 9)
-    tape.put(conv.weight, dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous())
+    tape.put(conv.weight, ops.unpack_conv3x3_wgrad_f32(dwp))
     if CHECK_LOG is not None:
         ref = torch.zeros_like(w)
         ops.conv3x3_wgrad_f32(_f32(rec["x0"]), _f32(dy), ref, None if rec["x1"] is None else _f32(rec["x1"]))
@@ -144,13 +171,13 @@ def _tc_cbr_bwd(rec, da, tape: _Tape, need_dx=True):
         CHECK_LOG.append(("wgrad", Cin, Cout, dy.shape[1], float((got - ref).norm() / ref.norm())))
     if not need_dx:
         return None, None
-    # data gradient: the forward tcgen05 kernel with W transposed (ci <-> co) and flipped, [ci][tap][co]
-    wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).to(torch.bfloat16)
-    dx0 = ops.conv_gemm_bf16(dy, wt[:C0].contiguous(), None, C0, 9, False)
+    # data gradient: the forward tcgen05 kernel with W transposed (ci <-> co) and flipped, [ci][tap][co] (packed in the forward)
+    wt = rec["wd"]
+    dx0 = ops.conv_gemm_bf16(dy, wt[:C0], None, C0, 9, False)
     if CHECK_LOG is not None:
         ref = ops.conv3x3_f32(_f32(dy), w.to(torch.bfloat16).float().flip(2, 3).transpose(0, 1)[:C0].contiguous(), None, relu=False)
         CHECK_LOG.append(("dgrad", Cin, Cout, dy.shape[1], float((_f32(dx0) - ref).norm() / ref.norm())))
-    dx1 = ops.conv_gemm_bf16(dy, wt[C0:].contiguous(), None, Cin - C0, 9, False) if rec["x1"] is not None else None
+    dx1 = ops.conv_gemm_bf16(dy, wt[C0:], None, Cin - C0, 9, False) if rec["x1"] is not None else None
     return dx0, dx1
 
 
@@ -228,7 +255,7 @@ def _unet_bwd(unet, st, dfeat, tape):
             tape.put(up.bias, ops.channel_sums_nhwc_bf16(du))
             # transposed-convolution backward on tcgen05: space-to-depth of du turns both gradients into 1x1 GEMMs
             D = ops.s2d_nhwc_bf16(du)                           # [B, H, W, (i, j, co)]
-            dwp = torch.zeros(4 * Co, 1, Cin, dtype=torch.float32, device=du.device)
+            dwp = _zeros(4 * Co, 1, Cin, device=du.device)
             ops.conv_wgrad_bf16(u["h_in"], D, dwp, None, 1)     # dwp[(i,j,co)][ci] = sum_pix D * x
             dw = dwp.reshape(2, 2, Co, Cin).permute(3, 2, 0, 1).contiguous()
             tape.put(up.weight, dw)
@@ -280,8 +307,8 @@ def _gauss_bwd(net, st, dmu, dls, tape):
     cl = net.conv_layer
     L = cl.weight.shape[0] // 2
     C = st["enc"].shape[3] if _tc() else st["enc"].shape[1]
-    dw = torch.zeros(2 * L, C, dtype=torch.float32, device=dmu.device)
-    db = torch.zeros(2 * L, dtype=torch.float32, device=dmu.device)
+    dw = _zeros(2 * L, C, device=dmu.device)
+    db = _zeros(2 * L, device=dmu.device)
     head_bwd = ops.gauss_head_bwd_nhwc_bf16 if _tc() else ops.gauss_head_bwd_f32
     d = head_bwd(st["enc"], _d(cl.weight).reshape(2 * L, -1), dmu.contiguous(), dls.contiguous(), dw, db)
     tape.put(cl.weight, dw)
@@ -348,6 +375,76 @@ def _fcomb_bwd(fc, st, dlogits, tape):
     return dfeat, dz
 
 
+# ------------------------------------------------------------------ fcomb, tensor-core mode (bf16 NHWC hidden maps)
+def _fcomb_tc_ok(fc, feat) -> bool:
+    """The tcgen05 form of the Fcomb training chain: feature / hidden width a multiple of 64, <= 4 classes, at least
+    one hidden 1x1 layer after the first, images of >= 128 pixels (a GEMM tile lies in one image: per-slice bias)."""
+    convs = _fcomb_convs(fc)
+    F_ = convs[0].weight.shape[0]
+    return (feat.dtype == torch.bfloat16 and F_ % 64 == 0 and feat.shape[3] == F_ and fc.last_layer.weight.shape[0] <= 4
+            and all(c.weight.shape[0] == F_ and c.weight.shape[1] == F_ for c in convs[1:])
+            and feat.shape[1] * feat.shape[2] >= 128 and feat.shape[2] >= 16 and feat.shape[1] >= 8)
+
+
+def _fcomb_fwd_tc(fc, feat, z):
+    """feat bf16 NHWC [B,H,W,F]; z fp32 [B,L].  Layer 0 = features GEMM + per-slice latent bias (the tiled z of
+    probabilistic_unet.py:167-176 never materialises); hidden maps stay bf16 NHWC; logits fp32 NCHW."""
+    convs = _fcomb_convs(fc)
+    F_ = convs[0].weight.shape[0]
+    L = convs[0].weight.shape[1] - F_
+    w0 = _d(convs[0].weight).reshape(F_, F_ + L)
+    zb = ops.fcomb_zbias_f32(z, w0, _d(convs[0].bias))                                  # [B, F]
+    w0f = w0[:, :F_].to(torch.bfloat16).contiguous()
+    hs = [ops.conv1x1_slicebias_bf16(feat, w0f, zb, True)]
+    for c in convs[1:]:
+        hs.append(ops.conv_gemm_bf16(hs[-1], _d(c.weight).reshape(F_, F_).to(torch.bfloat16), _d(c.bias), F_, 1, True))
+    last = fc.last_layer
+    C = last.weight.shape[0]
+    logits = ops.fcomb_last_fwd_bf16(hs[-1], _d(last.weight).reshape(C, F_).contiguous(), _d(last.bias))
+    return logits, {"feat": feat, "z": z, "hs": hs, "w0f": w0f, "tc": True}
+
+
+def _fcomb_bwd_tc(fc, st, dlogits, tape):
+    convs = _fcomb_convs(fc)
+    F_ = convs[0].weight.shape[0]
+    L = convs[0].weight.shape[1] - F_
+    last = fc.last_layer
+    C = last.weight.shape[0]
+    hs = st["hs"]
+    dev = dlogits.device
+    d, dwl = ops.fcomb_last_bwd_bf16(hs[-1], dlogits, _d(last.weight).reshape(C, F_).contiguous())   # ReLU of hs[-1] folded in
+    tape.put(last.weight, dwl)
+    tape.put(last.bias, ops.channel_sums_f32(dlogits))
+    for j in range(len(convs) - 1, 0, -1):
+        c = convs[j]
+        dwp = _zeros(F_, 1, F_, device=dev)
+        ops.conv_wgrad_bf16(hs[j - 1], d, dwp, None, 1)                 # dw[co][ci] = sum_pix d[co] * h[ci]
+        tape.put(c.weight, dwp)
+        tape.put(c.bias, ops.channel_sums_nhwc_bf16(d))
+        d = ops.conv_gemm_bf16(d, _d(c.weight).reshape(F_, F_).t().to(torch.bfloat16).contiguous(), None, F_, 1, False)
+        ops.relu_mask_bf16_(d, hs[j - 1])
+    # layer 0: weight [F, F+L] = [feature part | latent part]
+    w0 = _d(convs[0].weight).reshape(F_, F_ + L)
+    dw0 = _zeros(F_, F_ + L, device=dev)
+    db0 = _zeros(F_, device=dev)
+    dwf = _zeros(F_, 1, F_, device=dev)
+    ops.conv_wgrad_bf16(st["feat"], d, dwf, None, 1)
+    rs = ops.channel_sums_nhwc_bf16(d, per_image=True)                   # [B, F]: what reaches the per-slice latent bias
+    dz = ops.fcomb_zbias_bwd_f32(rs.reshape(-1), st["z"], w0, dw0, db0)
+    dw0[:, :F_].copy_(dwf.reshape(F_, F_))
+    tape.put(convs[0].weight, dw0)
+    tape.put(convs[0].bias, db0)
+    dfeat = ops.conv_gemm_bf16(d, st["w0f"].t().contiguous(), None, F_, 1, False)
+    return dfeat, dz
+
+
+def fcomb_forward(step, z):
+    """Fcomb logits at latent z from a recorded training forward (net.sample() inside a training step)."""
+    if step.tc_fcomb:
+        return _fcomb_fwd_tc(step.net.fcomb, step.feat, z)[0]
+    return _fcomb_fwd(step.net.fcomb, step.feat, z)[0]
+
+
 # ------------------------------------------------------------------ the step
 class TrainStep:
     """State of one forward(training=True) of a ProbabilisticUnet; consumed by elbo() / backward."""
@@ -364,15 +461,26 @@ class TrainStep:
 
     def _mode(self, on: bool):
         _BF16["on"] = on and self.bf16
+        if not on:
+            _BF16["arena"] = None
+            _PENDING_NBT.clear()
 
     def _forward(self, net, patch, segm):
         self.mu_q, self.ls_q, self.post = _gauss_fwd(net.posterior, patch, segm)
         self.mu_p, self.ls_p, self.prior = _gauss_fwd(net.prior, patch)
         self.feat, self.unet = _unet_fwd(net.unet, patch)
-        if self.bf16:
-            # the fcomb head (1x1 layers, 64 channels, per-slice latent bias) keeps its fp32 NCHW kernels: one cast in, one out
+        self.tc_fcomb = self.bf16 and _fcomb_tc_ok(net.fcomb, self.feat)
+        if self.bf16 and not self.tc_fcomb:
+            # shapes the tcgen05 Fcomb chain does not take: its fp32 NCHW kernels, one cast in, one out
             self.feat = ops.nhwc_bf16_to_nchw_f32(self.feat)
         self.fc = None
+        if _PENDING_NBT:
+            torch._foreach_add_(_PENDING_NBT, 1)
+            _PENDING_NBT.clear()
+
+    def features_nchw_f32(self) -> torch.Tensor:
+        """The U-Net feature map as the reference exposes it (net.unet_features: fp32 NCHW)."""
+        return ops.nhwc_bf16_to_nchw_f32(self.feat) if self.tc_fcomb else self.feat
 
     def _beta(self) -> float:
         # data parallel: the KL term averages over the GLOBAL batch (train_dp.py)
@@ -385,7 +493,7 @@ class TrainStep:
                                       "probabilistic_unet.py:281)")
         self.z_q, self.eps_q = z_q.contiguous(), eps
         self.kl_b = ops.kl_diag_gauss(self.mu_q, self.ls_q, self.mu_p, self.ls_p)
-        self.logits, self.fc = _fcomb_fwd(net.fcomb, self.feat, self.z_q)
+        self.logits, self.fc = (_fcomb_fwd_tc if self.tc_fcomb else _fcomb_fwd)(net.fcomb, self.feat, self.z_q)
         self.segm_t = segm.contiguous().float()
         self.rec = ops.ce_sum(self.logits, self.segm_t)
         self.kl = self.kl_b.mean()
@@ -408,8 +516,10 @@ class TrainStep:
     def _backward(self, g: float) -> Dict[int, torch.Tensor]:
         net, tape = self.net, _Tape()
         B = self.mu_q.shape[0]
+        if self.bf16:
+            _BF16["arena"] = _Arena(sum((p.numel() + 3) // 4 * 4 for p in net.parameters()), self.mu_q.device)
         dlogits = ops.ce_bwd_f32(self.logits, self.segm_t, -g)
-        dfeat, dz = _fcomb_bwd(net.fcomb, self.fc, dlogits, tape)
+        dfeat, dz = (_fcomb_bwd_tc if self.tc_fcomb else _fcomb_bwd)(net.fcomb, self.fc, dlogits, tape)
         dmu_q, dls_q, dmu_p, dls_p = ops.kl_bwd_f32(self.mu_q, self.ls_q, self.mu_p, self.ls_p, -g * self._beta() / B)
         if self.eps_q is not None:
             # z_q = mu_q + exp(log_sigma_q) * eps  (rsample): [B, L]-sized glue
@@ -417,7 +527,7 @@ class TrainStep:
             dls_q = dls_q + dz * self.eps_q * torch.exp(self.ls_q)
         _gauss_bwd(net.posterior, self.post, dmu_q, dls_q, tape)
         _gauss_bwd(net.prior, self.prior, dmu_p, dls_p, tape)
-        _unet_bwd(net.unet, self.unet, ops.nchw_f32_to_nhwc_bf16(dfeat) if self.bf16 else dfeat, tape)
+        _unet_bwd(net.unet, self.unet, ops.nchw_f32_to_nhwc_bf16(dfeat) if (self.bf16 and not self.tc_fcomb) else dfeat, tape)
         return tape.g
 
 

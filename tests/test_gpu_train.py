@@ -378,6 +378,128 @@ def test_pool_add_sums_head_bwd_nhwc_bf16(ops):
     _close(db, bias.grad, 1e-5, "head db")
 
 
+def test_weight_pack_unpack_bf16(ops):
+    """pmu_pack_conv3x3_weights_bf16 / pmu_unpack_conv3x3_wgrad_f32: pure data movement (+ one bf16 rounding), bit-exact
+    against the torch permutes the step used before."""
+    g = _g(60)
+    for Cout, Cin in ((64, 64), (128, 64), (64, 192), (256, 128)):
+        w = torch.randn(Cout, Cin, 3, 3, generator=g)
+        wf, wd = ops.pack_conv3x3_weights_bf16(w.cuda())
+        assert torch.equal(wf.cpu(), w.permute(0, 2, 3, 1).reshape(Cout, -1).to(torch.bfloat16))
+        assert torch.equal(wd.cpu(), w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).to(torch.bfloat16))
+        wf2, none = ops.pack_conv3x3_weights_bf16(w.cuda(), want_dgrad=False)
+        assert none is None and torch.equal(wf2, wf)
+        dwp = torch.randn(Cout, 9, Cin, generator=g)
+        assert torch.equal(ops.unpack_conv3x3_wgrad_f32(dwp.cuda()).cpu(), dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous())
+
+
+def test_fcomb_chain_kernels_bf16(ops):
+    """The pieces of the Fcomb training chain on bf16 NHWC: 1x1 GEMM with a per-slice bias (tcgen05), the last layer to
+    fp32 NCHW logits and its backward (ReLU mask folded in), the ReLU mask, per-image channel sums — each against torch on
+    the same bf16-rounded operands."""
+    g = _g(61)
+    B, H, W, F_, C = 3, 16, 24, 64, 3
+    x = _bf(torch.randn(B, H, W, F_, generator=g))
+    w = _bf(torch.randn(F_, F_, generator=g) * 0.2)
+    zb = torch.randn(B, F_, generator=g)
+    y = ops.conv1x1_slicebias_bf16(x.to(torch.bfloat16).cuda(), w.to(torch.bfloat16).cuda(), zb.cuda(), True)
+    ref = torch.relu(torch.einsum("bhwc,oc->bhwo", x, w) + zb[:, None, None, :])
+    _close(y.float(), ref, 6e-3, "1x1 GEMM with per-slice bias")
+    # last layer forward / backward
+    h = torch.relu(_bf(torch.randn(B, H, W, F_, generator=g))).requires_grad_(True)
+    wl = (torch.randn(C, F_, generator=g) * 0.3).requires_grad_(True)
+    bl = torch.randn(C, generator=g)
+    logits = torch.einsum("bhwc,kc->bkhw", h, wl) + bl[None, :, None, None]
+    got = ops.fcomb_last_fwd_bf16(h.detach().to(torch.bfloat16).cuda(), wl.detach().cuda(), bl.cuda())
+    _close(got, logits, 1e-5, "last layer logits")
+    dl = torch.randn(B, C, H, W, generator=g)
+    logits.backward(dl)
+    dh, dw = ops.fcomb_last_bwd_bf16(h.detach().to(torch.bfloat16).cuda(), dl.cuda(), wl.detach().cuda())
+    _close(dh.float(), h.grad * (h.detach() > 0), 6e-3, "last layer dh (masked)")
+    _close(dw, wl.grad, 1e-4, "last layer dw")
+    # relu mask + per-image sums
+    d = _bf(torch.randn(B, H, W, F_, generator=g))
+    hm = _bf(torch.randn(B, H, W, F_, generator=g))
+    assert torch.equal(ops.relu_mask_bf16_(d.to(torch.bfloat16).cuda(), hm.to(torch.bfloat16).cuda()).cpu().float(), d * (hm > 0))
+    torch.testing.assert_close(ops.channel_sums_nhwc_bf16(d.to(torch.bfloat16).cuda(), per_image=True).cpu(), d.sum((1, 2)), atol=1e-3, rtol=1e-5)
+    big = _bf(torch.randn(2, 256, 256, 64, generator=g))
+    torch.testing.assert_close(ops.channel_sums_nhwc_bf16(big.to(torch.bfloat16).cuda()).cpu(), big.double().sum((0, 1, 2)).float(), atol=2e-2, rtol=1e-5)
+
+
+def test_first_layer_wgrad_from_bf16_nhwc(ops):
+    """pmu_conv3x3_wgrad_smallcin_bf16 against torch autograd of F.conv2d on the same bf16-rounded gradient."""
+    g = _g(63)
+    for Cin, (H, W), Cout in ((1, (24, 40), 64), (2, (17, 33), 64), (1, (64, 64), 128)):
+        x = torch.randn(3, Cin, H, W, generator=g)
+        w = torch.randn(Cout, Cin, 3, 3, generator=g, requires_grad=True)
+        dy = _bf(torch.randn(3, Cout, H, W, generator=g))
+        F.conv2d(x, w, padding=1).backward(dy)
+        got = ops.conv3x3_wgrad_smallcin_bf16(x[:, :1].contiguous().cuda(), _nhwc(dy).to(torch.bfloat16).cuda(),
+                                              x[:, 1:].contiguous().cuda() if Cin == 2 else None)
+        _close(got, w.grad, 1e-4, f"first-layer wgrad Cin={Cin}")
+
+
+def test_fcomb_tensor_core_chain(ops):
+    """train_engine._fcomb_fwd_tc / _fcomb_bwd_tc (tcgen05 GEMMs, bf16 NHWC hidden maps, probabilistic_unet.py:137-181 +
+    its autograd) against the same chain written in torch with the same rounding points — bf16 weights for the hidden
+    GEMMs, bf16 hidden maps and bf16 gradients between layers, fp32 accumulation — so the ReLU masks agree and what is
+    left is summation order.  (Against the pure-fp32 chain, units whose pre-activation sits within bf16 rounding of zero
+    flip their mask: ~6e-2 relative L2 on dfeat, which measures conditioning and not these kernels; the logits, which no
+    mask amplifies, are held to 2e-2 against fp32.)"""
+    import pmu_b200
+    from pmu_b200 import train_engine
+    g = _g(62)
+    net = pmu_b200.ProbabilisticUnet(1, 3, [64, 128], 6, 4, 10).cuda()
+    fc = net.fcomb
+    B, H, W, F_, L = 2, 32, 48, 64, 6
+    feat = _bf(torch.randn(B, 64, H, W, generator=g))
+    z = torch.randn(B, L, generator=g)
+    dl = torch.randn(B, 3, H, W, generator=g) * 0.1
+    lf, _ = train_engine._fcomb_fwd(fc, feat.cuda(), z.cuda())
+    featb = _nhwc(feat).to(torch.bfloat16).cuda()
+    assert train_engine._fcomb_tc_ok(fc, featb)
+    lt, st_ = train_engine._fcomb_fwd_tc(fc, featb, z.cuda())
+    tt = train_engine._Tape()
+    dfeat_t, dz_t = train_engine._fcomb_bwd_tc(fc, st_, dl.cuda(), tt)
+    _close(lt, lf.cpu(), 2e-2, "logits vs the fp32 chain")
+    # ---- the reference with the same rounding points (CPU, fp32 accumulation)
+    convs = [m.cpu() for m in train_engine._fcomb_convs(fc)]
+    last = fc.last_layer.cpu()
+    x = _nhwc(feat).reshape(-1, F_)                                       # [npix, F], bf16 values
+    w0 = convs[0].weight.detach().reshape(F_, F_ + L)
+    zb = z @ w0[:, F_:].t() + convs[0].bias.detach()                      # [B, F]
+    hs = [_bf(torch.relu(x @ _bf(w0[:, :F_]).t() + zb.repeat_interleave(H * W, 0)))]
+    ws = [_bf(c.weight.detach().reshape(F_, F_)) for c in convs[1:]]
+    for c, wj in zip(convs[1:], ws):
+        hs.append(_bf(torch.relu(hs[-1] @ wj.t() + c.bias.detach())))
+    wl = last.weight.detach().reshape(3, F_)
+    dlp = dl.permute(0, 2, 3, 1).reshape(-1, 3)
+    want = {id(fc.last_layer.weight): dlp.t() @ hs[-1], id(fc.last_layer.bias): dlp.sum(0)}
+    d = _bf((dlp @ wl) * (hs[-1] > 0))
+    live = train_engine._fcomb_convs(fc)
+    for j in range(len(convs) - 1, 0, -1):
+        want[id(live[j].weight)] = d.t() @ hs[j - 1]
+        want[id(live[j].bias)] = d.sum(0)
+        d = _bf(_bf(d @ ws[j - 1]) * (hs[j - 1] > 0))
+    rs = d.reshape(B, H * W, F_).sum(1)
+    want[id(live[0].weight)] = torch.cat([d.t() @ x, rs.t() @ z], 1)
+    want[id(live[0].bias)] = rs.sum(0)
+    dz = rs @ w0[:, F_:]
+    dfeat = _bf(d @ _bf(w0[:, :F_]))
+
+    def l2(got, ref, tol, what):
+        err = float((got.float().cpu() - ref).norm() / ref.norm())
+        assert err <= tol, f"{what}: relative L2 error {err:.3e}"
+
+    l2(lt.permute(0, 2, 3, 1).reshape(-1, 3), hs[-1] @ wl.t() + last.bias.detach(), 1e-4, "logits")
+    l2(dfeat_t.reshape(-1, F_), dfeat, 5e-3, "dfeat")
+    l2(dz_t, dz, 2e-3, "dz")
+    assert set(tt.g) == set(want)
+    for n_, p_ in fc.named_parameters():
+        l2(tt.g[id(p_)].reshape(want[id(p_)].shape), want[id(p_)], 2e-3, "fcomb gradient of " + n_)
+    fc.cuda()
+
+
 def test_bf16_training_step(ops):
     """Trainer architecture [64..1024] in the bf16 tensor-core training mode (tcgen05 forward / dgrad / wgrad, activations
     and gradients bf16 NHWC end to end).  Every tensor-core GEMM of a real step is recomputed by the fp32 kernels on the

@@ -630,11 +630,21 @@ def run_config4(args):
                           "dtype": args.train_precision, "data": "synthetic",
                           "config": {"workload": f"BASELINE config 4: DP training step, {B} slices of 256x256 per GPU (global batch "
                                                  f"{B * world}), trainer model, SGD + clip, gradient all-reduce over NCCL"},
-                          "cuda_graph": not args.no_graph, "useful_tflops": flop / float(ms) / 1e9, "global_loss": float(gl), "replicas_identical": bool(lo == hi),
+                          "cuda_graph": not args.no_graph,
+                          "grad_exchange": ({"in_graph": True, "overlapped_with_backward": True, "ranges_mb": [round((hi_ - lo_) * 4 / 1e6, 1) for lo_, hi_ in trainer._graph_step[1].ar_ranges]}
+                                            if (not args.no_graph and getattr(trainer, "_graph_step", None) and trainer._graph_step[1].ar_in_graph)
+                                            else {"in_graph": False, "how": "after backward, flattened buckets" if world > 1 else "single GPU: none"}),
+                          "useful_tflops": flop / float(ms) / 1e9, "global_loss": float(gl), "replicas_identical": bool(lo == hi),
                           "gpu_launches": launches,
                           "kernel_time_shares": {k: round(v / ssum, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:14]},
-                          "kernel_ms_instrumented_step": round(ssum, 2)}))
+                          "kernel_ms_instrumented_step": round(ssum, 2)}), flush=True)
     if world > 1:
+        gs = getattr(trainer, "_graph_step", None)
+        if gs is not None:
+            gs[1].close()                 # the graph holds captured NCCL operations: release it before the communicator goes
+            trainer._graph_step = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -660,14 +660,14 @@ def bn_train_fwd_nhwc_bf16(y, gamma, beta, eps, relu, momentum=0.1, run_mean=Non
     return a, mean, var
 
 
-def bn_train_bwd_nhwc_bf16(da, y, mean, var, gamma, beta, eps, relu):
-    """-> (dy bf16, dgamma, dbeta)."""
-    _bf16(da, "da"); _bf16(y, "y")
+def bn_train_bwd_nhwc_bf16(da, y, mean, var, gamma, beta, eps, relu, dg_out=None, db_out=None):
+    """-> (dy bf16, dgamma, dbeta); dg_out / db_out: fp32 [C] tensors to write the parameter gradients into."""
+    _bf16(da, "da"); _bf16(y, "y"); _f32(dg_out, "dg_out"); _f32(db_out, "db_out")
     C = y.shape[-1]
     npix = y.numel() // C
     dy = torch.empty_like(y)
-    dg = torch.empty(C, dtype=torch.float32, device=y.device)
-    db = torch.empty_like(dg)
+    dg = torch.empty(C, dtype=torch.float32, device=y.device) if dg_out is None else dg_out
+    db = torch.empty(C, dtype=torch.float32, device=y.device) if db_out is None else db_out
     ws = _red_ws(2 * C, y.device)
     coef = torch.empty(4 * C, dtype=torch.float32, device=y.device)
     lib, st = _prep(da, y, mean, var, gamma, beta, dy, dg, db, ws, coef)
@@ -786,12 +786,12 @@ def relu_mask_bf16_(d, h):
     return d
 
 
-def conv3x3_wgrad_smallcin_bf16(x0, dy, x1=None):
+def conv3x3_wgrad_smallcin_bf16(x0, dy, x1=None, out=None):
     """First-layer weight gradient: x0 (and x1) fp32 [B,1,H,W], dy bf16 [B,H,W,Cout] -> dw fp32 [Cout, 1 or 2, 3, 3]."""
-    _f32(x0, "x0"); _f32(x1, "x1"); _bf16(dy, "dy")
+    _f32(x0, "x0"); _f32(x1, "x1"); _bf16(dy, "dy"); _f32(out, "out")
     B, H, W, Cout = dy.shape
     assert x0.shape[1] == 1 and (x1 is None or x1.shape[1] == 1)
-    dw = torch.empty(Cout, 1 if x1 is None else 2, 3, 3, dtype=torch.float32, device=dy.device)
+    dw = torch.empty(Cout, 1 if x1 is None else 2, 3, 3, dtype=torch.float32, device=dy.device) if out is None else out
     ws = _red_ws(9 * Cout, dy.device)
     lib, st = _prep(x0, x1, dy, dw, ws)
     _launch(lib, "pmu_conv3x3_wgrad_smallcin_bf16", (_p(x0), _p(x1), _p(dy), _p(dw), _p(ws), B, H, W, Cout, st,))

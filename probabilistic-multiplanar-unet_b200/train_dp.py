@@ -7,8 +7,10 @@ ADDS over shards, the KL part AVERAGES.  Each rank therefore steps its shard wit
 SUM-reduced — the result is exactly the gradient of the global objective evaluated with per-rank
 BatchNorm statistics (standard data parallelism; the reference has no SyncBN either).
 
-One exchange per step: the gradients are flattened into a few large buckets so the all-reduce cost
-is launch latency + bytes / NVLink bandwidth (275 MB of fp32 gradients for the trainer model).
+The exchange: 275 MB of fp32 gradients for the trainer model.  In the CUDA-graph step (graph=True, the fast path) the
+gradients of a backward live in ONE flat buffer laid out in completion order and each completed range is all-reduced
+inside the graph while the rest of the backward runs (train_engine.GraphedTrainStep); the eager step reduces after
+backward in a few large flattened buckets.
 """
 from __future__ import annotations
 
@@ -57,7 +59,9 @@ def dp_train_step(trainer, imgs, masks, optimizer, acc_steps: int = 1, clip_valu
         if gs is None or gs[0] != key:
             trainer.net.kl_world_size = world
             try:
-                gs = (key, train_engine.GraphedTrainStep(trainer.net, imgs, masks, loss_scale=1.0 / acc_steps))
+                # one micro-step per optimizer step: the gradient exchange rides inside the graph, overlapped with the backward
+                gs = (key, train_engine.GraphedTrainStep(trainer.net, imgs, masks, loss_scale=1.0 / acc_steps,
+                                                         allreduce_group=group, allreduce=world > 1 and acc_steps == 1))
             finally:
                 trainer.net.kl_world_size = 1
             trainer._graph_step = gs
@@ -67,7 +71,8 @@ def dp_train_step(trainer, imgs, masks, optimizer, acc_steps: int = 1, clip_valu
         finally:
             trainer.net.kl_world_size = 1
         if step_now:
-            allreduce_gradients(trainer.net.parameters(), group)
+            if not gs[1].ar_in_graph:
+                allreduce_gradients(trainer.net.parameters(), group)
             if clip_value is not None:
                 torch.nn.utils.clip_grad_value_(trainer.net.parameters(), clip_value)
             optimizer.step()

@@ -35,18 +35,74 @@ def _d(t):
     return t.detach()
 
 
+class _FlatLayout:
+    """Where each parameter's gradient lives in the ONE fp32 buffer of a backward: parameters in the order the backward
+    completes them (recorded from a previous backward of the same net), so that a finished prefix is a contiguous range —
+    the data-parallel step all-reduces range after range while the rest of the backward still runs, with no flatten /
+    unflatten copies (train_dp.py)."""
+
+    def __init__(self, order: List[nn.Parameter]):
+        self.slots: Dict[int, tuple] = {}
+        n = 0
+        for p in order:
+            self.slots[id(p)] = (n, p.numel(), tuple(p.shape))
+            n += (p.numel() + 3) // 4 * 4               # views stay 16-byte aligned
+        self.total = n
+        self.order = [id(p) for p in order]
+
+
 class _Tape:
-    """Gradients by parameter (id -> tensor); each parameter is written at most once per step."""
+    """Gradients by parameter (id -> tensor); each parameter is written at most once per step.
 
-    def __init__(self):
+    With a layout: the gradients are views of `buf` (zero-filled); kernels write them in place through `out(p)`, anything
+    else is copied in by `put`.  `on_ready(buf, lo, hi)` is called whenever the completed prefix has grown by
+    `bucket_bytes` (and once at `finish()`): the parameters of [lo, hi) are final."""
+
+    def __init__(self, layout: Optional[_FlatLayout] = None, device=None, on_ready=None, bucket_bytes: int = 32 << 20):
         self.g: Dict[int, torch.Tensor] = {}
+        self.order: List[nn.Parameter] = []
+        self.layout = layout
+        self.buf = torch.zeros(layout.total, dtype=torch.float32, device=device) if layout is not None else None
+        self.on_ready, self.bucket = on_ready, bucket_bytes // 4
+        self.done_lo = self.done_hi = 0
+        self.in_order = True
+        self.npos = 0
 
-    def put(self, p: nn.Parameter, g: torch.Tensor):
-        g = g.reshape(p.shape)
+    def out(self, p: nn.Parameter) -> Optional[torch.Tensor]:
+        """The (zero-filled) place of p's gradient in the flat buffer, for a kernel to write; None without a layout."""
+        if self.layout is None:
+            return None
+        off, n, shape = self.layout.slots[id(p)]
+        return self.buf[off:off + n].view(shape)
+
+    def put(self, p: nn.Parameter, g: Optional[torch.Tensor] = None):
+        """g = the gradient; None = it already sits in out(p) (written in place, or exactly zero)."""
         if id(p) in self.g:
-            ops.add_f32_(self.g[id(p)], g.contiguous())
+            ops.add_f32_(self.g[id(p)], g.reshape(p.shape).contiguous())
+            return
+        self.order.append(p)
+        if self.layout is None:
+            self.g[id(p)] = g.reshape(p.shape)
+            return
+        v = self.out(p)
+        if g is not None and g.data_ptr() != v.data_ptr():
+            v.copy_(g.reshape(p.shape))
+        self.g[id(p)] = v
+        # completed prefix (only meaningful while the backward follows the recorded order)
+        if self.in_order and self.npos < len(self.layout.order) and self.layout.order[self.npos] == id(p):
+            self.npos += 1
+            off, n, _ = self.layout.slots[id(p)]
+            self.done_hi = off + (n + 3) // 4 * 4
+            if self.on_ready is not None and self.done_hi - self.done_lo >= self.bucket:
+                self.on_ready(self.buf, self.done_lo, self.done_hi)
+                self.done_lo = self.done_hi
         else:
-            self.g[id(p)] = g
+            self.in_order = False
+
+    def finish(self):
+        if self.layout is not None and self.on_ready is not None and self.done_lo < self.layout.total:
+            self.on_ready(self.buf, self.done_lo, self.layout.total)
+            self.done_lo = self.layout.total
 
 
 # ------------------------------------------------------------------ conv3x3 + BN(train) + ReLU
@@ -149,21 +205,22 @@ def _tc_cbr_fwd(conv, bn, x0, x1=None):
 
 def _tc_cbr_bwd(rec, da, tape: _Tape, need_dx=True):
     conv, bn = rec["conv"], rec["bn"]
-    dy, dg, db = ops.bn_train_bwd_nhwc_bf16(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True)
+    dy, dg, db = ops.bn_train_bwd_nhwc_bf16(da, rec["y"], rec["mean"], rec["var"], _d(bn.weight), _d(bn.bias), bn.eps, True,
+                                            dg_out=tape.out(bn.weight), db_out=tape.out(bn.bias))
     tape.put(bn.weight, dg)
     tape.put(bn.bias, db)
     # a bias in front of a train-mode BatchNorm has an exactly zero gradient (BatchNorm subtracts the batch mean); autograd's
     # value is the rounding residue of sum(dy), which the fp32 path reproduces and a bf16 dy would only replace by other noise
-    tape.put(conv.bias, _zeros(conv.bias.numel(), device=dy.device))
+    tape.put(conv.bias, None if tape.layout is not None else _zeros(conv.bias.numel(), device=dy.device))
     w = _d(conv.weight)
     Cout, Cin = w.shape[0], w.shape[1]
     if rec["first"]:
-        tape.put(conv.weight, ops.conv3x3_wgrad_smallcin_bf16(rec["x0"], dy, rec["x1"]))
+        tape.put(conv.weight, ops.conv3x3_wgrad_smallcin_bf16(rec["x0"], dy, rec["x1"], out=tape.out(conv.weight)))
         return None, None
     C0 = rec["x0"].shape[3]
     dwp = _zeros(Cout, 9, Cin, device=dy.device)
     ops.conv_wgrad_bf16(rec["x0"], dy, dwp, rec["x1"], 9)
-    tape.put(conv.weight, ops.unpack_conv3x3_wgrad_f32(dwp))
+    tape.put(conv.weight, ops.unpack_conv3x3_wgrad_f32(dwp, out=tape.out(conv.weight)))
     if CHECK_LOG is not None:
         ref = torch.zeros_like(w)
         ops.conv3x3_wgrad_f32(_f32(rec["x0"]), _f32(dy), ref, None if rec["x1"] is None else _f32(rec["x1"]))
@@ -307,8 +364,11 @@ def _gauss_bwd(net, st, dmu, dls, tape):
     cl = net.conv_layer
     L = cl.weight.shape[0] // 2
     C = st["enc"].shape[3] if _tc() else st["enc"].shape[1]
-    dw = _zeros(2 * L, C, device=dmu.device)
-    db = _zeros(2 * L, device=dmu.device)
+    dw, db = tape.out(cl.weight), tape.out(cl.bias)          # accumulated with atomics: the flat buffer is zero-filled
+    if dw is None:
+        dw, db = _zeros(2 * L, C, device=dmu.device), _zeros(2 * L, device=dmu.device)
+    else:
+        dw = dw.view(2 * L, C)
     head_bwd = ops.gauss_head_bwd_nhwc_bf16 if _tc() else ops.gauss_head_bwd_f32
     d = head_bwd(st["enc"], _d(cl.weight).reshape(2 * L, -1), dmu.contiguous(), dls.contiguous(), dw, db)
     tape.put(cl.weight, dw)
@@ -445,6 +505,22 @@ def fcomb_forward(step, z):
     return _fcomb_fwd(step.net.fcomb, step.feat, z)[0]
 
 
+def _grad_layout(net) -> Optional[_FlatLayout]:
+    """The flat-gradient layout from the completion order a previous backward recorded on `net` (None before the first
+    one, or when a recorded parameter is no longer a trainable parameter of the net)."""
+    order = net.__dict__.get("_pmu_grad_order")
+    if order is None:
+        return None
+    live = {id(p) for p in net.parameters() if p.requires_grad}
+    if any(id(p) not in live for p in order):
+        net.__dict__["_pmu_grad_order"] = None
+        return None
+    lay = net.__dict__.get("_pmu_grad_layout")
+    if lay is None or lay.order != [id(p) for p in order]:
+        lay = net.__dict__["_pmu_grad_layout"] = _FlatLayout(order)
+    return lay
+
+
 # ------------------------------------------------------------------ the step
 class TrainStep:
     """State of one forward(training=True) of a ProbabilisticUnet; consumed by elbo() / backward."""
@@ -499,8 +575,11 @@ class TrainStep:
         self.kl = self.kl_b.mean()
         return -(self.rec + self._beta() * self.kl)
 
-    def backward(self, g: float) -> Dict[int, torch.Tensor]:
-        """g = d(loss)/d(elbo).  elbo = -(rec + beta * mean_b KL)."""
+    def backward(self, g: float, on_ready=None) -> Dict[int, torch.Tensor]:
+        """g = d(loss)/d(elbo).  elbo = -(rec + beta * mean_b KL).  Tensor-core mode: the gradients are views of one flat
+        buffer (a fresh one per backward), laid out in completion order once a previous backward of this net has recorded
+        it; `on_ready(buf, lo, hi)` is then called for every completed range (the data-parallel all-reduce)."""
+        self._on_ready = on_ready
         if self.unet is None:
             raise RuntimeError("this forward's activations were released by its first backward (one backward per "
                                "forward; retain_graph is not supported)")
@@ -514,7 +593,9 @@ class TrainStep:
             self.post = self.prior = self.unet = self.fc = self.logits = None
 
     def _backward(self, g: float) -> Dict[int, torch.Tensor]:
-        net, tape = self.net, _Tape()
+        net = self.net
+        layout = _grad_layout(net) if self.bf16 else None
+        tape = _Tape(layout, self.mu_q.device, getattr(self, "_on_ready", None))
         B = self.mu_q.shape[0]
         if self.bf16:
             _BF16["arena"] = _Arena(sum((p.numel() + 3) // 4 * 4 for p in net.parameters()), self.mu_q.device)
@@ -528,6 +609,10 @@ class TrainStep:
         _gauss_bwd(net.posterior, self.post, dmu_q, dls_q, tape)
         _gauss_bwd(net.prior, self.prior, dmu_p, dls_p, tape)
         _unet_bwd(net.unet, self.unet, ops.nchw_f32_to_nhwc_bf16(dfeat) if (self.bf16 and not self.tc_fcomb) else dfeat, tape)
+        tape.finish()
+        if self.bf16 and (layout is None or not tape.in_order or len(tape.order) != len(layout.order)):
+            net.__dict__["_pmu_grad_order"] = list(tape.order)           # (re)record the completion order for the next backward
+        self.flat = tape.buf
         return tape.g
 
 
@@ -563,7 +648,7 @@ class GraphedTrainStep:
     every `step()` unless `check_labels=False`."""
 
     def __init__(self, net, imgs: torch.Tensor, masks: torch.Tensor, loss_scale: float = 1.0, warmup: int = 3,
-                 eps: Optional[torch.Tensor] = None):
+                 eps: Optional[torch.Tensor] = None, allreduce_group=None, allreduce: bool = False):
         if not (net.training and any(p.requires_grad for p in net.parameters())):
             raise RuntimeError("GraphedTrainStep needs net.train() and trainable parameters")
         if imgs.device.type != "cuda":
@@ -576,6 +661,14 @@ class GraphedTrainStep:
         self.eps = None if eps is None else eps.detach().clone().contiguous().float()
         self.loss_scale = float(loss_scale)
         self.kl_world = int(getattr(net, "kl_world_size", 1))
+        # data parallel: SUM-all-reduce the flat gradient buffer INSIDE the graph, range by range as the backward completes
+        # them — each collective is a side branch of the graph (NCCL's own stream, joined at the end), so the exchange of
+        # the posterior's gradients runs under the prior's backward, the prior's under the U-Net's, and so on
+        import torch.distributed as dist
+        self.group = allreduce_group
+        self.ar = bool(allreduce) and dist.is_available() and dist.is_initialized() and dist.get_world_size(allreduce_group) > 1
+        self.ar_in_graph = False
+        self.ar_ranges = []
         dev = imgs.device
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
@@ -600,10 +693,30 @@ class GraphedTrainStep:
         z_q = st.mu_q + eps * torch.exp(st.ls_q)
         value = st.elbo(self.masks, z_q, eps, True)
         self.flag = ops.CE_LAST_FLAG
-        grads = st.backward(-self.loss_scale)              # loss = -elbo * loss_scale
+        works, ranges = [], []
+
+        def exchange(buf, lo, hi):
+            import torch.distributed as dist
+            ranges.append((lo, hi))
+            works.append(dist.all_reduce(buf[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+        grads = st.backward(-self.loss_scale, on_ready=exchange if self.ar else None)              # loss = -elbo * loss_scale
+        for w in works:
+            w.wait()                                       # joins NCCL's stream into the current one (a graph edge under capture)
+        self.ar_in_graph, self.ar_ranges = bool(works) and st.flat is not None, ranges
         self.loss = -value * self.loss_scale
         self.kl, self.rec = st.kl, st.rec
         self.grads = [grads.get(id(p)) for p in self.params]
+
+    def close(self):
+        """Release the captured graph (and with it the NCCL operations recorded in it).  A data-parallel caller must do
+        this before torch.distributed.destroy_process_group(): tearing down a communicator that a live CUDA graph still
+        references does not return."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+            self.grads = []
 
     def step(self, imgs: torch.Tensor, masks: torch.Tensor, accumulate: bool = False, check_labels: bool = True,
              eps: Optional[torch.Tensor] = None) -> torch.Tensor:

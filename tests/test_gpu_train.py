@@ -558,6 +558,52 @@ def test_bf16_training_step(ops):
     assert np.median(losses[-6:]) < 0.9 * np.mean(losses[:2]), losses
 
 
+def test_flat_gradient_buffer_ranges_are_final_when_announced(ops):
+    """Tensor-core mode: the gradients of a backward are views of one flat buffer in completion order, and
+    TrainStep.backward(on_ready=...) announces ranges [lo, hi) — what the data-parallel step all-reduces while the backward
+    still runs.  Every announced range must already hold its final values, the ranges must tile the buffer exactly once,
+    and the gradients must equal those of a step without the hook."""
+    import pmu_b200
+    from pmu_b200 import train_engine
+    sd = O.make_state_dict(seed=0)
+    g = _g(70)
+    x = torch.rand(2, 1, 64, 64, generator=g).cuda()
+    m = torch.randint(0, 3, (2, 1, 64, 64), generator=g).float().cuda()
+    eps = torch.randn(2, 6, generator=g).cuda()
+    net = pmu_b200.ProbabilisticUnet(1, 3, [64, 128, 256, 512, 1024], 6, 4, 10)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train().set_precision("bf16")
+
+    def run(hook):
+        net.load_state_dict(sd, strict=True)
+        st = train_engine.TrainStep(net, x, m)
+        z_q = st.mu_q + eps * torch.exp(st.ls_q)
+        st.elbo(m, z_q, eps, True)
+        return st, st.backward(-1.0, on_ready=hook)
+
+    run(None)                                              # records the completion order
+    assert net.__dict__["_pmu_grad_order"] is not None
+    seen = []
+    st, grads = run(lambda buf, lo, hi: seen.append((lo, hi, buf[lo:hi].clone())))
+    assert st.flat is not None and len(seen) >= 3, len(seen)
+    pos = 0
+    for lo, hi, snap in seen:
+        assert lo == pos and hi > lo
+        assert torch.equal(snap, st.flat[lo:hi]), (lo, hi)
+        pos = hi
+    assert pos == st.flat.numel()
+    for p_ in net.parameters():
+        v = grads.get(id(p_))
+        if v is not None:
+            assert v.untyped_storage().data_ptr() == st.flat.untyped_storage().data_ptr()
+    # same gradients as the first (unhooked, differently laid out) run up to the atomics' summation order
+    st2, grads2 = run(None)
+    for p_ in net.parameters():
+        if id(p_) in grads:
+            scale = max(float(grads2[id(p_)].abs().max()), 1e-6)
+            assert float((grads[id(p_)] - grads2[id(p_)]).abs().max()) <= 2e-2 * scale
+
+
 def test_graphed_training_step_matches_eager(ops):
     """GraphedTrainStep (forward + elbo + backward as ONE CUDA graph) against the eager step on the same inputs and the same
     injected posterior noise, in both modes: same kernels, so the same loss and the same gradients up to the run-to-run

@@ -63,6 +63,21 @@ int pmu_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * stream passed to every call must belong to this device. */
 int pmu_set_device(int device);
 
+/* ---- launch context ("the library allocates nothing except inside an opaque pmu_ctx* ... with explicit
+ * create/destroy").  The reference has no counterpart: a torch module keeps this state inside cuDNN / ATen handles
+ * (model/unet/unet_parts.py:15-20 -> at::cudnn_convolution).  A context caches, per device, what a tcgen05 launch needs
+ * besides its arguments: SM count and compute capability, the kernels' dynamic-shared-memory attributes and the TMA
+ * descriptors (cuTensorMapEncodeTiled results keyed by pointer / extents / strides / box), so that the launch path makes
+ * no driver query and encodes no descriptor in steady state.  pmu_ctx_bind makes a context current for the calling thread
+ * (and selects its device); every entry point below then uses it.  NULL unbinds: each launch queries and encodes what it
+ * needs, as pmu_set_device callers get.  A context may be bound by one thread at a time. */
+typedef struct pmu_ctx pmu_ctx;
+int pmu_ctx_create(int device, pmu_ctx** out);
+int pmu_ctx_destroy(pmu_ctx* ctx);
+int pmu_ctx_bind(pmu_ctx* ctx);
+/* cached descriptors, cache hits and misses so far (any pointer may be NULL) */
+int pmu_ctx_stats(pmu_ctx* ctx, int64_t* tensor_maps, int64_t* hits, int64_t* misses);
+
 /* ---- K1: plane slicing (data plane in) ---------------------------------- *
  * replaces MRI_Dataset.sample_slice + preprocess, mri_dataset.py:70-82,101-112 */
 

@@ -22,6 +22,10 @@ _SIG = {
     "pmu_version": (c_int, []),
     "pmu_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "pmu_set_device": (c_int, [c_int]),
+    "pmu_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "pmu_ctx_destroy": (c_int, [c_void_p]),
+    "pmu_ctx_bind": (c_int, [c_void_p]),
+    "pmu_ctx_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "pmu_plane_max": (c_int, [_P, POINTER(c_int32), _P, _P]),
     "pmu_slice_gather": (c_int, [_P, POINTER(c_int32), c_int, c_int, c_int, c_int, POINTER(c_float), c_int, c_int,
                                  _P, _P, _P, _P]),
@@ -115,6 +119,34 @@ def load(build_if_missing: bool = False):
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+USE_CTX = True        # False: the context-free launch path (pmu_set_device; every launch queries / encodes what it needs)
+_ctx = {}
+
+
+def bind_device(lib, device_index: int):
+    """Make `device_index` current for the library on this thread: through its launch context (created on first use;
+    cached TMA descriptors, kernel attributes, device properties), or through pmu_set_device when USE_CTX is off."""
+    if not USE_CTX:
+        check(lib.pmu_set_device(device_index), "pmu_set_device")
+        return
+    h = _ctx.get(device_index)
+    if h is None:
+        out = c_void_p()
+        check(lib.pmu_ctx_create(device_index, ctypes.byref(out)), "pmu_ctx_create")
+        h = _ctx[device_index] = out
+    check(lib.pmu_ctx_bind(h), "pmu_ctx_bind")
+
+
+def ctx_stats(device_index: int = 0):
+    """(cached tensor maps, hits, misses) of the device's launch context; None before its first use."""
+    h = _ctx.get(device_index)
+    if h is None:
+        return None
+    a, b, c = c_int64(), c_int64(), c_int64()
+    check(load().pmu_ctx_stats(h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "pmu_ctx_stats")
+    return a.value, b.value, c.value
 
 
 def check(rc: int, what: str = ""):

@@ -24,6 +24,7 @@
 #include "pmu_common.cuh"
 #include "h16.cuh"
 #include "sm100_ptx.cuh"
+#include "ctx.cuh"
 
 namespace pmu {
 
@@ -772,45 +773,30 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmY, const ConvTcParams
 // ------------------------------------------------------------------------------------
 // host side: tensor-map encoding through the driver entry point (no libcuda link)
 // ------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }
-  return fn;
+// TMA descriptors: encoded through the launch context (ctx.cuh) — cached when one is bound to the calling thread.
+static int tiled_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                     CUtensorMapL2promotion promo, const char* what) {
+  TensorMapSpec s{};
+  s.ptr = ptr; s.rank = rank; s.dtype = (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; s.swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  s.l2promo = (int)promo; s.oob = (int)CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE;
+  for (int i = 0; i < rank; ++i) { s.dims[i] = dims[i]; s.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s.strides[i] = strides[i];
+  return tensor_map(m, s, what);
 }
 
 // NHWC bf16 activation [B][H][W][C]: box = 64 channels x TW x TH x TB, 128 B swizzle, zero OOB fill
 static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB) {
-  auto fn = get_encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", B, H, W, C, (int)r); return PMU_ERR_CUDA; }
-  return PMU_OK;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  return tiled_map(m, ptr, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "activation");
 }
 // packed weights [N][K] bf16, K fastest: box = 64 x BN
 static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
-  auto fn = get_encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%d) failed: %d", N, K, (int)r); return PMU_ERR_CUDA; }
-  return PMU_OK;
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t strides[1] = {(uint64_t)K * 2};
+  const uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)BN};
+  return tiled_map(m, ptr, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "weights");
 }
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -822,7 +808,7 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   using L = ConvTcSmem<BN, STAGES, NSTG, RESW>;
   static_assert(MINB * (L::DYN_BYTES + 1024) <= 228 * 1024 && L::DYN_BYTES <= 227 * 1024, "shared memory budget");
   auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, RESW, TPAIR>;
-  PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+  { const int rc_ = set_max_dyn_smem(reinterpret_cast<const void*>(kern), L::DYN_BYTES); if (rc_) return rc_; }
   grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
   kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, ym[0], ym[1], ym[2], ym[3], p, bias,
                                                          reinterpret_cast<__nv_bfloat16*>(y),
@@ -837,35 +823,23 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 // (F.pad, unet_parts.py:58-62: the pad of an odd extent goes to the high side, so the data sits at the origin)
 static int make_convt_out_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int ij, int TW, int TH, int TB,
                               int Ho, int Wo) {
-  auto fn = get_encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
   const int i = ij >> 1, j = ij & 1;
   char* base = reinterpret_cast<char*>(y) + ((int64_t)i * Wo + j) * Cout * 2;
-  cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)2 * Cout * 2, (cuuint64_t)2 * Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(convT output phase %d) failed: %d", ij, (int)r); return PMU_ERR_CUDA; }
-  return PMU_OK;
+  const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)2 * Cout * 2, (uint64_t)2 * Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+  const uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  return tiled_map(m, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "convT output phase");
 }
 
 // rows of parity i of the ConvTranspose2d output y[B][2H][2W][Cout] as a [B][H][2W][Cout] tensor (row stride = two
 // output rows): one box {64 ch, 2 TW, TH, TB} covers both column parities of a tile (convt_pair_epilogue)
 static int make_convt_pair_map(CUtensorMap* m, void* y, int B, int H, int W, int Cout, int i, int TW, int TH, int TB,
                                int Ho, int Wo) {
-  auto fn = get_encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
   char* base = reinterpret_cast<char*>(y) + (int64_t)i * Wo * Cout * 2;
-  cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)(2 * W), (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)2 * Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(2 * TW), (cuuint32_t)TH, (cuuint32_t)TB};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(convT output rows of parity %d) failed: %d", i, (int)r); return PMU_ERR_CUDA; }
-  return PMU_OK;
+  const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)(2 * W), (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)2 * Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+  const uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)(2 * TW), (uint32_t)TH, (uint32_t)TB};
+  return tiled_map(m, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "convT output rows of one parity");
 }
 
 // Tile configuration (measured per layer on B200, scripts/time_convs.py, profiles/r01_conv_variants.txt,
@@ -880,10 +854,9 @@ static int make_convt_pair_map(CUtensorMap* m, void* y, int B, int H, int W, int
 // falls back to the CUDA-core stencil of layers_bf16.cu)
 int conv_first_tc_launch(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int relu,
                          int f16, cudaStream_t st) {
-  int cc_major = 0, dev = 0;
-  PMU_CUDA(cudaGetDevice(&dev));
-  PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
-  if (cc_major != 10 || W < 16 || H < 8 || !get_encode_fn()) return PMU_ERR_UNSUPPORTED;
+  int cc_major = 0;
+  { const int rc_ = device_cc_major(&cc_major); if (rc_) return rc_; }
+  if (cc_major != 10 || W < 16 || H < 8) return PMU_ERR_UNSUPPORTED;
   ConvTcParams p;
   p.B = B; p.H = H; p.W = W; p.C0 = 64; p.C1 = 0; p.Cout = 64; p.ntaps = 9; p.relu = relu;
   p.pool_mode = -1; p.tma_store = 1; p.f16 = f16 ? 1 : 0;
@@ -894,7 +867,7 @@ int conv_first_tc_launch(const float* x, const float* w, const float* bias, void
   CUtensorMap ym;
   int rc = make_act_map(&ym, y, B, H, W, 64, 16, 8, 1);
   if (rc) return rc;
-  PMU_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvFirstSmem::DYN_BYTES));
+  { const int rc_ = set_max_dyn_smem(reinterpret_cast<const void*>(conv_first_tc_kernel), ConvFirstSmem::DYN_BYTES); if (rc_) return rc_; }
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
   conv_first_tc_kernel<<<grid, CF_THREADS, ConvFirstSmem::DYN_BYTES, st>>>(ym, p, x, w, bias);
   PMU_LAUNCH_CHECK();
@@ -920,9 +893,8 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
                       "pmu_conv_gemm_bf16: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
   PMU_CHECK_ARG(aligned16(x0) && aligned16(wpack) && (!y || aligned16(y)) && (!x1 || aligned16(x1)),
                 "pmu_conv_gemm_bf16: pointers must be 16-byte aligned");
-  int cc_major = 0, dev = 0;
-  PMU_CUDA(cudaGetDevice(&dev));
-  PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  int cc_major = 0;
+  { const int rc_ = device_cc_major(&cc_major); if (rc_) return rc_; }
   PMU_CHECK_SUPPORTED(cc_major == 10, "pmu_conv_gemm_bf16: needs an sm_100 device (tcgen05/TMEM); found cc %d.x", cc_major);
 
   ConvTcParams p;
@@ -999,7 +971,7 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (rs) {
     auto launch_rs = [&](auto kern, int dyn) -> int {
-      PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      { const int rc_ = set_max_dyn_smem(reinterpret_cast<const void*>(kern), dyn); if (rc_) return rc_; }
       const unsigned g = (unsigned)std::min<int64_t>(grid, sm_count());
       kern<<<g, TC_THREADS, dyn, st>>>(a0, a1, wm, ym[0], p, bias, reinterpret_cast<__nv_bfloat16*>(y),
                                        reinterpret_cast<__nv_bfloat16*>(y_pool));

@@ -18,6 +18,7 @@
 
 #include "pmu_common.cuh"
 #include "sm100_ptx.cuh"
+#include "ctx.cuh"
 
 namespace pmu {
 
@@ -178,29 +179,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
   if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
 }
 
-static PFN_cuTensorMapEncodeTiled_v12000 wt_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  }
-  return fn;
-}
+// operand descriptor through the launch context (ctx.cuh): cached when a context is bound
 static int wt_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB) {
-  auto fn = wt_encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PMU_ERR_CUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wgrad operand %dx%dx%dx%d) failed: %d", B, H, W, C, (int)r); return PMU_ERR_CUDA; }
-  return PMU_OK;
+  TensorMapSpec s{};
+  s.ptr = ptr; s.rank = 4; s.dtype = (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; s.swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  s.l2promo = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B; s.oob = (int)CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE;
+  s.dims[0] = (uint64_t)C; s.dims[1] = (uint64_t)W; s.dims[2] = (uint64_t)H; s.dims[3] = (uint64_t)B;
+  s.strides[0] = (uint64_t)C * 2; s.strides[1] = (uint64_t)W * C * 2; s.strides[2] = (uint64_t)H * W * C * 2;
+  s.box[0] = 64; s.box[1] = (uint32_t)TW; s.box[2] = (uint32_t)TH; s.box[3] = (uint32_t)TB;
+  return tensor_map(m, s, "wgrad operand");
 }
 static int wt_pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -209,7 +196,7 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
                         float* dw, int64_t grid, cudaStream_t st) {
   using L = WgradSmem<N, STAGES>;
   auto kern = wgrad_tc_kernel<N, STAGES>;
-  PMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+  { const int rc_ = set_max_dyn_smem(reinterpret_cast<const void*>(kern), L::DYN_BYTES); if (rc_) return rc_; }
   kern<<<(unsigned)grid, WT_THREADS, L::DYN_BYTES, st>>>(x0, x1, dy, p, dw);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
@@ -227,9 +214,8 @@ extern "C" int pmu_conv_wgrad_bf16(const void* x0, int C0, const void* x1, int C
   PMU_CHECK_SUPPORTED(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0,
                       "pmu_conv_wgrad_bf16: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
   PMU_CHECK_ARG(aligned16(x0) && aligned16(dy) && (!x1 || aligned16(x1)), "pmu_conv_wgrad_bf16: pointers must be 16-byte aligned");
-  int cc_major = 0, dev = 0;
-  PMU_CUDA(cudaGetDevice(&dev));
-  PMU_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  int cc_major = 0;
+  { const int rc_ = device_cc_major(&cc_major); if (rc_) return rc_; }
   PMU_CHECK_SUPPORTED(cc_major == 10, "pmu_conv_wgrad_bf16: needs an sm_100 device (tcgen05/TMEM); found cc %d.x", cc_major);
 
   WgradTcParams p;

@@ -61,8 +61,9 @@ def _prep(*tensors: Optional[torch.Tensor]):
             raise RuntimeError("pmu_b200 ops: tensors on different devices")
     lib = _lib.load()
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    # the library has its own (statically linked) CUDA runtime with a per-thread current device
-    _lib.check(lib.pmu_set_device(idx), "pmu_set_device")
+    # the library has its own (statically linked) CUDA runtime with a per-thread current device; binding the device's
+    # launch context selects it and gives the launch its cached TMA descriptors / kernel attributes
+    _lib.bind_device(lib, idx)
     return lib, c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 

@@ -313,7 +313,7 @@ def test_ctypes_signatures_match_the_header():
 
 def test_every_compute_entry_point_cites_the_reference():
     """include/pmu_b200.h: the comment in front of every compute prototype names the reference file (file:line) whose
-    arithmetic it replaces; housekeeping entry points (error string, version, device, fill) have no counterpart."""
+    arithmetic it replaces; housekeeping entry points (error string, version, device, launch context, fill) have no counterpart."""
     import re
     from pmu_b200 import _lib
     src = open(_lib.HEADER_PATH).read()
@@ -324,7 +324,8 @@ def test_every_compute_entry_point_cites_the_reference():
             last = t
         elif not re.search(r"[a-z_]+\.py:\d+", last):
             missing.append(re.search(r"(pmu_[a-z0-9_]+)", t).group(1))
-    assert set(missing) <= {"pmu_last_error", "pmu_version", "pmu_device_info", "pmu_set_device", "pmu_fill_f32"}, missing
+    assert set(missing) <= {"pmu_last_error", "pmu_version", "pmu_device_info", "pmu_set_device", "pmu_fill_f32",
+                            "pmu_ctx_create", "pmu_ctx_destroy", "pmu_ctx_bind", "pmu_ctx_stats"}, missing
 
 
 def test_missing_library_raises_loudly(monkeypatch, tmp_path):

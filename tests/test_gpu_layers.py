@@ -316,3 +316,27 @@ def test_conv1x1_register_tiled(ops, B, Cin, Cout, H, W, relu):
     got = ops.conv1x1_bb_f32(x.reshape(B, Cin, H * W, 1).cuda(), wl.cuda(), ld, bb.cuda(), Cout, Cin, Cout, relu).cpu()
     ref = F.conv2d(x, w[:, :, None, None]) + bb[:, :, None, None]
     torch.testing.assert_close(got.reshape(B, Cout, H, W), F.relu(ref) if relu else ref, atol=2e-5, rtol=1e-5)
+
+
+def test_launch_context_caches_descriptors_and_changes_nothing(ops):
+    """pmu_ctx (include/pmu_b200.h): with a context bound, the TMA descriptors of a repeated launch come from its cache;
+    the results are bit-identical with the context-free path (pmu_set_device)."""
+    from pmu_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 32, 64, generator=g).half().cuda()
+    x1 = torch.randn(2, 32, 32, 64, generator=g).half().cuda()
+    w = (torch.randn(128, 9 * 128, generator=g) * 0.05).half().cuda()
+    wt = (torch.randn(4 * 64, 64, generator=g) * 0.05).half().cuda()
+    bias = torch.randn(128, generator=g).cuda()
+    outs = {}
+    try:
+        for use in (False, True, True):
+            _lib.USE_CTX = use
+            outs.setdefault(use, []).append((ops.conv_gemm_bf16(x, w, bias, 128, 9, True, x1=x1).clone(),
+                                             ops.conv_gemm_bf16(x, wt, None, 64, 4, False).clone()))
+    finally:
+        _lib.USE_CTX = True
+    for a, b in outs[True]:
+        assert torch.equal(a, outs[False][0][0]) and torch.equal(b, outs[False][0][1])
+    maps, hits, misses = _lib.ctx_stats(x.device.index or 0)
+    assert maps > 0 and misses > 0 and hits > 0, (maps, hits, misses)

@@ -337,6 +337,17 @@ int pmu_s2d_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* 
 int pmu_bn_train_fwd_nhwc_bf16(const void* y, const float* gamma, const float* beta, float eps, int relu,
                                float momentum, float* run_mean, float* run_var, float* mean, float* var,
                                void* a, float* ws, float* scale_shift, int64_t npix, int C, void* stream);
+/* nn.Conv2d + the batch statistics of the train()-mode nn.BatchNorm2d behind it in ONE kernel (DoubleConv,
+ * unet_parts.py:15-16,18-19; Encoder, probabilistic_unet.py:38-39,43-44; train.py:94): pmu_conv_gemm_bf16 (ntaps 9 or 1, no
+ * ReLU) whose epilogue also adds, per output channel, the sum and the sum of squares of the stored (16-bit rounded)
+ * outputs into stats[2*co], stats[2*co+1] (fp64; zero-filled by the caller) — the BatchNorm never re-reads y for them. */
+int pmu_conv_gemm_bnstats_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
+                               void* y, double* stats, int B, int H, int W, int Cout, int ntaps, int f16, void* stream);
+/* the rest of that BatchNorm (+ ReLU) from those sums: mean / biased variance, running statistics updated like torch,
+ * a = [relu](gamma * (y - mean) / sqrt(var + eps) + beta) as bf16 (unet_parts.py:16-17).  scale_shift: 2*C floats of scratch. */
+int pmu_bn_train_fwd_stats_nhwc_bf16(const void* y, const double* stats, const float* gamma, const float* beta, float eps,
+                                     int relu, float momentum, float* run_mean, float* run_var, float* mean, float* var,
+                                     void* a, float* scale_shift, int64_t npix, int C, void* stream);
 /* its backward (loss.backward(), train.py:95): dy (bf16), dgamma, dbeta from da (bf16) and the recorded y / mean / var;
  * the ReLU mask is recomputed from y.  ws: PMU_RED_MAX_BLOCKS * 2 * C floats; coef: 4*C floats of scratch (the elementwise
  * pass is dy = coef0 * dz + coef2 * y + coef3 with the mask y * coef0 + coef1 > 0). */

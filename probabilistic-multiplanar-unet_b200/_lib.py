@@ -49,6 +49,8 @@ _SIG = {
     "pmu_softmax_accum": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P]),
     "pmu_scatter_accum": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int32), c_int, _P, _P, _P]),
     "pmu_bn_train_fwd_nhwc_bf16": (c_int, [_P, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "pmu_conv_gemm_bnstats_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pmu_bn_train_fwd_stats_nhwc_bf16": (c_int, [_P, _P, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "pmu_bn_train_bwd_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "pmu_channel_sums_nhwc_bf16": (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P]),
     "pmu_pool2_bwd_nhwc_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -47,6 +47,8 @@ struct ConvTcParams {
   int pool_mode;      // -1 none; PMU_POOL_MAX / PMU_POOL_AVG_CEIL: also emit the 2x2-pooled map
   int tma_store;      // a full-resolution output exists: it leaves through the smem staging tile + TMA tensor stores
   int f16;            // the 16-bit operands and outputs are IEEE f16 (inference) instead of bf16 (training), see h16.cuh
+  double* stats = nullptr;  // training: per-channel {sum, sum^2} of the stored output y, stats[2 * co + k] += (BatchNorm batch
+                            // statistics fused into the epilogue, unet_parts.py:16 / probabilistic_unet.py:39 in train() mode)
   int bias_bstride = 0;  // > 0: the bias is per image, bias[b * bias_bstride + co] (Fcomb's first layer after the split of
                          // its latent part, probabilistic_unet.py:167-176); needs TB == 1 (a tile lies in one image)
 };
@@ -100,12 +102,26 @@ __device__ __forceinline__ float4 lds128_f4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t lds32_u(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32_f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32_f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 struct EpiCtx {
   uint32_t smem_base, stg_off, bar_tfull, bar_tempty, tmem_base;
   float* bias_s;
 };
 
-template <int BN, int NSTG>
+template <int BN, int NSTG, bool STATS = false>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCtx& e, const CUtensorMap* tmY0p,
                                               const CUtensorMap* tmY1p, const CUtensorMap* tmY2p,
                                               const CUtensorMap* tmY3p, const float* __restrict__ bias,
@@ -119,6 +135,34 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
   const int m = q * 32 + lane;       // row of the tile == pixel index in the brick
   const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
   uint32_t iter = 0, stg_count = 0;
+  // ---- fused BatchNorm statistics (p.stats, training): every thread keeps {sum, sum^2} of ONE channel pair over the 32
+  // pixel rows of its warp, per 64-channel group, across all tiles of this CTA (they share the N tile unless the grid is
+  // not a multiple of n_tiles); read back from the bf16 staging tile — the values the BatchNorm apply pass will read from
+  // HBM — while the TMA store of the same tile is in flight.  Flushed once: the four warps' partials meet in the (idle)
+  // staging buffer and leave as 2 * BN fp64 atomics per CTA.
+  float bst[STATS ? BN / 64 : 1][4];
+#pragma unroll
+  for (int g = 0; g < (STATS ? BN / 64 : 1); ++g) bst[g][0] = bst[g][1] = bst[g][2] = bst[g][3] = 0.f;
+  int stat_n0 = -1;
+  const int cp = lane;                       // channel pair of the 64-channel group this thread accumulates
+  auto stats_flush = [&]() {
+    if (et == 0) tma_store_wait_read0();     // every staging buffer is idle
+    named_bar_sync(2, 128);
+    const uint32_t scr = smem_base + e.stg_off;
+#pragma unroll
+    for (int g = 0; g < BN / 64; ++g)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sts32_f(scr + (uint32_t)(((g * 4 + q) * 128 + cp * 4 + k) * 4), bst[g][k]); bst[g][k] = 0.f; }
+    named_bar_sync(3, 128);
+    for (int o = et; o < 2 * BN; o += 128) {
+      const int c = o >> 1, k2 = o & 1, g = c >> 6, idx = ((c & 63) >> 1) * 4 + k2 * 2 + (c & 1);
+      float sum = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) sum += lds32_f(scr + (uint32_t)(((g * 4 + qq) * 128 + idx) * 4));
+      const int co = stat_n0 + c;
+      if (co < p.Cout) atomicAdd(p.stats + 2 * (int64_t)co + k2, (double)sum);
+    }
+  };
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
     const uint32_t as = iter & 1u, aph = (iter >> 1) & 1u;
     const int n_tile = tile % p.n_tiles;
@@ -136,6 +180,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
 
     const int b = b0 + tb, h = h0 + ty, w = w0 + tx;
     const bool valid = (b < p.B) && (h < p.H) && (w < p.W);
+    uint32_t vmask = 0;
+    if constexpr (STATS) {
+      if (stat_n0 >= 0 && stat_n0 != n0) stats_flush();
+      stat_n0 = n0;
+      vmask = __ballot_sync(0xffffffffu, valid);      // bit i: row q * 32 + i of the tile is a pixel of the image
+    }
     // fused 2x2 pooling (a warp holds 32 / TW complete image rows of the brick, so every pooling
     // window lives in lanes {l, l^1, l^TW, l^(1|TW)} of one warp — no extra pass over HBM)
     __nv_bfloat16* dstp = nullptr;
@@ -233,10 +283,26 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           }
           tma_store_commit();
         }
+        if constexpr (STATS) {
+          // column pair cp of the staged tile over this warp's 32 rows (conflict-free: a warp reads one 128-byte row per step)
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const uint32_t col = (uint32_t)(cp & 3) * 4u, c16 = (uint32_t)cp >> 2;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t r = (uint32_t)(q * 32 + i);
+            uint32_t v = lds32_u(stg + r * 128u + (((c16 ^ (r & 7u)) & 7u) << 4) + col);
+            if (!((vmask >> i) & 1u)) v = 0u;
+            const float2 f = p.f16 ? unpack16<true>(v) : unpack16<false>(v);
+            s0 += f.x; s1 += f.y; q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+          }
+          const int g = g0 >> 6;
+          bst[g][0] += s0; bst[g][1] += s1; bst[g][2] += q0; bst[g][3] += q1;
+        }
         ++stg_count;
       }
     }
   }
+  if constexpr (STATS) { if (stat_n0 >= 0) stats_flush(); }
   if (p.tma_store && et == 0) tma_store_wait_all();
 }
 
@@ -317,7 +383,7 @@ __device__ __forceinline__ void convt_pair_epilogue(const ConvTcParams& p, const
 // current one is still in the tensor pipe) and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and the
 // setup cost (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
-template <int BN, int STAGES, int MINB, int NSTG, int RESW = 0, bool TPAIR = false>
+template <int BN, int STAGES, int MINB, int NSTG, int RESW = 0, bool TPAIR = false, bool STATS = false>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0,
@@ -435,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // =========================== epilogue (warps 2..5) ===========================
     EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
     if constexpr (TPAIR) convt_pair_epilogue<NSTG>(p, ec, &tmY0, &tmY1, bias, total_tiles, warp, lane);
-    else conv_epilogue<BN, NSTG>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
+    else conv_epilogue<BN, NSTG, STATS>(p, ec, &tmY0, &tmY1, &tmY2, &tmY3, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -473,7 +539,7 @@ struct ConvRsSmem {
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int STAGES, int RESB>
+template <int BN, int STAGES, int RESB, bool STATS = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY0, const ConvTcParams p,
@@ -584,7 +650,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   } else {
     EpiCtx ec{smem_base, (uint32_t)L::STG_OFF, bar_tfull, bar_tempty, tmem_base, bias_s};
-    conv_epilogue<BN, 1>(p, ec, &tmY0, &tmY0, &tmY0, &tmY0, bias, y, y_pool, total_tiles, warp, lane);
+    conv_epilogue<BN, 1, STATS>(p, ec, &tmY0, &tmY0, &tmY0, &tmY0, bias, y, y_pool, total_tiles, warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -801,13 +867,13 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int N, int K, int BN) {
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN, int STAGES, int MINB, int NSTG = 1, int RESW = 0, bool TPAIR = false>
+template <int BN, int STAGES, int MINB, int NSTG = 1, int RESW = 0, bool TPAIR = false, bool STATS = false>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wm, const CUtensorMap* ym,
                           const ConvTcParams& p, const float* bias, void* y, void* y_pool, int64_t grid,
                           cudaStream_t st) {
   using L = ConvTcSmem<BN, STAGES, NSTG, RESW>;
   static_assert(MINB * (L::DYN_BYTES + 1024) <= 228 * 1024 && L::DYN_BYTES <= 227 * 1024, "shared memory budget");
-  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, RESW, TPAIR>;
+  auto kern = conv_tc_kernel<BN, STAGES, MINB, NSTG, RESW, TPAIR, STATS>;
   { const int rc_ = set_max_dyn_smem(reinterpret_cast<const void*>(kern), L::DYN_BYTES); if (rc_) return rc_; }
   grid = std::min<int64_t>(grid, (int64_t)sm_count() * MINB);   // persistent: MINB CTAs per SM
   kern<<<(unsigned)grid, TC_THREADS, L::DYN_BYTES, st>>>(a0, a1, wm, ym[0], ym[1], ym[2], ym[3], p, bias,
@@ -880,7 +946,8 @@ using namespace pmu;
 
 static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const void* wpack,
                           const float* bias, void* y, void* y_pool, int pool_mode, int B, int H, int W, int Cout,
-                          int ntaps, int relu, int f16, int out_h, int out_w, void* stream, int bias_bstride = 0) {
+                          int ntaps, int relu, int f16, int out_h, int out_w, void* stream, int bias_bstride = 0,
+                          double* stats = nullptr) {
   PMU_CHECK_ARG(x0 && wpack && (y || y_pool), "pmu_conv_gemm_bf16: null pointer");
   const int Ho = out_h > 0 ? out_h : 2 * H, Wo = out_w > 0 ? out_w : 2 * W;     // convT output tensor extents
   PMU_CHECK_ARG(ntaps == 4 ? (Ho >= 2 * H && Wo >= 2 * W) : (out_h <= 0 && out_w <= 0),
@@ -933,6 +1000,8 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
   const int64_t grid = (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   PMU_CHECK_ARG(grid > 0 && grid < (1ll << 31), "pmu_conv_gemm_bf16: grid too large");
   p.bias_bstride = bias_bstride;
+  p.stats = stats;
+  PMU_CHECK_ARG(!stats || (y != nullptr && ntaps != 4), "pmu_conv_gemm_bnstats_bf16: statistics need a stored output of a 3x3 / 1x1 convolution");
   PMU_CHECK_SUPPORTED(bias_bstride == 0 || (p.TB == 1 && ntaps == 1 && bias),
                       "pmu_conv1x1_slicebias_bf16: a per-image bias needs images of at least 128 pixels (got %dx%d)", H, W);
 
@@ -978,10 +1047,21 @@ static int conv_gemm_impl(const void* x0, int C0, const void* x1, int C1, const 
       PMU_LAUNCH_CHECK();
       return PMU_OK;
     };
+    if (stats) {     // training: BatchNorm statistics in the epilogue
+      if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, 1, true>, ConvRsSmem<64, 6, 1>::DYN_BYTES);
+      if (BN == 128 && Cin == 64) return launch_rs(conv_rs_kernel<128, 3, 1, true>, ConvRsSmem<128, 3, 1>::DYN_BYTES);
+      if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, 0, true>, ConvRsSmem<64, 4, 0>::DYN_BYTES);
+      return launch_rs(conv_rs_kernel<128, 3, 0, true>, ConvRsSmem<128, 3, 0>::DYN_BYTES);
+    }
     if (BN == 64 && Cin == 64) return launch_rs(conv_rs_kernel<64, 6, 1>, ConvRsSmem<64, 6, 1>::DYN_BYTES);      // 64 -> 64: weights resident
     if (BN == 128 && Cin == 64) return launch_rs(conv_rs_kernel<128, 3, 1>, ConvRsSmem<128, 3, 1>::DYN_BYTES);   // 64 -> 128: weights resident
     if (BN == 64) return launch_rs(conv_rs_kernel<64, 4, 0>, ConvRsSmem<64, 4, 0>::DYN_BYTES);
     return launch_rs(conv_rs_kernel<128, 3, 0>, ConvRsSmem<128, 3, 0>::DYN_BYTES);
+  }
+  if (stats) {
+    if (BN == 256) return launch_conv_tc<256, 4, 1, 2, 0, false, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+    if (BN == 128) return launch_conv_tc<128, 3, 2, 1, 0, false, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
+    return launch_conv_tc<64, 4, 2, 1, 0, false, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   }
   if (tpair) return launch_conv_tc<256, 5, 1, 4, 2, true>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
   if (BN == 256) return launch_conv_tc<256, 4, 1, 2>(a0, a1, wm, ym, p, bias, y, y_pool, grid, st);
@@ -1006,4 +1086,11 @@ extern "C" int pmu_conv1x1_slicebias_bf16(const void* x, int Cin, const void* wp
                                           int W, int Cout, int relu, int f16, void* stream) {
   PMU_CHECK_ARG(bias != nullptr, "pmu_conv1x1_slicebias_bf16: bias is null");
   return conv_gemm_impl(x, Cin, nullptr, 0, wpack, bias, y, nullptr, -1, B, H, W, Cout, 1, relu, f16, 0, 0, stream, Cout);
+}
+
+extern "C" int pmu_conv_gemm_bnstats_bf16(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
+                                          void* y, double* stats, int B, int H, int W, int Cout, int ntaps, int f16,
+                                          void* stream) {
+  PMU_CHECK_ARG(stats != nullptr, "pmu_conv_gemm_bnstats_bf16: stats is null");
+  return conv_gemm_impl(x0, C0, x1, C1, wpack, bias, y, nullptr, -1, B, H, W, Cout, ntaps, 0, f16, 0, 0, stream, 0, stats);
 }

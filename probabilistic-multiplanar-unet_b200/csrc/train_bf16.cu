@@ -158,6 +158,25 @@ bn_finalize_nhwc_kernel(const float* __restrict__ ws, int nb, int C, double n, f
   shift[c] = beta[c] - (float)m * gamma[c] * inv;
 }
 
+// BatchNorm finalize from the per-channel fp64 {sum, sum^2} the convolution epilogue accumulated (pmu_conv_gemm_bnstats_bf16)
+__global__ void bn_finalize_acc_nhwc_kernel(const double* __restrict__ acc, int C, double n, float eps, const float* __restrict__ gamma,
+                                            const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ var,
+                                            float* __restrict__ run_mean, float* __restrict__ run_var, float momentum,
+                                            float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = acc[2 * c] / n;
+  double v = acc[2 * c + 1] / n - m * m;
+  if (v < 0) v = 0;
+  mean[c] = (float)m;
+  var[c] = (float)v;
+  if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)m;
+  if (run_var) run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(n > 1 ? v * n / (n - 1) : v);
+  const float inv = 1.f / sqrtf((float)v + eps);
+  scale[c] = gamma[c] * inv;
+  shift[c] = beta[c] - (float)m * gamma[c] * inv;
+}
+
 // a = [relu](y * scale + shift), elementwise over [npix][C].  The grid stride (gridDim * 256) is a multiple of G = C / 8,
 // so a thread keeps ONE channel group for its whole loop: scale / shift live in registers.
 __global__ void __launch_bounds__(TB_THREADS)
@@ -819,6 +838,23 @@ extern "C" int pmu_conv3x3_wgrad_smallcin_bf16(const float* x0, const float* x1,
   wgrad_smallcin_nhwc_kernel<<<dim3(blocks, Cin), TB_THREADS, dyn, st>>>(x0, x1, reinterpret_cast<const uint4*>(dy), npix, H, W, C, chunk, ws);
   PMU_LAUNCH_CHECK();
   wgrad_smallcin_finalize_kernel<<<dim3(cdiv(9 * C, 32), Cin), FIN_THREADS, 0, st>>>(ws, (int)blocks, C, Cin, dw);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_bn_train_fwd_stats_nhwc_bf16(const void* y, const double* stats, const float* gamma, const float* beta, float eps,
+                                                int relu, float momentum, float* run_mean, float* run_var, float* mean, float* var,
+                                                void* a, float* scale_shift, int64_t npix, int C, void* stream) {
+  PMU_CHECK_ARG(y && stats && gamma && beta && mean && var && a && scale_shift, "pmu_bn_train_fwd_stats_nhwc_bf16: null pointer");
+  PMU_NHWC_ARGS("pmu_bn_train_fwd_stats_nhwc_bf16");
+  PMU_CHECK_ARG(aligned16(y) && aligned16(a), "pmu_bn_train_fwd_stats_nhwc_bf16: 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_finalize_acc_nhwc_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats, C, (double)npix, eps, gamma, beta, mean, var, run_mean, run_var, momentum,
+                                                           scale_shift, scale_shift + C);
+  PMU_LAUNCH_CHECK();
+  const int64_t total = npix * (C / 8);
+  bn_act_nhwc_kernel<<<ew_blocks(total), TB_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(y), scale_shift, scale_shift + C, relu,
+                                                             reinterpret_cast<uint4*>(a), total, C / 8);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

@@ -797,3 +797,36 @@ def conv3x3_wgrad_smallcin_bf16(x0, dy, x1=None, out=None):
     lib, st = _prep(x0, x1, dy, dw, ws)
     _launch(lib, "pmu_conv3x3_wgrad_smallcin_bf16", (_p(x0), _p(x1), _p(dy), _p(dw), _p(ws), B, H, W, Cout, st,))
     return dw
+
+
+def conv_gemm_bnstats_bf16(x0, wpack, bias, Cout, ntaps, stats, x1=None):
+    """tcgen05 conv (no ReLU) whose epilogue also accumulates the BatchNorm batch statistics of its output:
+    stats fp64 [2*Cout] (zero-filled by the caller) += per-channel {sum, sum of squares} interleaved.  Returns y."""
+    _f32(bias, "bias")
+    wf = _h16((x0, "x0"), (x1, "x1"), (wpack, "wpack"))
+    if stats.dtype != torch.float64 or stats.numel() != 2 * Cout:
+        raise RuntimeError("conv_gemm_bnstats_bf16: stats must be float64 [2 * Cout]")
+    B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    out = torch.empty(B, H, W, Cout, dtype=x0.dtype, device=x0.device)
+    lib, st = _prep(x0, x1, wpack, bias, out, stats)
+    global _META
+    _META = {"flops": 2.0 * B * H * W * Cout * (9 if ntaps == 9 else 1) * (C0 + C1)}
+    _launch(lib, "pmu_conv_gemm_bnstats_bf16", (_p(x0), C0, _p(x1), C1, _p(wpack), _p(bias), _p(out), _p(stats), B, H, W, Cout,
+                                              int(ntaps), wf, st,))
+    return out
+
+
+def bn_train_fwd_stats_nhwc_bf16(y, stats, gamma, beta, eps, relu, momentum=0.1, run_mean=None, run_var=None):
+    """Train-mode BatchNorm2d (+ReLU) on y bf16 [B,H,W,C] from the statistics the convolution accumulated: (a, mean, var)."""
+    _bf16(y, "y")
+    C = y.shape[-1]
+    npix = y.numel() // C
+    mean = torch.empty(C, dtype=torch.float32, device=y.device)
+    var = torch.empty_like(mean)
+    a = torch.empty_like(y)
+    ss = torch.empty(2 * C, dtype=torch.float32, device=y.device)
+    lib, st = _prep(y, stats, gamma, beta, run_mean, run_var, mean, var, a, ss)
+    _launch(lib, "pmu_bn_train_fwd_stats_nhwc_bf16", (_p(y), _p(stats), _p(gamma), _p(beta), float(eps), int(relu), float(momentum),
+                                                    _p(run_mean), _p(run_var), _p(mean), _p(var), _p(a), _p(ss), npix, C, st,))
+    return a, mean, var

@@ -134,6 +134,21 @@ class _Arena:
         return v
 
 
+FUSED_BN_STATS = True      # tensor-core mode: BatchNorm statistics in the convolution epilogue (False: the separate statistics pass)
+
+
+def _stats_take(C: int, device) -> Optional[torch.Tensor]:
+    """fp64 [2*C] zero-filled accumulator for the statistics of one conv + BatchNorm layer, cut from ONE buffer per forward."""
+    if not FUSED_BN_STATS:
+        return None
+    st = _BF16.get("stats")
+    if st is None or st[1] + 2 * C > st[0].numel():
+        st = _BF16["stats"] = [torch.zeros(max(1 << 16, 2 * C), dtype=torch.float64, device=device), 0]
+    v = st[0][st[1]:st[1] + 2 * C]
+    st[1] += 2 * C
+    return v
+
+
 def _zeros(*shape, device=None):
     a = _BF16["arena"]
     return a.take(*shape) if a is not None else torch.zeros(*shape, dtype=torch.float32, device=device)
@@ -193,12 +208,21 @@ def _tc_cbr_fwd(conv, bn, x0, x1=None):
         # both operand layouts of this layer from one read of the fp32 weights: wf [Cout][tap][Cin] for this GEMM,
         # wd [Cin][flipped tap][Cout] for the data gradient in the backward
         wf, wd = ops.pack_conv3x3_weights_bf16(w)
-        y = ops.conv_gemm_bf16(x0, wf, _d(conv.bias), Cout, 9, False, x1=x1)
+        stats = _stats_take(Cout, x0.device)
+        if stats is not None:
+            # BatchNorm batch statistics in the convolution's epilogue: the statistics pass over y is gone
+            y = ops.conv_gemm_bnstats_bf16(x0, wf, _d(conv.bias), Cout, 9, stats, x1=x1)
+        else:
+            y = ops.conv_gemm_bf16(x0, wf, _d(conv.bias), Cout, 9, False, x1=x1)
         if CHECK_LOG is not None:
             ref = ops.conv3x3_f32(_f32(x0), w.to(torch.bfloat16).float(), _d(conv.bias), relu=False, x1=None if x1 is None else _f32(x1))
             CHECK_LOG.append(("fwd", Cin, Cout, y.shape[1], float((_f32(y) - ref).norm() / ref.norm())))
-    a, mean, var = ops.bn_train_fwd_nhwc_bf16(y, _d(bn.weight), _d(bn.bias), bn.eps, True,
-                                              0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var)
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    if not first and stats is not None:
+        a, mean, var = ops.bn_train_fwd_stats_nhwc_bf16(y, stats, _d(bn.weight), _d(bn.bias), bn.eps, True, mom,
+                                                        bn.running_mean, bn.running_var)
+    else:
+        a, mean, var = ops.bn_train_fwd_nhwc_bf16(y, _d(bn.weight), _d(bn.bias), bn.eps, True, mom, bn.running_mean, bn.running_var)
     _PENDING_NBT.append(bn.num_batches_tracked)
     return a, {"conv": conv, "bn": bn, "x0": x0, "x1": x1, "y": y, "mean": mean, "var": var, "first": first, "wd": wd}
 
@@ -537,6 +561,7 @@ class TrainStep:
 
     def _mode(self, on: bool):
         _BF16["on"] = on and self.bf16
+        _BF16["stats"] = None
         if not on:
             _BF16["arena"] = None
             _PENDING_NBT.clear()

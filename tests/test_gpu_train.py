@@ -378,6 +378,37 @@ def test_pool_add_sums_head_bwd_nhwc_bf16(ops):
     _close(db, bias.grad, 1e-5, "head db")
 
 
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout", [(2, 32, 32, 64, 0, 64), (2, 24, 40, 64, 64, 64), (3, 16, 16, 64, 0, 128),
+                                              (2, 8, 8, 128, 0, 256), (1, 12, 20, 128, 0, 128), (8, 16, 16, 256, 0, 512),
+                                              (2, 64, 64, 128, 128, 128), (9, 32, 32, 64, 0, 256)])
+def test_conv_epilogue_batchnorm_statistics(ops, B, H, W, C0, C1, Cout):
+    """pmu_conv_gemm_bnstats_bf16: the convolution output is bit-identical with pmu_conv_gemm_bf16 and the fused per-channel
+    {sum, sum of squares} equal those of the STORED bf16 output (ragged tiles masked, every tile variant: row-shift,
+    generic, BN 64 / 128 / 256, halved few-tile grids, two sources); then the BatchNorm from those sums equals the
+    BatchNorm with its own statistics pass."""
+    g = _g(80 + Cout + H)
+    x0 = torch.randn(B, H, W, C0, generator=g).to(torch.bfloat16).cuda()
+    x1 = torch.randn(B, H, W, C1, generator=g).to(torch.bfloat16).cuda() if C1 else None
+    w = (torch.randn(Cout, 9 * (C0 + C1), generator=g) * 0.05).to(torch.bfloat16).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    y = ops.conv_gemm_bnstats_bf16(x0, w, bias, Cout, 9, stats, x1=x1)
+    y_ref = ops.conv_gemm_bf16(x0, w, bias, Cout, 9, False, x1=x1)
+    assert torch.equal(y, y_ref)
+    yd = y.double().reshape(-1, Cout)
+    want = torch.stack([yd.sum(0), (yd * yd).sum(0)], 1).reshape(-1)
+    torch.testing.assert_close(stats, want, rtol=2e-6, atol=2e-6 * float(want.abs().max()))
+    gamma, beta = (torch.rand(Cout, generator=g) + 0.5).cuda(), torch.randn(Cout, generator=g).cuda()
+    rm1, rv1, rm2, rv2 = (torch.zeros(Cout).cuda(), torch.ones(Cout).cuda(), torch.zeros(Cout).cuda(), torch.ones(Cout).cuda())
+    a1, m1, v1 = ops.bn_train_fwd_stats_nhwc_bf16(y, stats, gamma, beta, 1e-5, True, 0.1, rm1, rv1)
+    a2, m2, v2 = ops.bn_train_fwd_nhwc_bf16(y, gamma, beta, 1e-5, True, 0.1, rm2, rv2)
+    torch.testing.assert_close(m1, m2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(v1, v2, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(rm1, rm2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv1, rv2, rtol=1e-4, atol=1e-6)
+    assert float((a1.float() - a2.float()).abs().max()) <= 2e-2 * max(1.0, float(a2.float().abs().max()))
+
+
 def test_weight_pack_unpack_bf16(ops):
     """pmu_pack_conv3x3_weights_bf16 / pmu_unpack_conv3x3_wgrad_f32: pure data movement (+ one bf16 rounding), bit-exact
     against the torch permutes the step used before."""

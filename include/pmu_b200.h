@@ -92,8 +92,10 @@ int pmu_plane_max(const float* vol, const int32_t dims[3], float* maxes, void* s
  *  interp NEAREST/TRILINEAR: affine = 12 HOST floats [o(3), n(3), u(3), v(3)],
  *    q = o + s*n + r*u + c*v in fp32 (fixed op order, see oracle resample_slices).
  *  slice_max_in  (nullable, indexed by absolute slice s): fuse the normalisation
- *    x / max if max != 0, computed as (float)((double)x / (double)max) — the
- *    reference's fp64 divide + .float() (mri_dataset.py:110,142) bit for bit.
+ *    x / max if max != 0, computed with ONE IEEE fp32 division (div.rn.f32), which equals
+ *    the reference's fp64 divide + .float() (mri_dataset.py:110,142) bit for bit: the fp64
+ *    quotient of two fp32 values rounds to fp32 exactly like the correctly rounded fp32
+ *    quotient (double rounding is innocuous for division with >= 2p+2 = 50 wide bits).
  *  slice_max_out (nullable, indexed by s - s0, pre-filled with -inf): records the
  *    max of each gathered (raw) slice with atomic max, for pmu_slice_normalize.
  *  out_dtype: PMU_DTYPE_F32 only (bf16 conversion happens in the first conv). */
@@ -102,7 +104,7 @@ int pmu_slice_gather(const float* vol, const int32_t dims[3], int plane, int s0,
                      const float* slice_max_in, float* slice_max_out,
                      float* out, void* stream);
 
-/* In-place x/max per slice (same fp64 divide), slices [ns][hw], slice_max [ns]:
+/* In-place x/max per slice (the same div.rn.f32), slices [ns][hw], slice_max [ns]:
  * MRI_Dataset.preprocess, mri_dataset.py:109-110 (x / np.max(x) if the max is not 0). */
 int pmu_slice_normalize(float* slices, const float* slice_max, int ns, int64_t hw, void* stream);
 

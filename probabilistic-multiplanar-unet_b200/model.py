@@ -266,17 +266,6 @@ class ProbabilisticUnet(nn.Module, _PackedMixin):
     def _wants_grad(self) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def _fcomb_live(self):
-        """fcomb weights straight from the parameters (training: nothing is packed / folded)."""
-        convs = [m for m in self.fcomb.layers if isinstance(m, nn.Conv2d)]
-        F_ = convs[0].weight.shape[0]
-        last = self.fcomb.last_layer
-        return {"w0": convs[0].weight.detach().reshape(F_, -1), "b0": convs[0].bias.detach(),
-                "wmid": torch.stack([c.weight.detach().reshape(F_, F_) for c in convs[1:]]).contiguous() if len(convs) > 1 else None,
-                "bmid": torch.stack([c.bias.detach() for c in convs[1:]]).contiguous() if len(convs) > 1 else None,
-                "wlast": last.weight.detach().reshape(last.weight.shape[0], F_), "blast": last.bias.detach(),
-                "nl": 1 + len(convs), "F": F_, "L": convs[0].weight.shape[1] - F_, "C": last.weight.shape[0]}
-
     def _enter(self, what):
         _no_autograd(self, what)
         if self.training and not self._warned_train:

@@ -401,12 +401,15 @@ int pmu_relu_mask_bf16(void* d, const void* h, int64_t n, void* stream);
 int pmu_conv3x3_wgrad_smallcin_bf16(const float* x0, const float* x1, const void* dy, float* dw, float* ws, int B, int H,
                                     int W, int Cout, void* stream);
 /* tcgen05 weight gradient of conv3x3 pad 1 (ntaps = 9) / conv1x1 (ntaps = 1):
- * dw fp32 [Cout][ntaps][C0+C1] += sum_{b,h,w} dy[b,h,w,co] * cat(x0,x1)[b,h+ky-1,w+kx-1,ci]   (tap = ky*3+kx)
+ * dw fp32 [Cout][ntaps][C0+C1] (+)= sum_{b,h,w} dy[b,h,w,co] * cat(x0,x1)[b,h+ky-1,w+kx-1,ci]   (tap = ky*3+kx)
  * x0 bf16 [B,H,W,C0], x1 (nullable) bf16 [B,H,W,C1], dy bf16 [B,H,W,Cout]; channels multiples of 64.
- * The reduction over pixels is split across CTAs; partials are added with fp32 atomics (zero-fill dw).
+ * overwrite = 0: dw += (zero-fill it for a plain gradient); the reduction over pixels is split across CTAs and partials are
+ * added with fp32 atomics.  overwrite = 1: dw is written (no zero-fill by the caller): tiles that are not worth splitting —
+ * the layers with many (tap, channel) tiles, i.e. the large weights — leave with plain stores, split ones after a memset
+ * by the library.
  * Weight gradient of the nn.Conv2d layers of unet_parts.py:15,18 / probabilistic_unet.py:38,43 in loss.backward() (train.py:95). */
 int pmu_conv_wgrad_bf16(const void* x0, int C0, const void* x1, int C1, const void* dy, float* dw, int B,
-                        int H, int W, int Cout, int ntaps, void* stream);
+                        int H, int W, int Cout, int ntaps, int overwrite, void* stream);
 
 #ifdef __cplusplus
 }

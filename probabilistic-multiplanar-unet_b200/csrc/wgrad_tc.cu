@@ -34,6 +34,7 @@ struct WgradTcParams {
   int pairs;          // ceil(units / 2)
   int n_blocks;       // Cout / N
   int ksplit, kblocks_per_split, kblocks;
+  int store;          // 1: the tile is not split and dw is overwritten: plain stores instead of atomics
 };
 
 // MN-major operand, 128-byte swizzle: 64 MN elements (128 B) contiguous, k rows 128 B apart, 8-row groups
@@ -165,10 +166,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
         tmem_ld_32x32(trow + (uint32_t)c0, v);
         tmem_ld_wait();
         if (valid) {
+          if (p.store) {
+            // this CTA holds the whole pixel sum of its tile and dw is write-only: plain coalesced stores
+            // (128 B per warp and column) instead of 128 x N atomics
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int co = nb * N + c0 + j;
-            atomicAdd(dw + ((int64_t)co * p.ntaps + tap) * Cin + ci, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) {
+              const int co = nb * N + c0 + j;
+              dw[((int64_t)co * p.ntaps + tap) * Cin + ci] = __uint_as_float(v[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int co = nb * N + c0 + j;
+              atomicAdd(dw + ((int64_t)co * p.ntaps + tap) * Cin + ci, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -207,7 +218,7 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
 using namespace pmu;
 
 extern "C" int pmu_conv_wgrad_bf16(const void* x0, int C0, const void* x1, int C1, const void* dy, float* dw, int B,
-                                   int H, int W, int Cout, int ntaps, void* stream) {
+                                   int H, int W, int Cout, int ntaps, int overwrite, void* stream) {
   PMU_CHECK_ARG(x0 && dy && dw && (C1 == 0 || x1), "pmu_conv_wgrad_bf16: null pointer");
   PMU_CHECK_ARG(ntaps == 9 || ntaps == 1, "pmu_conv_wgrad_bf16: ntaps must be 9 or 1 (got %d)", ntaps);
   PMU_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && C1 >= 0, "pmu_conv_wgrad_bf16: bad shape");
@@ -231,9 +242,31 @@ extern "C" int pmu_conv_wgrad_bf16(const void* x0, int C0, const void* x1, int C
   const int N = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
   p.n_blocks = Cout / N;
   const int64_t tiles = (int64_t)p.pairs * p.n_blocks;
-  int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(p.kblocks, (2 * (int64_t)sm_count() + tiles - 1) / tiles));
+  // Split of the pixel range across CTAs.  A CTA costs its k-blocks (8 UMMAs of N columns each) plus its epilogue, and the
+  // epilogue of a split tile — 128 x N fp32 atomics — costs more than eight k-blocks (measured on the 1024-channel layers
+  // of a batch-8 step: 576 CTAs of 8 k-blocks took 55 us, i.e. ~10 us of atomics against 4.4 us of UMMAs per CTA), while an
+  // unsplit tile leaves with plain read-modify-write stores.  Pick the split that minimises waves x (k-block time + epilogue)
+  // (overwrite = 0, the accumulating form, always leaves with atomics).
+  int ksplit = 1;
+  {
+    // a k-block: 8 UMMAs of N columns (0.55 us at N = 256) or, for narrow N, the 2 + N / 64 operand boxes it loads
+    const double kb_us = std::max(0.55 * N / 256.0, 0.33), epi_store_us = 3.0 * N / 256.0, epi_atomic_us = 10.0 * N / 256.0;
+    const int64_t slots = (int64_t)sm_count();                                 // one resident CTA per SM (192 KB of stages)
+    double best = 1e30;
+    const int kmax = (int)std::min<int64_t>(p.kblocks, 256);
+    for (int ks = 1; ks <= kmax; ++ks) {
+      const int kper = cdiv(p.kblocks, ks);
+      if (ks > 1 && cdiv(p.kblocks, kper) != ks) continue;                      // same split as a smaller ks
+      const double waves = (double)cdiv64(tiles * ks, slots);
+      const double t = waves * (kper * kb_us + ((ks == 1 && overwrite) ? epi_store_us : epi_atomic_us));
+      if (t < best - 1e-9) { best = t; ksplit = ks; }
+    }
+  }
   p.kblocks_per_split = cdiv(p.kblocks, ksplit);
   p.ksplit = cdiv(p.kblocks, p.kblocks_per_split);
+  p.store = (overwrite && p.ksplit == 1) ? 1 : 0;
+  if (overwrite && !p.store)      // split tiles add their partials: the library clears the accumulator itself
+    PMU_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * ntaps * (C0 + C1), (cudaStream_t)stream));
   const int64_t grid = tiles * p.ksplit;
   PMU_CHECK_ARG(grid > 0 && grid < (1ll << 31), "pmu_conv_wgrad_bf16: grid too large");
 

@@ -631,8 +631,8 @@ def s2d_nhwc_bf16(x):
     return y
 
 
-def conv_wgrad_bf16(x0, dy, dw, x1=None, ntaps=9):
-    """dw fp32 [Cout, ntaps, C0+C1] += tcgen05 weight gradient; x0/x1/dy bf16 NHWC."""
+def conv_wgrad_bf16(x0, dy, dw, x1=None, ntaps=9, overwrite=False):
+    """dw fp32 [Cout, ntaps, C0+C1] += tcgen05 weight gradient (overwrite: dw = ..., no zero-fill needed); x0/x1/dy bf16 NHWC."""
     _bf16(x0, "x0"); _bf16(x1, "x1"); _bf16(dy, "dy"); _f32(dw, "dw")
     B, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
@@ -641,7 +641,7 @@ def conv_wgrad_bf16(x0, dy, dw, x1=None, ntaps=9):
     lib, st = _prep(x0, x1, dy, dw)
     global _META
     _META = {"flops": 2.0 * B * H * W * Cout * ntaps * (C0 + C1)}
-    _launch(lib, "pmu_conv_wgrad_bf16", (_p(x0), C0, _p(x1), C1, _p(dy), _p(dw), B, H, W, Cout, int(ntaps), st,))
+    _launch(lib, "pmu_conv_wgrad_bf16", (_p(x0), C0, _p(x1), C1, _p(dy), _p(dw), B, H, W, Cout, int(ntaps), int(overwrite), st,))
 
 
 # ----------------------------------------------------------------------------- training step on bf16 NHWC activations

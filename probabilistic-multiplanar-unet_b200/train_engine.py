@@ -115,9 +115,8 @@ _PENDING_NBT: List[torch.Tensor] = []     # BatchNorm num_batches_tracked counte
 
 
 class _Arena:
-    """Zero-filled fp32 scratch of one backward: every weight-gradient accumulator of the step (the tcgen05 wgrad kernel
-    adds its split-K partials with atomics) and the zero bias gradients are views of ONE buffer cleared by ONE fill,
-    instead of ~90 torch.zeros calls."""
+    """Zero-filled fp32 scratch of one backward: the small accumulators kernels add into and the zero bias gradients are
+    views of ONE buffer cleared by ONE fill (larger requests fall back to torch.zeros)."""
 
     def __init__(self, n: int, device):
         self.buf = torch.zeros(n, dtype=torch.float32, device=device)
@@ -242,8 +241,8 @@ def _tc_cbr_bwd(rec, da, tape: _Tape, need_dx=True):
         tape.put(conv.weight, ops.conv3x3_wgrad_smallcin_bf16(rec["x0"], dy, rec["x1"], out=tape.out(conv.weight)))
         return None, None
     C0 = rec["x0"].shape[3]
-    dwp = _zeros(Cout, 9, Cin, device=dy.device)
-    ops.conv_wgrad_bf16(rec["x0"], dy, dwp, rec["x1"], 9)
+    dwp = torch.empty(Cout, 9, Cin, dtype=torch.float32, device=dy.device)
+    ops.conv_wgrad_bf16(rec["x0"], dy, dwp, rec["x1"], 9, overwrite=True)
     tape.put(conv.weight, ops.unpack_conv3x3_wgrad_f32(dwp, out=tape.out(conv.weight)))
     if CHECK_LOG is not None:
         ref = torch.zeros_like(w)
@@ -336,8 +335,8 @@ def _unet_bwd(unet, st, dfeat, tape):
             tape.put(up.bias, ops.channel_sums_nhwc_bf16(du))
             # transposed-convolution backward on tcgen05: space-to-depth of du turns both gradients into 1x1 GEMMs
             D = ops.s2d_nhwc_bf16(du)                           # [B, H, W, (i, j, co)]
-            dwp = _zeros(4 * Co, 1, Cin, device=du.device)
-            ops.conv_wgrad_bf16(u["h_in"], D, dwp, None, 1)     # dwp[(i,j,co)][ci] = sum_pix D * x
+            dwp = torch.empty(4 * Co, 1, Cin, dtype=torch.float32, device=du.device)
+            ops.conv_wgrad_bf16(u["h_in"], D, dwp, None, 1, overwrite=True)     # dwp[(i,j,co)][ci] = sum_pix D * x
             dw = dwp.reshape(2, 2, Co, Cin).permute(3, 2, 0, 1).contiguous()
             tape.put(up.weight, dw)
             wd = wt.permute(0, 2, 3, 1).reshape(Cin, 4 * Co).to(torch.bfloat16).contiguous()       # [ci][(i,j,co)]
@@ -501,8 +500,9 @@ def _fcomb_bwd_tc(fc, st, dlogits, tape):
     tape.put(last.bias, ops.channel_sums_f32(dlogits))
     for j in range(len(convs) - 1, 0, -1):
         c = convs[j]
-        dwp = _zeros(F_, 1, F_, device=dev)
-        ops.conv_wgrad_bf16(hs[j - 1], d, dwp, None, 1)                 # dw[co][ci] = sum_pix d[co] * h[ci]
+        dwp = tape.out(c.weight)
+        dwp = torch.empty(F_, 1, F_, dtype=torch.float32, device=dev) if dwp is None else dwp.view(F_, 1, F_)
+        ops.conv_wgrad_bf16(hs[j - 1], d, dwp, None, 1, overwrite=True)                 # dw[co][ci] = sum_pix d[co] * h[ci]
         tape.put(c.weight, dwp)
         tape.put(c.bias, ops.channel_sums_nhwc_bf16(d))
         d = ops.conv_gemm_bf16(d, _d(c.weight).reshape(F_, F_).t().to(torch.bfloat16).contiguous(), None, F_, 1, False)
@@ -511,8 +511,8 @@ def _fcomb_bwd_tc(fc, st, dlogits, tape):
     w0 = _d(convs[0].weight).reshape(F_, F_ + L)
     dw0 = _zeros(F_, F_ + L, device=dev)
     db0 = _zeros(F_, device=dev)
-    dwf = _zeros(F_, 1, F_, device=dev)
-    ops.conv_wgrad_bf16(st["feat"], d, dwf, None, 1)
+    dwf = torch.empty(F_, 1, F_, dtype=torch.float32, device=dev)
+    ops.conv_wgrad_bf16(st["feat"], d, dwf, None, 1, overwrite=True)
     rs = ops.channel_sums_nhwc_bf16(d, per_image=True)                   # [B, F]: what reaches the per-slice latent bias
     dz = ops.fcomb_zbias_bwd_f32(rs.reshape(-1), st["z"], w0, dw0, db0)
     dw0[:, :F_].copy_(dwf.reshape(F_, F_))
@@ -623,7 +623,9 @@ class TrainStep:
         tape = _Tape(layout, self.mu_q.device, getattr(self, "_on_ready", None))
         B = self.mu_q.shape[0]
         if self.bf16:
-            _BF16["arena"] = _Arena(sum((p.numel() + 3) // 4 * 4 for p in net.parameters()), self.mu_q.device)
+            # zero-filled scratch for the few accumulators that are added into (the weight gradients are write-only:
+            # pmu_conv_wgrad_bf16(overwrite=1))
+            _BF16["arena"] = _Arena(1 << 18, self.mu_q.device)
         dlogits = ops.ce_bwd_f32(self.logits, self.segm_t, -g)
         dfeat, dz = (_fcomb_bwd_tc if self.tc_fcomb else _fcomb_bwd)(net.fcomb, self.fc, dlogits, tape)
         dmu_q, dls_q, dmu_p, dls_p = ops.kl_bwd_f32(self.mu_q, self.ls_q, self.mu_p, self.ls_p, -g * self._beta() / B)

@@ -295,9 +295,16 @@ def test_conv_wgrad_bf16_tcgen05(ops, B, C0, C1, Cout, H, W, ntaps):
     xn = _nhwc(x).to(torch.bfloat16).cuda()
     x0 = xn[..., :C0].contiguous()
     x1 = xn[..., C0:].contiguous() if C1 else None
+    dyn = _nhwc(dy).to(torch.bfloat16).cuda()
     dw = torch.zeros(Cout, ntaps, Cin, device="cuda")
-    ops.conv_wgrad_bf16(x0, _nhwc(dy).to(torch.bfloat16).cuda(), dw, x1, ntaps)
+    ops.conv_wgrad_bf16(x0, dyn, dw, x1, ntaps)
     _close(dw, ref, 2e-4, "tcgen05 wgrad")
+    ops.conv_wgrad_bf16(x0, dyn, dw, x1, ntaps)                          # the accumulating form adds
+    _close(dw, 2 * ref, 2e-4, "tcgen05 wgrad, second accumulation")
+    # overwrite form: no zero-fill by the caller, whatever split the library picks (plain stores when unsplit)
+    dw2 = torch.full((Cout, ntaps, Cin), float("nan"), device="cuda")
+    ops.conv_wgrad_bf16(x0, dyn, dw2, x1, ntaps, overwrite=True)
+    _close(dw2, ref, 2e-4, "tcgen05 wgrad, overwrite")
 
 
 def test_space_to_depth_and_convt_backward_as_gemms(ops):

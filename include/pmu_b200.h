@@ -375,6 +375,10 @@ int pmu_gauss_head_bwd_nhwc_bf16(const void* enc, const float* w, const float* d
  * operand layouts of the tcgen05 GEMMs in one pass: wf [Cout][9][Cin] (forward, tap = ky*3+kx; nullable) and
  * wd [Cin][9][Cout] with the taps flipped (data gradient of loss.backward(), train.py:95; nullable).  Channels % 32 == 0. */
 int pmu_pack_conv3x3_weights_bf16(const float* w, void* wf, void* wd, int Cout, int Cin, void* stream);
+/* the same for every 3x3 layer of a network in ONE launch (the 35 conv layers of the trainer model: unet_parts.py:15,18,
+ * probabilistic_unet.py:38,43): `table` is a DEVICE array of nlayers x 6 int64 {w, wf, wd, Cout, Cin, first_tile} — device
+ * pointers as integers, wf / wd nullable, first_tile = running sum of (Cout/32)*(Cin/32), total_tiles = its end. */
+int pmu_pack_conv3x3_weights_multi_bf16(const int64_t* table, int nlayers, int64_t total_tiles, void* stream);
 /* the weight gradient pmu_conv_wgrad_bf16 produced, fp32 [Cout][9][Cin] -> the parameter's OIHW [Cout][Cin][3][3]
  * (what autograd hands to nn.Conv2d.weight.grad, train.py:95).  Cin % 64 == 0. */
 int pmu_unpack_conv3x3_wgrad_f32(const float* dwp, float* dw, int Cout, int Cin, void* stream);

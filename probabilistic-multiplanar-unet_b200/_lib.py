@@ -84,6 +84,7 @@ _SIG = {
     "pmu_s2d_nhwc_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pmu_conv_wgrad_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_pack_conv3x3_weights_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "pmu_pack_conv3x3_weights_multi_bf16": (c_int, [_P, c_int, c_int64, _P]),
     "pmu_unpack_conv3x3_wgrad_f32": (c_int, [_P, _P, c_int, c_int, _P]),
     "pmu_conv1x1_slicebias_bf16": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "pmu_fcomb_last_fwd_bf16": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P]),

@@ -454,10 +454,8 @@ gauss_head_bwd_nhwc_kernel(const uint4* __restrict__ enc, const float* __restric
 // forward  wf[co][tap][ci], data gradient (= convolution with the transposed, flipped weights) wd[ci][8 - tap][co].
 // Round 2a built both with torch (to(bf16) / permute / flip / contiguous: ~230 small kernels and 2 ms per step for 69 M
 // parameters); here one kernel reads a 32 x 32 (co, ci) tile once and writes both layouts with 4-byte stores.
-__global__ void __launch_bounds__(TB_THREADS)
-pack_conv3x3_kernel(const float* __restrict__ w, uint32_t* __restrict__ wf, uint32_t* __restrict__ wd, int Cout, int Cin) {
-  __shared__ float s[32][289];
-  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+__device__ __forceinline__ void pack_conv3x3_tile(const float* __restrict__ w, uint32_t* __restrict__ wf, uint32_t* __restrict__ wd,
+                                                  int Cout, int Cin, int co0, int ci0, float (*s)[289]) {
   // a row of the tile = 32 input channels x 9 taps = 288 contiguous floats (16-byte aligned: ci0 % 32 == 0): 72 float4
 #pragma unroll 3
   for (int i = threadIdx.x; i < 32 * 72; i += TB_THREADS) {
@@ -476,6 +474,24 @@ pack_conv3x3_kernel(const float* __restrict__ w, uint32_t* __restrict__ wf, uint
       const int cp = i & 15, t = (i >> 4) % 9, c = i / 144;
       wd[(((int64_t)(ci0 + c) * 9 + (8 - t)) * Cout + co0) / 2 + cp] = pack16_rn<false>(s[2 * cp][c * 9 + t], s[2 * cp + 1][c * 9 + t]);
     }
+}
+__global__ void __launch_bounds__(TB_THREADS)
+pack_conv3x3_kernel(const float* __restrict__ w, uint32_t* __restrict__ wf, uint32_t* __restrict__ wd, int Cout, int Cin) {
+  __shared__ float s[32][289];
+  pack_conv3x3_tile(w, wf, wd, Cout, Cin, blockIdx.y * 32, blockIdx.x * 32, s);
+}
+// every 3x3 layer of a network in ONE launch: table[l] = {w, wf, wd, Cout, Cin, first tile} (int64 each), a block = one
+// 32 x 32 tile of one layer (35 launches of 5-30 us, most of them latency, become one pass at memory rate)
+__global__ void __launch_bounds__(TB_THREADS)
+pack_conv3x3_multi_kernel(const int64_t* __restrict__ table, int nlayers) {
+  __shared__ float s[32][289];
+  int l = 0;
+  while (l + 1 < nlayers && (int64_t)blockIdx.x >= __ldg(table + (l + 1) * 6 + 5)) ++l;
+  const int64_t* e = table + l * 6;
+  const int Cout = (int)__ldg(e + 3), Cin = (int)__ldg(e + 4);
+  const int t = (int)((int64_t)blockIdx.x - __ldg(e + 5)), tiles_ci = Cin / 32;
+  pack_conv3x3_tile(reinterpret_cast<const float*>(__ldg(e)), reinterpret_cast<uint32_t*>(__ldg(e + 1)),
+                    reinterpret_cast<uint32_t*>(__ldg(e + 2)), Cout, Cin, (t / tiles_ci) * 32, (t % tiles_ci) * 32, s);
 }
 // weight gradient of the tcgen05 wgrad kernel, fp32 [Cout][9][Cin] -> the parameter's OIHW [Cout][Cin][3][3]
 __global__ void __launch_bounds__(TB_THREADS)
@@ -855,6 +871,13 @@ extern "C" int pmu_bn_train_fwd_stats_nhwc_bf16(const void* y, const double* sta
   const int64_t total = npix * (C / 8);
   bn_act_nhwc_kernel<<<ew_blocks(total), TB_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(y), scale_shift, scale_shift + C, relu,
                                                              reinterpret_cast<uint4*>(a), total, C / 8);
+  PMU_LAUNCH_CHECK();
+  return PMU_OK;
+}
+
+extern "C" int pmu_pack_conv3x3_weights_multi_bf16(const int64_t* table, int nlayers, int64_t total_tiles, void* stream) {
+  PMU_CHECK_ARG(table && nlayers > 0 && total_tiles > 0 && total_tiles < (1ll << 31), "pmu_pack_conv3x3_weights_multi_bf16: bad arguments");
+  pack_conv3x3_multi_kernel<<<(unsigned)total_tiles, TB_THREADS, 0, (cudaStream_t)stream>>>(table, nlayers);
   PMU_LAUNCH_CHECK();
   return PMU_OK;
 }

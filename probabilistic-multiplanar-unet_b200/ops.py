@@ -830,3 +830,40 @@ def bn_train_fwd_stats_nhwc_bf16(y, stats, gamma, beta, eps, relu, momentum=0.1,
     _launch(lib, "pmu_bn_train_fwd_stats_nhwc_bf16", (_p(y), _p(stats), _p(gamma), _p(beta), float(eps), int(relu), float(momentum),
                                                     _p(run_mean), _p(run_var), _p(mean), _p(var), _p(a), _p(ss), npix, C, st,))
     return a, mean, var
+
+
+class PackedConvWeights:
+    """Persistent bf16 operand copies (forward + data-gradient layouts) of a list of fp32 OIHW 3x3 conv weights, refreshed
+    by ONE kernel launch (`refresh()`); `get(w)` -> (wf [Cout, 9*Cin], wd [Cin, 9*Cout])."""
+
+    def __init__(self, weights):
+        self.weights = [w for w in weights]
+        dev = self.weights[0].device
+        total = sum(2 * w.numel() for w in self.weights)
+        self.buf = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        rows, self.views, off, tile = [], {}, 0, 0
+        for w in self.weights:
+            _f32(w, "w")
+            Cout, Cin = int(w.shape[0]), int(w.shape[1])
+            if w.shape[2:] != (3, 3) or Cout % 32 or Cin % 32 or not w.is_contiguous():
+                raise RuntimeError("PackedConvWeights: contiguous [Cout, Cin, 3, 3] weights with channels % 32 == 0")
+            n = w.numel()
+            wf = self.buf[off:off + n].view(Cout, 9 * Cin)
+            wd = self.buf[off + n:off + 2 * n].view(Cin, 9 * Cout)
+            off += 2 * n
+            rows.append([w.data_ptr(), wf.data_ptr(), wd.data_ptr(), Cout, Cin, tile])
+            tile += (Cout // 32) * (Cin // 32)
+            self.views[w.data_ptr()] = (wf, wd)
+        self.total_tiles = tile
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.key = tuple(w.data_ptr() for w in self.weights)
+
+    def matches(self, weights) -> bool:
+        return self.key == tuple(w.data_ptr() for w in weights)
+
+    def refresh(self):
+        lib, st = _prep(self.buf, self.table)
+        _launch(lib, "pmu_pack_conv3x3_weights_multi_bf16", (_p(self.table), len(self.weights), self.total_tiles, st,))
+
+    def get(self, w):
+        return self.views.get(w.data_ptr())

@@ -206,7 +206,9 @@ def _tc_cbr_fwd(conv, bn, x0, x1=None):
     else:
         # both operand layouts of this layer from one read of the fp32 weights: wf [Cout][tap][Cin] for this GEMM,
         # wd [Cin][flipped tap][Cout] for the data gradient in the backward
-        wf, wd = ops.pack_conv3x3_weights_bf16(w)
+        pk = _BF16.get("packed")
+        pre = pk.get(w) if pk is not None else None
+        wf, wd = pre if pre is not None else ops.pack_conv3x3_weights_bf16(w)
         stats = _stats_take(Cout, x0.device)
         if stats is not None:
             # BatchNorm batch statistics in the convolution's epilogue: the statistics pass over y is gone
@@ -529,6 +531,21 @@ def fcomb_forward(step, z):
     return _fcomb_fwd(step.net.fcomb, step.feat, z)[0]
 
 
+def _prepack(net):
+    """bf16 operand copies of every tensor-core 3x3 layer of the net for this step, one launch (ops.PackedConvWeights; the
+    buffers persist on the net, so a CUDA graph sees static addresses)."""
+    ws = [m.weight.detach() for part in (net.posterior, net.prior, net.unet) for m in part.modules()
+          if isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3) and m.weight.shape[1] > 2
+          and m.weight.shape[0] % 32 == 0 and m.weight.shape[1] % 32 == 0 and m.weight.is_contiguous()]
+    if not ws:
+        return None
+    pk = net.__dict__.get("_pmu_packed")
+    if pk is None or not pk.matches(ws):
+        pk = net.__dict__["_pmu_packed"] = ops.PackedConvWeights(ws)
+    pk.refresh()
+    return pk
+
+
 def _grad_layout(net) -> Optional[_FlatLayout]:
     """The flat-gradient layout from the completion order a previous backward recorded on `net` (None before the first
     one, or when a recorded parameter is no longer a trainable parameter of the net)."""
@@ -563,10 +580,13 @@ class TrainStep:
         _BF16["on"] = on and self.bf16
         _BF16["stats"] = None
         if not on:
+            _BF16["packed"] = None
             _BF16["arena"] = None
             _PENDING_NBT.clear()
 
     def _forward(self, net, patch, segm):
+        if self.bf16:
+            _BF16["packed"] = _prepack(net)
         self.mu_q, self.ls_q, self.post = _gauss_fwd(net.posterior, patch, segm)
         self.mu_p, self.ls_p, self.prior = _gauss_fwd(net.prior, patch)
         self.feat, self.unet = _unet_fwd(net.unet, patch)

@@ -435,6 +435,18 @@ def test_weight_pack_unpack_bf16(ops):
         assert none is None and torch.equal(wf2, wf)
         dwp = torch.randn(Cout, 9, Cin, generator=g)
         assert torch.equal(ops.unpack_conv3x3_wgrad_f32(dwp.cuda()).cpu(), dwp.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous())
+    # every layer of a net in one launch (ops.PackedConvWeights) == layer by layer; refresh() follows in-place weight updates
+    ws = [torch.randn(co, ci, 3, 3, generator=g).cuda() for co, ci in ((64, 64), (128, 64), (64, 192), (256, 128), (96, 32))]
+    pk = ops.PackedConvWeights(ws)
+    for rep in range(2):
+        pk.refresh()
+        for w in ws:
+            wf, wd = pk.get(w)
+            wf1, wd1 = ops.pack_conv3x3_weights_bf16(w)
+            assert torch.equal(wf, wf1) and torch.equal(wd, wd1)
+        for w in ws:
+            w.mul_(1.5).add_(0.25)
+    assert pk.matches(ws) and not pk.matches(ws[:-1])
 
 
 def test_fcomb_chain_kernels_bf16(ops):

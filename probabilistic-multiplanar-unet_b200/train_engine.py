@@ -23,6 +23,7 @@ CrossEntropyLoss(reduction none -> sum), kl_divergence of Independent Normals).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -33,6 +34,18 @@ from . import ops
 
 def _d(t):
     return t.detach()
+
+
+# per-net state of the tensor-core step (completion order of the gradients, flat layout, persistent packed weights): kept
+# here, weakly keyed by the module, so that nothing of it is pickled, deep-copied or saved with the model
+_NET_STATE = weakref.WeakKeyDictionary()
+
+
+def _net_state(net) -> dict:
+    st = _NET_STATE.get(net)
+    if st is None:
+        st = _NET_STATE[net] = {}
+    return st
 
 
 class _FlatLayout:
@@ -539,9 +552,10 @@ def _prepack(net):
           and m.weight.shape[0] % 32 == 0 and m.weight.shape[1] % 32 == 0 and m.weight.is_contiguous()]
     if not ws:
         return None
-    pk = net.__dict__.get("_pmu_packed")
+    ns = _net_state(net)
+    pk = ns.get("packed")
     if pk is None or not pk.matches(ws):
-        pk = net.__dict__["_pmu_packed"] = ops.PackedConvWeights(ws)
+        pk = ns["packed"] = ops.PackedConvWeights(ws)
     pk.refresh()
     return pk
 
@@ -549,16 +563,17 @@ def _prepack(net):
 def _grad_layout(net) -> Optional[_FlatLayout]:
     """The flat-gradient layout from the completion order a previous backward recorded on `net` (None before the first
     one, or when a recorded parameter is no longer a trainable parameter of the net)."""
-    order = net.__dict__.get("_pmu_grad_order")
+    ns = _net_state(net)
+    order = ns.get("grad_order")
     if order is None:
         return None
     live = {id(p) for p in net.parameters() if p.requires_grad}
     if any(id(p) not in live for p in order):
-        net.__dict__["_pmu_grad_order"] = None
+        ns["grad_order"] = None
         return None
-    lay = net.__dict__.get("_pmu_grad_layout")
+    lay = ns.get("grad_layout")
     if lay is None or lay.order != [id(p) for p in order]:
-        lay = net.__dict__["_pmu_grad_layout"] = _FlatLayout(order)
+        lay = ns["grad_layout"] = _FlatLayout(order)
     return lay
 
 
@@ -658,7 +673,7 @@ class TrainStep:
         _unet_bwd(net.unet, self.unet, ops.nchw_f32_to_nhwc_bf16(dfeat) if (self.bf16 and not self.tc_fcomb) else dfeat, tape)
         tape.finish()
         if self.bf16 and (layout is None or not tape.in_order or len(tape.order) != len(layout.order)):
-            net.__dict__["_pmu_grad_order"] = list(tape.order)           # (re)record the completion order for the next backward
+            _net_state(net)["grad_order"] = list(tape.order)             # (re)record the completion order for the next backward
         self.flat = tape.buf
         return tape.g
 

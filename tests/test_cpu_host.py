@@ -220,6 +220,60 @@ def test_data_parallel_gradient_allreduce_over_gloo():
     assert n_coll > 1
 
 
+def _gloo_tape_worker(rank, world, port, ret):
+    """The range-announcing gradient tape of the tensor-core training step (train_engine._Tape with a _FlatLayout) on 2 gloo
+    ranks: gradients are put in completion order, every announced range is all-reduced at once (what GraphedTrainStep does
+    inside its CUDA graph); the result must equal an all-reduce of every gradient after the fact, the ranges must tile the
+    buffer, and an out-of-order put must fall back to one final range without losing anything."""
+    import torch.distributed as dist
+    from pmu_b200 import train_engine as te
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(11)
+    params = [torch.nn.Parameter(torch.zeros(*shp)) for shp in ((64, 33), (7,), (128, 64, 3, 3), (5, 5), (256, 130), (3,))]
+    grads = [[torch.randn(p.shape, generator=g) for p in params] for _ in range(world)]       # every rank draws all, uses its own
+    layout = te._FlatLayout(params)
+    out = {}
+    for name, order in (("in_order", list(range(len(params)))), ("shuffled", [0, 2, 1, 3, 5, 4])):
+        ranges = []
+
+        def exchange(buf, lo, hi):
+            ranges.append((lo, hi))
+            dist.all_reduce(buf[lo:hi])
+
+        tape = te._Tape(layout, "cpu", exchange, bucket_bytes=64 * 1024)
+        for i in order:
+            if i % 2 == 0:                                    # written in place through out(p) ...
+                tape.out(params[i]).copy_(grads[rank][i])
+                tape.put(params[i])
+            else:                                             # ... or handed over and copied in
+                tape.put(params[i], grads[rank][i].clone())
+        tape.finish()
+        want = [sum(grads[r][i] for r in range(world)) for i in range(len(params))]
+        err = max(float((tape.g[id(p)] - w).abs().max()) for p, w in zip(params, want))
+        tiles = ranges[0][0] == 0 and ranges[-1][1] == layout.total and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        out[name] = (err, len(ranges), tiles, tape.in_order)
+    if rank == 0:
+        ret.put(out)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_ranges_allreduce_over_gloo():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_tape_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    err, n, tiles, in_order = out["in_order"]
+    assert err < 1e-6 and n >= 3 and tiles and in_order, out
+    err, n, tiles, in_order = out["shuffled"]
+    assert err < 1e-6 and tiles and not in_order, out
+
+
 def test_nifti_roundtrip(tmp_path):
     from pmu_b200 import nifti_io
     v = np.random.default_rng(0).random((5, 6, 7))

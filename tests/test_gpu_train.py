@@ -638,7 +638,7 @@ def test_flat_gradient_buffer_ranges_are_final_when_announced(ops):
         return st, st.backward(-1.0, on_ready=hook)
 
     run(None)                                              # records the completion order
-    assert net.__dict__["_pmu_grad_order"] is not None
+    assert train_engine._net_state(net).get("grad_order") is not None
     seen = []
     st, grads = run(lambda buf, lo, hi: seen.append((lo, hi, buf[lo:hi].clone())))
     assert st.flat is not None and len(seen) >= 3, len(seen)

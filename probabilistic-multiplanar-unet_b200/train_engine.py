@@ -1,7 +1,9 @@
 """Training step of ProbabilisticUnet through the CUDA kernels: fp32 NCHW parity mode and the bf16
-tensor-core mode (precision="bf16" / "f16": every convolution GEMM — forward, dgrad, wgrad — on tcgen05, activations
-and their gradients bf16 NHWC END TO END: BatchNorm / pooling / skip adds / the Gaussian head run on that layout
-(csrc/train_bf16.cu), so no layout or precision cast sits between two GEMMs of the step).
+tensor-core mode (precision="bf16" / "f16": every GEMM of the step — convolution forward / dgrad / wgrad, the transposed
+convolutions, the Fcomb 1x1 chain — on tcgen05, activations and their gradients bf16 NHWC END TO END: BatchNorm (its batch
+statistics come out of the convolution epilogue) / pooling / skip adds / the Gaussian head run on that layout
+(csrc/train_bf16.cu), so no layout or precision cast sits between two GEMMs of the step; gradients land in one flat buffer
+in completion order, which the data-parallel CUDA-graph step all-reduces range by range under the backward).
 
 What the reference's training loop asks of autograd (train.py:85-110 via
 ProbUNetTrainer.predict / loss, trainer/probunet_trainer.py:27-39):
@@ -784,6 +786,8 @@ class GraphedTrainStep:
              eps: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Replay on new inputs; gradients land in p.grad (added when `accumulate`).  Returns the loss (a static tensor:
         read it before the next step())."""
+        if self.graph is None:
+            raise RuntimeError("this GraphedTrainStep was closed")
         if tuple(imgs.shape) != tuple(self.imgs.shape) or tuple(masks.shape) != tuple(self.masks.shape):
             raise ValueError("GraphedTrainStep was captured for inputs of shape "
                              f"{tuple(self.imgs.shape)} / {tuple(self.masks.shape)}")

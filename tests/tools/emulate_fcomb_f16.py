@@ -1,4 +1,4 @@
-"""CPU emulation of the numerics of the f16 fcomb variants (PMU_FCOMB_TS=2 / PMU_FCOMB_F16=1) against today's bf16 path,
+"""CPU emulation of the numerics of the f16 fcomb variants (the f16 hidden-layer form that became the default tensor-core inference format in round 2; the environment switches it was written for are gone) against today's bf16 path,
 both measured against fp32 on the same bf16 features: layer 0 as in the kernels (bf16 feature GEMM with fp32 accumulate +
 exact fp32 per-sample bias), hidden layers with bf16 or f16 operands; "f16 accumulate" rounds the running sum to f16 after
 every K = 16 step and adds the bias in f16 — a worst case for what the tensor core does.

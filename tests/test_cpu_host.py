@@ -382,6 +382,16 @@ def test_every_compute_entry_point_cites_the_reference():
                             "pmu_ctx_create", "pmu_ctx_destroy", "pmu_ctx_bind", "pmu_ctx_stats"}, missing
 
 
+def test_python_constants_match_the_header():
+    """Workspace sizes the Python wrappers allocate follow include/pmu_b200.h (PMU_RED_MAX_BLOCKS rows per reduction)."""
+    import re
+    from pmu_b200 import _lib, ops
+    src = open(_lib.HEADER_PATH).read()
+    assert int(re.search(r"#define\s+PMU_RED_MAX_BLOCKS\s+(\d+)", src).group(1)) == ops.RED_MAX_BLOCKS
+    assert int(re.search(r"#define\s+PMU_POOL_MAX\s+(\d+)", src).group(1)) == ops.POOL_MAX
+    assert int(re.search(r"#define\s+PMU_POOL_AVG_CEIL\s+(\d+)", src).group(1)) == ops.POOL_AVG_CEIL
+
+
 def test_missing_library_raises_loudly(monkeypatch, tmp_path):
     """The product never builds or falls back on its own: with no libpmu_b200.so, loading — and therefore every op —
     raises a RuntimeError that says how to build it."""
